@@ -1,0 +1,210 @@
+/*
+ * hg_sm100a.h -- C ABI of libhg_sm100a.so: the B200 (sm_100a) implementation of the stacked-hourglass
+ * heatmap-regression hot path of Xinjie-Qiu/progressive_process_for_human_pose_estimation.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below replaces the
+ * library kernels PyTorch dispatches for one reference call site (cited as file:line into the reference
+ * tree).  A maintainer binds these with ctypes; the in-tree Python host
+ * (progressive_process_for_human_pose_estimation_b200/_lib.py) does exactly that.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers;
+ *   - activations are NHWC ("channels last"), element type HgDType (bf16 on the tensor-core path, fp32 on
+ *     the CUDA-core path); parameters, statistics and gradients of parameters are fp32;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are only enqueued, never synchronised;
+ *   - return value: HG_OK (0) or a negative HgStatus; hg_last_error_string() gives the text;
+ *   - there is no CPU fallback: an unsupported shape is HG_ERR_UNSUPPORTED.
+ */
+#ifndef HG_SM100A_H_
+#define HG_SM100A_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define HG_API __attribute__((visibility("default")))
+#else
+#define HG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum HgStatus {
+  HG_OK = 0,
+  HG_ERR_BAD_ARG = -1,
+  HG_ERR_UNSUPPORTED = -2,
+  HG_ERR_CUDA = -3
+} HgStatus;
+
+/* HG_F16 is accepted only by the decode / PCKh entry points (the reference evaluates .half() models). */
+typedef enum HgDType { HG_BF16 = 0, HG_F32 = 1, HG_F16 = 2 } HgDType;
+
+/* Convolution geometry.  Input [N,H,W,Cin] -> output [N,Ho,Wo,Cout], Ho = (H + 2*pad - dil*(R-1) - 1)/stride + 1.
+ * Mirrors nn.Conv2d(Cin, Cout, (R,S), stride, pad, dil) as used by ResidualBlock / lin / creatModel
+ * (try_with_torch.py:186-193,248,262,271-273). */
+typedef struct HgConvDesc {
+  int32_t N, H, W;
+  int32_t Cin, Cout;
+  int32_t R, S;
+  int32_t stride, pad, dil;
+  int32_t dtype; /* HgDType of activations */
+} HgConvDesc;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+HG_API const char* hg_last_error_string(void);
+/* Number of kernel launches issued through this library since it was loaded. */
+HG_API unsigned long long hg_launch_count(void);
+/* 1 when the device behind the current context is compute capability 10.x. */
+HG_API int hg_device_ok(void);
+
+/* ---- convolution (nn.Conv2d: try_with_torch.py:186-193,199-207,248,253,262,271-273,291-297) -------- */
+/* Repack an fp32 OIHW weight [Cout,Cin,R,S] into the two GEMM operand layouts the kernels read:
+ *   w_fprop [R*S][Cout][Cin]  (B operand of y = x (*) w)        element type desc->dtype
+ *   w_dgrad [R*S][Cin][Cout]  (B operand of dx = dy (*) w^T)    element type desc->dtype
+ * Either destination may be NULL. */
+HG_API int hg_pack_conv_weight(const HgConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream);
+
+/* y = conv(x, w) + bias [+ residual]; optional per-channel statistics of y for the BatchNorm that
+ * follows: stats[0..Cout) += sum(y), stats[Cout..2Cout) += sum(y*y) (the caller zeroes stats).
+ * bias, residual, stats may be NULL.  residual has the shape of y. */
+HG_API int hg_conv_fprop(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias,
+                  const void* residual, void* y, float* stats, void* stream);
+
+/* dx = conv_transpose(dy, w) [+ addend]  (stride 1).  addend has the shape of dx, may be NULL. */
+HG_API int hg_conv_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
+                  void* stream);
+
+/* Same as hg_conv_fprop plus an optional fp32 NCHW copy [N,Cout,H,W] of the result: the tensors
+ * creatModel.forward returns to the training loop (try_with_torch.py:291-292,298). */
+HG_API int hg_conv_fprop_ex(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias,
+                     const void* residual, void* y, float* stats, float* out_nchw, void* stream);
+
+/* dw_packed[R*S][Cout_p][Cin_p] (fp32, channels padded to 64) += sum over pixels of dy (x) x ;
+ * dbias[Cout] += sum(dy).  Both ACCUMULATE: the reference shares one weight between many call sites
+ * (try_with_torch.py:217,224-237), so one buffer collects all of them.  Either may be NULL. */
+HG_API int hg_conv_wgrad(const HgConvDesc* d, const void* x, const void* dy, float* dw_packed, float* dbias,
+                  void* stream);
+
+/* dw_oihw[Cout,Cin,R,S] (=|+=) dw_packed : the layout torch.optim.Adam sees (try_with_torch.py:317,344). */
+HG_API int hg_unpack_conv_wgrad(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int accumulate,
+                         void* stream);
+
+/* Debug/validation switches: "force_ref_conv" = 1 routes bf16 convolutions to the CUDA-core kernels. */
+HG_API int hg_set_option(const char* name, int value);
+
+/* ---- BatchNorm2d + ReLU (try_with_torch.py:184-192,196-204,249-250,254-255) ------------------------- */
+/* x is [M, C] NHWC-flattened (M = N*H*W, channels padded to 64 in memory).  Training mode
+ * (use_running = 0) normalises with the batch statistics `stats` = {sum[Cp], sum of squares[Cp]} that the
+ * producing kernel accumulated (hg_conv_fprop's `stats`, or hg_bn_stats); eval mode uses running_mean/var. */
+typedef struct HgBnDesc {
+  int64_t M;
+  int32_t C;
+  int32_t dtype;
+  float eps;
+  int32_t relu;        /* fuse nn.ReLU after the affine transform */
+  int32_t use_running; /* 0 = batch statistics (train), 1 = running statistics (eval) */
+} HgBnDesc;
+
+HG_API int hg_bn_stats(const HgBnDesc* d, const void* x, float* stats, void* stream); /* stats += ; caller zeroes */
+HG_API int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const float* gamma, const float* beta,
+                const float* running_mean, const float* running_var, void* y, void* stream);
+/* red[0..Cp) += sum g, red[Cp..2Cp) += sum g*xhat, g = da * [bn(x) > 0]  (caller zeroes red) */
+HG_API int hg_bn_bwd_reduce(const HgBnDesc* d, const void* da, const void* x, const float* stats, const float* gamma,
+                     const float* beta, float* red, void* stream);
+/* dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) [+ addend]; dgamma += , dbeta += ; colsum[C] (optional)
+ * += sum over rows of dx without the addend = bias gradient of the convolution that produced x. */
+HG_API int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const float* stats, const float* gamma,
+                    const float* beta, const float* running_mean, const float* running_var, const float* red,
+                    const void* addend, void* dx, float* dgamma, float* dbeta, float* colsum, void* stream);
+
+/* Running-statistics update for a whole forward pass: module `i` applies the EMA of its call sites
+ * sites[first_site .. first_site+num_sites) in order and adds num_sites to num_batches_tracked (a shared
+ * BatchNorm is called 6-8 x nStack times per forward: try_with_torch.py:224-237).  Both tables live in
+ * device memory. */
+typedef struct HgBnRunningSite {
+  const float* stats;
+  float count;
+  int32_t pad_;
+} HgBnRunningSite;
+typedef struct HgBnRunningModule {
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  int32_t C, Cp;
+  int32_t first_site, num_sites;
+  float momentum;
+  int32_t pad_;
+} HgBnRunningModule;
+HG_API int hg_bn_update_running(const void* modules_dev, const void* sites_dev, int num_modules, void* stream);
+
+/* ---- spatial ops -------------------------------------------------------------------------------- */
+/* nn.MaxPool2d(2) (try_with_torch.py:220,226,265); backward routes to the first row-major maximum. */
+HG_API int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream);
+HG_API int hg_maxpool2_bwd(int dtype, const void* x, const void* dy, const void* addend, int N, int H, int W, int C,
+                    void* dx, void* stream);
+/* out[N,2h,2w,C] = upsample_x2(low[N,h,w,C]) [+ skip]; mode 0 = bilinear align_corners=True
+ * (try_with_torch.py:238-239), mode 1 = nearest (hourglass_compare.py:532-542). */
+HG_API int hg_upsample2x_add_fwd(int dtype, int mode, const void* low, const void* skip, int N, int h, int w, int C,
+                          void* out, void* stream);
+HG_API int hg_upsample2x_bwd(int dtype, int mode, const void* dout, const void* addend, int N, int h, int w, int C,
+                      void* dlow, void* stream);
+HG_API int hg_add(int dtype, const void* a, const void* b, void* out, long long n_elems, void* stream);
+/* layout changes at the module boundary (NCHW fp32 tensors of the training loop <-> NHWC activations) */
+HG_API int hg_nchw_f32_to_nhwc(int dtype, const float* src_nchw, const void* addend, int N, int C, int H, int W, void* dst,
+                        void* stream);
+HG_API int hg_nhwc_to_nchw_f32(int dtype, const void* src, int N, int C, int H, int W, float* dst_nchw, void* stream);
+
+/* ---- stem: Conv2d(3,64,7,2,3) + ReLU on the fp32 NCHW image batch (try_with_torch.py:262,276-277) ---- */
+HG_API int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W, void* y,
+                void* stream);
+/* dw_oihw += , dbias += , with the ReLU mask taken from y */
+HG_API int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, int N, int H, int W, float* dw_oihw,
+                float* dbias, void* stream);
+
+/* ---- target rendering ---------------------------------------------------------------------------- */
+/* Gaussian keypoint heatmaps, evaluated in float64 like the numpy code, stored as float32
+ * (try_with_torch.py:107-132; variants try_with_torch_100.py:64-85, only_one_hourgless.py:112-132,
+ * hourglass_compare.py:286-313,713-734).  keypoints [B,P,J,3] = (x, y, v) in image pixels, img_wh [B,2]. */
+typedef struct HgGaussDesc {
+  int32_t B, P, J, H, W;
+  int32_t center_mode; /* 0: c = kp / size * W   1: c = kp * 256 / size / 4 (MPII) */
+  int32_t truncate;    /* 1: centre truncated to an integer (astype(np.int)) */
+  int32_t accumulate;  /* 0: only the LAST person is kept (quirk Q7)  1: sum over persons */
+  double pre_scale;    /* 1, or 100 (try_with_torch_100.py:81) */
+  double sigma;
+  double amplitude;    /* 1, or 1/(2 pi sigma^2) */
+} HgGaussDesc;
+HG_API int hg_render_gauss(const HgGaussDesc* d, const double* keypoints, const int32_t* num_persons, const double* img_wh,
+                    float* out, void* stream);
+
+/* PIL ImageDraw.point / ImageDraw.line label maps, int64 [B,H,W]
+ * (try_different_stack.py:114-155, try_skeleton_and_keypoints.py:93-114). */
+typedef struct HgLabelDesc {
+  int32_t B, P, J, L, H, W;
+  int32_t center_mode;
+  int32_t draw_points; /* draw.point value k+1 for visible joints */
+  int32_t draw_lines;  /* draw.line for limbs whose both ends are visible */
+  int32_t line_value;  /* 0: limb index + 1, otherwise this constant (background map = 1) */
+} HgLabelDesc;
+HG_API int hg_render_labels(const HgLabelDesc* d, const double* keypoints, const int32_t* num_persons, const double* img_wh,
+                     const int32_t* limbs, int64_t* out, void* stream);
+
+/* ---- decode + PCKh -------------------------------------------------------------------------------- */
+/* first row-major (y, x) of the maximum of each of num_maps [H,W] maps
+ * (hourglass_compare.py:831,1092; only_one_hourgless.py:294-295). */
+HG_API int hg_decode_argmax(const void* heatmaps, int dtype, int num_maps, int H, int W, int32_t* out_yx, float* out_max,
+                     void* stream);
+/* PCKh threshold sweep (hourglass_compare.py:812-844; performance_compare.py:544-615). Counters are int32
+ * [B,nthr] and must be zeroed by the caller; found[B,njoints] marks joints present in the label map. */
+HG_API int hg_pckh_sweep(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
+                  int chan_offset, int njoints, const float* thresholds, int nthr, int32_t* correct, int32_t* total,
+                  int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream);
+/* PCKh "A" (only_one_hourgless.py:285-313): counts[0] += correct, counts[1] += total. */
+HG_API int hg_pckh_a(const void* x, int x_dtype, const void* target, int t_dtype, int B, int Cx, int Ct, int H, int W,
+              int njoints, int head_ch, int neck_ch, int32_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HG_SM100A_H_ */

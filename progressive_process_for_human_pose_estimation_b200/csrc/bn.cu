@@ -1,0 +1,427 @@
+// BatchNorm (training-mode batch statistics and eval-mode running statistics) + ReLU, forward and backward,
+// on NHWC activations.  HBM-bound streaming kernels: 128-bit accesses, one thread = 8 consecutive channels,
+// per-channel reductions finish with a handful of fp32 atomics per block.
+//
+// The saved state of a BatchNorm call site is just its raw statistics (sum, sum of squares over N*H*W); mean,
+// 1/std, scale and shift are re-derived in registers wherever they are needed, so no "finalize" pass exists.
+//
+// Replaces nn.BatchNorm2d + nn.ReLU(True) in ResidualBlock / lin
+// (reference try_with_torch.py:184-192,196-204,249-250,254-255).
+#include "hg_common.cuh"
+
+namespace hg {
+
+struct BnArgs {
+  const float* stats;   // [2*Cp]: sum, sum of squares  (training mode)
+  const float* gamma;   // [C]
+  const float* beta;    // [C]
+  const float* rmean;   // [C] running mean (eval mode)
+  const float* rvar;    // [C] running var  (eval mode)
+  float count;          // N*H*W
+  float eps;
+  int use_running;
+  int relu;
+  int C, Cp;
+};
+
+// scale/shift/mean/invstd of 8 consecutive channels starting at c0
+__device__ __forceinline__ void bn_coeffs(const BnArgs& a, int c0, float (&mean)[8], float (&invstd)[8],
+                                          float (&scale)[8], float (&shift)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    if (c < a.C) {
+      float mu, var;
+      if (a.use_running) {
+        mu = a.rmean[c];
+        var = a.rvar[c];
+      } else {
+        mu = a.stats[c] / a.count;
+        var = fmaxf(a.stats[a.Cp + c] / a.count - mu * mu, 0.f);
+      }
+      const float is = rsqrtf(var + a.eps);
+      mean[e] = mu;
+      invstd[e] = is;
+      scale[e] = a.gamma[c] * is;
+      shift[e] = a.beta[c] - mu * scale[e];
+    } else {
+      mean[e] = 0.f;
+      invstd[e] = 0.f;
+      scale[e] = 0.f;
+      shift[e] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// statistics: stats[c] += sum_m x[m,c]; stats[Cp+c] += sum_m x[m,c]^2
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long long M, int Cp,
+                                                       float* __restrict__ stats, int rows_per_block) {
+  __shared__ float red[2][256][9];
+  const int vecs = Cp >> 3;            // 8-channel vectors per row (8, 16 or 32)
+  const int vc = threadIdx.x % vecs;   // vector column
+  const int rl = threadIdx.x / vecs;   // row lane
+  const int rlanes = 256 / vecs;
+  const long long m0 = (long long)blockIdx.x * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float s[8] = {}, ss[8] = {};
+  for (long long m = m0 + rl; m < m1; m += rlanes) {
+    float v[8];
+    load8(x + m * Cp + vc * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e] += v[e];
+      ss[e] = fmaf(v[e], v[e], ss[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][threadIdx.x][e] = s[e];
+    red[1][threadIdx.x][e] = ss[e];
+  }
+  __syncthreads();
+  // thread t < Cp reduces channel t over the row lanes
+  for (int c = threadIdx.x; c < Cp; c += 256) {
+    const int v = c >> 3, e = c & 7;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < rlanes; ++r) {
+      a += red[0][r * vecs + v][e];
+      b += red[1][r * vecs + v][e];
+    }
+    atomicAdd(stats + c, a);
+    atomicAdd(stats + Cp + c, b);
+  }
+}
+
+int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats, cudaStream_t st) {
+  if (Cp % 64 != 0 || Cp > 2048) {
+    set_error("bn_stats: padded channel count %d unsupported", Cp);
+    return HG_ERR_UNSUPPORTED;
+  }
+  if (Cp > 256) {  // wide tensors (virtual cat inputs): one launch per 256-channel slab is not needed today
+    set_error("bn_stats: Cp > 256 unsupported");
+    return HG_ERR_UNSUPPORTED;
+  }
+  int rpb = (int)((M + 2 * kNumSMs * 4 - 1) / (2 * kNumSMs * 4));
+  if (rpb < 64) rpb = 64;
+  const int blocks = ceil_div(M, rpb);
+  if (dtype == HG_BF16)
+    bn_stats_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, M, Cp, stats, rpb);
+  else
+    bn_stats_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, M, Cp, stats, rpb);
+  HG_LAUNCH_OK("bn_stats_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// apply: y = [relu](gamma * (x - mean) * invstd + beta)
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long M,
+                                                       BnArgs a) {
+  const int vecs = a.Cp >> 3;
+  const int vc = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int rlanes = 256 / vecs;
+  float mean[8], invstd[8], scale[8], shift[8];
+  bn_coeffs(a, vc * 8, mean, invstd, scale, shift);
+  for (long long m = (long long)blockIdx.x * rlanes + rl; m < M; m += (long long)gridDim.x * rlanes) {
+    float v[8];
+    load8(x + m * a.Cp + vc * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float o = fmaf(v[e], scale[e], shift[e]);
+      if (a.relu) o = fmaxf(o, 0.f);
+      v[e] = o;
+    }
+    store8(y + m * a.Cp + vc * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward, pass 1: red[c] += sum_m g, red[Cp+c] += sum_m g*xhat, with g = da * [bn(x) > 0]
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ x,
+                                                            long long M, BnArgs a, float* __restrict__ redout,
+                                                            int rows_per_block) {
+  __shared__ float red[2][256][9];
+  const int vecs = a.Cp >> 3;
+  const int vc = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int rlanes = 256 / vecs;
+  float mean[8], invstd[8], scale[8], shift[8];
+  bn_coeffs(a, vc * 8, mean, invstd, scale, shift);
+  const long long m0 = (long long)blockIdx.x * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float s[8] = {}, sx[8] = {};
+  for (long long m = m0 + rl; m < m1; m += rlanes) {
+    float xv[8], gv[8];
+    load8(x + m * a.Cp + vc * 8, xv);
+    load8(da + m * a.Cp + vc * 8, gv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float g = gv[e];
+      if (a.relu && !(fmaf(xv[e], scale[e], shift[e]) > 0.f)) g = 0.f;
+      s[e] += g;
+      sx[e] = fmaf(g, (xv[e] - mean[e]) * invstd[e], sx[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][threadIdx.x][e] = s[e];
+    red[1][threadIdx.x][e] = sx[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.Cp; c += 256) {
+    const int v = c >> 3, e = c & 7;
+    float p = 0.f, q = 0.f;
+    for (int r = 0; r < rlanes; ++r) {
+      p += red[0][r * vecs + v][e];
+      q += red[1][r * vecs + v][e];
+    }
+    atomicAdd(redout + c, p);
+    atomicAdd(redout + a.Cp + c, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward, pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) [+ addend]
+//   training mode; in eval mode (running statistics are constants) dx = gamma*invstd*g [+ addend].
+//   Block 0 adds dgamma += sum g*xhat, dbeta += sum g.  colsum (optional) += sum_m dx-without-addend,
+//   i.e. the bias gradient of the convolution that produced x.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ x,
+                                                           const T* __restrict__ addend, T* __restrict__ dx,
+                                                           long long M, BnArgs a, const float* __restrict__ redin,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ colsum, int rows_per_block) {
+  __shared__ float red[256][9];
+  const int vecs = a.Cp >> 3;
+  const int vc = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int rlanes = 256 / vecs;
+  float mean[8], invstd[8], scale[8], shift[8];
+  bn_coeffs(a, vc * 8, mean, invstd, scale, shift);
+  float mg[8], mgx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = vc * 8 + e;
+    if (a.use_running || c >= a.C) {
+      mg[e] = 0.f;
+      mgx[e] = 0.f;
+    } else {
+      mg[e] = redin[c] / a.count;
+      mgx[e] = redin[a.Cp + c] / a.count;
+    }
+  }
+  if (blockIdx.x == 0 && rl == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = vc * 8 + e;
+      if (c < a.C) {
+        if (dgamma) atomicAdd(dgamma + c, redin[a.Cp + c]);
+        if (dbeta) atomicAdd(dbeta + c, redin[c]);
+      }
+    }
+  }
+  const long long m0 = (long long)blockIdx.x * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float cs[8] = {};
+  for (long long m = m0 + rl; m < m1; m += rlanes) {
+    float xv[8], gv[8], o[8];
+    load8(x + m * a.Cp + vc * 8, xv);
+    load8(da + m * a.Cp + vc * 8, gv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float g = gv[e];
+      if (a.relu && !(fmaf(xv[e], scale[e], shift[e]) > 0.f)) g = 0.f;
+      const float xh = (xv[e] - mean[e]) * invstd[e];
+      o[e] = scale[e] * (g - mg[e] - xh * mgx[e]);
+      cs[e] += o[e];
+    }
+    if (addend) {
+      float ad[8];
+      load8(addend + m * a.Cp + vc * 8, ad);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += ad[e];
+    }
+    store8(dx + m * a.Cp + vc * 8, o);
+  }
+  if (colsum) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = cs[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.C; c += 256) {
+      const int v = c >> 3, e = c & 7;
+      float p = 0.f;
+      for (int r = 0; r < rlanes; ++r) p += red[r * vecs + v][e];
+      atomicAdd(colsum + c, p);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// running statistics: one block per BatchNorm module applies the EMA updates of all its call sites in the
+// order the reference's forward executes them (a shared module is called 6-8 x nStack times per forward,
+// reference try_with_torch.py:224-237; num_batches_tracked counts every call).
+// ------------------------------------------------------------------------------------------------------
+struct BnRunningSite {
+  const float* stats;
+  float count;
+  int pad;
+};
+struct BnRunningModule {
+  float* rmean;
+  float* rvar;
+  long long* nbt;
+  int C, Cp;
+  int first_site, num_sites;
+  float momentum;
+  int pad;
+};
+
+__global__ void bn_running_kernel(const BnRunningModule* __restrict__ mods, const BnRunningSite* __restrict__ sites) {
+  const BnRunningModule md = mods[blockIdx.x];
+  for (int c = threadIdx.x; c < md.C; c += blockDim.x) {
+    float rm = md.rmean[c], rv = md.rvar[c];
+    for (int i = 0; i < md.num_sites; ++i) {
+      const BnRunningSite s = sites[md.first_site + i];
+      const float mu = s.stats[c] / s.count;
+      const float var = fmaxf(s.stats[md.Cp + c] / s.count - mu * mu, 0.f);
+      const float unb = s.count > 1.f ? var * s.count / (s.count - 1.f) : var;
+      rm = (1.f - md.momentum) * rm + md.momentum * mu;
+      rv = (1.f - md.momentum) * rv + md.momentum * unb;
+    }
+    md.rmean[c] = rm;
+    md.rvar[c] = rv;
+  }
+  if (threadIdx.x == 0 && md.nbt) *md.nbt += md.num_sites;
+}
+
+static int check_bn(const HgBnDesc* d) {
+  HG_REQUIRE(d != nullptr, "HgBnDesc is NULL");
+  HG_REQUIRE(d->M > 0 && d->C > 0, "HgBnDesc: non-positive size");
+  HG_REQUIRE(d->dtype == HG_BF16 || d->dtype == HG_F32, "HgBnDesc: bad dtype");
+  const int Cp = (d->C + 63) & ~63;
+  if (Cp > 256) {
+    set_error("BatchNorm over %d channels unsupported (max 256)", d->C);
+    return HG_ERR_UNSUPPORTED;
+  }
+  return HG_OK;
+}
+
+static BnArgs make_args(const HgBnDesc* d, const float* stats, const float* gamma, const float* beta,
+                        const float* rmean, const float* rvar) {
+  BnArgs a;
+  a.stats = stats;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.rmean = rmean;
+  a.rvar = rvar;
+  a.count = (float)d->M;
+  a.eps = d->eps;
+  a.use_running = d->use_running;
+  a.relu = d->relu;
+  a.C = d->C;
+  a.Cp = (d->C + 63) & ~63;
+  return a;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+int hg_bn_stats(const HgBnDesc* d, const void* x, float* stats, void* stream) {
+  int rc = check_bn(d);
+  if (rc) return rc;
+  HG_REQUIRE(x && stats, "hg_bn_stats: NULL pointer");
+  return bn_stats_launch(d->dtype, x, d->M, (d->C + 63) & ~63, stats, (cudaStream_t)stream);
+}
+
+int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const float* gamma, const float* beta,
+                const float* running_mean, const float* running_var, void* y, void* stream) {
+  int rc = check_bn(d);
+  if (rc) return rc;
+  HG_REQUIRE(x && y && gamma && beta, "hg_bn_apply: NULL pointer");
+  HG_REQUIRE(d->use_running ? (running_mean && running_var) : (stats != nullptr),
+             "hg_bn_apply: statistics missing for the selected mode");
+  BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
+  const int rlanes = 256 / (a.Cp >> 3);
+  int blocks = ceil_div(d->M, rlanes * 4);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == HG_BF16)
+    bn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, d->M, a);
+  else
+    bn_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, d->M, a);
+  HG_LAUNCH_OK("bn_apply_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_bn_bwd_reduce(const HgBnDesc* d, const void* da, const void* x, const float* stats, const float* gamma,
+                     const float* beta, float* red, void* stream) {
+  int rc = check_bn(d);
+  if (rc) return rc;
+  HG_REQUIRE(da && x && stats && gamma && beta && red, "hg_bn_bwd_reduce: NULL pointer");
+  HG_REQUIRE(!d->use_running, "hg_bn_bwd_reduce: not needed in eval mode");
+  BnArgs a = make_args(d, stats, gamma, beta, nullptr, nullptr);
+  int rpb = (int)((d->M + 2 * kNumSMs * 4 - 1) / (2 * kNumSMs * 4));
+  if (rpb < 64) rpb = 64;
+  const int blocks = ceil_div(d->M, rpb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == HG_BF16)
+    bn_bwd_reduce_kernel<__nv_bfloat16>
+        <<<blocks, 256, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, d->M, a, red, rpb);
+  else
+    bn_bwd_reduce_kernel<float><<<blocks, 256, 0, st>>>((const float*)da, (const float*)x, d->M, a, red, rpb);
+  HG_LAUNCH_OK("bn_bwd_reduce_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const float* stats, const float* gamma,
+                    const float* beta, const float* running_mean, const float* running_var, const float* red,
+                    const void* addend, void* dx, float* dgamma, float* dbeta, float* colsum, void* stream) {
+  int rc = check_bn(d);
+  if (rc) return rc;
+  HG_REQUIRE(da && x && gamma && beta && dx, "hg_bn_bwd_apply: NULL pointer");
+  HG_REQUIRE(d->use_running ? (running_mean && running_var) : (stats && red),
+             "hg_bn_bwd_apply: statistics missing for the selected mode");
+  BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
+  int rpb = (int)((d->M + 2 * kNumSMs * 4 - 1) / (2 * kNumSMs * 4));
+  if (rpb < 64) rpb = 64;
+  const int blocks = ceil_div(d->M, rpb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == HG_BF16)
+    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        (const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, d->M, a,
+        red, dgamma, dbeta, colsum, rpb);
+  else
+    bn_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)da, (const float*)x, (const float*)addend,
+                                                        (float*)dx, d->M, a, red, dgamma, dbeta, colsum, rpb);
+  HG_LAUNCH_OK("bn_bwd_apply_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_bn_update_running(const void* modules_dev, const void* sites_dev, int num_modules, void* stream) {
+  HG_REQUIRE(modules_dev && sites_dev && num_modules > 0, "hg_bn_update_running: bad arguments");
+  bn_running_kernel<<<num_modules, 256, 0, (cudaStream_t)stream>>>((const BnRunningModule*)modules_dev,
+                                                                   (const BnRunningSite*)sites_dev);
+  HG_LAUNCH_OK("bn_running_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+}  // extern "C"

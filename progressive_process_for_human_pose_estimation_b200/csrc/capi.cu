@@ -1,0 +1,191 @@
+// C ABI entry points shared by all kernels: error reporting, TMA descriptor encoding, dispatch between the
+// tensor-core (bf16) and CUDA-core (fp32 / odd geometry) convolution kernels.
+#include <stdarg.h>
+
+#include "hg_common.cuh"
+
+namespace hg {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
+static int g_force_ref_conv = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return HG_ERR_CUDA;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                CUtensorMapSwizzle swz) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || p == nullptr) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+      return HG_ERR_CUDA;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = elem_strides[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, base %p, dims %llu %llu %llu %llu)", (int)r,
+              rank, base, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0));
+    return HG_ERR_CUDA;
+  }
+  return HG_OK;
+}
+
+// implemented in conv_tc.cu / conv_ref.cu
+int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, int dil, int sign, const void* act,
+                   const void* wpk, const float* bias, const void* res, void* out, float* stats, float* out_nchw,
+                   int c_real, cudaStream_t st);
+int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, cudaStream_t st);
+template <typename T>
+int conv_ref_fprop(const HgConvDesc*, const void*, const void*, const float*, const void*, void*, float*,
+                   cudaStream_t);
+template <typename T>
+int conv_ref_dgrad(const HgConvDesc*, const void*, const void*, const void*, void*, cudaStream_t);
+template <typename T>
+int conv_ref_wgrad(const HgConvDesc*, const void*, const void*, float*, float*, cudaStream_t);
+template <typename T>
+int pack_weight(const HgConvDesc*, const float*, void*, void*, cudaStream_t);
+int unpack_wgrad(const HgConvDesc* d, const float* g, float* dw, int accumulate, cudaStream_t st);
+int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats, cudaStream_t st);
+
+static inline int pad64(int c) { return (c + 63) & ~63; }
+
+static int check_desc(const HgConvDesc* d) {
+  HG_REQUIRE(d != nullptr, "HgConvDesc is NULL");
+  HG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "HgConvDesc: non-positive size");
+  HG_REQUIRE(d->R > 0 && d->S > 0 && d->stride > 0 && d->dil > 0 && d->pad >= 0, "HgConvDesc: bad filter geometry");
+  HG_REQUIRE(d->dtype == HG_BF16 || d->dtype == HG_F32, "HgConvDesc: dtype must be HG_BF16 or HG_F32");
+  return HG_OK;
+}
+
+// The tensor-core kernel takes stride-1 "same" convolutions on power-of-two maps.
+static bool tc_eligible(const HgConvDesc* d) {
+  if (g_force_ref_conv || d->dtype != HG_BF16) return false;
+  if (d->stride != 1 || d->R != d->S) return false;
+  if (2 * d->pad != d->dil * (d->R - 1)) return false;
+  if (!is_pow2(d->H) || !is_pow2(d->W) || d->W > 128) return false;
+  const int ci = pad64(d->Cin), co = pad64(d->Cout);
+  if (ci > 256 || co > 256 || co == 192 || ci == 192) return false;
+  return true;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+const char* hg_last_error_string(void) { return g_err; }
+unsigned long long hg_launch_count(void) { return g_launches; }
+
+int hg_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+int hg_set_option(const char* name, int value) {
+  if (strcmp(name, "force_ref_conv") == 0) {
+    g_force_ref_conv = value;
+    return HG_OK;
+  }
+  set_error("hg_set_option: unknown option '%s'", name);
+  return HG_ERR_BAD_ARG;
+}
+
+int hg_pack_conv_weight(const HgConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HG_REQUIRE(w_oihw != nullptr, "hg_pack_conv_weight: w_oihw is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  return d->dtype == HG_BF16 ? pack_weight<__nv_bfloat16>(d, w_oihw, w_fprop, w_dgrad, st)
+                             : pack_weight<float>(d, w_oihw, w_fprop, w_dgrad, st);
+}
+
+int hg_conv_fprop_ex(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias,
+                     const void* residual, void* y, float* stats, float* out_nchw, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HG_REQUIRE(x && w_fprop && y, "hg_conv_fprop: x, w_fprop and y must be non-NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_eligible(d)) {
+    return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cin), pad64(d->Cout), d->R, d->S, d->pad, d->dil, +1, x,
+                          w_fprop, bias, residual, y, stats, out_nchw, d->Cout, st);
+  }
+  rc = d->dtype == HG_BF16 ? conv_ref_fprop<__nv_bfloat16>(d, x, w_fprop, bias, residual, y, out_nchw, st)
+                           : conv_ref_fprop<float>(d, x, w_fprop, bias, residual, y, out_nchw, st);
+  if (rc) return rc;
+  if (stats) {
+    const int Ho = (d->H + 2 * d->pad - d->dil * (d->R - 1) - 1) / d->stride + 1;
+    const int Wo = (d->W + 2 * d->pad - d->dil * (d->S - 1) - 1) / d->stride + 1;
+    return bn_stats_launch(d->dtype, y, (long long)d->N * Ho * Wo, pad64(d->Cout), stats, st);
+  }
+  return HG_OK;
+}
+
+int hg_conv_fprop(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias, const void* residual,
+                  void* y, float* stats, void* stream) {
+  return hg_conv_fprop_ex(d, x, w_fprop, bias, residual, y, stats, nullptr, stream);
+}
+
+int hg_conv_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
+                  void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HG_REQUIRE(dy && w_dgrad && dx, "hg_conv_dgrad: dy, w_dgrad and dx must be non-NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_eligible(d)) {
+    return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cout), pad64(d->Cin), d->R, d->S, d->pad, d->dil, -1, dy,
+                          w_dgrad, nullptr, addend, dx, nullptr, nullptr, 0, st);
+  }
+  return d->dtype == HG_BF16 ? conv_ref_dgrad<__nv_bfloat16>(d, dy, w_dgrad, addend, dx, st)
+                             : conv_ref_dgrad<float>(d, dy, w_dgrad, addend, dx, st);
+}
+
+int hg_unpack_conv_wgrad(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int accumulate, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HG_REQUIRE(dw_packed && dw_oihw, "hg_unpack_conv_wgrad: NULL pointer");
+  return unpack_wgrad(d, dw_packed, dw_oihw, accumulate, (cudaStream_t)stream);
+}
+
+int hg_conv_wgrad(const HgConvDesc* d, const void* x, const void* dy, float* dw_oihw, float* dbias, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HG_REQUIRE(x && dy, "hg_conv_wgrad: x and dy must be non-NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_eligible(d)) return conv_wgrad_bf16(d, x, dy, dw_oihw, dbias, st);
+  return d->dtype == HG_BF16 ? conv_ref_wgrad<__nv_bfloat16>(d, x, dy, dw_oihw, dbias, st)
+                             : conv_ref_wgrad<float>(d, x, dy, dw_oihw, dbias, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+// Memory-bound spatial kernels of the hourglass on NHWC activations: 2x2 max-pool, x2 up-sampling fused with
+// the skip add (bilinear align_corners=True and nearest), their adjoints, tensor add, and the NCHW<->NHWC
+// conversions at the module boundary.  One thread = 8 consecutive channels of one output pixel (128-bit
+// accesses for bf16), grid-stride over pixels.
+//
+// Replaces nn.MaxPool2d(2), F.interpolate(scale_factor=2, mode='bilinear', align_corners=True) + `up1 + up2`
+// (reference try_with_torch.py:220,226,238-239,265) and the nearest variant (hourglass_compare.py:532-542).
+#include "hg_common.cuh"
+
+namespace hg {
+
+// ------------------------------------------------------------------------------------------------------
+// max-pool 2x2 stride 2
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H,
+                                                           int W, int Cp) {
+  const int vecs = Cp >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vecs);
+    long long pix = i / vecs;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    const T* p = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * Cp + vc * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    load8(p, a);
+    load8(p + Cp, b);
+    load8(p + (long long)W * Cp, c);
+    load8(p + (long long)W * Cp + Cp, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
+    store8(y + i * 8, o);
+  }
+}
+
+// dx[window] = dy routed to the FIRST row-major maximum of the window (PyTorch's tie-break), [+ addend]
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                           const T* __restrict__ addend, T* __restrict__ dx, int N,
+                                                           int H, int W, int Cp) {
+  const int vecs = Cp >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vecs);
+    long long pix = i / vecs;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    const long long base = (((long long)n * H + 2 * ho) * W + 2 * wo) * Cp + vc * 8;
+    const long long off[4] = {0, Cp, (long long)W * Cp, (long long)W * Cp + Cp};
+    float v[4][8], g[8], o[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) load8(x + base + off[q], v[q]);
+    load8(dy + i * 8, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int best = 0;
+      float bv = v[0][e];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q][e] > bv) {
+          bv = v[q][e];
+          best = q;
+        }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][e] = (q == best) ? g[e] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (addend) {
+        float ad[8];
+        load8(addend + base + off[q], ad);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[q][e] += ad[e];
+      }
+      store8(dx + base + off[q], o[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// x2 up-sampling (+ skip add).  mode 0 = bilinear, align_corners=True; mode 1 = nearest.
+// PyTorch's index arithmetic is reproduced in fp32: scale = (in-1)/(out-1), src = scale*dst, i0 = (int)src,
+// i1 = i0 + (i0 < in-1), l1 = src - i0, l0 = 1 - l1.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilin_coord(int o, int in_size, float scale, int& i0, int& i1, float& l0, float& l1) {
+  const float src = scale * (float)o;
+  i0 = (int)src;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_add_fwd_kernel(const T* __restrict__ low, const T* __restrict__ skip,
+                                                                T* __restrict__ out, int N, int h, int w, int Cp,
+                                                                int mode) {
+  const int vecs = Cp >> 3, H = 2 * h, W = 2 * w;
+  const float sh = h > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sw = w > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const long long total = (long long)N * H * W * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vecs);
+    long long pix = i / vecs;
+    const int x = (int)(pix % W);
+    pix /= W;
+    const int y = (int)(pix % H);
+    const int n = (int)(pix / H);
+    float o[8];
+    const T* lb = low + (long long)n * h * w * Cp + vc * 8;
+    if (mode == 1) {
+      load8(lb + ((long long)(y >> 1) * w + (x >> 1)) * Cp, o);
+    } else {
+      int y0, y1, x0, x1;
+      float ly0, ly1, lx0, lx1;
+      bilin_coord(y, h, sh, y0, y1, ly0, ly1);
+      bilin_coord(x, w, sw, x0, x1, lx0, lx1);
+      float a[8], b[8], c[8], d[8];
+      load8(lb + ((long long)y0 * w + x0) * Cp, a);
+      load8(lb + ((long long)y0 * w + x1) * Cp, b);
+      load8(lb + ((long long)y1 * w + x0) * Cp, c);
+      load8(lb + ((long long)y1 * w + x1) * Cp, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = ly0 * (lx0 * a[e] + lx1 * b[e]) + ly1 * (lx0 * c[e] + lx1 * d[e]);
+    }
+    if (skip) {
+      float s[8];
+      load8(skip + i * 8, s);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += s[e];
+    }
+    store8(out + i * 8, o);
+  }
+}
+
+// adjoint as a GATHER over the low-resolution pixels (deterministic, no atomics):
+// dlow[yi, xi] = sum over outputs (y, x) that read (yi, xi) of weight * dout[y, x]   [+ addend]
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ addend,
+                                                            T* __restrict__ dlow, int N, int h, int w, int Cp,
+                                                            int mode) {
+  const int vecs = Cp >> 3, H = 2 * h, W = 2 * w;
+  const float sh = h > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sw = w > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const long long total = (long long)N * h * w * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vecs);
+    long long pix = i / vecs;
+    const int xi = (int)(pix % w);
+    pix /= w;
+    const int yi = (int)(pix % h);
+    const int n = (int)(pix / h);
+    const T* db = dout + (long long)n * H * W * Cp + vc * 8;
+    float acc[8] = {};
+    if (mode == 1) {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float g[8];
+          load8(db + ((long long)(2 * yi + dy) * W + (2 * xi + dx)) * Cp, g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += g[e];
+        }
+    } else {
+      // candidate outputs: src in (yi-1, yi+1)  ->  y in [2*yi-2, 2*yi+3] is a safe superset for scale ~ 1/2
+      const int ylo = max(0, 2 * yi - 2), yhi = min(H - 1, 2 * yi + 3);
+      const int xlo = max(0, 2 * xi - 2), xhi = min(W - 1, 2 * xi + 3);
+      for (int y = ylo; y <= yhi; ++y) {
+        int y0, y1;
+        float ly0, ly1;
+        bilin_coord(y, h, sh, y0, y1, ly0, ly1);
+        float wy = 0.f;
+        if (y0 == yi) wy += ly0;
+        if (y1 == yi) wy += ly1;
+        if (wy == 0.f) continue;
+        for (int x = xlo; x <= xhi; ++x) {
+          int x0, x1;
+          float lx0, lx1;
+          bilin_coord(x, w, sw, x0, x1, lx0, lx1);
+          float wx = 0.f;
+          if (x0 == xi) wx += lx0;
+          if (x1 == xi) wx += lx1;
+          if (wx == 0.f) continue;
+          float g[8];
+          load8(db + ((long long)y * W + x) * Cp, g);
+          const float wgt = wy * wx;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, g[e], acc[e]);
+        }
+      }
+    }
+    if (addend) {
+      float ad[8];
+      load8(addend + i * 8, ad);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += ad[e];
+    }
+    store8(dlow + i * 8, acc);
+  }
+}
+
+// out = a + b
+template <typename T>
+__global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                                                  long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    load8(a + i * 8, x);
+    load8(b + i * 8, y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    store8(out + i * 8, x);
+  }
+}
+
+// fp32 NCHW [N,C,H,W] -> NHWC T [N,H,W,Cp] (zero padded channels) [+ addend NHWC]: gradients of the heatmaps
+// coming back from the loss.  One thread = one pixel x 8 channels; reads are coalesced across pixels.
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, const T* __restrict__ addend,
+                                                           T* __restrict__ dst, int N, int C, int HW, int Cp) {
+  const int vecs = Cp >> 3;
+  const long long total = (long long)N * HW * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // pixel fastest so that a warp reads consecutive pixels of one channel plane
+    const int p = (int)(i % HW);
+    long long r = i / HW;
+    const int vc = (int)(r % vecs);
+    const int n = (int)(r / vecs);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = vc * 8 + e;
+      o[e] = (src != nullptr && c < C) ? src[((long long)n * C + c) * HW + p] : 0.f;
+    }
+    const long long di = ((long long)n * HW + p) * Cp + vc * 8;
+    if (addend) {
+      float ad[8];
+      load8(addend + di, ad);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += ad[e];
+    }
+    store8(dst + di, o);
+  }
+}
+
+// NHWC T [N,H,W,Cp] -> fp32 NCHW [N,C,H,W]
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N,
+                                                           int C, int HW, int Cp) {
+  const long long total = (long long)N * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    long long r = i / HW;
+    const int c = (int)(r % C);
+    const int n = (int)(r / C);
+    dst[i] = to_f(src[((long long)n * HW + p) * Cp + c]);
+  }
+}
+
+static inline int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+#define HG_DISPATCH_T(dtype, CALL)                    \
+  do {                                                \
+    if ((dtype) == HG_BF16) {                         \
+      typedef __nv_bfloat16 T;                        \
+      CALL;                                           \
+    } else {                                          \
+      typedef float T;                                \
+      CALL;                                           \
+    }                                                 \
+  } while (0)
+
+extern "C" {
+
+static int check_spatial(int dtype, int N, int H, int W, int C, const char* who) {
+  HG_REQUIRE(dtype == HG_BF16 || dtype == HG_F32, "%s: bad dtype", who);
+  HG_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "%s: non-positive size", who);
+  return HG_OK;
+}
+
+int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream) {
+  int rc = check_spatial(dtype, N, H, W, C, "hg_maxpool2_fwd");
+  if (rc) return rc;
+  HG_REQUIRE(x && y, "hg_maxpool2_fwd: NULL pointer");
+  HG_REQUIRE(H % 2 == 0 && W % 2 == 0, "hg_maxpool2_fwd: odd spatial size %dx%d", H, W);
+  const int Cp = (C + 63) & ~63;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (Cp / 8);
+  HG_DISPATCH_T(dtype, (maxpool2_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                           (const T*)x, (T*)y, N, H, W, Cp)));
+  HG_LAUNCH_OK("maxpool2_fwd_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_maxpool2_bwd(int dtype, const void* x, const void* dy, const void* addend, int N, int H, int W, int C,
+                    void* dx, void* stream) {
+  int rc = check_spatial(dtype, N, H, W, C, "hg_maxpool2_bwd");
+  if (rc) return rc;
+  HG_REQUIRE(x && dy && dx, "hg_maxpool2_bwd: NULL pointer");
+  HG_REQUIRE(H % 2 == 0 && W % 2 == 0, "hg_maxpool2_bwd: odd spatial size %dx%d", H, W);
+  const int Cp = (C + 63) & ~63;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (Cp / 8);
+  HG_DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                           (const T*)x, (const T*)dy, (const T*)addend, (T*)dx, N, H, W, Cp)));
+  HG_LAUNCH_OK("maxpool2_bwd_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_upsample2x_add_fwd(int dtype, int mode, const void* low, const void* skip, int N, int h, int w, int C,
+                          void* out, void* stream) {
+  int rc = check_spatial(dtype, N, h, w, C, "hg_upsample2x_add_fwd");
+  if (rc) return rc;
+  HG_REQUIRE(low && out, "hg_upsample2x_add_fwd: NULL pointer");
+  HG_REQUIRE(mode == 0 || mode == 1, "hg_upsample2x_add_fwd: mode must be 0 (bilinear_ac) or 1 (nearest)");
+  const int Cp = (C + 63) & ~63;
+  const long long total = (long long)N * 4 * h * w * (Cp / 8);
+  HG_DISPATCH_T(dtype, (upsample2_add_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                           (const T*)low, (const T*)skip, (T*)out, N, h, w, Cp, mode)));
+  HG_LAUNCH_OK("upsample2_add_fwd_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_upsample2x_bwd(int dtype, int mode, const void* dout, const void* addend, int N, int h, int w, int C,
+                      void* dlow, void* stream) {
+  int rc = check_spatial(dtype, N, h, w, C, "hg_upsample2x_bwd");
+  if (rc) return rc;
+  HG_REQUIRE(dout && dlow, "hg_upsample2x_bwd: NULL pointer");
+  HG_REQUIRE(mode == 0 || mode == 1, "hg_upsample2x_bwd: mode must be 0 (bilinear_ac) or 1 (nearest)");
+  const int Cp = (C + 63) & ~63;
+  const long long total = (long long)N * h * w * (Cp / 8);
+  HG_DISPATCH_T(dtype, (upsample2_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                           (const T*)dout, (const T*)addend, (T*)dlow, N, h, w, Cp, mode)));
+  HG_LAUNCH_OK("upsample2_bwd_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_add(int dtype, const void* a, const void* b, void* out, long long n_elems, void* stream) {
+  HG_REQUIRE(dtype == HG_BF16 || dtype == HG_F32, "hg_add: bad dtype");
+  HG_REQUIRE(a && b && out && n_elems > 0 && n_elems % 8 == 0, "hg_add: bad arguments");
+  const long long nvec = n_elems / 8;
+  HG_DISPATCH_T(dtype, (add_kernel<T><<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b,
+                                                                                        (T*)out, nvec)));
+  HG_LAUNCH_OK("add_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_nchw_f32_to_nhwc(int dtype, const float* src_nchw, const void* addend, int N, int C, int H, int W, void* dst,
+                        void* stream) {
+  int rc = check_spatial(dtype, N, H, W, C, "hg_nchw_f32_to_nhwc");
+  if (rc) return rc;
+  HG_REQUIRE(dst != nullptr, "hg_nchw_f32_to_nhwc: NULL dst");
+  const int Cp = (C + 63) & ~63;
+  const long long total = (long long)N * H * W * (Cp / 8);
+  HG_DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                           src_nchw, (const T*)addend, (T*)dst, N, C, H * W, Cp)));
+  HG_LAUNCH_OK("nchw_to_nhwc_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_nhwc_to_nchw_f32(int dtype, const void* src, int N, int C, int H, int W, float* dst_nchw, void* stream) {
+  int rc = check_spatial(dtype, N, H, W, C, "hg_nhwc_to_nchw_f32");
+  if (rc) return rc;
+  HG_REQUIRE(src && dst_nchw, "hg_nhwc_to_nchw_f32: NULL pointer");
+  const int Cp = (C + 63) & ~63;
+  const long long total = (long long)N * C * H * W;
+  HG_DISPATCH_T(dtype, (nhwc_to_nchw_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                           (const T*)src, dst_nchw, N, C, H * W, Cp)));
+  HG_LAUNCH_OK("nhwc_to_nchw_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+}  // extern "C"

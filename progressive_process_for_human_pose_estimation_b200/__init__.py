@@ -1,0 +1,13 @@
+"""B200 (sm_100a) implementation of the stacked-hourglass heatmap-regression hot path of
+Xinjie-Qiu/progressive_process_for_human_pose_estimation.
+
+Mirror modules keep the reference's script-level API (module-global configuration, class names, state_dict
+keys): try_with_torch, try_with_torch_100, only_one_hourgless.  Kernels live in libhg_sm100a.so
+(include/hg_sm100a.h); see DESIGN.md.
+"""
+from ._modules import get_compute_dtype, set_compute_dtype  # noqa: F401
+from .evaluate import PCKh_hourglass, PCKh_softmax, decode_argmax, pckh_sweep_counts  # noqa: F401
+from .targets import gaussian_heatmaps, label_maps  # noqa: F401
+
+__all__ = ["set_compute_dtype", "get_compute_dtype", "gaussian_heatmaps", "label_maps", "decode_argmax",
+           "pckh_sweep_counts", "PCKh_hourglass", "PCKh_softmax"]

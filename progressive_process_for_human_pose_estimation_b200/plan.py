@@ -1,0 +1,648 @@
+"""Execution plans: the host side of the hourglass hot path.
+
+A reference model is a Python call tree of tiny nn.Modules (716 convolutions + 689 BatchNorms per 8-stack
+forward, try_with_torch.py:275-298).  Driving that many kernels from autograd would leave the GPU idle, so the
+drop-in modules (see _family_s.py) do not execute op by op.  On first call for a given input shape a module
+*emits* its forward into a `Builder` (a small SSA graph of NHWC activations), the graph is *lowered* once to a
+flat list of pre-marshalled C-ABI calls (forward and hand-derived backward) on statically allocated buffers,
+and both lists are captured into CUDA graphs.  A training step is then: one graph launch for the forward, the
+stock loss on the returned heatmaps, one graph launch for the backward, the stock optimizer.
+
+All arithmetic happens in libhg_sm100a.so (include/hg_sm100a.h); nothing here computes on tensors except
+buffer bookkeeping (zero-fill, input copy, output clone).
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+
+_USE_GRAPHS = os.environ.get("HG_CUDA_GRAPHS", "1") != "0"
+
+
+class Val:
+    """An NHWC activation [N,H,W,Cp] (channels padded to 64) and, during lowering, its gradient."""
+
+    __slots__ = ("N", "H", "W", "C", "buf", "grad", "grad_owned", "requires_grad", "needs_stats", "stats",
+                 "producer", "consumers", "name")
+
+    def __init__(self, N, H, W, C, requires_grad, name=""):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.buf = None
+        self.grad = None
+        self.grad_owned = False
+        self.requires_grad = requires_grad
+        self.needs_stats = False
+        self.stats = None
+        self.producer = None
+        self.consumers = []
+        self.name = name
+
+    @property
+    def Cp(self):
+        return L.pad64(self.C)
+
+    @property
+    def M(self):
+        return self.N * self.H * self.W
+
+    def numel_padded(self):
+        return self.M * self.Cp
+
+
+class Op:
+    def __init__(self, kind, ins, out, **attrs):
+        self.kind = kind
+        self.ins = ins
+        self.out = out
+        self.attrs = attrs
+        for v in ins:
+            if v is not None:
+                v.consumers.append(self)
+        if out is not None:
+            out.producer = self
+
+
+class Builder:
+    """Collects the ops a module tree emits.  Methods mirror the nn calls of the reference forward."""
+
+    def __init__(self, training, train_params):
+        self.training = training
+        self.train_params = train_params  # parameters require grad -> activations feeding them too
+        self.ops = []
+        self.inputs = []    # (Val, kind)
+        self.outputs = []   # (Val, real channels)
+
+    # -- graph inputs -------------------------------------------------------------------------------
+    def input_image(self, N, H, W):
+        """fp32 NCHW image batch consumed directly by the stem kernel."""
+        v = Val(N, H, W, 3, False, "image")
+        self.inputs.append((v, "image"))
+        return v
+
+    def input_nchw(self, N, C, H, W, requires_grad):
+        v = Val(N, H, W, C, requires_grad, "input")
+        self.inputs.append((v, "nchw"))
+        return v
+
+    def _rg(self, *vals):
+        return self.train_params or any(v.requires_grad for v in vals if v is not None)
+
+    # -- ops ----------------------------------------------------------------------------------------
+    def stem(self, conv, x):
+        assert conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3)
+        out = Val(x.N, x.H // 2, x.W // 2, conv.out_channels, self.train_params, "stem")
+        self.ops.append(Op("stem", [x], out, conv=conv))
+        return out
+
+    def conv(self, conv, x, residual=None, head=False):
+        """nn.Conv2d (+ fused residual add).  head=True also produces the fp32 NCHW tensor the module returns."""
+        k, s, p, d = conv.kernel_size, conv.stride, conv.padding, conv.dilation
+        assert k[0] == k[1] and s[0] == s[1] and p[0] == p[1] and d[0] == d[1]
+        assert conv.in_channels == x.C, (conv.in_channels, x.C)
+        Ho = (x.H + 2 * p[0] - d[0] * (k[0] - 1) - 1) // s[0] + 1
+        Wo = (x.W + 2 * p[0] - d[0] * (k[0] - 1) - 1) // s[0] + 1
+        out = Val(x.N, Ho, Wo, conv.out_channels, self._rg(x, residual), "conv")
+        self.ops.append(Op("conv", [x, residual], out, conv=conv, head=head))
+        if head:
+            self.outputs.append((out, conv.out_channels))
+        return out
+
+    def bn_relu(self, bn, x, relu=True):
+        assert bn.num_features == x.C
+        if self.training or not bn.track_running_stats:
+            x.needs_stats = True
+        out = Val(x.N, x.H, x.W, x.C, self._rg(x), "bn")
+        self.ops.append(Op("bn", [x], out, bn=bn, relu=relu))
+        return out
+
+    def maxpool2(self, x):
+        out = Val(x.N, x.H // 2, x.W // 2, x.C, x.requires_grad, "pool")
+        self.ops.append(Op("pool", [x], out))
+        return out
+
+    def upsample2x_add(self, low, skip, mode="bilinear"):
+        out = Val(low.N, low.H * 2, low.W * 2, low.C, self._rg(low, skip), "up")
+        self.ops.append(Op("up", [low, skip], out, mode=0 if mode == "bilinear" else 1))
+        return out
+
+    def add(self, a, b):
+        out = Val(a.N, a.H, a.W, a.C, self._rg(a, b), "add")
+        self.ops.append(Op("add", [a, b], out))
+        return out
+
+    def output(self, v):
+        """Return `v` to the caller as an fp32 NCHW tensor."""
+        self.outputs.append((v, v.C))
+        self.ops.append(Op("export", [v], None))
+        return v
+
+
+class _Call:
+    """One pre-marshalled C-ABI call."""
+
+    __slots__ = ("fn", "args", "name", "keep")
+
+    def __init__(self, name, args, keep=()):
+        self.fn = getattr(L.load(), name)
+        self.args = args
+        self.name = name
+        self.keep = keep  # python objects whose memory the ctypes args point to
+
+
+def _unique(seq):
+    seen, out = set(), []
+    for s in seq:
+        if id(s) not in seen:
+            seen.add(id(s))
+            out.append(s)
+    return out
+
+
+class Plan:
+    def __init__(self, builder, params, device, compute_dtype):
+        """params: ordered list of (name, nn.Parameter) of the root module (the autograd inputs)."""
+        self.b = builder
+        self.device = device
+        self.dt = compute_dtype
+        self.hdt = L.hg_dtype(compute_dtype)
+        self.params = params
+        self.param_index = {id(p): i for i, (_, p) in enumerate(params)}
+        self.training = builder.training
+        self.need_bwd = builder.train_params or any(v.requires_grad for v, _ in builder.inputs)
+        self.stream = C.c_void_p(0)
+        self._keep = []
+        self.fwd_calls = []
+        self.bwd_calls = []
+        self.fwd_graph = None
+        self.bwd_graph = None
+        self.n_fwd_runs = 0
+        self._lower()
+
+    # ------------------------------------------------------------------------------------------------
+    # buffer helpers
+    # ------------------------------------------------------------------------------------------------
+    def _act(self, v):
+        return torch.zeros(v.N, v.H, v.W, v.Cp, device=self.device, dtype=self.dt)
+
+    def _p32(self, p):
+        """fp32 view of a parameter / buffer (shadow copy when the module was cast to half)."""
+        if p.dtype == torch.float32:
+            return p.data
+        key = id(p)
+        if key not in self._shadow:
+            self._shadow[key] = (p, torch.empty_like(p.data, dtype=torch.float32))
+        return self._shadow[key][1]
+
+    def _gslot(self, p):
+        """fp32 gradient slot of parameter p inside the flat gradient arena (None if p is frozen)."""
+        i = self.param_index.get(id(p))
+        if i is None or not p.requires_grad:
+            return None
+        self.param_used[i] = True
+        return self.grad_views[i]
+
+    def _emit(self, lst, name, *args, keep=()):
+        lst.append(_Call(name, args, keep))
+
+    # ------------------------------------------------------------------------------------------------
+    # gradient bookkeeping (see module docstring of _family_s for the conventions)
+    # ------------------------------------------------------------------------------------------------
+    def _grad_target(self, v):
+        """(addend, out) buffers for a kernel that ADDS a computed contribution to v.grad."""
+        if v.grad is None:
+            v.grad = self._act(v)
+            v.grad_owned = True
+            return None, v.grad
+        if v.grad_owned:
+            return v.grad, v.grad
+        old = v.grad
+        v.grad = self._act(v)
+        v.grad_owned = True
+        return old, v.grad
+
+    def _grad_passthrough(self, v, g):
+        """v.grad += g where g is an existing buffer (no kernel when it is the first contribution)."""
+        if not v.requires_grad:
+            return
+        if v.grad is None:
+            v.grad = g
+            v.grad_owned = False
+            return
+        addend, out = self._grad_target(v)
+        self._emit(self.bwd_calls, "hg_add", self.hdt, L.ptr(addend), L.ptr(g), L.ptr(out),
+                   C.c_longlong(v.numel_padded()), self.stream)
+
+    # ------------------------------------------------------------------------------------------------
+    def _lower(self):
+        b, dev = self.b, self.device
+        self._shadow = {}
+        ops = b.ops
+        # ---- parameters: flat gradient arena in named_parameters() order --------------------------
+        sizes = [p.numel() for _, p in self.params]
+        self.grad_arena = torch.zeros(max(1, sum(sizes)), device=dev, dtype=torch.float32)
+        self.grad_views, off = [], 0
+        for (_, p), n in zip(self.params, sizes):
+            self.grad_views.append(self.grad_arena[off:off + n].view(p.shape))
+            off += n
+        self.param_used = [False] * len(self.params)
+
+        # ---- convolutions: packed operands, packed gradient accumulators -------------------------
+        convs = _unique([op.attrs["conv"] for op in ops if op.kind == "conv"])
+        self.conv_info = {}
+        packed_total = 0
+        for cv in convs:
+            k = cv.kernel_size[0]
+            cin_p, cout_p = L.pad64(cv.in_channels), L.pad64(cv.out_channels)
+            direct = (k == 1 and cin_p == cv.in_channels and cout_p == cv.out_channels)
+            info = dict(wf=torch.zeros(k * k, cout_p, cin_p, device=dev, dtype=self.dt),
+                        wd=torch.zeros(k * k, cin_p, cout_p, device=dev, dtype=self.dt),
+                        bias=torch.zeros(cout_p, device=dev, dtype=torch.float32), direct=direct,
+                        gsize=k * k * cout_p * cin_p, goff=packed_total)
+            if not direct:
+                packed_total += info["gsize"]
+            self.conv_info[id(cv)] = info
+        self.packed_arena = torch.zeros(max(1, packed_total), device=dev, dtype=torch.float32)
+
+        # ---- activations and BatchNorm statistics ---------------------------------------------
+        stat_vals = []
+        for v, kind in b.inputs:
+            if kind == "image":
+                v.buf = torch.zeros(v.N, 3, v.H, v.W, device=dev, dtype=torch.float32)
+            else:
+                v.buf = self._act(v)
+                self.in_nchw = torch.zeros(v.N, v.C, v.H, v.W, device=dev, dtype=torch.float32)
+        for op in ops:
+            if op.out is not None:
+                op.out.buf = self._act(op.out)
+        all_vals = [v for v, _ in b.inputs] + [op.out for op in ops if op.out is not None]
+        for v in all_vals:
+            if v.needs_stats:
+                stat_vals.append(v)
+        n_stats = sum(2 * v.Cp for v in stat_vals)
+        self.stats_arena = torch.zeros(max(1, n_stats), device=dev, dtype=torch.float32)
+        off = 0
+        for v in stat_vals:
+            v.stats = self.stats_arena[off:off + 2 * v.Cp]
+            off += 2 * v.Cp
+        bn_ops = [op for op in ops if op.kind == "bn"]
+        self.red_arena = torch.zeros(max(1, sum(2 * op.ins[0].Cp for op in bn_ops)), device=dev, dtype=torch.float32)
+        off = 0
+        for op in bn_ops:
+            op.attrs["red"] = self.red_arena[off:off + 2 * op.ins[0].Cp]
+            off += 2 * op.ins[0].Cp
+
+        # ---- outputs -------------------------------------------------------------------------------
+        self.out_static = [torch.zeros(v.N, c, v.H, v.W, device=dev, dtype=torch.float32) for v, c in b.outputs]
+        self.gout_static = [torch.zeros_like(t) for t in self.out_static] if self.need_bwd else []
+        self.out_index = {id(v): i for i, (v, _) in enumerate(b.outputs)}
+
+        self._lower_forward(convs)
+        if self.need_bwd:
+            self._lower_backward(convs)
+
+    # ------------------------------------------------------------------------------------------------
+    def _conv_desc(self, cv, x):
+        d = L.HgConvDesc(x.N, x.H, x.W, cv.in_channels, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1],
+                         cv.stride[0], cv.padding[0], cv.dilation[0], self.hdt)
+        self._keep.append(d)
+        return d
+
+    def _bn_desc(self, bn, x, relu):
+        use_running = 0 if (self.training or not bn.track_running_stats) else 1
+        d = L.HgBnDesc(x.M, x.C, self.hdt, float(bn.eps), 1 if relu else 0, use_running)
+        self._keep.append(d)
+        return d
+
+    def _lower_forward(self, convs):
+        f, st = self.fwd_calls, self.stream
+        # weights -> GEMM operand layouts (the optimizer changed them since the last step)
+        for cv in convs:
+            info = self.conv_info[id(cv)]
+            d = L.HgConvDesc(1, 1, 1, cv.in_channels, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1], 1, 0, 1,
+                             self.hdt)
+            self._keep.append(d)
+            need_wd = self.need_bwd
+            self._emit(f, "hg_pack_conv_weight", C.byref(d), L.ptr(self._p32(cv.weight)), L.ptr(info["wf"]),
+                       L.ptr(info["wd"]) if need_wd else None, st)
+        for v, kind in self.b.inputs:
+            if kind == "nchw":
+                self._emit(f, "hg_nchw_f32_to_nhwc", self.hdt, L.ptr(self.in_nchw), None, v.N, v.C, v.H, v.W,
+                           L.ptr(v.buf), st)
+                if v.needs_stats:
+                    self._stats_call(f, v)
+        running = {}  # bn module -> list of (stats, count) in call order
+        for op in self.b.ops:
+            k = op.kind
+            if k == "stem":
+                cv, x, out = op.attrs["conv"], op.ins[0], op.out
+                self._emit(f, "hg_stem_fwd", self.hdt, L.ptr(x.buf), L.ptr(self._p32(cv.weight)),
+                           L.ptr(self._p32(cv.bias)), x.N, x.H, x.W, L.ptr(out.buf), st)
+                if out.needs_stats:
+                    self._stats_call(f, out)
+            elif k == "conv":
+                cv, x, res, out = op.attrs["conv"], op.ins[0], op.ins[1], op.out
+                info = self.conv_info[id(cv)]
+                d = self._conv_desc(cv, x)
+                nchw = self.out_static[self.out_index[id(out)]] if op.attrs["head"] else None
+                self._emit(f, "hg_conv_fprop_ex", C.byref(d), L.ptr(x.buf), L.ptr(info["wf"]),
+                           self._bias_ptr(cv, info), L.ptr(res.buf) if res else None,
+                           L.ptr(out.buf), L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw), st)
+            elif k == "bn":
+                bn, x, out = op.attrs["bn"], op.ins[0], op.out
+                d = self._bn_desc(bn, x, op.attrs["relu"])
+                self._emit(f, "hg_bn_apply", C.byref(d), L.ptr(x.buf), L.ptr(x.stats) if x.stats is not None else None,
+                           L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias)),
+                           L.ptr(bn.running_mean) if bn.running_mean is not None else None,
+                           L.ptr(bn.running_var) if bn.running_var is not None else None, L.ptr(out.buf), st)
+                if self.training and bn.track_running_stats:
+                    running.setdefault(id(bn), (bn, []))[1].append((x.stats, float(x.M)))
+            elif k == "pool":
+                x, out = op.ins[0], op.out
+                self._emit(f, "hg_maxpool2_fwd", self.hdt, L.ptr(x.buf), x.N, x.H, x.W, x.C, L.ptr(out.buf), st)
+                if out.needs_stats:
+                    self._stats_call(f, out)
+            elif k == "up":
+                low, skip, out = op.ins[0], op.ins[1], op.out
+                self._emit(f, "hg_upsample2x_add_fwd", self.hdt, op.attrs["mode"], L.ptr(low.buf),
+                           L.ptr(skip.buf) if skip else None, low.N, low.H, low.W, low.C, L.ptr(out.buf), st)
+                if out.needs_stats:
+                    self._stats_call(f, out)
+            elif k == "add":
+                a, bb, out = op.ins[0], op.ins[1], op.out
+                self._emit(f, "hg_add", self.hdt, L.ptr(a.buf), L.ptr(bb.buf), L.ptr(out.buf),
+                           C.c_longlong(out.numel_padded()), st)
+                if out.needs_stats:
+                    self._stats_call(f, out)
+            elif k == "export":
+                v = op.ins[0]
+                self._emit(f, "hg_nhwc_to_nchw_f32", self.hdt, L.ptr(v.buf), v.N, v.C, v.H, v.W,
+                           L.ptr(self.out_static[self.out_index[id(v)]]), st)
+            else:
+                raise RuntimeError(f"unknown op {k}")
+        # running statistics: one launch for every BatchNorm module of the forward, call sites in order
+        self.running_tables = None
+        if running:
+            mods, sites = [], []
+            for bn, lst in running.values():
+                mods.append(L.HgBnRunningModule(bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                                bn.num_batches_tracked.data_ptr(), bn.num_features,
+                                                L.pad64(bn.num_features), len(sites), len(lst),
+                                                float(bn.momentum if bn.momentum is not None else 0.1), 0))
+                for stats, cnt in lst:
+                    sites.append(L.HgBnRunningSite(stats.data_ptr(), cnt, 0))
+            mod_arr = (L.HgBnRunningModule * len(mods))(*mods)
+            site_arr = (L.HgBnRunningSite * len(sites))(*sites)
+            mod_dev = torch.frombuffer(bytearray(bytes(mod_arr)), dtype=torch.uint8).to(self.device)
+            site_dev = torch.frombuffer(bytearray(bytes(site_arr)), dtype=torch.uint8).to(self.device)
+            self.running_tables = (mod_dev, site_dev)
+            self._emit(f, "hg_bn_update_running", L.ptr(mod_dev), L.ptr(site_dev), len(mods), st)
+
+    def _bias_ptr(self, cv, info):
+        """Bias vector padded to Cout_p: the live fp32 parameter itself when no padding / cast is needed."""
+        if cv.bias is None:
+            return None
+        if cv.bias.dtype == torch.float32 and L.pad64(cv.out_channels) == cv.out_channels:
+            return L.ptr(cv.bias.data)
+        info["bias_copy"] = True
+        return L.ptr(info["bias"])
+
+    def _stats_call(self, lst, v):
+        d = L.HgBnDesc(v.M, v.C, self.hdt, 1e-5, 0, 0)
+        self._keep.append(d)
+        self._emit(lst, "hg_bn_stats", C.byref(d), L.ptr(v.buf), L.ptr(v.stats), self.stream)
+
+    # ------------------------------------------------------------------------------------------------
+    def _lower_backward(self, convs):
+        g, st = self.bwd_calls, self.stream
+        for op in reversed(self.b.ops):
+            k = op.kind
+            if k == "export":
+                v = op.ins[0]
+                if v.requires_grad:
+                    addend, out = self._grad_target(v)
+                    self._emit(g, "hg_nchw_f32_to_nhwc", self.hdt, L.ptr(self.gout_static[self.out_index[id(v)]]),
+                               L.ptr(addend), v.N, v.C, v.H, v.W, L.ptr(out), st)
+                continue
+            out = op.out
+            if k == "conv" and op.attrs["head"] and out.requires_grad:
+                # gradient arriving from the loss for this returned heatmap
+                addend, dst = self._grad_target(out)
+                self._emit(g, "hg_nchw_f32_to_nhwc", self.hdt, L.ptr(self.gout_static[self.out_index[id(out)]]),
+                           L.ptr(addend), out.N, out.C, out.H, out.W, L.ptr(dst), st)
+            if out.grad is None:
+                continue  # nothing downstream of this value reaches a loss (e.g. the last `inter`, quirk Q5)
+            G = out.grad
+            if k == "conv":
+                cv, x, res = op.attrs["conv"], op.ins[0], op.ins[1]
+                info = self.conv_info[id(cv)]
+                d = self._conv_desc(cv, x)
+                if res is not None:
+                    self._grad_passthrough(res, G)
+                wslot = self._gslot(cv.weight)
+                bslot = self._gslot(cv.bias) if cv.bias is not None else None
+                # bias gradient comes for free from the BatchNorm backward when y only feeds a BatchNorm
+                bn_only = (len(out.consumers) == 1 and out.consumers[0].kind == "bn" and res is None
+                           and not op.attrs["head"])
+                if bn_only:
+                    bslot = None
+                if wslot is not None or bslot is not None:
+                    if wslot is None:
+                        dwp = None
+                    elif info["direct"]:
+                        dwp = wslot
+                    else:
+                        dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
+                        info["used"] = True
+                    self._emit(g, "hg_conv_wgrad", C.byref(d), L.ptr(x.buf), L.ptr(G), L.ptr(dwp), L.ptr(bslot), st)
+                if x.requires_grad:
+                    addend, dst = self._grad_target(x)
+                    self._emit(g, "hg_conv_dgrad", C.byref(d), L.ptr(G), L.ptr(info["wd"]), L.ptr(addend), L.ptr(dst),
+                               st)
+            elif k == "bn":
+                bn, x = op.attrs["bn"], op.ins[0]
+                d = self._bn_desc(bn, x, op.attrs["relu"])
+                red = op.attrs["red"]
+                gam, bet = L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias))
+                stats = L.ptr(x.stats) if x.stats is not None else None
+                if not d.use_running:
+                    self._emit(g, "hg_bn_bwd_reduce", C.byref(d), L.ptr(G), L.ptr(x.buf), stats, gam, bet, L.ptr(red), st)
+                colsum = None
+                prod = x.producer
+                if (prod is not None and prod.kind == "conv" and len(x.consumers) == 1 and prod.ins[1] is None
+                        and not prod.attrs["head"] and prod.attrs["conv"].bias is not None):
+                    colsum = self._gslot(prod.attrs["conv"].bias)
+                if x.requires_grad:
+                    addend, dst = self._grad_target(x)
+                else:
+                    addend, dst = None, self._scratch(x)
+                self._emit(g, "hg_bn_bwd_apply", C.byref(d), L.ptr(G), L.ptr(x.buf), stats, gam, bet,
+                           L.ptr(bn.running_mean) if bn.running_mean is not None else None,
+                           L.ptr(bn.running_var) if bn.running_var is not None else None, L.ptr(red), L.ptr(addend),
+                           L.ptr(dst), L.ptr(self._gslot(bn.weight)), L.ptr(self._gslot(bn.bias)), L.ptr(colsum), st)
+            elif k == "pool":
+                x = op.ins[0]
+                if x.requires_grad:
+                    addend, dst = self._grad_target(x)
+                    self._emit(g, "hg_maxpool2_bwd", self.hdt, L.ptr(x.buf), L.ptr(G), L.ptr(addend), x.N, x.H, x.W,
+                               x.C, L.ptr(dst), st)
+            elif k == "up":
+                low, skip = op.ins[0], op.ins[1]
+                if skip is not None:
+                    self._grad_passthrough(skip, G)
+                if low.requires_grad:
+                    addend, dst = self._grad_target(low)
+                    self._emit(g, "hg_upsample2x_bwd", self.hdt, op.attrs["mode"], L.ptr(G), L.ptr(addend), low.N,
+                               low.H, low.W, low.C, L.ptr(dst), st)
+            elif k == "add":
+                self._grad_passthrough(op.ins[0], G)
+                self._grad_passthrough(op.ins[1], G)
+            elif k == "stem":
+                cv, x = op.attrs["conv"], op.ins[0]
+                self._emit(g, "hg_stem_bwd", self.hdt, L.ptr(x.buf), L.ptr(out.buf), L.ptr(G), x.N, x.H, x.W,
+                           L.ptr(self._gslot(cv.weight)), L.ptr(self._gslot(cv.bias)), st)
+        # graph inputs that want a gradient (sub-module use): NHWC -> NCHW fp32
+        self.gin_static = None
+        for v, kind in self.b.inputs:
+            if kind == "nchw" and v.requires_grad:
+                self.gin_static = torch.zeros(v.N, v.C, v.H, v.W, device=self.device, dtype=torch.float32)
+                if v.grad is not None:
+                    self._emit(g, "hg_nhwc_to_nchw_f32", self.hdt, L.ptr(v.grad), v.N, v.C, v.H, v.W,
+                               L.ptr(self.gin_static), st)
+        # packed weight gradients -> OIHW slots
+        for cv in convs:
+            info = self.conv_info[id(cv)]
+            if info.get("used"):
+                d = L.HgConvDesc(1, 1, 1, cv.in_channels, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1], 1, 0,
+                                 1, self.hdt)
+                self._keep.append(d)
+                dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
+                self._emit(g, "hg_unpack_conv_wgrad", C.byref(d), L.ptr(dwp), L.ptr(self._gslot(cv.weight)), 0, st)
+
+    def _scratch(self, v):
+        t = self._act(v)
+        self._keep.append(t)
+        return t
+
+    # ------------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------------
+    def _run_calls(self, calls):
+        self.stream.value = torch.cuda.current_stream().cuda_stream
+        for c in calls:
+            rc = c.fn(*c.args)
+            if rc != 0:
+                raise RuntimeError(f"libhg_sm100a: {c.name} failed with status {rc}: {L.last_error()}")
+
+    def _fwd_body(self):
+        for p, shadow in self._shadow.values():
+            shadow.copy_(p.data)
+        self._refresh_bias()
+        self.stats_arena.zero_()
+        self._run_calls(self.fwd_calls)
+
+    def _refresh_bias(self):
+        # padded fp32 bias vectors (device-to-device copies of the live parameters)
+        for cv, info in self._bias_pairs:
+            info["bias"][:cv.out_channels].copy_(cv.bias.data)
+
+    def _bwd_body(self):
+        self.grad_arena.zero_()
+        self.packed_arena.zero_()
+        self.red_arena.zero_()
+        self._run_calls(self.bwd_calls)
+
+    def prepare(self):
+        convs = _unique([op.attrs["conv"] for op in self.b.ops if op.kind == "conv"])
+        self._bias_pairs = [(cv, self.conv_info[id(cv)]) for cv in convs
+                            if cv.bias is not None and self.conv_info[id(cv)].get("bias_copy")]
+
+    def run_forward(self, x):
+        inp = self.b.inputs[0][0]
+        target = inp.buf if self.b.inputs[0][1] == "image" else self.in_nchw
+        target.copy_(x)
+        if not hasattr(self, "_bias_pairs"):
+            self.prepare()
+        if _USE_GRAPHS and self.n_fwd_runs >= 1:
+            if self.fwd_graph is None:
+                self.fwd_graph = self._capture(self._fwd_body)
+            self.fwd_graph.replay()
+        else:
+            self._fwd_body()
+        self.n_fwd_runs += 1
+        return [t.clone() for t in self.out_static]
+
+    def run_backward(self, gouts):
+        for i, gbuf in enumerate(self.gout_static):
+            go = gouts[i] if i < len(gouts) else None
+            if go is None:
+                gbuf.zero_()
+            else:
+                gbuf.copy_(go)
+        if _USE_GRAPHS and self.n_fwd_runs >= 2:
+            if self.bwd_graph is None:
+                self.bwd_graph = self._capture(self._bwd_body)
+            self.bwd_graph.replay()
+        else:
+            self._bwd_body()
+        grads = []
+        flat = self.grad_arena.clone()
+        off = 0
+        for i, (_, p) in enumerate(self.params):
+            n = p.numel()
+            if self.param_used[i]:
+                gp = flat[off:off + n].view(p.shape)
+                grads.append(gp if p.dtype == torch.float32 else gp.to(p.dtype))
+            else:
+                grads.append(None)
+            off += n
+        gin = self.gin_static.clone() if self.gin_static is not None else None
+        return gin, grads
+
+    def _capture(self, body):
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(graph, stream=s):
+                body()
+        torch.cuda.current_stream().wait_stream(s)
+        return graph
+
+    @property
+    def launches_fwd(self):
+        return len(self.fwd_calls)
+
+    @property
+    def launches_bwd(self):
+        return len(self.bwd_calls)
+
+
+class _PlanFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, *params):
+        outs = plan.run_forward(x)
+        ctx.plan = plan
+        ctx.generation = plan.n_fwd_runs
+        ctx.x_needs_grad = x.requires_grad
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        if ctx.generation != ctx.plan.n_fwd_runs:
+            raise RuntimeError("backward() of a forward pass whose saved activations were overwritten by a later "
+                               "forward of the same module/shape: plans own one static set of buffers (like a CUDA "
+                               "graph); run backward before the next forward")
+        gin, grads = ctx.plan.run_backward(gouts)
+        return (None, gin if ctx.x_needs_grad else None, *grads)
+
+
+def run_plan(plan, x):
+    params = [p for _, p in plan.params]
+    if plan.need_bwd and torch.is_grad_enabled():
+        outs = _PlanFunction.apply(plan, x, *params)
+    else:
+        outs = tuple(plan.run_forward(x))
+    return list(outs)

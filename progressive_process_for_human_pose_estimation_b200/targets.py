@@ -1,0 +1,72 @@
+"""Host API of the target-rendering kernels (csrc/targets.cu).
+
+The reference renders targets with numpy / PIL inside DataLoader workers, one image at a time
+(try_with_torch.py:107-132, try_different_stack.py:114-155).  Here a whole batch of annotations is rendered by
+one kernel launch on the GPU; the arithmetic (float64 Gaussian, Pillow's Bresenham) is restated bit for bit.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _prep(persons, img_wh, num_persons, device):
+    persons = torch.as_tensor(np.asarray(persons, dtype=np.float64)) if not torch.is_tensor(persons) else persons
+    if persons.dim() == 3:  # [B, J, 3] -> one person per image
+        persons = persons.unsqueeze(1)
+    if persons.dim() != 4 or persons.shape[-1] != 3:
+        raise ValueError("persons must be [B, P, J, 3] (x, y, v)")
+    persons = persons.to(device=device, dtype=torch.float64).contiguous()
+    B, P, J, _ = persons.shape
+    img_wh = torch.as_tensor(np.asarray(img_wh, dtype=np.float64)) if not torch.is_tensor(img_wh) else img_wh
+    img_wh = img_wh.to(device=device, dtype=torch.float64).contiguous()
+    if tuple(img_wh.shape) != (B, 2):
+        raise ValueError("img_wh must be [B, 2] (width, height)")
+    if num_persons is not None:
+        num_persons = torch.as_tensor(num_persons).to(device=device, dtype=torch.int32).contiguous()
+        if tuple(num_persons.shape) != (B,):
+            raise ValueError("num_persons must be [B]")
+    return persons, img_wh, num_persons, B, P, J
+
+
+def gaussian_heatmaps(persons, img_wh, J=None, H=64, W=64, num_persons=None, center_mode=0, truncate=True,
+                      accumulate=False, pre_scale=1.0, sigma=1.0, amplitude=1.0, device="cuda"):
+    """Gaussian keypoint heatmaps [B, J, H, W] float32.
+
+    persons [B,P,J,3] (x, y, v) in image pixels, img_wh [B,2].  Variants:
+      truncate=True,  accumulate=False : try_with_torch.py:107-132 (last person wins, quirk Q7)
+      truncate=False, pre_scale=100    : try_with_torch_100.py:64-85
+      truncate=False                   : only_one_hourgless.py:112-132, read_mscoco.py:46-67
+      accumulate=True, center_mode=1   : hourglass_compare.py:713-734 (MPII);  center_mode=0: :286-313 (COCO)
+      amplitude=1/(2 pi sigma^2)       : data_argumentation.py:33-52
+    """
+    persons, img_wh, num_persons, B, P, Jp = _prep(persons, img_wh, num_persons, device)
+    if J is not None and J != Jp:
+        raise ValueError(f"expected {J} joints, got {Jp}")
+    out = torch.empty(B, Jp, H, W, device=persons.device, dtype=torch.float32)
+    d = L.HgGaussDesc(B, P, Jp, H, W, center_mode, 1 if truncate else 0, 1 if accumulate else 0, float(pre_scale),
+                      float(sigma), float(amplitude))
+    with torch.cuda.device(persons.device):
+        L.call("hg_render_gauss", C.byref(d), L.ptr(persons), L.ptr(num_persons), L.ptr(img_wh), L.ptr(out),
+               L.stream_ptr())
+    return out
+
+
+def label_maps(persons, img_wh, limbs, H=64, W=64, num_persons=None, center_mode=0, draw_points=False,
+               draw_lines=True, line_value=0, device="cuda"):
+    """Integer label maps [B, H, W] int64 drawn like PIL's ImageDraw.point / ImageDraw.line
+    (try_different_stack.py:146-155: skeleton map = limbs with value i+1, background map = limbs with value 1;
+    try_skeleton_and_keypoints.py:104-111: keypoint map = points with value k+1)."""
+    persons, img_wh, num_persons, B, P, J = _prep(persons, img_wh, num_persons, device)
+    limbs_t = torch.as_tensor(np.asarray(limbs, dtype=np.int32).reshape(-1, 2)).to(persons.device).contiguous()
+    if limbs_t.numel() and (int(limbs_t.max()) >= J or int(limbs_t.min()) < 0):
+        raise ValueError("limb end point index out of range")
+    out = torch.empty(B, H, W, device=persons.device, dtype=torch.int64)
+    d = L.HgLabelDesc(B, P, J, limbs_t.shape[0], H, W, center_mode, 1 if draw_points else 0, 1 if draw_lines else 0,
+                      int(line_value))
+    with torch.cuda.device(persons.device):
+        L.call("hg_render_labels", C.byref(d), L.ptr(persons), L.ptr(num_persons), L.ptr(img_wh), L.ptr(limbs_t),
+               L.ptr(out), L.stream_ptr())
+    return out

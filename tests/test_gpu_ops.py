@@ -1,0 +1,327 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes), against plain PyTorch fp32
+ops on the same inputs.  bf16 tolerance: rtol 2e-2 of the tensor's max (north_star); fp32 path: 1e-5."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from progressive_process_for_human_pose_estimation_b200 import _lib as L  # noqa: E402
+
+DTYPES = [torch.bfloat16, torch.float32]
+
+
+@pytest.fixture(autouse=True)
+def _exact_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def nhwc(t, dtype):
+    n, c, h, w = t.shape
+    out = torch.zeros(n, h, w, L.pad64(c), device=t.device, dtype=dtype)
+    out[..., :c] = t.permute(0, 2, 3, 1).to(dtype)
+    return out.contiguous()
+
+
+def nchw(t, c):
+    return t[..., :c].float().permute(0, 3, 1, 2).contiguous()
+
+
+def tol(dtype):
+    return 2e-2 if dtype == torch.bfloat16 else 1e-5
+
+
+def close(got, ref, rtol, what=""):
+    scale = ref.abs().max().item() + 1e-20
+    err = (got - ref).abs().max().item()
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, dil, residual, head
+    (2, 16, 16, 64, 64, 1, 1, False, False),
+    (2, 16, 16, 256, 128, 1, 1, False, False),
+    (2, 64, 64, 128, 128, 3, 1, False, False),
+    (2, 64, 64, 128, 256, 1, 1, True, False),
+    (4, 4, 4, 128, 128, 3, 1, False, False),
+    (3, 8, 8, 128, 128, 3, 1, False, False),
+    (1, 128, 128, 64, 64, 3, 1, False, False),
+    (1, 128, 128, 64, 128, 1, 1, True, False),
+    (2, 32, 32, 256, 256, 1, 1, True, False),
+    (2, 64, 64, 256, 16, 1, 1, False, True),
+    (2, 64, 64, 16, 256, 1, 1, True, False),
+    (2, 64, 64, 256, 17, 1, 1, False, True),
+    (2, 64, 64, 256, 38, 1, 1, False, True),
+    (2, 4, 4, 256, 256, 3, 6, False, False),
+    (5, 32, 32, 128, 128, 3, 1, False, False),   # M not a multiple of the CTA tile at N=5? (5*1024 = 40 tiles) fine
+    (1, 8, 8, 256, 128, 1, 1, False, False),     # M = 64 < one tile: TMA clips / zero-fills
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad(case, dtype):
+    N, H, W, Cin, Cout, k, dil, res, head = case
+    torch.manual_seed(0)
+    dev = "cuda"
+    pad = dil * (k // 2)
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    r = torch.randn(N, Cout, H, W, device=dev) if res else None
+    d = L.HgConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, dil, L.hg_dtype(dtype))
+    Cin_p, Cout_p = L.pad64(Cin), L.pad64(Cout)
+    xq, rq = nhwc(x, dtype), (nhwc(r, dtype) if res else None)
+    wf = torch.empty(k * k, Cout_p, Cin_p, device=dev, dtype=dtype)
+    wd = torch.empty(k * k, Cin_p, Cout_p, device=dev, dtype=dtype)
+    bias_p = torch.zeros(Cout_p, device=dev)
+    bias_p[:Cout] = b
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
+    y = torch.full((N, H, W, Cout_p), float("nan"), device=dev, dtype=dtype)
+    stats = torch.zeros(2 * Cout_p, device=dev)
+    out_nchw = torch.full((N, Cout, H, W), float("nan"), device=dev) if head else None
+    L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), L.ptr(rq), L.ptr(y), L.ptr(stats),
+           L.ptr(out_nchw), st)
+    xr, wr = nchw(xq, Cin), w.to(dtype).float()
+    ref = F.conv2d(xr, wr, b, 1, pad, dil)
+    if res:
+        ref = ref + nchw(rq, Cout)
+    close(nchw(y, Cout), ref, tol(dtype), "fprop")
+    if Cout_p > Cout:
+        assert y[..., Cout:].float().abs().max().item() == 0.0, "padded output channels must stay zero"
+    if head:
+        close(out_nchw, ref, 1e-4 if dtype == torch.bfloat16 else 1e-5, "fprop fp32 NCHW copy")
+    yv = y[..., :Cout].float()
+    close(stats[:Cout], yv.sum((0, 1, 2)), 1e-3, "stats sum")
+    close(stats[Cout_p:Cout_p + Cout], (yv * yv).sum((0, 1, 2)), 1e-3, "stats sumsq")
+
+    dy = torch.randn(N, Cout, H, W, device=dev)
+    dyq = nhwc(dy, dtype)
+    dyr = nchw(dyq, Cout)
+    add = torch.randn(N, Cin, H, W, device=dev)
+    addq = nhwc(add, dtype)
+    dx = torch.full((N, H, W, Cin_p), float("nan"), device=dev, dtype=dtype)
+    L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), L.ptr(addq), L.ptr(dx), st)
+    ref_dx = torch.nn.grad.conv2d_input(xr.shape, wr, dyr, 1, pad, dil) + nchw(addq, Cin)
+    close(nchw(dx, Cin), ref_dx, tol(dtype), "dgrad (+addend)")
+    # in-place accumulation (addend == dx), as the plan uses it
+    dx2 = addq.clone()
+    L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), L.ptr(dx2), L.ptr(dx2), st)
+    assert torch.equal(dx2, dx), "in-place dgrad accumulation differs"
+
+    dwp = torch.zeros(k * k, Cout_p, Cin_p, device=dev)
+    dbias = torch.zeros(Cout, device=dev)
+    for _ in range(2):  # accumulates over call sites
+        L.call("hg_conv_wgrad", C.byref(d), L.ptr(xq), L.ptr(dyq), L.ptr(dwp), L.ptr(dbias), st)
+    dw = torch.zeros_like(w)
+    L.call("hg_unpack_conv_wgrad", C.byref(d), L.ptr(dwp), L.ptr(dw), 0, st)
+    ref_dw = 2 * torch.nn.grad.conv2d_weight(xr, w.shape, dyr, 1, pad, dil)
+    close(dw, ref_dw, 1e-3 if dtype == torch.bfloat16 else 2e-5, "wgrad")
+    close(dbias, 2 * dyr.sum((0, 2, 3)), 1e-3, "dbias")
+
+
+def test_conv_tensor_core_matches_cuda_core_kernel():
+    """The tcgen05 kernel and the FFMA kernel compute the same bf16 convolution."""
+    torch.manual_seed(1)
+    N, H, W, Cin, Cout, k = 2, 32, 32, 128, 128, 3
+    d = L.HgConvDesc(N, H, W, Cin, Cout, k, k, 1, 1, 1, L.HG_BF16)
+    x = nhwc(torch.randn(N, Cin, H, W, device="cuda"), torch.bfloat16)
+    w = torch.randn(Cout, Cin, k, k, device="cuda") / 34.0
+    wf = torch.empty(9, Cout, Cin, device="cuda", dtype=torch.bfloat16)
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), None, st)
+    outs = []
+    try:
+        for force in (0, 1):
+            L.call("hg_set_option", b"force_ref_conv", force)
+            y = torch.empty(N, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+            L.call("hg_conv_fprop", C.byref(d), L.ptr(x), L.ptr(wf), None, None, L.ptr(y), None, st)
+            outs.append(y.float())
+    finally:
+        L.call("hg_set_option", b"force_ref_conv", 0)
+    close(outs[0], outs[1], 1e-2, "tc vs ref")
+
+
+def test_conv_rejects_bad_descriptor():
+    d = L.HgConvDesc(0, 8, 8, 64, 64, 1, 1, 1, 0, 1, L.HG_BF16)
+    t = torch.zeros(64, device="cuda")
+    rc = L.load().hg_conv_fprop(C.byref(d), L.ptr(t), L.ptr(t), None, None, L.ptr(t), None, L.stream_ptr())
+    assert rc == -1 and "non-positive" in L.last_error()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 64, 32, 32), (3, 128, 8, 8), (2, 256, 4, 4), (2, 16, 16, 16)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_batchnorm_train_fwd_bwd(shape, dtype, relu):
+    N, Cc, H, W = shape
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(N, Cc, H, W, device=dev) * 1.7 + 0.4
+    gamma = torch.rand(Cc, device=dev) + 0.5
+    beta = torch.randn(Cc, device=dev) * 0.3
+    xq = nhwc(x, dtype)
+    Cp = L.pad64(Cc)
+    M = N * H * W
+    d = L.HgBnDesc(M, Cc, L.hg_dtype(dtype), 1e-5, 1 if relu else 0, 0)
+    st = L.stream_ptr()
+    stats = torch.zeros(2 * Cp, device=dev)
+    L.call("hg_bn_stats", C.byref(d), L.ptr(xq), L.ptr(stats), st)
+    y = torch.empty_like(xq)
+    L.call("hg_bn_apply", C.byref(d), L.ptr(xq), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, L.ptr(y), st)
+    xr = nchw(xq, Cc).requires_grad_(True)
+    g_ref, b_ref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.batch_norm(xr, None, None, g_ref, b_ref, True, 0.1, 1e-5)
+    close(nchw(y, Cc), (F.relu(ref) if relu else ref).detach(), tol(dtype), "bn fwd")
+    if relu:  # the ReLU mask of the reference is the kernel's own (an element at 0 +- 1 ulp may go either way)
+        ref = ref * (nchw(y, Cc) > 0).float()
+    da = torch.randn(N, Cc, H, W, device=dev)
+    daq = nhwc(da, dtype)
+    ref.backward(nchw(daq, Cc))
+    red = torch.zeros(2 * Cp, device=dev)
+    L.call("hg_bn_bwd_reduce", C.byref(d), L.ptr(daq), L.ptr(xq), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(red), st)
+    addq = nhwc(torch.randn(N, Cc, H, W, device=dev), dtype)
+    dx = torch.empty_like(xq)
+    dgamma, dbeta, colsum = (torch.zeros(Cc, device=dev) for _ in range(3))
+    L.call("hg_bn_bwd_apply", C.byref(d), L.ptr(daq), L.ptr(xq), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None,
+           L.ptr(red), L.ptr(addq), L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(colsum), st)
+    t = 3e-2 if dtype == torch.bfloat16 else 2e-4
+    close(nchw(dx, Cc), xr.grad + nchw(addq, Cc), t, "bn dx")
+    close(dgamma, g_ref.grad, 1e-3 if dtype == torch.float32 else 2e-2, "bn dgamma")
+    close(dbeta, b_ref.grad, 1e-3 if dtype == torch.float32 else 2e-2, "bn dbeta")
+    assert colsum.abs().max().item() <= 1e-2 * (xr.grad.abs().sum((0, 2, 3)).max().item() + 1e-6), "sum(dx) ~ 0"
+
+
+def test_batchnorm_eval_and_running_update():
+    torch.manual_seed(0)
+    dev = "cuda"
+    N, Cc, H, W = 2, 128, 16, 16
+    bn = torch.nn.BatchNorm2d(Cc).to(dev)
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    ref_bn = torch.nn.BatchNorm2d(Cc).to(dev)
+    ref_bn.load_state_dict(bn.state_dict())
+    xs = [torch.randn(N, Cc, H, W, device=dev) * (i + 1) for i in range(3)]
+    st = L.stream_ptr()
+    d = L.HgBnDesc(N * H * W, Cc, L.HG_F32, 1e-5, 1, 1)
+    xq = nhwc(xs[0], torch.float32)
+    y = torch.empty_like(xq)
+    L.call("hg_bn_apply", C.byref(d), L.ptr(xq), None, L.ptr(bn.weight), L.ptr(bn.bias), L.ptr(bn.running_mean),
+           L.ptr(bn.running_var), L.ptr(y), st)
+    ref_bn.eval()
+    close(nchw(y, Cc), F.relu(ref_bn(xs[0])).detach(), 1e-5, "bn eval fwd")
+    # three call sites of one module, applied in order by one launch
+    ref_bn.train()
+    stats = []
+    dtr = L.HgBnDesc(N * H * W, Cc, L.HG_F32, 1e-5, 1, 0)
+    for x in xs:
+        ref_bn(x)
+        s = torch.zeros(2 * Cc, device=dev)
+        L.call("hg_bn_stats", C.byref(dtr), L.ptr(nhwc(x, torch.float32)), L.ptr(s), st)
+        stats.append(s)
+    sites = (L.HgBnRunningSite * 3)(*[L.HgBnRunningSite(s.data_ptr(), float(N * H * W), 0) for s in stats])
+    mods = (L.HgBnRunningModule * 1)(L.HgBnRunningModule(bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                                         bn.num_batches_tracked.data_ptr(), Cc, Cc, 0, 3, 0.1, 0))
+    sd = torch.frombuffer(bytearray(bytes(sites)), dtype=torch.uint8).cuda()
+    md = torch.frombuffer(bytearray(bytes(mods)), dtype=torch.uint8).cuda()
+    L.call("hg_bn_update_running", L.ptr(md), L.ptr(sd), 1, st)
+    close(bn.running_mean, ref_bn.running_mean, 1e-5, "running_mean")
+    close(bn.running_var, ref_bn.running_var, 1e-5, "running_var")
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_maxpool_fwd_bwd_first_max_tiebreak(dtype):
+    torch.manual_seed(0)
+    dev = "cuda"
+    N, Cc, H, W = 2, 64, 8, 8
+    x = torch.randint(0, 3, (N, Cc, H, W), device=dev).float()  # many ties
+    xq = nhwc(x, dtype)
+    y = torch.empty(N, H // 2, W // 2, 64, device=dev, dtype=dtype)
+    st = L.stream_ptr()
+    L.call("hg_maxpool2_fwd", L.hg_dtype(dtype), L.ptr(xq), N, H, W, Cc, L.ptr(y), st)
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 2)
+    assert torch.equal(nchw(y, Cc), ref.detach())
+    dy = torch.randn(N, Cc, H // 2, W // 2, device=dev)
+    dyq = nhwc(dy, dtype)
+    ref.backward(nchw(dyq, Cc))
+    addq = nhwc(torch.randn(N, Cc, H, W, device=dev), dtype)
+    dx = torch.empty_like(xq)
+    L.call("hg_maxpool2_bwd", L.hg_dtype(dtype), L.ptr(xq), L.ptr(dyq), L.ptr(addq), N, H, W, Cc, L.ptr(dx), st)
+    close(nchw(dx, Cc), xr.grad + nchw(addq, Cc), tol(dtype), "maxpool bwd")
+    dx0 = torch.empty_like(xq)
+    L.call("hg_maxpool2_bwd", L.hg_dtype(dtype), L.ptr(xq), L.ptr(dyq), None, N, H, W, Cc, L.ptr(dx0), st)
+    assert torch.equal(nchw(dx0, Cc), xr.grad), "gradient must go to the first row-major maximum"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("hw", [4, 8, 32])
+def test_upsample_add_fwd_bwd(dtype, mode, hw):
+    torch.manual_seed(0)
+    dev = "cuda"
+    N, Cc = 2, 64
+    low = torch.randn(N, Cc, hw, hw, device=dev)
+    skip = torch.randn(N, Cc, 2 * hw, 2 * hw, device=dev)
+    lq, sq = nhwc(low, dtype), nhwc(skip, dtype)
+    out = torch.empty_like(sq)
+    st = L.stream_ptr()
+    L.call("hg_upsample2x_add_fwd", L.hg_dtype(dtype), mode, L.ptr(lq), L.ptr(sq), N, hw, hw, Cc, L.ptr(out), st)
+    lr = nchw(lq, Cc).requires_grad_(True)
+    if mode == 0:
+        up = F.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=True)
+    else:
+        up = F.interpolate(lr, scale_factor=2, mode="nearest")
+    ref = up + nchw(sq, Cc)
+    close(nchw(out, Cc), ref.detach(), tol(dtype), "upsample+add fwd")
+    dout = nhwc(torch.randn(N, Cc, 2 * hw, 2 * hw, device=dev), dtype)
+    up.backward(nchw(dout, Cc))
+    dlow = torch.empty_like(lq)
+    L.call("hg_upsample2x_bwd", L.hg_dtype(dtype), mode, L.ptr(dout), None, N, hw, hw, Cc, L.ptr(dlow), st)
+    close(nchw(dlow, Cc), lr.grad, tol(dtype) if dtype == torch.bfloat16 else 1e-5, "upsample bwd")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_stem_fwd_bwd(dtype):
+    torch.manual_seed(0)
+    dev = "cuda"
+    N, H, W = 2, 64, 96
+    x = torch.randn(N, 3, H, W, device=dev)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3).to(dev)
+    y = torch.empty(N, H // 2, W // 2, 64, device=dev, dtype=dtype)
+    st = L.stream_ptr()
+    L.call("hg_stem_fwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(conv.weight), L.ptr(conv.bias), N, H, W, L.ptr(y), st)
+    ref = F.relu(conv(x))
+    close(nchw(y, 64), ref.detach(), 1e-2 if dtype == torch.bfloat16 else 1e-5, "stem fwd")
+    dy = nhwc(torch.randn(N, 64, H // 2, W // 2, device=dev), dtype)
+    # reference backward with the kernel's own stored activation as ReLU mask
+    mask = (nchw(y, 64) > 0).float()
+    g = nchw(dy, 64) * mask
+    ref_dw = torch.nn.grad.conv2d_weight(x, conv.weight.shape, g, 2, 3)
+    dw = torch.zeros_like(conv.weight)
+    db = torch.zeros(64, device=dev)
+    L.call("hg_stem_bwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(y), L.ptr(dy), N, H, W, L.ptr(dw), L.ptr(db), st)
+    close(dw, ref_dw, 1e-4, "stem dw")
+    close(db, g.sum((0, 2, 3)), 1e-4, "stem db")
+
+
+def test_layout_roundtrip_and_add():
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(2, 17, 8, 8, device=dev)
+    st = L.stream_ptr()
+    for dtype in DTYPES:
+        q = torch.full((2, 8, 8, 64), float("nan"), device=dev, dtype=dtype)
+        L.call("hg_nchw_f32_to_nhwc", L.hg_dtype(dtype), L.ptr(x), None, 2, 17, 8, 8, L.ptr(q), st)
+        assert torch.equal(q, nhwc(x, dtype))
+        back = torch.empty_like(x)
+        L.call("hg_nhwc_to_nchw_f32", L.hg_dtype(dtype), L.ptr(q), 2, 17, 8, 8, L.ptr(back), st)
+        assert torch.equal(back, x.to(dtype).float())
+        s = torch.empty_like(q)
+        L.call("hg_add", L.hg_dtype(dtype), L.ptr(q), L.ptr(q), L.ptr(s), C.c_longlong(q.numel()), st)
+        assert torch.equal(s.float(), (q.float() * 2).to(dtype).float())

@@ -1,0 +1,184 @@
+"""GPU parity tests of target rendering, argmax decode and PCKh against the numpy oracles (oracle/targets_np.py,
+oracle/pckh_np.py, both pinned to the reference / Pillow by the `not gpu` tests).  Integer results (label maps,
+decoded indices, PCKh counts) must be bit-exact; Gaussians are float64-evaluated and must match to the last
+float32 bit except for the documented <= 1 ulp allowance of the device exp()."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import progressive_process_for_human_pose_estimation_b200 as hg  # noqa: E402
+import progressive_process_for_human_pose_estimation_b200.only_one_hourgless as ooh  # noqa: E402
+import progressive_process_for_human_pose_estimation_b200.try_with_torch as twt  # noqa: E402
+from oracle import pckh_np, targets_np  # noqa: E402
+
+
+def synth_people(seed, B, P, J, float_xy=False):
+    r = np.random.RandomState(seed)
+    wh = np.stack([r.randint(200, 700, B), r.randint(200, 700, B)], 1).astype(np.float64)
+    kp = np.zeros([B, P, J, 3])
+    for b in range(B):
+        kp[b, :, :, 0] = r.uniform(0, wh[b, 0], [P, J]) if float_xy else r.randint(0, wh[b, 0], [P, J])
+        kp[b, :, :, 1] = r.uniform(0, wh[b, 1], [P, J]) if float_xy else r.randint(0, wh[b, 1], [P, J])
+    kp[..., 2] = r.randint(0, 3, [B, P, J])
+    npers = r.randint(1, P + 1, B).astype(np.int32)
+    return kp, wh, npers
+
+
+def ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+VARIANTS = [
+    dict(truncate=True, accumulate=False),                       # G1 try_with_torch.py:107-132
+    dict(truncate=False, accumulate=False, pre_scale=100.0),     # G2 try_with_torch_100.py:64-85
+    dict(truncate=False, accumulate=False),                      # G3 only_one_hourgless.py:112-132
+    dict(truncate=False, accumulate=True, center_mode=1),        # G4 hourglass_compare.py:713-734
+    dict(truncate=True, accumulate=True),                        # G5 hourglass_compare.py:286-313
+    dict(truncate=False, accumulate=False, amplitude=1.0 / (2 * np.pi)),  # G6 data_argumentation.py:33-52
+]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_gaussian_heatmaps_match_numpy(variant):
+    kp, wh, npers = synth_people(3, 6, 3, 17, float_xy=not variant["truncate"])
+    got = hg.gaussian_heatmaps(kp, wh, num_persons=npers, **variant).cpu().numpy()
+    worst = 0
+    for b in range(kp.shape[0]):
+        ref = targets_np.gauss_map(kp[b, :npers[b]], wh[b], 17, **variant)
+        d = ulp_diff(got[b], ref)
+        # subnormal / tiny tails: compare absolutely as well
+        bad = (d > 1) & (np.abs(got[b] - ref) > 1e-37)
+        assert not bad.any(), f"image {b}: {bad.sum()} elements differ by more than 1 ulp"
+        worst = max(worst, int(d[np.abs(ref) > 1e-30].max(initial=0)))
+    assert worst <= 1
+    if variant["truncate"]:
+        # integer centres: d2 is an exact integer, every element must be bit-identical in practice
+        frac_exact = np.mean([np.array_equal(got[b], targets_np.gauss_map(kp[b, :npers[b]], wh[b], 17, **variant))
+                              for b in range(kp.shape[0])])
+        assert frac_exact >= 0.5
+
+
+def test_gaussian_module_api_and_last_person_wins():
+    kp, wh, _ = synth_people(5, 4, 2, 17)
+    kp[..., 2] = 2
+    out = twt.render_targets(kp, wh)
+    assert out.shape == (4, 17, 64, 64) and out.dtype == torch.float32
+    last_only = twt.render_targets(kp[:, 1:], wh)
+    assert torch.equal(out, last_only)  # quirk Q7
+    peak = hg.decode_argmax(out)[0].cpu().numpy()
+    cx = np.trunc(kp[:, 1, :, 0] / wh[:, None, 0] * 64)
+    cy = np.trunc(kp[:, 1, :, 1] / wh[:, None, 1] * 64)
+    assert np.array_equal(peak[..., 1], cx.astype(np.int32)) and np.array_equal(peak[..., 0], cy.astype(np.int32))
+
+
+@pytest.mark.parametrize("mode", ["skeleton", "background", "keypoints", "both"])
+def test_label_maps_bit_exact(mode):
+    kp, wh, npers = synth_people(11, 8, 3, 17)
+    kp[0, :, :, 2] = 0          # image without visible joints -> empty map
+    kp[1, 0, 3, 0] = wh[1, 0]   # x == w -> column 64, clipped by the canvas
+    kw = dict(skeleton=dict(draw_lines=True), background=dict(draw_lines=True, line_value=1),
+              keypoints=dict(draw_points=True, draw_lines=False), both=dict(draw_points=True, draw_lines=True))[mode]
+    got = hg.label_maps(kp, wh, twt.sks, num_persons=npers, **kw)
+    assert got.dtype == torch.int64 and got.shape == (8, 64, 64)
+    for b in range(8):
+        ref = targets_np.label_map(kp[b, :npers[b]], wh[b], 17, twt.sks, **kw)
+        assert np.array_equal(got[b].cpu().numpy(), ref), f"image {b}"
+    assert int(got[0].abs().sum()) == 0
+
+
+def _heatmaps(seed, B, C, dtype):
+    r = np.random.RandomState(seed)
+    x = torch.from_numpy(r.randn(B, C, 64, 64).astype(np.float32))
+    x[0, 0] = 0.0                           # constant map -> index 0
+    x[1, 3, 10, 5] = 9.0
+    x[1, 3, 10, 7] = 9.0                    # duplicated maximum -> lowest index
+    x[2, 1] = x[2, 1].half().float()        # fp16-quantised maps have many ties
+    x[3, 2, 63, 63] = 50.0                  # last element
+    return x.to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_decode_argmax_bit_exact(dtype):
+    x = _heatmaps(0, 4, 16, dtype)
+    yx, mx = hg.decode_argmax(x.cuda())
+    ref = np.array([[pckh_np.argmax_first(x[b, c].float().numpy()) for c in range(16)] for b in range(4)])
+    assert np.array_equal(yx.cpu().numpy(), ref)
+    assert torch.equal(mx.cpu(), x.float().amax((2, 3)))
+    # first index of torch.nonzero(x >= max), the reference's own expression (hourglass_compare.py:831)
+    for b, c in [(0, 0), (1, 3), (2, 1), (3, 2)]:
+        hm = x[b, c].float()
+        assert tuple(torch.nonzero(hm >= hm.max())[0].tolist()) == tuple(yx[b, c].tolist())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("chan_offset", [0, 1])
+def test_pckh_sweep_bit_exact(dtype, chan_offset):
+    for seed in range(5):
+        r = np.random.RandomState(100 + seed)
+        B, J = 6, 16
+        x = _heatmaps(seed, B, J + chan_offset, dtype)
+        tgt = torch.zeros(B, 64, 64, dtype=torch.long)
+        for b in range(B):
+            for j in range(J):
+                if b != 4 and r.rand() < 0.85:   # image 4: no joints at all -> NaN accuracy row
+                    tgt[b, r.randint(64), r.randint(64)] = j + 1
+        tgt[5, 0, 0] = 3
+        tgt[5, 40, 2] = 3                        # a joint labelled twice -> first row-major position
+        rect = torch.from_numpy(r.uniform(0, 64, size=(B, 4)).astype(np.float32))
+        got = hg.pckh_sweep_counts(x.cuda(), tgt.cuda(), rect.cuda(), chan_offset)
+        ref = pckh_np.pckh_sweep(x.float().numpy(), tgt.numpy(), rect.numpy(), chan_offset)
+        for k in ("correct", "total", "predict", "label", "found"):
+            assert np.array_equal(got[k].cpu().numpy(), ref[k]), (seed, k)
+        assert np.array_equal(got["standard"].cpu().numpy(), ref["standard"])
+        mod = hg.PCKh_hourglass() if chan_offset == 0 else hg.PCKh_softmax()
+        res = mod(x.cuda(), tgt.cuda(), rect.cuda())
+        acc = res[0]
+        assert acc.shape == (B, 11) and acc.dtype == np.float64
+        assert np.array_equal(np.isnan(acc), np.isnan(ref["accuracy"]))
+        assert np.array_equal(np.nan_to_num(acc), np.nan_to_num(ref["accuracy"]))
+        assert np.isnan(acc[4]).all()
+
+
+def test_pckh_a_bit_exact_counts():
+    for seed in range(4):
+        r = np.random.RandomState(seed)
+        B = 5
+        ooh.batch_size = B
+        tgt = torch.from_numpy(r.rand(B, 14, 64, 64).astype(np.float32))
+        tgt[0, 2] = 0                           # absent joint -> skipped
+        tgt[1, 13, 5, 5] = 3.0
+        tgt[1, 13, 5, 9] = 3.0                  # tie in the head map
+        x = torch.from_numpy(r.rand(B, 18, 64, 64).astype(np.float32))
+        x[:, :14] = 0.7 * tgt + 0.3 * x[:, :14]
+        pck = ooh.PCKh()
+        c = pck.counts(x.cuda(), tgt.cuda()).cpu().numpy()
+        rc, rt = pckh_np.pckh_a(x.numpy(), tgt.numpy(), B)
+        assert (int(c[0]), int(c[1])) == (rc, rt)
+        assert pck(x.cuda(), tgt.cuda()) == rc / rt
+    ooh.batch_size = 16
+
+
+def test_render_decode_roundtrip_at_scale():
+    """Full-size property (BASELINE config 5 batch): decode(render(kp)) returns the truncated centres."""
+    B, J = 256, 17
+    r = np.random.RandomState(7)
+    wh = np.tile(np.array([[640.0, 480.0]]), (B, 1))
+    kp = np.zeros([B, 1, J, 3])
+    kp[..., 0] = r.randint(0, 640, [B, 1, J])
+    kp[..., 1] = r.randint(0, 480, [B, 1, J])
+    kp[..., 2] = 2
+    hm = hg.gaussian_heatmaps(kp, wh)
+    yx, mx = hg.decode_argmax(hm)
+    assert torch.all(mx == 1.0)
+    cx = np.trunc(kp[:, 0, :, 0] / 640.0 * 64).astype(np.int32)
+    cy = np.trunc(kp[:, 0, :, 1] / 480.0 * 64).astype(np.int32)
+    assert np.array_equal(yx[..., 1].cpu().numpy(), cx) and np.array_equal(yx[..., 0].cpu().numpy(), cy)
+
+
+def test_decode_requires_cuda_tensor():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hg.decode_argmax(torch.zeros(1, 1, 64, 64))

@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- training throughput of the 8-stack hourglass (BASELINE.json configs[1]) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's CPU implementation (oracle port) on the host cores
+
+A step = forward of the weight-shared 8-stack network (try_with_torch.creatModel, nStack=8, 16 heatmaps) on a
+batch of 32 images per GPU at 256x256, eight nn.MSELoss terms on Gaussian targets, backward, Adam update.
+`value` times that with the batch resident in HBM; `e2e` adds, inside the timed region of every step, the copy of
+the step's images+targets from pinned host memory and a device->host read of the loss.  One JSON line on stdout.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train images/sec, 8-stack hourglass 256x256"
+UNIT = "images/s"
+NSTACK, NJOINT, IMG = 8, 16, 256
+# conv FLOPs (2*MAC) per image of this network, hook-counted on the reference
+FWD_GFLOP_PER_IMG = 97.272
+TRAIN_GFLOP_PER_IMG = 291.51
+
+
+def dist_info():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d, "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_batch(B, seed, device):
+    """Seeded synthetic batch: N(0,1) images and Gaussian targets rendered by the library's own render kernel
+    from random MPII-style annotations (one person, 16 joints, 640x480 image)."""
+    import numpy as np
+
+    import progressive_process_for_human_pose_estimation_b200 as hg
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, IMG, IMG, generator=g)
+    r = np.random.RandomState(seed + 1)
+    kp = np.zeros([B, 1, NJOINT, 3])
+    kp[..., 0] = r.randint(0, 640, [B, 1, NJOINT])
+    kp[..., 1] = r.randint(0, 480, [B, 1, NJOINT])
+    kp[..., 2] = r.randint(0, 3, [B, 1, NJOINT])
+    wh = np.tile(np.array([[640.0, 480.0]]), (B, 1))
+    y = hg.gaussian_heatmaps(kp, wh, truncate=True, device=device)
+    return x, y
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import progressive_process_for_human_pose_estimation_b200 as hg
+    import progressive_process_for_human_pose_estimation_b200.try_with_torch as m
+    from progressive_process_for_human_pose_estimation_b200 import _lib as L
+    from progressive_process_for_human_pose_estimation_b200.parallel import DataParallel
+
+    world, rank, local = dist_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    if not L.load().hg_device_ok():
+        raise SystemExit("bench.py: device is not compute capability 10.x")
+    B = args.batch
+    warmup = max(3, args.warmup)
+    hg.set_compute_dtype(torch.bfloat16)
+    m.nStack, m.nOutChannels = NSTACK, NJOINT
+    torch.manual_seed(0)
+    net = m.creatModel().to(dev)
+    model = DataParallel(net) if world > 1 else net
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    mse = [torch.nn.MSELoss() for _ in range(NSTACK)]
+    x_cpu, y = synth_batch(B, 100 + rank, dev)
+    x = x_cpu.to(dev)
+
+    def step(xb, yb):
+        out = model(xb)
+        loss = mse[0](out[0], yb)
+        for k in range(1, NSTACK):
+            loss = loss + mse[k](out[k], yb)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    l0 = L.launch_count()
+    for i in range(warmup):
+        loss = step(x, y)
+        if i == 0:
+            torch.cuda.synchronize()
+            launches_per_step = L.launch_count() - l0  # step 0 runs every C-ABI call eagerly
+    torch.cuda.synchronize()
+    loss0 = loss.item()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: step(x, y), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host batch -> device every step, loss read back every step ---------------
+    xh = x_cpu.pin_memory()
+    yh = y.cpu().pin_memory()
+    bufs = [(torch.empty_like(x), torch.empty_like(y)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    state = {"i": 0, "last": 0.0}
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            bufs[slot][0].copy_(xh, non_blocking=True)
+            bufs[slot][1].copy_(yh, non_blocking=True)
+
+    def e2e_step():
+        i = state["i"]
+        if i == 0:
+            upload(0)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        xb, yb = bufs[i % 2]
+        copy_stream.wait_stream(torch.cuda.current_stream())  # the other slot is free once the previous step is queued
+        upload((i + 1) % 2)  # next step's batch travels while this step computes
+        state["last"] = step(xb, yb).item()  # device -> host read of the loss
+        state["i"] = i + 1
+
+    e2e_step()
+    state["i"] = 0
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = xh.numel() * 4 + yh.numel() * 4
+    # (the prefetch uploads one extra batch at the very end; bytes are counted per step as copied)
+
+    # ---- per-kernel profile of one step (eager, CUDA events around every C-ABI call) ------------------
+    roofline, table = None, None
+    if rank == 0:
+        plan = list(net.__dict__["_plans"].values())[-1]
+        plan.profile_records = []
+        saved_reducer, plan.reducer = plan.reducer, None
+        torch.cuda._sleep(int(1.5e9))  # let the host run ahead so kernels execute back to back
+        out = net(x)
+        lp = mse[0](out[0], y)
+        for k in range(1, NSTACK):
+            lp = lp + mse[k](out[k], y)
+        opt.zero_grad()
+        lp.backward()
+        torch.cuda.synchronize()
+        recs, plan.profile_records, plan.reducer = plan.profile_records, None, saved_reducer
+        agg = {}
+        for name, tag, e0, e1 in recs:
+            k = (name, tag)
+            t = e0.elapsed_time(e1)
+            a = agg.setdefault(k, [0, 0.0])
+            a[0] += 1
+            a[1] += t
+        total_ms = sum(v[1] for v in agg.values())
+        table = sorted(((k[0], k[1], v[0], v[1]) for k, v in agg.items()), key=lambda r: -r[3])
+        peaks, src = measured_peaks()
+        dom = ("hg_conv_fprop_ex", "128->128 k3 @64x64")
+        if dom in agg:
+            n, t = agg[dom]
+            flops = 2.0 * B * 64 * 64 * 128 * 128 * 9
+            ach = flops / (t / n * 1e-3) / 1e12
+            peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+            roofline = {"kernel": "conv_gemm_kernel<128,4> (fprop 3x3 128->128 @64x64, tcgen05)", "bound": "tensor",
+                        "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                        "traffic": None, "peak_source": f"{src} bf16_tflops_sustained",
+                        "launches_per_step": n, "avg_us": round(t / n * 1e3, 2),
+                        "share_of_step_kernel_time": round(t / total_ms, 4)}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "kernel_table.txt"), "w") as f:
+            f.write(f"# per-call CUDA-event times of one eager step, B={B}/GPU, total {total_ms:.3f} ms\n")
+            f.write("# entry point | shape | calls | total ms | avg us | share\n")
+            for name, tag, n, t in table:
+                f.write(f"{name:24s} {tag:28s} {n:5d} {t:9.3f} {t / n * 1e3:9.2f} {t / total_ms:7.4f}\n")
+
+    # ---- CPU baseline: the oracle port of the reference on the host cores (bounded sample) ------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(steps=2, warmup=1, B=2)
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "8-stack weight-shared hourglass (try_with_torch.creatModel, nStack=8), 16 joints, "
+                                   "256x256, fwd + 8x MSE + bwd + Adam", "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "l2": "inputs >> L2: ~35 GB of activations touched per step"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches_per_step) * args.steps,
+            "launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "model_tflops": round(value / world * TRAIN_GFLOP_PER_IMG / 1e3, 1),
+            "frac_of_bf16_sustained_peak": round(value / world * TRAIN_GFLOP_PER_IMG / 1e3
+                                                 / float(measured_peaks()[0]["bf16_tflops_sustained"]), 4),
+            "loss_after_warmup": loss0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference(steps, warmup, B):
+    """The reference's own CPU implementation of the path -- restated by oracle/hourglass_torch.py, pinned
+    bit-for-bit to the reference classes (tests/test_oracle_model.py) -- timed on the host cores: forward of the
+    8-stack network, eight MSE losses, backward, Adam, on a bounded sample of B images per step."""
+    import progressive_process_for_human_pose_estimation_b200.try_with_torch as m
+    from oracle import hourglass_torch as ho
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m.nStack, m.nOutChannels = NSTACK, NJOINT
+    torch.manual_seed(0)
+    sd = ho.clone_state(m.creatModel().state_dict(), requires_grad=True)
+    params = [v for k, v in sd.items() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    g = torch.Generator().manual_seed(100)
+    x = torch.randn(B, 3, IMG, IMG, generator=g)
+    y = torch.rand(B, NJOINT, IMG // 4, IMG // 4, generator=g)
+    cfg = ho.Config(nStack=NSTACK, nOutChannels=NJOINT)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = ho.creat_model_s(sd, x, cfg)
+        total, _ = ho.mse_losses(out, y)
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": round(B / med, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} timed steps (+{warmup} warm-up) of the same 8-stack train step on {B} images/step, "
+                      f"fp32, torch CPU {torch.__version__}, median step {med:.2f} s"}
+
+
+def run_reference(args):
+    """--impl reference: rank 0 times the CPU implementation; other ranks exit without work."""
+    world, rank, _ = dist_info()
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = max(1, min(args.warmup, 1))
+    cpu = cpu_reference(steps=steps, warmup=warmup, B=2)
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(2 / cpu["value"] * 1e3, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "8-stack weight-shared hourglass (try_with_torch.creatModel, nStack=8), 16 joints, "
+                                   "256x256, fwd + 8x MSE + bwd + Adam", "batch_per_gpu": 32,
+                       "parallelism": "cpu", "note": "CPU arm: each step is a bounded sample of 2 images"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -160,8 +160,11 @@ def make_s_family(g):
         def _emit(self, b, x):
             nModules = g["nModules"]
             up1 = x
-            for _ in range(nModules):
-                up1 = self.residual_block._emit(b, up1)
+            # the skip branch is independent of the whole low-resolution path: it gets its own stream lane so the
+            # launch-latency-bound 4x4 .. 16x16 chain overlaps the large high-resolution kernels
+            with b.on_lane(self.n):
+                for _ in range(nModules):
+                    up1 = self.residual_block._emit(b, up1)
             low1 = b.maxpool2(x)
             for _ in range(nModules):
                 low1 = self.residual_block._emit(b, low1)

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   long long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
   float s[8] = {}, ss[8] = {};
+#pragma unroll 4
   for (long long m = m0 + rl; m < m1; m += rlanes) {
     float v[8];
     load8(x + m * Cp + vc * 8, v);
@@ -96,6 +97,14 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   }
 }
 
+// rows per block: enough blocks to fill the machine, few enough that the per-channel atomics stay cheap
+static inline int rows_per_block_for(long long M, int rlanes) {
+  long long blocks = M / (rlanes * 8);
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  return (int)((M + blocks - 1) / blocks);
+}
+
 int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats, cudaStream_t st) {
   if (Cp % 64 != 0 || Cp > 2048) {
     set_error("bn_stats: padded channel count %d unsupported", Cp);
@@ -105,14 +114,60 @@ int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats,
     set_error("bn_stats: Cp > 256 unsupported");
     return HG_ERR_UNSUPPORTED;
   }
-  int rpb = (int)((M + 2 * kNumSMs * 4 - 1) / (2 * kNumSMs * 4));
-  if (rpb < 64) rpb = 64;
+  const int rpb = rows_per_block_for(M, 256 / (Cp >> 3));
   const int blocks = ceil_div(M, rpb);
   if (dtype == HG_BF16)
     bn_stats_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, M, Cp, stats, rpb);
   else
     bn_stats_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, M, Cp, stats, rpb);
   HG_LAUNCH_OK("bn_stats_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+// column sums only (bias gradient of a convolution: dbias[c] += sum_m dy[m, c])
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long M, int Cp, int C,
+                                                     float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[256][9];
+  const int vecs = Cp >> 3;
+  const int vc = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int rlanes = 256 / vecs;
+  const long long m0 = (long long)blockIdx.x * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float s[8] = {};
+#pragma unroll 4
+  for (long long m = m0 + rl; m < m1; m += rlanes) {
+    float v[8];
+    load8(x + m * Cp + vc * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] += v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = s[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int v = c >> 3, e = c & 7;
+    float a = 0.f;
+    for (int r = 0; r < rlanes; ++r) a += red[r * vecs + v][e];
+    atomicAdd(out + c, a);
+  }
+}
+
+int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* out, cudaStream_t st) {
+  if (Cp % 64 != 0 || Cp > 256) {
+    set_error("colsum: padded channel count %d unsupported", Cp);
+    return HG_ERR_UNSUPPORTED;
+  }
+  const int rpb = rows_per_block_for(M, 256 / (Cp >> 3));
+  const int blocks = ceil_div(M, rpb);
+  if (dtype == HG_BF16)
+    colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, M, Cp, C, out, rpb);
+  else
+    colsum_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, M, Cp, C, out, rpb);
+  HG_LAUNCH_OK("colsum_kernel");
   count_launch();
   return HG_OK;
 }
@@ -160,6 +215,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
   long long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
   float s[8] = {}, sx[8] = {};
+#pragma unroll 2
   for (long long m = m0 + rl; m < m1; m += rlanes) {
     float xv[8], gv[8];
     load8(x + m * a.Cp + vc * 8, xv);
@@ -235,6 +291,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   long long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
   float cs[8] = {};
+#pragma unroll 2
   for (long long m = m0 + rl; m < m1; m += rlanes) {
     float xv[8], gv[8], o[8];
     load8(x + m * a.Cp + vc * 8, xv);
@@ -376,8 +433,7 @@ int hg_bn_bwd_reduce(const HgBnDesc* d, const void* da, const void* x, const flo
   HG_REQUIRE(da && x && stats && gamma && beta && red, "hg_bn_bwd_reduce: NULL pointer");
   HG_REQUIRE(!d->use_running, "hg_bn_bwd_reduce: not needed in eval mode");
   BnArgs a = make_args(d, stats, gamma, beta, nullptr, nullptr);
-  int rpb = (int)((d->M + 2 * kNumSMs * 4 - 1) / (2 * kNumSMs * 4));
-  if (rpb < 64) rpb = 64;
+  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3));
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == HG_BF16)
@@ -399,8 +455,7 @@ int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const floa
   HG_REQUIRE(d->use_running ? (running_mean && running_var) : (stats && red),
              "hg_bn_bwd_apply: statistics missing for the selected mode");
   BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
-  int rpb = (int)((d->M + 2 * kNumSMs * 4 - 1) / (2 * kNumSMs * 4));
-  if (rpb < 64) rpb = 64;
+  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3));
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == HG_BF16)

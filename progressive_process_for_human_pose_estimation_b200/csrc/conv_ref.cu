@@ -179,32 +179,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_ref_kernel(ConvRefParams p, co
   }
 }
 
-// dbias[c] += sum_m dy[m, c]
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, long long M, int Cp, int C,
-                                                     float* __restrict__ out, int rows_per_block) {
-  // thread -> channel (coalesced across the warp), loop over rows
-  const int c = blockIdx.y * 256 + threadIdx.x;
-  if (c >= C) return;
-  const long long m0 = (long long)blockIdx.x * rows_per_block;
-  long long m1 = m0 + rows_per_block;
-  if (m1 > M) m1 = M;
-  float s = 0.f;
-  for (long long m = m0; m < m1; ++m) s += to_f(dy[m * Cp + c]);
-  atomicAdd(out + c, s);
-}
-
-int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* out, cudaStream_t st) {
-  const int rpb = 1024;
-  dim3 grid(ceil_div(M, rpb), ceil_div(C, 256));
-  if (dtype == HG_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, M, Cp, C, out, rpb);
-  else
-    colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, M, Cp, C, out, rpb);
-  HG_LAUNCH_OK("colsum_kernel");
-  count_launch();
-  return HG_OK;
-}
+int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* out, cudaStream_t st);
 
 static inline int pad64(int c) { return (c + 63) & ~63; }
 

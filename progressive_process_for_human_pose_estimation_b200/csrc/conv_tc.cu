@@ -33,6 +33,7 @@ struct ConvGemmParams {
   float* stats;       // [2*n_total] or null
   float* out_nchw;    // optional fp32 NCHW copy of the first c_real channels (heatmap heads)
   int has_res;
+  int n_tiles;        // padded Cout / BN
 };
 
 template <int BN, int STAGES>
@@ -45,8 +46,8 @@ struct ConvGemmSmem {
   static constexpr int kTotal = STAGES * (kABytes + kBBytes) + kCBytes + kBarBytes + 1024 /*align slack*/;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(192, MINB)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvGemmParams p) {
@@ -66,8 +67,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;
-  const int n_off = blockIdx.y * BN;
+  // 1-D grid, N tile fastest: the CTAs that share an activation tile run back to back (second read hits L2)
+  const int m0 = (blockIdx.x / p.n_tiles) * 128;
+  const int n_off = (blockIdx.x % p.n_tiles) * BN;
   const int num_kb = p.taps_r * p.taps_s * p.kchunks;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
 
@@ -206,20 +208,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_store_commit();
     }
     if (p.stats != nullptr) {
+      // per-channel sum / sum of squares of the bf16 values just staged: thread = 2 adjacent channels x a slice
+      // of the 128 rows (fixed trip count so the loop unrolls and the LDS latencies overlap)
       int valid = p.M_total - m0;
       valid = valid > 128 ? 128 : valid;
-      for (int c = et; c < BN; c += 128) {
+      constexpr int kPairs = BN / 2;
+      constexpr int kGroups = 128 / kPairs > 0 ? 128 / kPairs : 1;
+      constexpr int kRows = 128 / kGroups;
+      for (int pi = et; pi < kPairs * kGroups; pi += 128) {
+        const int cpair = pi % kPairs, grp = pi / kPairs;
+        const int c = cpair * 2;
         const uint8_t* colp = sC + (c >> 6) * 16384 + (c & 7) * 2;
         const int chunk = (c & 63) >> 3;
-        float s = 0.f, ss = 0.f;
-        for (int r = 0; r < valid; ++r) {
-          const float x = __bfloat162float(
-              *reinterpret_cast<const __nv_bfloat16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
-          s += x;
-          ss += x * x;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < kRows; ++i) {
+          const int r = grp * kRows + i;
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4));
+          float2 f = __bfloat1622float2(h);
+          if (r >= valid) f = make_float2(0.f, 0.f);
+          s0 += f.x;
+          s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0);
+          q1 = fmaf(f.y, f.y, q1);
         }
-        atomicAdd(p.stats + n_off + c, s);
-        atomicAdd(p.stats + p.n_total + n_off + c, ss);
+        atomicAdd(p.stats + n_off + c, s0);
+        atomicAdd(p.stats + n_off + c + 1, s1);
+        atomicAdd(p.stats + p.n_total + n_off + c, q0);
+        atomicAdd(p.stats + p.n_total + n_off + c + 1, q1);
       }
     }
     if (et == 0) tma_store_wait_read();
@@ -236,18 +252,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------------
 static inline int pad64(int c) { return (c + 63) & ~63; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MINB>
 static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                            const CUtensorMap& tmR, const ConvGemmParams& p, int n_tiles, cudaStream_t st) {
+                            const CUtensorMap& tmR, const ConvGemmParams& p, cudaStream_t st) {
   using L = ConvGemmSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    HG_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     L::kTotal));
     attr_set = true;
   }
-  dim3 grid(ceil_div(p.M_total, 128), n_tiles);
-  conv_gemm_kernel<BN, STAGES><<<grid, 192, L::kTotal, st>>>(tmA, tmB, tmC, tmR, p);
+  dim3 grid(ceil_div(p.M_total, 128) * p.n_tiles);
+  conv_gemm_kernel<BN, STAGES, MINB><<<grid, 192, L::kTotal, st>>>(tmA, tmB, tmC, tmR, p);
   HG_LAUNCH_OK("conv_gemm_kernel");
   count_launch();
   return HG_OK;
@@ -270,8 +286,10 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   if (bh > H) bh = H;
   const int bn = 128 / (bw * bh);
   const long long M = (long long)N * H * W;
-  const int BN = Np;  // one N tile covers all output channels (64 / 128 / 192->unsupported / 256)
-  if (BN != 64 && BN != 128 && BN != 256) {
+  // N tile of at most 128 channels: short-K (1x1) kernels then fit two CTAs per SM (one CTA's epilogue overlaps
+  // the other's TMA/MMA phase); 256 output channels = two N tiles that share the activation tile through L2.
+  const int BN = Np > 128 ? 128 : Np;
+  if (BN != 64 && BN != 128) {
     set_error("conv_gemm_bf16: unsupported padded Cout %d", Np);
     return HG_ERR_UNSUPPORTED;
   }
@@ -322,11 +340,12 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   p.stats = stats;
   p.out_nchw = out_nchw;
   p.has_res = res != nullptr;
-  switch (BN) {
-    case 64: return launch_conv_gemm<64, 4>(tmA, tmB, tmC, tmR, p, 1, st);
-    case 128: return launch_conv_gemm<128, 4>(tmA, tmB, tmC, tmR, p, 1, st);
-    default: return launch_conv_gemm<256, 3>(tmA, tmB, tmC, tmR, p, 1, st);
-  }
+  p.n_tiles = Np / BN;
+  const bool long_k = R * S * (Kp / 64) > 4;
+  if (BN == 64) return long_k ? launch_conv_gemm<64, 4, 2>(tmA, tmB, tmC, tmR, p, st)
+                              : launch_conv_gemm<64, 2, 3>(tmA, tmB, tmC, tmR, p, st);
+  return long_k ? launch_conv_gemm<128, 4, 1>(tmA, tmB, tmC, tmR, p, st)
+                : launch_conv_gemm<128, 2, 2>(tmA, tmB, tmC, tmR, p, st);
 }
 
 
@@ -452,17 +471,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-      for (int t = 0; t < T; ++t) {
+      // All CTAs of a split finish together and add into the SAME tile: start each CTA at a different column so
+      // that concurrent atomics hit different addresses (the L2 atomic unit serialises per address).
+      const int nchunk = N / 32;
+      for (int tt = 0; tt < T; ++tt) {
+        const int t = (tt + blockIdx.x) % T;
         float* dst = p.dw + ((size_t)(tap0 + t) * p.Cout_p + co) * p.Cin_p;
-        for (int j = 0; j < N / 32; ++j) {
+        for (int jj = 0; jj < nchunk; ++jj) {
+          const int j = (jj + blockIdx.x) % nchunk;
           float v[32];
           tmem_ld32(taddr + t * N + j * 32, v);
           tmem_ld_wait();
           if (row_ok) {
+            const int rot = (blockIdx.x / nchunk) & 7;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 32 + q * 4),
-                           "f"(v[q * 4]), "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3])
+              const int qq = (q + rot) & 7;
+              float a = v[0], b = v[1], c = v[2], d = v[3];
+#pragma unroll
+              for (int z = 1; z < 8; ++z)
+                if (qq == z) { a = v[z * 4]; b = v[z * 4 + 1]; c = v[z * 4 + 2]; d = v[z * 4 + 3]; }
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 32 + qq * 4), "f"(a),
+                           "f"(b), "f"(c), "f"(d)
                            : "memory");
             }
           }
@@ -527,9 +557,11 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     if (p.stages > 6) p.stages = 6;
     const int tap_groups = taps / T;
     const int mgroups = (Cout_p + 127) / 128;
-    int nsplit = (2 * kNumSMs) / (tap_groups * mgroups);
+    // one wave of CTAs, and at least 8 K-blocks (512 pixels) of work per CTA: the split-K partial sums are
+    // reduced with atomics, so small problems must not be cut into many slices
+    int nsplit = kNumSMs / (tap_groups * mgroups);
+    if (nsplit > p.total_kb / 8) nsplit = p.total_kb / 8;
     if (nsplit < 1) nsplit = 1;
-    if (nsplit > p.total_kb) nsplit = p.total_kb;
     p.kb_per_cta = (p.total_kb + nsplit - 1) / nsplit;
     nsplit = (p.total_kb + p.kb_per_cta - 1) / p.kb_per_cta;
     p.dw = dw;

@@ -19,6 +19,7 @@ import torch
 from . import _lib as L
 
 _USE_GRAPHS = os.environ.get("HG_CUDA_GRAPHS", "1") != "0"
+_USE_LANES = os.environ.get("HG_STREAM_LANES", "1") != "0"
 
 
 class Val:
@@ -52,6 +53,8 @@ class Val:
 
 
 class Op:
+    lane = 0
+
     def __init__(self, kind, ins, out, **attrs):
         self.kind = kind
         self.ins = ins
@@ -70,9 +73,16 @@ class Builder:
     def __init__(self, training, train_params):
         self.training = training
         self.train_params = train_params  # parameters require grad -> activations feeding them too
-        self.ops = []
+        self.ops = _LaneList(self)
         self.inputs = []    # (Val, kind)
         self.outputs = []   # (Val, real channels)
+        self.cur_lane = 0   # stream lane new ops are assigned to (0 = main)
+        self.num_lanes = 1
+
+    def on_lane(self, lane):
+        """Context manager: ops emitted inside run on stream lane `lane` (independent branches of the network --
+        the skip branch of an hourglass level vs. its low-resolution path -- execute concurrently)."""
+        return _LaneCtx(self, lane)
 
     # -- graph inputs -------------------------------------------------------------------------------
     def input_image(self, N, H, W):
@@ -139,16 +149,58 @@ class Builder:
         return v
 
 
+class _LaneList(list):
+    """Op list that stamps every appended op with the builder's current lane."""
+
+    def __init__(self, builder):
+        super().__init__()
+        self._b = builder
+
+    def append(self, op):
+        op.lane = self._b.cur_lane
+        super().append(op)
+
+
+class _LaneCtx:
+    def __init__(self, b, lane):
+        self.b, self.lane = b, lane
+
+    def __enter__(self):
+        self.prev = self.b.cur_lane
+        self.b.cur_lane = self.lane
+        self.b.num_lanes = max(self.b.num_lanes, self.lane + 1)
+
+    def __exit__(self, *exc):
+        self.b.cur_lane = self.prev
+        return False
+
+
+# positions (in the ctypes argument tuple) of the tensors each entry point WRITES; every other tracked pointer
+# argument is a read.  Parameter / weight-gradient pointers are not tracked (read-only or commutative atomics).
+_WRITES = {
+    "hg_nchw_f32_to_nhwc": (7,), "hg_nhwc_to_nchw_f32": (6,), "hg_stem_fwd": (7,), "hg_conv_fprop_ex": (5, 6, 7),
+    "hg_conv_dgrad": (4,), "hg_bn_stats": (2,), "hg_bn_apply": (7,), "hg_bn_bwd_apply": (10,),
+    "hg_maxpool2_fwd": (6,), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8,), "hg_upsample2x_bwd": (8,),
+    "hg_add": (3,),
+}
+
+
 class _Call:
     """One pre-marshalled C-ABI call."""
 
-    __slots__ = ("fn", "args", "name", "keep")
+    __slots__ = ("fn", "args", "name", "keep", "writes", "tag", "lane", "deps", "event", "barrier")
 
     def __init__(self, name, args, keep=()):
         self.fn = getattr(L.load(), name)
         self.args = args
         self.name = name
         self.keep = keep  # python objects whose memory the ctypes args point to
+        self.writes = ()  # indices of parameters whose gradient slot this call writes
+        self.tag = ""     # human-readable shape tag for the per-kernel profile (bench.py)
+        self.lane = 0     # stream lane
+        self.deps = ()    # calls on OTHER lanes that must complete first
+        self.event = None  # recorded after this call when another lane depends on it
+        self.barrier = False  # wait for every lane before this call
 
 
 def _unique(seq):
@@ -176,15 +228,26 @@ class Plan:
         self.fwd_calls = []
         self.bwd_calls = []
         self.fwd_graph = None
-        self.bwd_graph = None
+        self.bwd_graphs = {}
         self.n_fwd_runs = 0
+        self._pending_writes = []
+        self._tracked = set()       # data_ptrs of activation / gradient / statistics buffers (dependency tracking)
+        self._last_writer = {}      # data_ptr -> _Call that last wrote it (per call list)
+        self._cur_lane = 0
+        self.num_lanes = builder.num_lanes if _USE_LANES else 1
+        self.lane_streams = None
+        self.profile_records = None  # list while an instrumented (eager, event-timed) step is being recorded
+        self.reducer = None        # set by parallel.DataParallel: all-reduces ranges of grad_arena
+        self.bwd_segments = None   # [(first_call, end_call, [(lo, hi) element ranges of grad_arena ready after it])]
         self._lower()
 
     # ------------------------------------------------------------------------------------------------
     # buffer helpers
     # ------------------------------------------------------------------------------------------------
     def _act(self, v):
-        return torch.zeros(v.N, v.H, v.W, v.Cp, device=self.device, dtype=self.dt)
+        t = torch.zeros(v.N, v.H, v.W, v.Cp, device=self.device, dtype=self.dt)
+        self._tracked.add(t.data_ptr())
+        return t
 
     def _p32(self, p):
         """fp32 view of a parameter / buffer (shadow copy when the module was cast to half)."""
@@ -201,10 +264,28 @@ class Plan:
         if i is None or not p.requires_grad:
             return None
         self.param_used[i] = True
+        self._pending_writes.append(i)
         return self.grad_views[i]
 
     def _emit(self, lst, name, *args, keep=()):
-        lst.append(_Call(name, args, keep))
+        c = _Call(name, args, keep)
+        if lst is self.bwd_calls and self._pending_writes:
+            c.writes = tuple(self._pending_writes)
+            self._pending_writes = []
+        c.lane = self._cur_lane if self.num_lanes > 1 else 0
+        # cross-lane dependencies from the tracked buffers this call reads / writes
+        wpos = _WRITES.get(name, ())
+        deps = []
+        for i, a in enumerate(args):
+            if isinstance(a, C.c_void_p) and a.value in self._tracked:
+                lw = self._last_writer.get(a.value)
+                if lw is not None and lw.lane != c.lane and lw not in deps:
+                    deps.append(lw)
+                if i in wpos:
+                    self._last_writer[a.value] = c
+        c.deps = tuple(deps)
+        lst.append(c)
+        return c
 
     # ------------------------------------------------------------------------------------------------
     # gradient bookkeeping (see module docstring of _family_s for the conventions)
@@ -285,6 +366,7 @@ class Plan:
         off = 0
         for v in stat_vals:
             v.stats = self.stats_arena[off:off + 2 * v.Cp]
+            self._tracked.add(v.stats.data_ptr())
             off += 2 * v.Cp
         bn_ops = [op for op in ops if op.kind == "bn"]
         self.red_arena = torch.zeros(max(1, sum(2 * op.ins[0].Cp for op in bn_ops)), device=dev, dtype=torch.float32)
@@ -297,6 +379,8 @@ class Plan:
         self.out_static = [torch.zeros(v.N, c, v.H, v.W, device=dev, dtype=torch.float32) for v, c in b.outputs]
         self.gout_static = [torch.zeros_like(t) for t in self.out_static] if self.need_bwd else []
         self.out_index = {id(v): i for i, (v, _) in enumerate(b.outputs)}
+        for t in self.out_static + self.gout_static:
+            self._tracked.add(t.data_ptr())
 
         self._lower_forward(convs)
         if self.need_bwd:
@@ -308,6 +392,10 @@ class Plan:
                          cv.stride[0], cv.padding[0], cv.dilation[0], self.hdt)
         self._keep.append(d)
         return d
+
+    @staticmethod
+    def _conv_tag(cv, x):
+        return f"{cv.in_channels}->{cv.out_channels} k{cv.kernel_size[0]} @{x.H}x{x.W}"
 
     def _bn_desc(self, bn, x, relu):
         use_running = 0 if (self.training or not bn.track_running_stats) else 1
@@ -335,6 +423,7 @@ class Plan:
         running = {}  # bn module -> list of (stats, count) in call order
         for op in self.b.ops:
             k = op.kind
+            self._cur_lane = op.lane
             if k == "stem":
                 cv, x, out = op.attrs["conv"], op.ins[0], op.out
                 self._emit(f, "hg_stem_fwd", self.hdt, L.ptr(x.buf), L.ptr(self._p32(cv.weight)),
@@ -348,7 +437,8 @@ class Plan:
                 nchw = self.out_static[self.out_index[id(out)]] if op.attrs["head"] else None
                 self._emit(f, "hg_conv_fprop_ex", C.byref(d), L.ptr(x.buf), L.ptr(info["wf"]),
                            self._bias_ptr(cv, info), L.ptr(res.buf) if res else None,
-                           L.ptr(out.buf), L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw), st)
+                           L.ptr(out.buf), L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw),
+                           st).tag = self._conv_tag(cv, x)
             elif k == "bn":
                 bn, x, out = op.attrs["bn"], op.ins[0], op.out
                 d = self._bn_desc(bn, x, op.attrs["relu"])
@@ -397,7 +487,8 @@ class Plan:
             mod_dev = torch.frombuffer(bytearray(bytes(mod_arr)), dtype=torch.uint8).to(self.device)
             site_dev = torch.frombuffer(bytearray(bytes(site_arr)), dtype=torch.uint8).to(self.device)
             self.running_tables = (mod_dev, site_dev)
-            self._emit(f, "hg_bn_update_running", L.ptr(mod_dev), L.ptr(site_dev), len(mods), st)
+            self._cur_lane = 0
+            self._emit(f, "hg_bn_update_running", L.ptr(mod_dev), L.ptr(site_dev), len(mods), st).barrier = True
 
     def _bias_ptr(self, cv, info):
         """Bias vector padded to Cout_p: the live fp32 parameter itself when no padding / cast is needed."""
@@ -416,8 +507,10 @@ class Plan:
     # ------------------------------------------------------------------------------------------------
     def _lower_backward(self, convs):
         g, st = self.bwd_calls, self.stream
+        self._last_writer = {}
         for op in reversed(self.b.ops):
             k = op.kind
+            self._cur_lane = op.lane
             if k == "export":
                 v = op.ins[0]
                 if v.requires_grad:
@@ -455,11 +548,14 @@ class Plan:
                     else:
                         dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
                         info["used"] = True
-                    self._emit(g, "hg_conv_wgrad", C.byref(d), L.ptr(x.buf), L.ptr(G), L.ptr(dwp), L.ptr(bslot), st)
+                    self._emit(g, "hg_conv_wgrad", C.byref(d), L.ptr(x.buf), L.ptr(G), L.ptr(dwp), L.ptr(bslot),
+                               st).tag = self._conv_tag(cv, x)
+                    if wslot is not None and not info["direct"]:
+                        info["last_wgrad"] = g[-1]
                 if x.requires_grad:
                     addend, dst = self._grad_target(x)
                     self._emit(g, "hg_conv_dgrad", C.byref(d), L.ptr(G), L.ptr(info["wd"]), L.ptr(addend), L.ptr(dst),
-                               st)
+                               st).tag = self._conv_tag(cv, x)
             elif k == "bn":
                 bn, x = op.attrs["bn"], op.ins[0]
                 d = self._bn_desc(bn, x, op.attrs["relu"])
@@ -502,6 +598,7 @@ class Plan:
                 cv, x = op.attrs["conv"], op.ins[0]
                 self._emit(g, "hg_stem_bwd", self.hdt, L.ptr(x.buf), L.ptr(out.buf), L.ptr(G), x.N, x.H, x.W,
                            L.ptr(self._gslot(cv.weight)), L.ptr(self._gslot(cv.bias)), st)
+        self._cur_lane = 0
         # graph inputs that want a gradient (sub-module use): NHWC -> NCHW fp32
         self.gin_static = None
         for v, kind in self.b.inputs:
@@ -510,7 +607,8 @@ class Plan:
                 if v.grad is not None:
                     self._emit(g, "hg_nhwc_to_nchw_f32", self.hdt, L.ptr(v.grad), v.N, v.C, v.H, v.W,
                                L.ptr(self.gin_static), st)
-        # packed weight gradients -> OIHW slots
+        # packed weight gradients -> OIHW slots, right after the LAST call site of each shared weight so that the
+        # gradient is final as early as possible (bucketed all-reduce, parallel.py)
         for cv in convs:
             info = self.conv_info[id(cv)]
             if info.get("used"):
@@ -518,7 +616,57 @@ class Plan:
                                  1, self.hdt)
                 self._keep.append(d)
                 dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
-                self._emit(g, "hg_unpack_conv_wgrad", C.byref(d), L.ptr(dwp), L.ptr(self._gslot(cv.weight)), 0, st)
+                self._pending_writes = []
+                slot = self._gslot(cv.weight)
+                c = _Call("hg_unpack_conv_wgrad", (C.byref(d), L.ptr(dwp), L.ptr(slot), 0, st))
+                c.writes = tuple(self._pending_writes)
+                self._pending_writes = []
+                # the wgrad calls themselves only touch the packed accumulator, not the OIHW slot
+                for call in g:
+                    if call.name == "hg_conv_wgrad" and self.param_index[id(cv.weight)] in call.writes:
+                        call.writes = tuple(w for w in call.writes if w != self.param_index[id(cv.weight)])
+                # other call sites of this weight may still be running on other lanes: wait for all issued work
+                c.lane = 0
+                c.barrier = True
+                g.insert(g.index(info["last_wgrad"]) + 1, c)
+
+    def plan_gradient_buckets(self, quantiles=(0.5, 0.97)):
+        """Split the backward call list at the points where the given fractions of the gradient volume are final.
+        In the weight-shared family every hourglass weight is complete only during the FIRST stack's backward
+        ('bucket by last grad accumulation'), the stem's weights at the very end.  Returns the segments
+        run_backward executes: (first_call, end_call, element ranges of grad_arena that are final after it)."""
+        g = self.bwd_calls
+        ready = [-1] * len(self.params)
+        for idx, call in enumerate(g):
+            for w in call.writes:
+                ready[w] = idx
+        sizes = [p.numel() for _, p in self.params]
+        order = sorted(range(len(sizes)), key=lambda i: ready[i])
+        total = float(sum(sizes))
+        cuts, acc, qi = [], 0, 0
+        for i in order:
+            acc += sizes[i]
+            while qi < len(quantiles) and acc >= quantiles[qi] * total:
+                cuts.append(ready[i] + 1)
+                qi += 1
+        bounds = sorted(set(c for c in cuts if 0 < c < len(g))) + [len(g)]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += n
+        out, first = [], 0
+        for end in bounds:
+            ranges = []
+            for i in range(len(sizes)):
+                if first <= ready[i] < end or (first == 0 and ready[i] < 0):
+                    if ranges and ranges[-1][1] == offs[i]:
+                        ranges[-1][1] = offs[i] + sizes[i]
+                    else:
+                        ranges.append([offs[i], offs[i] + sizes[i]])
+            out.append((first, end, [tuple(r) for r in ranges]))
+            first = end
+        self.bwd_segments = out
+        return out
 
     def _scratch(self, v):
         t = self._act(v)
@@ -529,11 +677,72 @@ class Plan:
     # execution
     # ------------------------------------------------------------------------------------------------
     def _run_calls(self, calls):
+        if self.num_lanes > 1 and self.profile_records is None:
+            return self._run_calls_lanes(calls)
         self.stream.value = torch.cuda.current_stream().cuda_stream
+        if self.profile_records is not None:
+            # per-call CUDA events on the launching stream (bench.py's per-kernel table / roofline)
+            for c in calls:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = c.fn(*c.args)
+                e1.record()
+                if rc != 0:
+                    raise RuntimeError(f"libhg_sm100a: {c.name} failed with status {rc}: {L.last_error()}")
+                self.profile_records.append((c.name, c.tag, e0, e1))
+            return
         for c in calls:
             rc = c.fn(*c.args)
             if rc != 0:
                 raise RuntimeError(f"libhg_sm100a: {c.name} failed with status {rc}: {L.last_error()}")
+
+    def _run_calls_lanes(self, calls):
+        """Issue the calls on their stream lanes; cross-lane dependencies become event waits (graph edges when
+        captured).  Every lane is joined back into the main stream at the end."""
+        main = torch.cuda.current_stream()
+        if self.lane_streams is None:
+            self.lane_streams = [None] + [torch.cuda.Stream() for _ in range(self.num_lanes - 1)]
+        streams = [main] + self.lane_streams[1:]
+        needed = set()
+        for c in calls:
+            for d in c.deps:
+                needed.add(id(d))
+        in_list = set(id(c) for c in calls)
+        touched = [False] * self.num_lanes
+        touched[0] = True
+        fork = None
+        for c in calls:
+            s = streams[c.lane]
+            if not touched[c.lane]:
+                # First use of a side lane.  Its data dependencies (events recorded on the main lane right after
+                # the producing calls) fork it off the main stream at the right point; only a call without any
+                # dependency needs an explicit fork from "now".
+                if not any(id(d) in in_list and d.event is not None for d in c.deps):
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    s.wait_event(fork)
+                touched[c.lane] = True
+            if c.barrier:
+                for l in range(1, self.num_lanes):
+                    if touched[l]:
+                        e = torch.cuda.Event()
+                        e.record(streams[l])
+                        s.wait_event(e)
+            for d in c.deps:
+                if id(d) in in_list and d.event is not None:
+                    s.wait_event(d.event)
+            self.stream.value = s.cuda_stream
+            rc = c.fn(*c.args)
+            if rc != 0:
+                raise RuntimeError(f"libhg_sm100a: {c.name} failed with status {rc}: {L.last_error()}")
+            if id(c) in needed:
+                c.event = torch.cuda.Event()
+                c.event.record(s)
+        for l in range(1, self.num_lanes):
+            if touched[l]:
+                e = torch.cuda.Event()
+                e.record(streams[l])
+                main.wait_event(e)
 
     def _fwd_body(self):
         for p, shadow in self._shadow.values():
@@ -547,11 +756,12 @@ class Plan:
         for cv, info in self._bias_pairs:
             info["bias"][:cv.out_channels].copy_(cv.bias.data)
 
-    def _bwd_body(self):
-        self.grad_arena.zero_()
-        self.packed_arena.zero_()
-        self.red_arena.zero_()
-        self._run_calls(self.bwd_calls)
+    def _bwd_body(self, a=0, b=None):
+        if a == 0:
+            self.grad_arena.zero_()
+            self.packed_arena.zero_()
+            self.red_arena.zero_()
+        self._run_calls(self.bwd_calls[a:b])
 
     def prepare(self):
         convs = _unique([op.attrs["conv"] for op in self.b.ops if op.kind == "conv"])
@@ -564,7 +774,7 @@ class Plan:
         target.copy_(x)
         if not hasattr(self, "_bias_pairs"):
             self.prepare()
-        if _USE_GRAPHS and self.n_fwd_runs >= 1:
+        if _USE_GRAPHS and self.n_fwd_runs >= 1 and self.profile_records is None:
             if self.fwd_graph is None:
                 self.fwd_graph = self._capture(self._fwd_body)
             self.fwd_graph.replay()
@@ -580,12 +790,18 @@ class Plan:
                 gbuf.zero_()
             else:
                 gbuf.copy_(go)
-        if _USE_GRAPHS and self.n_fwd_runs >= 2:
-            if self.bwd_graph is None:
-                self.bwd_graph = self._capture(self._bwd_body)
-            self.bwd_graph.replay()
-        else:
-            self._bwd_body()
+        segments = self.bwd_segments if (self.reducer is not None and self.bwd_segments) else [(0, None, None)]
+        for a, b, ranges in segments:
+            if _USE_GRAPHS and self.n_fwd_runs >= 2 and self.profile_records is None:
+                if (a, b) not in self.bwd_graphs:
+                    self.bwd_graphs[(a, b)] = self._capture(lambda a=a, b=b: self._bwd_body(a, b))
+                self.bwd_graphs[(a, b)].replay()
+            else:
+                self._bwd_body(a, b)
+            if self.reducer is not None:
+                self.reducer.reduce_async(self.grad_arena, ranges)  # overlaps the next segment
+        if self.reducer is not None:
+            self.reducer.wait()
         grads = []
         flat = self.grad_arena.clone()
         off = 0

@@ -90,6 +90,22 @@ HG_API int hg_conv_wgrad(const HgConvDesc* d, const void* x, const void* dy, flo
 HG_API int hg_unpack_conv_wgrad(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int accumulate,
                          void* stream);
 
+/* Slices of a wider weight: the convolution over torch.cat([a, b, c], 1) is evaluated as three chained
+ * convolutions (residual = previous partial sum) over the input-channel slices [cin_offset, cin_offset + d->Cin)
+ * of the [Cout, cin_total, R, S] weight, so the concatenated tensor never exists
+ * (try_different_stack.py:316-328, try_with_aspp_remove_max_pool.py:239-240,291-303). */
+HG_API int hg_pack_conv_weight_slice(const HgConvDesc* d, const float* w_oihw, int cin_total, int cin_offset,
+                                     void* w_fprop, void* w_dgrad, void* stream);
+HG_API int hg_unpack_conv_wgrad_slice(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int cin_total,
+                                      int cin_offset, int accumulate, void* stream);
+
+/* out[R,cols] (=|+=) T[R,R] (transpose ? ^T : ) * in[R,cols], all fp32: linear recombination of head channels.
+ * The in-place limb mix of try_skeleton_and_keypoints.py:279-298 (t[:,19+l] = t[:,19+l] - t[:,0] + t[:,a_l] +
+ * t[:,b_l]) is linear in the head's output, so it is folded into the head's weights (W_eff = T W, b_eff = T b)
+ * and un-folded from their gradients (dW = T^T dW_eff). */
+HG_API int hg_mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
+                       void* stream);
+
 /* Debug/validation switches: "force_ref_conv" = 1 routes bf16 convolutions to the CUDA-core kernels. */
 HG_API int hg_set_option(const char* name, int value);
 
@@ -156,11 +172,13 @@ HG_API int hg_nchw_f32_to_nhwc(int dtype, const float* src_nchw, const void* add
 HG_API int hg_nhwc_to_nchw_f32(int dtype, const void* src, int N, int C, int H, int W, float* dst_nchw, void* stream);
 
 /* ---- stem: Conv2d(3,64,7,2,3) + ReLU on the fp32 NCHW image batch (try_with_torch.py:262,276-277) ---- */
-HG_API int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W, void* y,
-                void* stream);
-/* dw_oihw += , dbias += , with the ReLU mask taken from y */
-HG_API int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, int N, int H, int W, float* dw_oihw,
-                float* dbias, void* stream);
+/* relu = 1: ReLU fused (try_with_torch.py:276-277); relu = 0: raw output for the BatchNorm that follows in
+ * hourglass_compare.py:549-552.  bias may be NULL. */
+HG_API int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W,
+                       int relu, void* y, void* stream);
+/* dw_oihw += , dbias += ; with relu = 1 the ReLU mask is taken from y */
+HG_API int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, int N, int H, int W, int relu,
+                       float* dw_oihw, float* dbias, void* stream);
 
 /* ---- target rendering ---------------------------------------------------------------------------- */
 /* Gaussian keypoint heatmaps, evaluated in float64 like the numpy code, stored as float32

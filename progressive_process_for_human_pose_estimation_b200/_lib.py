@@ -72,8 +72,11 @@ SIGNATURES = {
     "hg_add": [_I, _P, _P, _P, _LL, _P],
     "hg_nchw_f32_to_nhwc": [_I, _P, _P, _I, _I, _I, _I, _P, _P],
     "hg_nhwc_to_nchw_f32": [_I, _P, _I, _I, _I, _I, _P, _P],
-    "hg_stem_fwd": [_I, _P, _P, _P, _I, _I, _I, _P, _P],
-    "hg_stem_bwd": [_I, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "hg_stem_fwd": [_I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "hg_stem_bwd": [_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "hg_pack_conv_weight_slice": [C.POINTER(HgConvDesc), _P, _I, _I, _P, _P, _P],
+    "hg_unpack_conv_wgrad_slice": [C.POINTER(HgConvDesc), _P, _P, _I, _I, _I, _P],
+    "hg_mix_rows": [_P, _P, _P, _I, _I, _I, _I, _P],
     "hg_render_gauss": [C.POINTER(HgGaussDesc), _P, _P, _P, _P, _P],
     "hg_render_labels": [C.POINTER(HgLabelDesc), _P, _P, _P, _P, _P, _P],
     "hg_decode_argmax": [_P, _I, _I, _I, _I, _P, _P, _P],

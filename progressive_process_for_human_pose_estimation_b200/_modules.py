@@ -244,3 +244,408 @@ def make_s_family(g):
         cls.__module__ = g.get("__name__", cls.__module__)
         cls.__qualname__ = cls.__name__
     return ResidualBlock, hourglass, lin, creatModel
+
+
+def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4):
+    """Shared body of the multi-head creatModel variants: per-stack heads conv2_k and re-injection conv4_k over a
+    concatenation (try_different_stack.py:300-329; try_with_aspp_remove_max_pool.py:277-304)."""
+    nStack = g["nStack"]
+    x = b.stem(self.conv1, x)
+    x = self.residual1._emit(b, x)
+    if with_pool:
+        x = b.maxpool2(x)
+    x = self.residual2._emit(b, x)
+    x = self.residual3._emit(b, x)
+    out = []
+    inter = x
+    heads = [getattr(self, f"conv2_{k}") for k in range(3) if hasattr(self, f"conv2_{k}")]
+    reinj = [getattr(self, f"conv4_{k}") for k in range(2) if hasattr(self, f"conv4_{k}")]
+    for i in range(nStack):
+        hg = self.hourglass1._emit(b, inter)
+        ll = hg
+        for _ in range(n_res4):
+            ll = self.residual4._emit(b, ll)
+        ll = self.lin._emit(b, ll)
+        if i >= len(heads):
+            continue  # the reference has no branch for further stacks: nothing is appended
+        tmpOut = b.conv(heads[i], ll, head=True)
+        out.insert(i, tmpOut)
+        if i < len(reinj):
+            parts = [inter, ll, tmpOut] if cat_inter else [ll, tmpOut]
+            inter = b.conv_cat(reinj[i], parts)
+    return out
+
+
+def make_multihead_family(g, aspp_members=False, num_heads=3):
+    """try_different_stack.py / try_different_stack_without_skeleton.py (aspp_members=False) and try_with_aspp.py
+    (aspp_members=True: ASPP modules are constructed -- they are in the state_dict -- but never executed, and the
+    bottom level has no extra residual blocks, try_with_aspp.py:250-279)."""
+    ResidualBlock, hourglass_s, lin, _ = make_s_family(g)
+
+    class _ASPPModule(nn.Module):
+        """Parameter container only: never called by the reference's forward (quirk Q6)."""
+
+        def __init__(self, inplanes, planes, kernel_size, padding, dilation):
+            super(_ASPPModule, self).__init__()
+            self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, stride=1, padding=padding,
+                                         dilation=dilation, bias=False)
+            self.bn = nn.BatchNorm2d(planes)
+            self.relu = nn.ReLU()
+
+    if aspp_members:
+        class hourglass(HGModule):
+            def __init__(self, n, f):
+                super(hourglass, self).__init__()
+                self.n = n
+                self.f = f
+                self.residual_block = ResidualBlock(f, f)
+                if n > 1:
+                    self.hourglass1 = hourglass(n - 1, f)
+                self.maxpool = nn.MaxPool2d(2)
+                inplanes = 256
+                dilations = [1, 6, 12, 18]
+                self.aspp1 = _ASPPModule(inplanes, 256, 1, padding=0, dilation=dilations[0])
+                self.aspp2 = _ASPPModule(inplanes, 256, 3, padding=dilations[1], dilation=dilations[1])
+                self.aspp3 = _ASPPModule(inplanes, 256, 3, padding=dilations[2], dilation=dilations[2])
+                self.aspp4 = _ASPPModule(inplanes, 256, 3, padding=dilations[3], dilation=dilations[3])
+                self.global_avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)),
+                                                     nn.Conv2d(inplanes, 256, 1, stride=1, bias=False),
+                                                     nn.BatchNorm2d(256), nn.ReLU())
+                self.conv1 = nn.Conv2d(1280, 256, 1, bias=False)
+
+            def _config_key(self):
+                return (g["nModules"],)
+
+            def _emit(self, b, x):
+                nModules = g["nModules"]
+                up1 = x
+                with b.on_lane(self.n):
+                    for _ in range(nModules):
+                        up1 = self.residual_block._emit(b, up1)
+                low1 = b.maxpool2(x)
+                for _ in range(nModules):
+                    low1 = self.residual_block._emit(b, low1)
+                low2 = self.hourglass1._emit(b, low1) if self.n > 1 else low1
+                low3 = low2
+                for _ in range(nModules):
+                    low3 = self.residual_block._emit(b, low3)
+                return b.upsample2x_add(low3, up1, mode="bilinear")
+    else:
+        hourglass = hourglass_s
+
+    class creatModel(HGModule):
+        """3-stack network with a different head per stack: 2-ch background, 20-ch limb, 17-ch keypoint maps
+        (try_different_stack.py:282-329)."""
+
+        _is_model = True
+
+        def __init__(self):
+            super(creatModel, self).__init__()
+            nFeats = g["nFeats"]
+            self.conv1 = nn.Conv2d(3, 64, 7, 2, 3)
+            self.relu = nn.ReLU()
+            self.residual1 = ResidualBlock(64, 128)
+            self.max_pool1 = nn.MaxPool2d(2)
+            self.residual2 = ResidualBlock(128, 128)
+            self.residual3 = ResidualBlock(128, nFeats)
+            self.hourglass1 = hourglass(4, nFeats)
+            self.residual4 = ResidualBlock(nFeats, nFeats)
+            self.lin = lin(nFeats, nFeats)
+            self.conv2_0 = nn.Conv2d(nFeats, g["nOutChannels_0"], 1, 1, 0, bias=False)
+            self.conv4_0 = nn.Conv2d(nFeats + g["nOutChannels_0"], nFeats, 1, 1, 0)
+            self.conv2_1 = nn.Conv2d(nFeats, g["nOutChannels_1"], 1, 1, 0, bias=False)
+            if num_heads >= 3:  # try_different_stack_without_skeleton.py:294-297 stops after conv2_1
+                self.conv4_1 = nn.Conv2d(nFeats + g["nOutChannels_1"], nFeats, 1, 1, 0, bias=False)
+                self.conv2_2 = nn.Conv2d(nFeats, g["nOutChannels_2"], 1, 1, 0, bias=False)
+
+        def _config_key(self):
+            return (g["nStack"], g["nModules"])
+
+        def _emit(self, b, x):
+            return _multihead_forward(self, b, x, g, cat_inter=False, with_pool=True, n_res4=g["nModules"])
+
+    for cls in (hourglass, creatModel, _ASPPModule):
+        cls.__module__ = g.get("__name__", cls.__module__)
+        cls.__qualname__ = cls.__name__
+    return ResidualBlock, hourglass, lin, creatModel, _ASPPModule
+
+
+def make_skeleton_family(g):
+    """try_skeleton_and_keypoints.py: S-family network whose 38-channel head (18 keypoint classes + 20 limb classes)
+    is mixed in place after being appended to the output list (quirk Q11, :274-300):
+        t[:, 19+l] = t[:, 19+l] - t[:, 0] + t[:, sks[l][0]] + t[:, sks[l][1]],  l = 0..18.
+    The mix is linear in the head output, so it is folded into the head's weights (plan.py `mix`)."""
+    ResidualBlock, hourglass, lin, _ = make_s_family(g)
+
+    def mix_matrix():
+        C = g["nOutChannels"]
+        sks = g["sks"]
+        T = torch.eye(C)
+        for l, (a, c) in enumerate(sks):
+            r = 19 + l
+            T[r, 0] -= 1.0
+            T[r, a] += 1.0
+            T[r, c] += 1.0
+        return T
+
+    class creatModel(HGModule):
+        _is_model = True
+
+        def __init__(self):
+            super(creatModel, self).__init__()
+            nFeats, nOutChannels = g["nFeats"], g["nOutChannels"]
+            self.conv1 = nn.Conv2d(3, 64, 7, 2, 3)
+            self.relu = nn.ReLU()
+            self.residual1 = ResidualBlock(64, 128)
+            self.max_pool1 = nn.MaxPool2d(2)
+            self.residual2 = ResidualBlock(128, 128)
+            self.residual3 = ResidualBlock(128, nFeats)
+            self.hourglass1 = hourglass(4, nFeats)
+            self.residual4 = ResidualBlock(nFeats, nFeats)
+            self.lin = lin(nFeats, nFeats)
+            self.conv2 = nn.Conv2d(nFeats, nOutChannels, 1, 1, 0)
+            self.conv3 = nn.Conv2d(nFeats, nFeats, 1, 1, 0)
+            self.conv4 = nn.Conv2d(nOutChannels, nFeats, 1, 1, 0)
+
+        def _config_key(self):
+            return (g["nStack"], g["nModules"], tuple(map(tuple, g["sks"])))
+
+        def _emit(self, b, x):
+            nStack, nModules = g["nStack"], g["nModules"]
+            T = mix_matrix()
+            x = b.stem(self.conv1, x)
+            x = self.residual1._emit(b, x)
+            x = b.maxpool2(x)
+            x = self.residual2._emit(b, x)
+            x = self.residual3._emit(b, x)
+            out = []
+            inter = x
+            for i in range(nStack):
+                hg = self.hourglass1._emit(b, inter)
+                ll = hg
+                for _ in range(nModules):
+                    ll = self.residual4._emit(b, ll)
+                ll = self.lin._emit(b, ll)
+                tmpOut = b.conv(self.conv2, ll, head=True, mix=T)  # the list holds the MIXED tensor (in-place op)
+                out.insert(i, tmpOut)
+                if i < nStack:
+                    ll_ = b.conv(self.conv3, ll)
+                    inter = b.conv(self.conv4, tmpOut, residual=ll_)
+            return out
+
+    creatModel.__module__ = g.get("__name__", creatModel.__module__)
+    creatModel.__qualname__ = "creatModel"
+    return ResidualBlock, hourglass, lin, creatModel
+
+
+def make_q4_block(g):
+    """ResidualBlock of the later scripts (try_with_aspp_remove_max_pool.py:165-201 = hourglass_compare.py:405-441 =
+    train.py:411-447): stride on the 3x3, bn4 after conv3, and -- because `self.stride != 1 | self.numIn !=
+    self.numOut` parses as a chained comparison that is always true (quirk Q4) -- the skip is ALWAYS
+    BN(conv1x1(x, stride)), even for 256->256 stride 1."""
+
+    class ResidualBlock(HGModule):
+        def __init__(self, numIn, numOut, stride=1):
+            super(ResidualBlock, self).__init__()
+            self.stride = stride
+            self.numIn = numIn
+            self.numOut = numOut
+            self.bn1 = nn.BatchNorm2d(numIn)
+            self.relu = nn.ReLU(True)
+            self.conv1 = nn.Conv2d(numIn, int(numOut / 2), 1, 1)
+            self.bn2 = nn.BatchNorm2d(int(numOut / 2))
+            self.relu = nn.ReLU(True)
+            self.conv2 = nn.Conv2d(int(numOut / 2), int(numOut / 2), 3, stride, 1)
+            self.bn3 = nn.BatchNorm2d(int(numOut / 2))
+            self.relu = nn.ReLU(True)
+            self.conv3 = nn.Conv2d(int(numOut / 2), numOut, 1, 1)
+            self.bn4 = nn.BatchNorm2d(numOut)
+            self.downsaple = nn.Sequential(nn.Conv2d(numIn, numOut, 1, stride=stride, bias=False),
+                                           nn.BatchNorm2d(numOut))
+
+        def _emit(self, b, x):
+            a1 = b.bn_relu(self.bn1, x)
+            y1 = b.conv(self.conv1, a1)
+            a2 = b.bn_relu(self.bn2, y1)
+            y2 = b.conv(self.conv2, a2)
+            a3 = b.bn_relu(self.bn3, y2)
+            y3 = b.conv(self.conv3, a3)
+            out = b.bn_relu(self.bn4, y3, relu=False)
+            assert (self.stride != 1 | self.numIn != self.numOut), "quirk Q4: true for every shape the reference uses"
+            r = b.conv(self.downsaple[0], x)
+            r = b.bn_relu(self.downsaple[1], r, relu=False)
+            return b.add(out, r)
+
+    ResidualBlock.__module__ = g.get("__name__", ResidualBlock.__module__)
+    ResidualBlock.__qualname__ = "ResidualBlock"
+    return ResidualBlock
+
+
+def make_nopool_family(g):
+    """try_with_aspp_remove_max_pool.py (BASELINE config 4): max-pool replaced by a stride-2 block, skip merged by
+    cat + 1x1 conv, unused ASPP members, multi-head creatModel with cat[inter, ll, tmpOut] re-injection."""
+    ResidualBlock = make_q4_block(g)
+    _, _, lin, _ = make_s_family(g)
+
+    class _ASPPModule(nn.Module):
+        def __init__(self, inplanes, planes, kernel_size, padding, dilation):
+            super(_ASPPModule, self).__init__()
+            self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, stride=1, padding=padding,
+                                         dilation=dilation, bias=False)
+            self.bn = nn.BatchNorm2d(planes)
+            self.relu = nn.ReLU()
+
+    class hourglass(HGModule):
+        def __init__(self, n, f):
+            super(hourglass, self).__init__()
+            self.n = n
+            self.f = f
+            self.residual_block = ResidualBlock(f, f)
+            self.residual_block_stride = ResidualBlock(f, f, stride=2)
+            if n > 1:
+                self.hourglass1 = hourglass(n - 1, f)
+            self.maxpool = nn.MaxPool2d(2)
+            inplanes = 256
+            dilations = [1, 6, 12, 18]
+            self.aspp1 = _ASPPModule(inplanes, 256, 1, padding=0, dilation=dilations[0])
+            self.aspp2 = _ASPPModule(inplanes, 256, 3, padding=dilations[1], dilation=dilations[1])
+            self.aspp3 = _ASPPModule(inplanes, 256, 3, padding=dilations[2], dilation=dilations[2])
+            self.aspp4 = _ASPPModule(inplanes, 256, 3, padding=dilations[3], dilation=dilations[3])
+            self.global_avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)),
+                                                 nn.Conv2d(inplanes, 256, 1, stride=1, bias=False),
+                                                 nn.BatchNorm2d(256), nn.ReLU())
+            self.conv1 = nn.Conv2d(1280, 256, 1, bias=False)
+            self.conv2 = nn.Conv2d(2 * f, f, 1, bias=False)
+            self.conv3 = nn.Conv2d(f, f, 3, 2, 1)
+
+        def _emit(self, b, x):
+            up1 = x
+            low1 = self.residual_block_stride._emit(b, x)
+            low2 = self.hourglass1._emit(b, low1) if self.n > 1 else low1
+            low3 = self.residual_block._emit(b, low2)
+            up2 = b.upsample2x_add(low3, None, mode="bilinear")
+            return b.conv_cat(self.conv2, [up1, up2])
+
+    class creatModel(HGModule):
+        _is_model = True
+
+        def __init__(self):
+            super(creatModel, self).__init__()
+            nFeats = g["nFeats"]
+            self.conv1 = nn.Conv2d(3, 64, 7, 2, 3)
+            self.relu = nn.ReLU()
+            self.residual1 = ResidualBlock(64, 128, stride=2)
+            self.residual2 = ResidualBlock(128, 128)
+            self.residual3 = ResidualBlock(128, nFeats)
+            self.hourglass1 = hourglass(4, nFeats)
+            self.residual4 = ResidualBlock(nFeats, nFeats)
+            self.lin = lin(nFeats, nFeats)
+            self.conv2_0 = nn.Conv2d(nFeats, g["nOutChannels_0"], 1, 1, 0, bias=False)
+            self.conv4_0 = nn.Conv2d(2 * nFeats + g["nOutChannels_0"], nFeats, 1, 1, 0)
+            self.conv2_1 = nn.Conv2d(nFeats, g["nOutChannels_1"], 1, 1, 0, bias=False)
+            self.conv4_1 = nn.Conv2d(2 * nFeats + g["nOutChannels_1"], nFeats, 1, 1, 0, bias=False)
+            self.conv2_2 = nn.Conv2d(nFeats, g["nOutChannels_2"], 1, 1, 0, bias=False)
+
+        def _config_key(self):
+            return (g["nStack"],)
+
+        def _emit(self, b, x):
+            return _multihead_forward(self, b, x, g, cat_inter=True, with_pool=False, n_res4=1)
+
+    for cls in (hourglass, creatModel, _ASPPModule):
+        cls.__module__ = g.get("__name__", cls.__module__)
+        cls.__qualname__ = cls.__name__
+    return ResidualBlock, hourglass, lin, creatModel, _ASPPModule
+
+
+def make_u_family(g):
+    """hourglass_compare.py:405-638 (= creatModel_hourglass of performance_compare.py:335-427): the un-shared
+    4-stage 'stacked hourglass' baseline on MPII-16 -- explicit 4-level hourglass with separate blocks, NEAREST
+    up-sampling, stem conv + BN + ReLU, bias-free heads, inter = return(out) + inter + down_feature(ll)."""
+    ResidualBlock = make_q4_block(g)
+
+    class hourglass(HGModule):
+        def __init__(self, f):
+            super(hourglass, self).__init__()
+            self.f = f
+            self.downsample1 = nn.Sequential(nn.MaxPool2d(2, 2), ResidualBlock(f, f))
+            self.downsample2 = nn.Sequential(nn.MaxPool2d(2, 2), ResidualBlock(f, f))
+            self.downsample3 = nn.Sequential(nn.MaxPool2d(2, 2), ResidualBlock(f, f))
+            self.downsample4 = nn.Sequential(nn.MaxPool2d(2, 2), ResidualBlock(f, f))
+            self.residual1 = ResidualBlock(f, f)
+            self.residual2 = ResidualBlock(f, f)
+            self.residual3 = ResidualBlock(f, f)
+            self.residual4 = ResidualBlock(f, f)
+            self.residual5 = ResidualBlock(f, f)
+            self.upsample1 = ResidualBlock(f, f)
+            self.upsample2 = ResidualBlock(f, f)
+            self.upsample3 = ResidualBlock(f, f)
+            self.upsample4 = ResidualBlock(f, f)
+
+        def _emit(self, b, x):
+            with b.on_lane(4):
+                up1 = self.residual1._emit(b, x)
+            down1 = self.downsample1[1]._emit(b, b.maxpool2(x))
+            with b.on_lane(3):
+                up2 = self.residual2._emit(b, down1)
+            down2 = self.downsample2[1]._emit(b, b.maxpool2(down1))
+            with b.on_lane(2):
+                up3 = self.residual3._emit(b, down2)
+            down3 = self.downsample3[1]._emit(b, b.maxpool2(down2))
+            with b.on_lane(1):
+                up4 = self.residual4._emit(b, down3)
+            down4 = self.downsample4[1]._emit(b, b.maxpool2(down3))
+            out = self.residual5._emit(b, down4)
+            out = self.upsample4._emit(b, out)
+            out = b.upsample2x_add(out, up4, mode="nearest")
+            out = self.upsample3._emit(b, out)
+            out = b.upsample2x_add(out, up3, mode="nearest")
+            out = self.upsample2._emit(b, out)
+            out = b.upsample2x_add(out, up2, mode="nearest")
+            out = self.upsample1._emit(b, out)
+            out = b.upsample2x_add(out, up1, mode="nearest")
+            return out
+
+    class creatModel(HGModule):
+        _is_model = True
+
+        def __init__(self):
+            super(creatModel, self).__init__()
+            nFeats = g["nFeats"]
+            self.preprocess1 = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3), nn.BatchNorm2d(64), nn.ReLU(),
+                                             ResidualBlock(64, 128), nn.MaxPool2d(2, 2), ResidualBlock(128, 128),
+                                             ResidualBlock(128, nFeats))
+            for k in (1, 2, 3, 4):
+                setattr(self, f"stage{k}", nn.Sequential(hourglass(nFeats), ResidualBlock(nFeats, nFeats),
+                                                         nn.Conv2d(nFeats, nFeats, 1, 1, 0), nn.BatchNorm2d(nFeats),
+                                                         nn.ReLU()))
+                setattr(self, f"stage{k}_out", nn.Conv2d(nFeats, 16, 1, 1, 0, bias=False))
+                if k < 4:
+                    setattr(self, f"stage{k}_return", nn.Conv2d(16, nFeats, 1, 1, 0, bias=False))
+                    setattr(self, f"stage{k}_down_feature", nn.Conv2d(nFeats, nFeats, 1, 1, 0, bias=False))
+
+        def _emit(self, b, x):
+            pre = self.preprocess1
+            x = b.stem(pre[0], x, relu=False)
+            x = b.bn_relu(pre[1], x)
+            x = pre[3]._emit(b, x)
+            x = b.maxpool2(x)
+            x = pre[5]._emit(b, x)
+            inter = pre[6]._emit(b, x)
+            out = []
+            for k in (1, 2, 3, 4):
+                stage = getattr(self, f"stage{k}")
+                ll = stage[0]._emit(b, inter)
+                ll = stage[1]._emit(b, ll)
+                ll = b.bn_relu(stage[3], b.conv(stage[2], ll))
+                tmpOut = b.conv(getattr(self, f"stage{k}_out"), ll, head=True)
+                out.insert(k - 1, tmpOut)
+                if k < 4:
+                    ll_ = b.conv(getattr(self, f"stage{k}_down_feature"), ll, residual=inter)
+                    inter = b.conv(getattr(self, f"stage{k}_return"), tmpOut, residual=ll_)
+            return out
+
+    for cls in (hourglass, creatModel):
+        cls.__module__ = g.get("__name__", cls.__module__)
+        cls.__qualname__ = cls.__name__
+    return ResidualBlock, hourglass, creatModel

@@ -71,8 +71,11 @@ int conv_ref_dgrad(const HgConvDesc*, const void*, const void*, const void*, voi
 template <typename T>
 int conv_ref_wgrad(const HgConvDesc*, const void*, const void*, float*, float*, cudaStream_t);
 template <typename T>
-int pack_weight(const HgConvDesc*, const float*, void*, void*, cudaStream_t);
-int unpack_wgrad(const HgConvDesc* d, const float* g, float* dw, int accumulate, cudaStream_t st);
+int pack_weight(const HgConvDesc*, const float*, void*, void*, int, int, cudaStream_t);
+int unpack_wgrad(const HgConvDesc* d, const float* g, float* dw, int accumulate, int cin_total, int cin_off,
+                 cudaStream_t st);
+int mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
+             cudaStream_t st);
 int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats, cudaStream_t st);
 
 static inline int pad64(int c) { return (c + 63) & ~63; }
@@ -122,13 +125,26 @@ int hg_set_option(const char* name, int value) {
   return HG_ERR_BAD_ARG;
 }
 
-int hg_pack_conv_weight(const HgConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream) {
+int hg_pack_conv_weight_slice(const HgConvDesc* d, const float* w_oihw, int cin_total, int cin_offset, void* w_fprop,
+                              void* w_dgrad, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   HG_REQUIRE(w_oihw != nullptr, "hg_pack_conv_weight: w_oihw is NULL");
+  HG_REQUIRE(cin_offset >= 0 && cin_offset + d->Cin <= cin_total, "hg_pack_conv_weight_slice: slice out of range");
   cudaStream_t st = (cudaStream_t)stream;
-  return d->dtype == HG_BF16 ? pack_weight<__nv_bfloat16>(d, w_oihw, w_fprop, w_dgrad, st)
-                             : pack_weight<float>(d, w_oihw, w_fprop, w_dgrad, st);
+  return d->dtype == HG_BF16 ? pack_weight<__nv_bfloat16>(d, w_oihw, w_fprop, w_dgrad, cin_total, cin_offset, st)
+                             : pack_weight<float>(d, w_oihw, w_fprop, w_dgrad, cin_total, cin_offset, st);
+}
+
+int hg_pack_conv_weight(const HgConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream) {
+  return hg_pack_conv_weight_slice(d, w_oihw, d ? d->Cin : 0, 0, w_fprop, w_dgrad, stream);
+}
+
+int hg_mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
+                void* stream) {
+  HG_REQUIRE(T && in && out && R > 0 && cols > 0, "hg_mix_rows: bad arguments");
+  HG_REQUIRE(in != out, "hg_mix_rows: in-place recombination is not supported");
+  return mix_rows(T, in, out, R, cols, transpose, accumulate, (cudaStream_t)stream);
 }
 
 int hg_conv_fprop_ex(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias,
@@ -171,11 +187,17 @@ int hg_conv_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, cons
                              : conv_ref_dgrad<float>(d, dy, w_dgrad, addend, dx, st);
 }
 
-int hg_unpack_conv_wgrad(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int accumulate, void* stream) {
+int hg_unpack_conv_wgrad_slice(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int cin_total,
+                               int cin_offset, int accumulate, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   HG_REQUIRE(dw_packed && dw_oihw, "hg_unpack_conv_wgrad: NULL pointer");
-  return unpack_wgrad(d, dw_packed, dw_oihw, accumulate, (cudaStream_t)stream);
+  HG_REQUIRE(cin_offset >= 0 && cin_offset + d->Cin <= cin_total, "hg_unpack_conv_wgrad_slice: slice out of range");
+  return unpack_wgrad(d, dw_packed, dw_oihw, accumulate, cin_total, cin_offset, (cudaStream_t)stream);
+}
+
+int hg_unpack_conv_wgrad(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int accumulate, void* stream) {
+  return hg_unpack_conv_wgrad_slice(d, dw_packed, dw_oihw, d ? d->Cin : 0, 0, accumulate, stream);
 }
 
 int hg_conv_wgrad(const HgConvDesc* d, const void* x, const void* dy, float* dw_oihw, float* dbias, void* stream) {

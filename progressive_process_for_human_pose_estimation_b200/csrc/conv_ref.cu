@@ -258,16 +258,18 @@ template int conv_ref_wgrad<__nv_bfloat16>(const HgConvDesc*, const void*, const
 // ------------------------------------------------------------------------------------------------------
 // weight repack: fp32 OIHW -> [tap][Cout_p][Cin_p] and [tap][Cin_p][Cout_p] in T (zero padded)
 // ------------------------------------------------------------------------------------------------------
+// (the source may be a slice [cin_off, cin_off + Cin) of a wider weight with cin_total input channels: the
+//  "virtual concat" convolutions of try_different_stack.py:316-328 / try_with_aspp_remove_max_pool.py:239-240)
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout,
-                                   int Cin, int taps, int Cout_p, int Cin_p) {
+                                   int Cin, int taps, int Cout_p, int Cin_p, int cin_total, int cin_off) {
   const long long total = (long long)taps * Cout_p * Cin_p;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin_p);
     const int co = (int)((i / Cin_p) % Cout_p);
     const int tap = (int)(i / ((long long)Cin_p * Cout_p));
-    const float v = (ci < Cin && co < Cout) ? w[((long long)co * Cin + ci) * taps + tap] : 0.f;
+    const float v = (ci < Cin && co < Cout) ? w[((long long)co * cin_total + cin_off + ci) * taps + tap] : 0.f;
     if (wf) wf[i] = from_f<T>(v);
     if (wd) wd[((long long)tap * Cin_p + ci) * Cout_p + co] = from_f<T>(v);
   }
@@ -275,7 +277,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 
 // GEMM-layout fp32 gradient [tap][Cout_p][Cin_p] -> OIHW [Cout][Cin][R][S]  (assign or accumulate)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ g, float* __restrict__ dw, int Cout, int Cin, int taps,
-                                    int Cout_p, int Cin_p, int accumulate) {
+                                    int Cout_p, int Cin_p, int accumulate, int cin_total, int cin_off) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -283,32 +285,64 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ g, float* __restri
     const int ci = (int)((i / taps) % Cin);
     const int co = (int)(i / ((long long)taps * Cin));
     const float v = g[((long long)tap * Cout_p + co) * Cin_p + ci];
-    dw[i] = accumulate ? dw[i] + v : v;
+    const long long o = ((long long)co * cin_total + cin_off + ci) * taps + tap;
+    dw[o] = accumulate ? dw[o] + v : v;
   }
 }
-int unpack_wgrad(const HgConvDesc* d, const float* g, float* dw, int accumulate, cudaStream_t st) {
+int unpack_wgrad(const HgConvDesc* d, const float* g, float* dw, int accumulate, int cin_total, int cin_off,
+                 cudaStream_t st) {
   const int taps = d->R * d->S;
   const long long total = (long long)d->Cout * d->Cin * taps;
   int blocks = ceil_div(total, 256);
   if (blocks > 1184) blocks = 1184;
-  unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(g, dw, d->Cout, d->Cin, taps, pad64(d->Cout), pad64(d->Cin), accumulate);
+  unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(g, dw, d->Cout, d->Cin, taps, pad64(d->Cout), pad64(d->Cin), accumulate,
+                                              cin_total, cin_off);
   HG_LAUNCH_OK("unpack_wgrad_kernel");
   count_launch();
   return HG_OK;
 }
 
 template <typename T>
-int pack_weight(const HgConvDesc* d, const float* w, void* wf, void* wd, cudaStream_t st) {
+int pack_weight(const HgConvDesc* d, const float* w, void* wf, void* wd, int cin_total, int cin_off,
+                cudaStream_t st) {
   const int taps = d->R * d->S, Cout_p = pad64(d->Cout), Cin_p = pad64(d->Cin);
   const long long total = (long long)taps * Cout_p * Cin_p;
   int blocks = ceil_div(total, 256);
   if (blocks > 1184) blocks = 1184;
-  pack_weight_kernel<T><<<blocks, 256, 0, st>>>(w, (T*)wf, (T*)wd, d->Cout, d->Cin, taps, Cout_p, Cin_p);
+  pack_weight_kernel<T><<<blocks, 256, 0, st>>>(w, (T*)wf, (T*)wd, d->Cout, d->Cin, taps, Cout_p, Cin_p, cin_total,
+                                                cin_off);
   HG_LAUNCH_OK("pack_weight_kernel");
   count_launch();
   return HG_OK;
 }
-template int pack_weight<float>(const HgConvDesc*, const float*, void*, void*, cudaStream_t);
-template int pack_weight<__nv_bfloat16>(const HgConvDesc*, const float*, void*, void*, cudaStream_t);
+template int pack_weight<float>(const HgConvDesc*, const float*, void*, void*, int, int, cudaStream_t);
+template int pack_weight<__nv_bfloat16>(const HgConvDesc*, const float*, void*, void*, int, int, cudaStream_t);
+
+// out[R, cols] (=|+=) T[R, R] (or its transpose) * in[R, cols]: recombination of head channels
+// (limb mix of try_skeleton_and_keypoints.py:279-298 folded into the head's weights and gradients)
+__global__ void mix_rows_kernel(const float* __restrict__ T, const float* __restrict__ in, float* __restrict__ out,
+                                int R, int cols, int transpose, int accumulate) {
+  const long long total = (long long)R * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols), r = (int)(i / cols);
+    float acc = 0.f;
+    for (int k = 0; k < R; ++k) {
+      const float t = transpose ? T[k * R + r] : T[r * R + k];
+      if (t != 0.f) acc = fmaf(t, in[(long long)k * cols + c], acc);
+    }
+    out[i] = accumulate ? out[i] + acc : acc;
+  }
+}
+int mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
+             cudaStream_t st) {
+  const long long total = (long long)R * cols;
+  int blocks = ceil_div(total, 256);
+  if (blocks > 1184) blocks = 1184;
+  mix_rows_kernel<<<blocks, 256, 0, st>>>(T, in, out, R, cols, transpose, accumulate);
+  HG_LAUNCH_OK("mix_rows_kernel");
+  count_launch();
+  return HG_OK;
+}
 
 }  // namespace hg

@@ -32,7 +32,7 @@ __device__ __forceinline__ void load_patch(float* patch, const float* __restrict
 template <typename T>
 __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, T* __restrict__ y, int N, int H,
-                                                       int W) {
+                                                       int W, int relu) {
   extern __shared__ float sm[];
   float* ws = sm;               // [147][64]
   float* patch = sm + 147 * 64; // [3][21][38]
@@ -85,7 +85,10 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc[j][h * 8 + e] + bias[cg * 16 + h * 8 + e], 0.f);
+        for (int e = 0; e < 8; ++e) {
+          const float v = acc[j][h * 8 + e] + (bias ? bias[cg * 16 + h * 8 + e] : 0.f);
+          o[e] = relu ? fmaxf(v, 0.f) : v;
+        }
         store8(dst + h * 8, o);
       }
     }
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(160) stem_bwd_kernel(const float* __restrict__ x, const T* __restrict__ y,
                                                        const T* __restrict__ dy, float* __restrict__ dw,
-                                                       float* __restrict__ db, int N, int H, int W) {
+                                                       float* __restrict__ db, int N, int H, int W, int relu) {
   extern __shared__ float sm[];
   float* patch = sm;            // [3][21][38] + 1 (constant one)
   float* gs = sm + kPatchPad;    // [128][64]
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(160) stem_bwd_kernel(const float* __restrict__
       load8(y + off, yy);
       load8(dy + off, gg);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) gs[p * 64 + v * 8 + e] = yy[e] > 0.f ? gg[e] : 0.f;
+      for (int e = 0; e < 8; ++e) gs[p * 64 + v * 8 + e] = (!relu || yy[e] > 0.f) ? gg[e] : 0.f;
     }
     __syncthreads();
     if (worker) {
@@ -187,10 +190,10 @@ using namespace hg;
 
 extern "C" {
 
-int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W, void* y,
-                void* stream) {
+int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W, int relu,
+                void* y, void* stream) {
   HG_REQUIRE(dtype == HG_BF16 || dtype == HG_F32, "hg_stem_fwd: bad dtype");
-  HG_REQUIRE(x_nchw && w_oihw && bias && y, "hg_stem_fwd: NULL pointer");
+  HG_REQUIRE(x_nchw && w_oihw && y, "hg_stem_fwd: NULL pointer");
   HG_REQUIRE(N > 0 && H > 0 && W > 0, "hg_stem_fwd: non-positive size");
   if (H % 16 != 0 || W % 32 != 0) {
     set_error("hg_stem_fwd: image size %dx%d must be a multiple of 16x32", H, W);
@@ -205,22 +208,22 @@ int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float
       HG_CUDA_OK(cudaFuncSetAttribute(stem_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       set = true;
     }
-    stem_fwd_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(x_nchw, w_oihw, bias, (__nv_bfloat16*)y, N, H, W);
+    stem_fwd_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(x_nchw, w_oihw, bias, (__nv_bfloat16*)y, N, H, W, relu);
   } else {
     static bool set = false;
     if (!set) {
       HG_CUDA_OK(cudaFuncSetAttribute(stem_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       set = true;
     }
-    stem_fwd_kernel<float><<<grid, 128, smem, st>>>(x_nchw, w_oihw, bias, (float*)y, N, H, W);
+    stem_fwd_kernel<float><<<grid, 128, smem, st>>>(x_nchw, w_oihw, bias, (float*)y, N, H, W, relu);
   }
   HG_LAUNCH_OK("stem_fwd_kernel");
   count_launch();
   return HG_OK;
 }
 
-int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, int N, int H, int W, float* dw_oihw,
-                float* dbias, void* stream) {
+int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, int N, int H, int W, int relu,
+                float* dw_oihw, float* dbias, void* stream) {
   HG_REQUIRE(dtype == HG_BF16 || dtype == HG_F32, "hg_stem_bwd: bad dtype");
   HG_REQUIRE(x_nchw && y && dy, "hg_stem_bwd: NULL pointer");
   if (H % 16 != 0 || W % 32 != 0) {
@@ -239,14 +242,15 @@ int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, i
       set = true;
     }
     stem_bwd_kernel<__nv_bfloat16><<<blocks, 160, smem, st>>>(x_nchw, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy,
-                                                             dw_oihw, dbias, N, H, W);
+                                                             dw_oihw, dbias, N, H, W, relu);
   } else {
     static bool set = false;
     if (!set) {
       HG_CUDA_OK(cudaFuncSetAttribute(stem_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       set = true;
     }
-    stem_bwd_kernel<float><<<blocks, 160, smem, st>>>(x_nchw, (const float*)y, (const float*)dy, dw_oihw, dbias, N, H, W);
+    stem_bwd_kernel<float><<<blocks, 160, smem, st>>>(x_nchw, (const float*)y, (const float*)dy, dw_oihw, dbias, N, H, W,
+                                                       relu);
   }
   HG_LAUNCH_OK("stem_bwd_kernel");
   count_launch();

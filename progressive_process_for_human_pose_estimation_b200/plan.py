@@ -100,24 +100,38 @@ class Builder:
         return self.train_params or any(v.requires_grad for v in vals if v is not None)
 
     # -- ops ----------------------------------------------------------------------------------------
-    def stem(self, conv, x):
+    def stem(self, conv, x, relu=True):
+        """7x7 stride-2 stem on the fp32 NCHW image; relu=False when a BatchNorm follows (hourglass_compare.py:549)."""
         assert conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3)
         out = Val(x.N, x.H // 2, x.W // 2, conv.out_channels, self.train_params, "stem")
-        self.ops.append(Op("stem", [x], out, conv=conv))
+        self.ops.append(Op("stem", [x], out, conv=conv, relu=relu))
         return out
 
-    def conv(self, conv, x, residual=None, head=False):
-        """nn.Conv2d (+ fused residual add).  head=True also produces the fp32 NCHW tensor the module returns."""
+    def conv(self, conv, x, residual=None, head=False, cin_off=0, use_bias=True, mix=None):
+        """nn.Conv2d (+ fused residual add).  head=True also produces the fp32 NCHW tensor the module returns.
+        cin_off: x feeds the input-channel slice [cin_off, cin_off + x.C) of the weight (see conv_cat).
+        mix: [Cout, Cout] matrix T applied to the output channels (folded into the weights: T W, T b)."""
         k, s, p, d = conv.kernel_size, conv.stride, conv.padding, conv.dilation
         assert k[0] == k[1] and s[0] == s[1] and p[0] == p[1] and d[0] == d[1]
-        assert conv.in_channels == x.C, (conv.in_channels, x.C)
+        assert cin_off + x.C <= conv.in_channels and (cin_off > 0 or x.C <= conv.in_channels), (conv.in_channels, x.C)
         Ho = (x.H + 2 * p[0] - d[0] * (k[0] - 1) - 1) // s[0] + 1
         Wo = (x.W + 2 * p[0] - d[0] * (k[0] - 1) - 1) // s[0] + 1
         out = Val(x.N, Ho, Wo, conv.out_channels, self._rg(x, residual), "conv")
-        self.ops.append(Op("conv", [x, residual], out, conv=conv, head=head))
+        self.ops.append(Op("conv", [x, residual], out, conv=conv, head=head, cin_off=cin_off,
+                           use_bias=use_bias and conv.bias is not None, mix=mix))
         if head:
             self.outputs.append((out, conv.out_channels))
         return out
+
+    def conv_cat(self, conv, xs, head=False):
+        """conv(torch.cat(xs, 1)) without materialising the concatenation: one chained convolution per input over
+        the matching slice of the weight, each adding to the previous partial sum through the residual epilogue."""
+        assert sum(v.C for v in xs) == conv.in_channels, ([v.C for v in xs], conv.in_channels)
+        y, off = None, 0
+        for i, v in enumerate(xs):
+            y = self.conv(conv, v, residual=y, head=head and i == len(xs) - 1, cin_off=off, use_bias=(i == 0))
+            off += v.C
+        return y
 
     def bn_relu(self, bn, x, relu=True):
         assert bn.num_features == x.C
@@ -178,7 +192,7 @@ class _LaneCtx:
 # positions (in the ctypes argument tuple) of the tensors each entry point WRITES; every other tracked pointer
 # argument is a read.  Parameter / weight-gradient pointers are not tracked (read-only or commutative atomics).
 _WRITES = {
-    "hg_nchw_f32_to_nhwc": (7,), "hg_nhwc_to_nchw_f32": (6,), "hg_stem_fwd": (7,), "hg_conv_fprop_ex": (5, 6, 7),
+    "hg_nchw_f32_to_nhwc": (7,), "hg_nhwc_to_nchw_f32": (6,), "hg_stem_fwd": (8,), "hg_conv_fprop_ex": (5, 6, 7),
     "hg_conv_dgrad": (4,), "hg_bn_stats": (2,), "hg_bn_apply": (7,), "hg_bn_bwd_apply": (10,),
     "hg_maxpool2_fwd": (6,), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8,), "hg_upsample2x_bwd": (8,),
     "hg_add": (3,),
@@ -330,20 +344,42 @@ class Plan:
         self.param_used = [False] * len(self.params)
 
         # ---- convolutions: packed operands, packed gradient accumulators -------------------------
-        convs = _unique([op.attrs["conv"] for op in ops if op.kind == "conv"])
+        # one entry per (conv module, input-channel slice): a shared weight has ONE entry for all its call sites
+        conv_ops = [op for op in ops if op.kind == "conv"]
         self.conv_info = {}
+        self.conv_keys = []
         packed_total = 0
-        for cv in convs:
+        for op in conv_ops:
+            cv, x = op.attrs["conv"], op.ins[0]
+            key = (id(cv), op.attrs["cin_off"])
+            op.attrs["key"] = key
+            if key in self.conv_info:
+                assert self.conv_info[key]["cin_seg"] == x.C
+                continue
             k = cv.kernel_size[0]
-            cin_p, cout_p = L.pad64(cv.in_channels), L.pad64(cv.out_channels)
-            direct = (k == 1 and cin_p == cv.in_channels and cout_p == cv.out_channels)
-            info = dict(wf=torch.zeros(k * k, cout_p, cin_p, device=dev, dtype=self.dt),
+            cin_p, cout_p = L.pad64(x.C), L.pad64(cv.out_channels)
+            mix = op.attrs["mix"]
+            whole = (op.attrs["cin_off"] == 0 and x.C == cv.in_channels)
+            direct = (k == 1 and whole and mix is None and cin_p == x.C and cout_p == cv.out_channels)
+            info = dict(conv=cv, cin_off=op.attrs["cin_off"], cin_seg=x.C, mix=None,
+                        wf=torch.zeros(k * k, cout_p, cin_p, device=dev, dtype=self.dt),
                         wd=torch.zeros(k * k, cin_p, cout_p, device=dev, dtype=self.dt),
                         bias=torch.zeros(cout_p, device=dev, dtype=torch.float32), direct=direct,
                         gsize=k * k * cout_p * cin_p, goff=packed_total)
             if not direct:
                 packed_total += info["gsize"]
-            self.conv_info[id(cv)] = info
+            if mix is not None:
+                assert whole, "channel mixing is only supported on un-sliced convolutions"
+                info["mix"] = mix.to(device=dev, dtype=torch.float32).contiguous()
+                info["w_eff"] = torch.zeros(cv.out_channels, cv.in_channels * k * k, device=dev)
+                info["dweff_off"] = packed_total
+                packed_total += cv.out_channels * cv.in_channels * k * k
+                info["dbeff_off"] = packed_total
+                packed_total += cout_p
+                info["bias_copy"] = False
+            self.conv_info[key] = info
+            self.conv_keys.append(key)
+        convs = self.conv_keys
         self.packed_arena = torch.zeros(max(1, packed_total), device=dev, dtype=torch.float32)
 
         # ---- activations and BatchNorm statistics ---------------------------------------------
@@ -388,7 +424,7 @@ class Plan:
 
     # ------------------------------------------------------------------------------------------------
     def _conv_desc(self, cv, x):
-        d = L.HgConvDesc(x.N, x.H, x.W, cv.in_channels, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1],
+        d = L.HgConvDesc(x.N, x.H, x.W, x.C, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1],
                          cv.stride[0], cv.padding[0], cv.dilation[0], self.hdt)
         self._keep.append(d)
         return d
@@ -406,14 +442,22 @@ class Plan:
     def _lower_forward(self, convs):
         f, st = self.fwd_calls, self.stream
         # weights -> GEMM operand layouts (the optimizer changed them since the last step)
-        for cv in convs:
-            info = self.conv_info[id(cv)]
-            d = L.HgConvDesc(1, 1, 1, cv.in_channels, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1], 1, 0, 1,
-                             self.hdt)
+        for key in convs:
+            info = self.conv_info[key]
+            cv = info["conv"]
+            k = cv.kernel_size[0]
+            d = L.HgConvDesc(1, 1, 1, info["cin_seg"], cv.out_channels, k, k, 1, 0, 1, self.hdt)
             self._keep.append(d)
-            need_wd = self.need_bwd
-            self._emit(f, "hg_pack_conv_weight", C.byref(d), L.ptr(self._p32(cv.weight)), L.ptr(info["wf"]),
-                       L.ptr(info["wd"]) if need_wd else None, st)
+            src = self._p32(cv.weight)
+            if info["mix"] is not None:  # W_eff = T W, b_eff = T b
+                self._emit(f, "hg_mix_rows", L.ptr(info["mix"]), L.ptr(src), L.ptr(info["w_eff"]), cv.out_channels,
+                           cv.in_channels * k * k, 0, 0, st)
+                src = info["w_eff"]
+                if cv.bias is not None:
+                    self._emit(f, "hg_mix_rows", L.ptr(info["mix"]), L.ptr(self._p32(cv.bias)), L.ptr(info["bias"]),
+                               cv.out_channels, 1, 0, 0, st)
+            self._emit(f, "hg_pack_conv_weight_slice", C.byref(d), L.ptr(src), cv.in_channels, info["cin_off"],
+                       L.ptr(info["wf"]), L.ptr(info["wd"]) if self.need_bwd else None, st)
         for v, kind in self.b.inputs:
             if kind == "nchw":
                 self._emit(f, "hg_nchw_f32_to_nhwc", self.hdt, L.ptr(self.in_nchw), None, v.N, v.C, v.H, v.W,
@@ -427,16 +471,18 @@ class Plan:
             if k == "stem":
                 cv, x, out = op.attrs["conv"], op.ins[0], op.out
                 self._emit(f, "hg_stem_fwd", self.hdt, L.ptr(x.buf), L.ptr(self._p32(cv.weight)),
-                           L.ptr(self._p32(cv.bias)), x.N, x.H, x.W, L.ptr(out.buf), st)
+                           L.ptr(self._p32(cv.bias)) if cv.bias is not None else None, x.N, x.H, x.W,
+                           1 if op.attrs["relu"] else 0, L.ptr(out.buf), st)
                 if out.needs_stats:
                     self._stats_call(f, out)
             elif k == "conv":
                 cv, x, res, out = op.attrs["conv"], op.ins[0], op.ins[1], op.out
-                info = self.conv_info[id(cv)]
+                info = self.conv_info[op.attrs["key"]]
                 d = self._conv_desc(cv, x)
                 nchw = self.out_static[self.out_index[id(out)]] if op.attrs["head"] else None
                 self._emit(f, "hg_conv_fprop_ex", C.byref(d), L.ptr(x.buf), L.ptr(info["wf"]),
-                           self._bias_ptr(cv, info), L.ptr(res.buf) if res else None,
+                           self._bias_ptr(cv, info) if op.attrs["use_bias"] else None,
+                           L.ptr(res.buf) if res else None,
                            L.ptr(out.buf), L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw),
                            st).tag = self._conv_tag(cv, x)
             elif k == "bn":
@@ -494,6 +540,8 @@ class Plan:
         """Bias vector padded to Cout_p: the live fp32 parameter itself when no padding / cast is needed."""
         if cv.bias is None:
             return None
+        if info["mix"] is not None:
+            return L.ptr(info["bias"])  # b_eff, refreshed by hg_mix_rows every forward
         if cv.bias.dtype == torch.float32 and L.pad64(cv.out_channels) == cv.out_channels:
             return L.ptr(cv.bias.data)
         info["bias_copy"] = True
@@ -529,17 +577,19 @@ class Plan:
             G = out.grad
             if k == "conv":
                 cv, x, res = op.attrs["conv"], op.ins[0], op.ins[1]
-                info = self.conv_info[id(cv)]
+                info = self.conv_info[op.attrs["key"]]
                 d = self._conv_desc(cv, x)
                 if res is not None:
                     self._grad_passthrough(res, G)
                 wslot = self._gslot(cv.weight)
-                bslot = self._gslot(cv.bias) if cv.bias is not None else None
+                bslot = self._gslot(cv.bias) if op.attrs["use_bias"] else None
                 # bias gradient comes for free from the BatchNorm backward when y only feeds a BatchNorm
                 bn_only = (len(out.consumers) == 1 and out.consumers[0].kind == "bn" and res is None
-                           and not op.attrs["head"])
+                           and not op.attrs["head"] and info["mix"] is None)
                 if bn_only:
                     bslot = None
+                if info["mix"] is not None and bslot is not None:  # db_eff first, un-mixed at the end
+                    bslot = self.packed_arena[info["dbeff_off"]:info["dbeff_off"] + cv.out_channels]
                 if wslot is not None or bslot is not None:
                     if wslot is None:
                         dwp = None
@@ -567,7 +617,7 @@ class Plan:
                 colsum = None
                 prod = x.producer
                 if (prod is not None and prod.kind == "conv" and len(x.consumers) == 1 and prod.ins[1] is None
-                        and not prod.attrs["head"] and prod.attrs["conv"].bias is not None):
+                        and not prod.attrs["head"] and prod.attrs["use_bias"] and prod.attrs["mix"] is None):
                     colsum = self._gslot(prod.attrs["conv"].bias)
                 if x.requires_grad:
                     addend, dst = self._grad_target(x)
@@ -597,7 +647,8 @@ class Plan:
             elif k == "stem":
                 cv, x = op.attrs["conv"], op.ins[0]
                 self._emit(g, "hg_stem_bwd", self.hdt, L.ptr(x.buf), L.ptr(out.buf), L.ptr(G), x.N, x.H, x.W,
-                           L.ptr(self._gslot(cv.weight)), L.ptr(self._gslot(cv.bias)), st)
+                           1 if op.attrs["relu"] else 0, L.ptr(self._gslot(cv.weight)),
+                           L.ptr(self._gslot(cv.bias)) if cv.bias is not None else None, st)
         self._cur_lane = 0
         # graph inputs that want a gradient (sub-module use): NHWC -> NCHW fp32
         self.gin_static = None
@@ -609,26 +660,45 @@ class Plan:
                                L.ptr(self.gin_static), st)
         # packed weight gradients -> OIHW slots, right after the LAST call site of each shared weight so that the
         # gradient is final as early as possible (bucketed all-reduce, parallel.py)
-        for cv in convs:
-            info = self.conv_info[id(cv)]
-            if info.get("used"):
-                d = L.HgConvDesc(1, 1, 1, cv.in_channels, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1], 1, 0,
-                                 1, self.hdt)
-                self._keep.append(d)
-                dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
-                self._pending_writes = []
-                slot = self._gslot(cv.weight)
-                c = _Call("hg_unpack_conv_wgrad", (C.byref(d), L.ptr(dwp), L.ptr(slot), 0, st))
-                c.writes = tuple(self._pending_writes)
-                self._pending_writes = []
-                # the wgrad calls themselves only touch the packed accumulator, not the OIHW slot
-                for call in g:
-                    if call.name == "hg_conv_wgrad" and self.param_index[id(cv.weight)] in call.writes:
-                        call.writes = tuple(w for w in call.writes if w != self.param_index[id(cv.weight)])
-                # other call sites of this weight may still be running on other lanes: wait for all issued work
+        for key in convs:
+            info = self.conv_info[key]
+            if not info.get("used"):
+                continue
+            cv = info["conv"]
+            k = cv.kernel_size[0]
+            d = L.HgConvDesc(1, 1, 1, info["cin_seg"], cv.out_channels, k, k, 1, 0, 1, self.hdt)
+            self._keep.append(d)
+            dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
+            self._pending_writes = []
+            slot = self._gslot(cv.weight)
+            widx = self.param_index[id(cv.weight)]
+            tail = []
+            if info["mix"] is None:
+                tail.append(_Call("hg_unpack_conv_wgrad_slice", (C.byref(d), L.ptr(dwp), L.ptr(slot), cv.in_channels,
+                                                                 info["cin_off"], 1, st)))
+            else:  # dW = T^T dW_eff, db = T^T db_eff
+                n = cv.out_channels * cv.in_channels * k * k
+                dweff = self.packed_arena[info["dweff_off"]:info["dweff_off"] + n]
+                tail.append(_Call("hg_unpack_conv_wgrad_slice", (C.byref(d), L.ptr(dwp), L.ptr(dweff), cv.in_channels,
+                                                                 0, 0, st)))
+                tail.append(_Call("hg_mix_rows", (L.ptr(info["mix"]), L.ptr(dweff), L.ptr(slot), cv.out_channels,
+                                                  cv.in_channels * k * k, 1, 1, st)))
+                if cv.bias is not None and self._gslot(cv.bias) is not None:
+                    dbeff = self.packed_arena[info["dbeff_off"]:info["dbeff_off"] + cv.out_channels]
+                    tail.append(_Call("hg_mix_rows", (L.ptr(info["mix"]), L.ptr(dbeff), L.ptr(self._gslot(cv.bias)),
+                                                      cv.out_channels, 1, 1, 1, st)))
+            tail[-1].writes = tuple(self._pending_writes)
+            self._pending_writes = []
+            # the wgrad calls themselves only touch the packed accumulator, not the OIHW slot
+            for call in g:
+                if call.name == "hg_conv_wgrad" and widx in call.writes:
+                    call.writes = tuple(w for w in call.writes if w != widx)
+            # other call sites of this weight may still be running on other lanes: wait for all issued work
+            pos = g.index(info["last_wgrad"]) + 1
+            for i, c in enumerate(tail):
                 c.lane = 0
-                c.barrier = True
-                g.insert(g.index(info["last_wgrad"]) + 1, c)
+                c.barrier = (i == 0)
+                g.insert(pos + i, c)
 
     def plan_gradient_buckets(self, quantiles=(0.5, 0.97)):
         """Split the backward call list at the points where the given fractions of the gradient volume are final.
@@ -764,9 +834,8 @@ class Plan:
         self._run_calls(self.bwd_calls[a:b])
 
     def prepare(self):
-        convs = _unique([op.attrs["conv"] for op in self.b.ops if op.kind == "conv"])
-        self._bias_pairs = [(cv, self.conv_info[id(cv)]) for cv in convs
-                            if cv.bias is not None and self.conv_info[id(cv)].get("bias_copy")]
+        self._bias_pairs = [(info["conv"], info) for info in self.conv_info.values()
+                            if info["conv"].bias is not None and info.get("bias_copy")]
 
     def run_forward(self, x):
         inp = self.b.inputs[0][0]

@@ -1,0 +1,22 @@
+"""Drop-in for try_with_aspp.py: 3-stack multi-head network whose hourglass levels construct ASPP branches that
+the forward never calls (quirk Q6) and whose bottom level has no extra residual blocks
+(reference try_with_aspp.py:22-35,193-345)."""
+from ._modules import make_multihead_family
+
+nModules = 2
+nFeats = 256
+nStack = 3
+nKeypoint = 17
+nSkeleton = 19
+nOutChannels_0 = 2
+nOutChannels_1 = nSkeleton + 1
+nOutChannels_2 = nKeypoint
+batch_size = 16
+keypoints = 17
+skeleton = 20
+threshold = 0.8
+
+sks = [[15, 13], [13, 11], [16, 14], [14, 12], [11, 12], [5, 11], [6, 12], [5, 6], [5, 7], [6, 8], [7, 9], [8, 10],
+       [1, 2], [0, 1], [0, 2], [1, 3], [2, 4], [3, 5], [4, 6]]
+
+ResidualBlock, hourglass, lin, creatModel, _ASPPModule = make_multihead_family(globals(), aspp_members=True)

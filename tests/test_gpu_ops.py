@@ -295,7 +295,7 @@ def test_stem_fwd_bwd(dtype):
     conv = torch.nn.Conv2d(3, 64, 7, 2, 3).to(dev)
     y = torch.empty(N, H // 2, W // 2, 64, device=dev, dtype=dtype)
     st = L.stream_ptr()
-    L.call("hg_stem_fwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(conv.weight), L.ptr(conv.bias), N, H, W, L.ptr(y), st)
+    L.call("hg_stem_fwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(conv.weight), L.ptr(conv.bias), N, H, W, 1, L.ptr(y), st)
     ref = F.relu(conv(x))
     close(nchw(y, 64), ref.detach(), 1e-2 if dtype == torch.bfloat16 else 1e-5, "stem fwd")
     dy = nhwc(torch.randn(N, 64, H // 2, W // 2, device=dev), dtype)
@@ -305,7 +305,7 @@ def test_stem_fwd_bwd(dtype):
     ref_dw = torch.nn.grad.conv2d_weight(x, conv.weight.shape, g, 2, 3)
     dw = torch.zeros_like(conv.weight)
     db = torch.zeros(64, device=dev)
-    L.call("hg_stem_bwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(y), L.ptr(dy), N, H, W, L.ptr(dw), L.ptr(db), st)
+    L.call("hg_stem_bwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(y), L.ptr(dy), N, H, W, 1, L.ptr(dw), L.ptr(db), st)
     close(dw, ref_dw, 1e-4, "stem dw")
     close(db, g.sum((0, 2, 3)), 1e-4, "stem db")
 

@@ -125,9 +125,11 @@ typedef struct HgBnDesc {
 HG_API int hg_bn_stats(const HgBnDesc* d, const void* x, float* stats, void* stream); /* stats += ; caller zeroes */
 HG_API int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const float* gamma, const float* beta,
                 const float* running_mean, const float* running_var, void* y, void* stream);
-/* red[0..Cp) += sum g, red[Cp..2Cp) += sum g*xhat, g = da * [bn(x) > 0]  (caller zeroes red) */
+/* red[0..Cp) += sum g, red[Cp..2Cp) += sum g*xhat, g = da * [bn(x) > 0]  (caller zeroes red).  In eval mode xhat is
+ * taken from the running statistics; the sums are then only the parameter gradients (dbeta, dgamma). */
 HG_API int hg_bn_bwd_reduce(const HgBnDesc* d, const void* da, const void* x, const float* stats, const float* gamma,
-                     const float* beta, float* red, void* stream);
+                     const float* beta, const float* running_mean, const float* running_var, float* red,
+                     void* stream);
 /* dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) [+ addend]; dgamma += , dbeta += ; colsum[C] (optional)
  * += sum over rows of dx without the addend = bias gradient of the convolution that produced x. */
 HG_API int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const float* stats, const float* gamma,

@@ -169,6 +169,94 @@ def golden_pckh():
                         std_b=np.array([float(s) for s in std_b], dtype=np.float32), acc_a=np.float64(acc_a))
 
 
+# (reference script, model factory attribute, drop-in module name)
+FAMILIES = [
+    ("try_different_stack", "creatModel"),
+    ("try_different_stack_without_skeleton", "creatModel"),
+    ("try_with_aspp", "creatModel"),
+    ("try_with_aspp_remove_max_pool", "creatModel"),
+    ("try_skeleton_and_keypoints", "creatModel"),
+    ("hourglass_compare", "creatModel"),  # = performance_compare.creatModel_hourglass (same network, same fixture)
+]
+
+
+def family_inputs(seed, B, S):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 3, S, S, generator=g), g
+
+
+def randomize_running_stats(net, seed=5):
+    """Non-trivial BatchNorm running statistics for the eval-mode goldens (seeded; same recipe in the tests)."""
+    g = torch.Generator().manual_seed(seed)
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+
+
+def golden_families():
+    """One seeded fp32 step (forward, sum of per-output MSE against uniform random targets, backward) of every
+    other model family the drop-in mirrors, executed by the REFERENCE classes: outputs, losses, digests of every
+    gradient and of the state_dict before / after (BN running statistics).  B=2, 128x128 input.  Two variants:
+    `train` (batch statistics: chaotic at random init, SURVEY Q13 -- checked against the fp64 yardstick stored with
+    it) and `eval` (seeded running statistics: well conditioned, so forward AND backward parity are tight)."""
+    for script, factory in FAMILIES:
+        for mode in ("train", "eval"):
+            ref = refload.load(script)
+            torch.manual_seed(0)
+            net = getattr(ref, factory)()
+            if mode == "eval":
+                randomize_running_stats(net)
+                net.eval()
+            sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+            x, g = family_inputs(11, 2, 128)
+            out = net(x)
+            tgts = [torch.rand(o.shape, generator=g) for o in out]
+            losses = [torch.nn.functional.mse_loss(o, t) for o, t in zip(out, tgts)]
+            sum(losses).backward()
+            keys = list(sd0.keys())
+            named = list(net.named_parameters())
+            arrays = {f"out{i}": o.detach().numpy() for i, o in enumerate(out)}
+            # yardstick (SURVEY Q13): the reference's OWN fp32-vs-fp64 divergence on this step -- what the rounding
+            # noise of a correct implementation amounts to after the network amplified it
+            torch.manual_seed(0)
+            net64 = getattr(ref, factory)()
+            net64.load_state_dict(sd0)
+            net64 = net64.double()
+            if mode == "eval":
+                net64.eval()
+            out64 = net64(x.double())
+            sum(torch.nn.functional.mse_loss(o, t.double()) for o, t in zip(out64, tgts)).backward()
+            relf = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))  # noqa: E731
+            out_noise = np.array([relf(a.detach(), b.detach()) for a, b in zip(out, out64)])
+            grad_noise = np.array([relf(p.grad, q.grad) if p.grad is not None else 0.0
+                                   for (_, p), (_, q) in zip(named, net64.named_parameters())])
+            # second yardstick: the reference's own divergence when IT computes in bf16 (torch.autocast on CPU)
+            torch.manual_seed(0)
+            net16 = getattr(ref, factory)()
+            net16.load_state_dict(sd0)
+            if mode == "eval":
+                net16.eval()
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                out16 = net16(x)
+            sum(torch.nn.functional.mse_loss(o.float(), t) for o, t in zip(out16, tgts)).backward()
+            out_noise16 = np.array([relf(a.detach().float(), b.detach()) for a, b in zip(out16, out64)])
+            grad_noise16 = np.array([relf(p.grad, q.grad) if p.grad is not None else 0.0
+                                     for (_, p), (_, q) in zip(net16.named_parameters(), net64.named_parameters())])
+            arrays["out_noise_bf16"], arrays["grad_noise_bf16"] = out_noise16, grad_noise16
+            np.savez_compressed(
+                os.path.join(GOLDEN, f"family_{script}_{mode}.npz"), seed=0, input_seed=11, B=2, S=128,
+                n_out=len(out), keys=np.array(keys), param_names=np.array([n for n, _ in named]),
+                state_digest=np.stack([digest(sd0[k].float()) for k in keys]),
+                losses=np.array([l.item() for l in losses], dtype=np.float64),
+                grad_is_none=np.array([p.grad is None for _, p in named]),
+                grad_digest=np.stack([digest(p.grad) if p.grad is not None else np.zeros(SAMPLE + 2)
+                                      for _, p in named]),
+                grad_norm=np.array([p.grad.double().norm().item() if p.grad is not None else 0.0 for _, p in named]),
+                after_digest=np.stack([digest(net.state_dict()[k].float()) for k in keys]),
+                out_noise_fp64=out_noise, grad_noise_fp64=grad_noise, **arrays)
+
+
 def main():
     if not refload.available():
         raise SystemExit("reference tree not found; goldens can only be generated where /root/reference exists")
@@ -177,6 +265,7 @@ def main():
     golden_model_c1()
     golden_targets()
     golden_pckh()
+    golden_families()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

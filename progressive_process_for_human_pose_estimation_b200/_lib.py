@@ -62,7 +62,7 @@ SIGNATURES = {
     "hg_unpack_conv_wgrad": [C.POINTER(HgConvDesc), _P, _P, _I, _P],
     "hg_bn_stats": [C.POINTER(HgBnDesc), _P, _P, _P],
     "hg_bn_apply": [C.POINTER(HgBnDesc), _P, _P, _P, _P, _P, _P, _P, _P],
-    "hg_bn_bwd_reduce": [C.POINTER(HgBnDesc), _P, _P, _P, _P, _P, _P, _P],
+    "hg_bn_bwd_reduce": [C.POINTER(HgBnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_bn_bwd_apply": [C.POINTER(HgBnDesc)] + [_P] * 14,
     "hg_bn_update_running": [_P, _P, _I, _P],
     "hg_maxpool2_fwd": [_I, _P, _I, _I, _I, _I, _P, _P],

@@ -427,12 +427,14 @@ int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const floa
 }
 
 int hg_bn_bwd_reduce(const HgBnDesc* d, const void* da, const void* x, const float* stats, const float* gamma,
-                     const float* beta, float* red, void* stream) {
+                     const float* beta, const float* running_mean, const float* running_var, float* red,
+                     void* stream) {
   int rc = check_bn(d);
   if (rc) return rc;
-  HG_REQUIRE(da && x && stats && gamma && beta && red, "hg_bn_bwd_reduce: NULL pointer");
-  HG_REQUIRE(!d->use_running, "hg_bn_bwd_reduce: not needed in eval mode");
-  BnArgs a = make_args(d, stats, gamma, beta, nullptr, nullptr);
+  HG_REQUIRE(da && x && gamma && beta && red, "hg_bn_bwd_reduce: NULL pointer");
+  HG_REQUIRE(d->use_running ? (running_mean && running_var) : (stats != nullptr),
+             "hg_bn_bwd_reduce: statistics missing for the selected mode");
+  BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
   const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3));
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;

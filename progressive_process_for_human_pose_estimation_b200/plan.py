@@ -281,6 +281,11 @@ class Plan:
         self._pending_writes.append(i)
         return self.grad_views[i]
 
+    def _gslot_peek(self, p):
+        """True when parameter p receives a gradient (without registering a write)."""
+        i = self.param_index.get(id(p))
+        return i is not None and p.requires_grad
+
     def _emit(self, lst, name, *args, keep=()):
         c = _Call(name, args, keep)
         if lst is self.bwd_calls and self._pending_writes:
@@ -335,12 +340,16 @@ class Plan:
         self._shadow = {}
         ops = b.ops
         # ---- parameters: flat gradient arena in named_parameters() order --------------------------
+        # every slot starts on a 16-byte boundary: the wgrad kernel reduces straight into the slots of un-padded
+        # 1x1 weights with red.global.add.v4.f32
         sizes = [p.numel() for _, p in self.params]
-        self.grad_arena = torch.zeros(max(1, sum(sizes)), device=dev, dtype=torch.float32)
-        self.grad_views, off = [], 0
-        for (_, p), n in zip(self.params, sizes):
-            self.grad_views.append(self.grad_arena[off:off + n].view(p.shape))
-            off += n
+        self.grad_offsets, off = [], 0
+        for n in sizes:
+            self.grad_offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.grad_arena = torch.zeros(max(4, off), device=dev, dtype=torch.float32)
+        self.grad_views = [self.grad_arena[o:o + n].view(p.shape)
+                           for (_, p), n, o in zip(self.params, sizes, self.grad_offsets)]
         self.param_used = [False] * len(self.params)
 
         # ---- convolutions: packed operands, packed gradient accumulators -------------------------
@@ -494,6 +503,8 @@ class Plan:
                            L.ptr(bn.running_var) if bn.running_var is not None else None, L.ptr(out.buf), st)
                 if self.training and bn.track_running_stats:
                     running.setdefault(id(bn), (bn, []))[1].append((x.stats, float(x.M)))
+                if out.needs_stats:  # BN output feeding another BN directly (hourglass_compare.py:549-553)
+                    self._stats_call(f, out)
             elif k == "pool":
                 x, out = op.ins[0], op.out
                 self._emit(f, "hg_maxpool2_fwd", self.hdt, L.ptr(x.buf), x.N, x.H, x.W, x.C, L.ptr(out.buf), st)
@@ -612,8 +623,11 @@ class Plan:
                 red = op.attrs["red"]
                 gam, bet = L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias))
                 stats = L.ptr(x.stats) if x.stats is not None else None
-                if not d.use_running:
-                    self._emit(g, "hg_bn_bwd_reduce", C.byref(d), L.ptr(G), L.ptr(x.buf), stats, gam, bet, L.ptr(red), st)
+                rmean = L.ptr(bn.running_mean) if bn.running_mean is not None else None
+                rvar = L.ptr(bn.running_var) if bn.running_var is not None else None
+                if not d.use_running or self._gslot_peek(bn.weight) or self._gslot_peek(bn.bias):
+                    self._emit(g, "hg_bn_bwd_reduce", C.byref(d), L.ptr(G), L.ptr(x.buf), stats, gam, bet, rmean, rvar,
+                               L.ptr(red), st)
                 colsum = None
                 prod = x.producer
                 if (prod is not None and prod.kind == "conv" and len(x.consumers) == 1 and prod.ins[1] is None
@@ -720,19 +734,17 @@ class Plan:
                 cuts.append(ready[i] + 1)
                 qi += 1
         bounds = sorted(set(c for c in cuts if 0 < c < len(g))) + [len(g)]
-        offs, o = [], 0
-        for n in sizes:
-            offs.append(o)
-            o += n
+        offs = self.grad_offsets
         out, first = [], 0
         for end in bounds:
             ranges = []
             for i in range(len(sizes)):
                 if first <= ready[i] < end or (first == 0 and ready[i] < 0):
+                    hi = offs[i] + (sizes[i] + 3) // 4 * 4  # slots are padded to 16 B; the padding stays zero
                     if ranges and ranges[-1][1] == offs[i]:
-                        ranges[-1][1] = offs[i] + sizes[i]
+                        ranges[-1][1] = hi
                     else:
-                        ranges.append([offs[i], offs[i] + sizes[i]])
+                        ranges.append([offs[i], hi])
             out.append((first, end, [tuple(r) for r in ranges]))
             first = end
         self.bwd_segments = out
@@ -873,15 +885,13 @@ class Plan:
             self.reducer.wait()
         grads = []
         flat = self.grad_arena.clone()
-        off = 0
         for i, (_, p) in enumerate(self.params):
-            n = p.numel()
+            n, off = p.numel(), self.grad_offsets[i]
             if self.param_used[i]:
                 gp = flat[off:off + n].view(p.shape)
                 grads.append(gp if p.dtype == torch.float32 else gp.to(p.dtype))
             else:
                 grads.append(None)
-            off += n
         gin = self.gin_static.clone() if self.gin_static is not None else None
         return gin, grads
 

@@ -1,0 +1,213 @@
+"""The other model families of the reference (multi-head, skeleton+keypoint, ASPP-declared, no-max-pool / Q4 block,
+un-shared U-family) against golden vectors produced by executing the REFERENCE classes themselves
+(oracle/make_golden.py:golden_families -> tests/golden/family_<script>_<mode>.npz: one seeded fp32 step at B=2,
+128x128, forward + per-output MSE + backward).
+
+Two variants per family:
+  * `eval`  -- seeded running statistics: well conditioned (the reference's own fp32-vs-fp64 divergence is ~3e-7 on
+               outputs, ~1e-6 on gradients), so forward AND backward are checked tightly: this is the parity test of
+               the plan lowering (virtual cat, folded limb mix, strided blocks, nearest up-sampling, shared weights);
+  * `train` -- batch statistics at random init: the network amplifies rounding (fp32 vs fp64 of the reference itself
+               differs by up to 35 % on the last output of the U-family), so errors are bounded by a multiple of the
+               fp64 yardstick stored in the fixture; BN bookkeeping (num_batches_tracked, running stats) is exact.
+
+CPU part: the drop-in builds the same state_dict (keys, shapes, seeded values) as the reference.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PKG = "progressive_process_for_human_pose_estimation_b200"
+SAMPLE = 24
+
+# (mirror module, factory, fixture name)
+FAMILIES = [
+    ("try_different_stack", "creatModel", "try_different_stack"),
+    ("try_different_stack_without_skeleton", "creatModel", "try_different_stack_without_skeleton"),
+    ("try_with_aspp", "creatModel", "try_with_aspp"),
+    ("try_with_aspp_remove_max_pool", "creatModel", "try_with_aspp_remove_max_pool"),
+    ("try_skeleton_and_keypoints", "creatModel", "try_skeleton_and_keypoints"),
+    ("hourglass_compare", "creatModel", "hourglass_compare"),
+    ("performance_compare", "creatModel_hourglass", "hourglass_compare"),  # same network as hourglass_compare
+]
+IDS = [f[0] for f in FAMILIES]
+
+
+def digest(t):
+    f = t.detach().cpu().double().reshape(-1)  # summed on the CPU, like the generator
+    idx = torch.linspace(0, f.numel() - 1, SAMPLE).long()
+    return np.concatenate([[f.sum().item(), f.abs().sum().item()], f[idx].numpy()])
+
+
+def randomize_running_stats(net, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+
+
+def build(script, factory, mode="train"):
+    mod = importlib.import_module(f"{PKG}.{script}")
+    torch.manual_seed(0)
+    net = getattr(mod, factory)()
+    if mode == "eval":
+        randomize_running_stats(net)
+        net.eval()
+    return net
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def load(fixture, mode):
+    return np.load(os.path.join(GOLDEN, f"family_{fixture}_{mode}.npz"))
+
+
+def run_step(net, g):
+    gen = torch.Generator().manual_seed(int(g["input_seed"]))
+    x = torch.randn(int(g["B"]), 3, int(g["S"]), int(g["S"]), generator=gen)
+    out = net(x.cuda())
+    tgts = [torch.rand(o.shape, generator=gen) for o in out]
+    losses = [torch.nn.functional.mse_loss(o, t.cuda()) for o, t in zip(out, tgts)]
+    sum(losses).backward()
+    return out, losses
+
+
+@pytest.mark.parametrize("script,factory,fixture", FAMILIES, ids=IDS)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_family_state_dict_matches_reference(script, factory, fixture, mode):
+    g = load(fixture, mode)
+    sd = build(script, factory, mode).state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    for i, k in enumerate(sd):
+        np.testing.assert_array_equal(digest(sd[k].float()), g["state_digest"][i], err_msg=k)
+
+
+def _check_grads(net, g, floor, mult, vacuous=0.25, noise_key="grad_noise_fp64"):
+    names = [str(n) for n in g["param_names"]]
+    params = dict(net.named_parameters())
+    assert list(params.keys()) == names
+    gnorm = g["grad_norm"]
+    small = 1e-4 * np.median(gnorm[gnorm > 0])
+    checked = 0
+    for i, n in enumerate(names):
+        p = params[n]
+        if g["grad_is_none"][i]:
+            assert p.grad is None or p.grad.abs().max().item() == 0, n
+            continue
+        assert p.grad is not None, n
+        noise = float(g[noise_key][i])
+        if gnorm[i] < small or noise > vacuous:
+            continue  # analytically-zero gradients (conv biases that only feed BatchNorms) / chaos-dominated
+        d = digest(p.grad)
+        tol = max(floor, mult * noise)
+        assert abs(d[1] - g["grad_digest"][i][1]) <= tol * g["grad_digest"][i][1], (n, tol)
+        err = rel(d[2:], g["grad_digest"][i][2:])
+        assert err <= 2 * tol, (n, err, tol)
+        checked += 1
+    return checked
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script,factory,fixture", FAMILIES, ids=IDS)
+def test_family_fp32_eval_step_tight(script, factory, fixture):
+    """Well-conditioned variant: fp32 CUDA-core path within 5e-5 on every output and 2e-3 on sampled gradients."""
+    import progressive_process_for_human_pose_estimation_b200 as hg
+
+    g = load(fixture, "eval")
+    hg.set_compute_dtype(torch.float32)
+    try:
+        net = build(script, factory, "eval").cuda()
+        out, losses = run_step(net, g)
+        assert isinstance(out, list) and len(out) == int(g["n_out"])
+        for i, o in enumerate(out):
+            ref = g[f"out{i}"]
+            assert tuple(o.shape) == ref.shape
+            err = rel(o.detach().cpu().numpy(), ref)
+            assert err <= 5e-5, (i, err)
+            assert abs(losses[i].item() - g["losses"][i]) <= 1e-5 * abs(g["losses"][i])
+        assert _check_grads(net, g, 2e-3, 10) > 20
+        sd = net.state_dict()
+        for i, k in enumerate(str(k) for k in g["keys"]):  # eval never touches the buffers
+            np.testing.assert_array_equal(digest(sd[k].float()), g["state_digest"][i], err_msg=k)
+    finally:
+        hg.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script,factory,fixture", FAMILIES, ids=IDS)
+def test_family_bf16_eval_step(script, factory, fixture):
+    """Tensor-core path on the well-conditioned variant: rtol 2e-2 (north_star) on every output; gradients within
+    twice the divergence the reference ITSELF shows when it computes in bf16 (torch.autocast on CPU, stored in the
+    fixture: median 1-2 %, 18-23 % on the stem weight whose gradient is a heavily cancelling sum)."""
+    import progressive_process_for_human_pose_estimation_b200 as hg
+
+    g = load(fixture, "eval")
+    hg.set_compute_dtype(torch.bfloat16)
+    net = build(script, factory, "eval").cuda()
+    out, losses = run_step(net, g)
+    for i, o in enumerate(out):
+        err = rel(o.detach().cpu().numpy(), g[f"out{i}"])
+        assert err <= max(2e-2, 2 * float(g["out_noise_bf16"][i])), (i, err)
+        assert abs(losses[i].item() - g["losses"][i]) <= 2e-2 * abs(g["losses"][i])
+    assert _check_grads(net, g, 4e-2, 2, noise_key="grad_noise_bf16") > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script,factory,fixture", FAMILIES, ids=IDS)
+def test_family_fp32_train_step_vs_yardstick(script, factory, fixture):
+    import progressive_process_for_human_pose_estimation_b200 as hg
+
+    g = load(fixture, "train")
+    hg.set_compute_dtype(torch.float32)
+    try:
+        net = build(script, factory).cuda()
+        out, losses = run_step(net, g)
+        for i, o in enumerate(out):
+            err = rel(o.detach().cpu().numpy(), g[f"out{i}"])
+            tol = max(1e-4, 10 * float(g["out_noise_fp64"][i]))
+            if tol < 0.5:
+                assert err <= tol, (i, err, tol)
+            assert abs(losses[i].item() - g["losses"][i]) <= max(1e-4, tol) * abs(g["losses"][i])
+        _check_grads(net, g, 2e-2, 4)
+        sd = net.state_dict()
+        for i, k in enumerate(str(k) for k in g["keys"]):
+            if "num_batches_tracked" in k:
+                assert digest(sd[k].float())[2] == g["after_digest"][i][2], k
+            elif "running" in k:  # a shared BN is updated 6-8 x nStack times: late call sites carry the amplified noise
+                a, b = digest(sd[k].float())[2:], g["after_digest"][i][2:]
+                rtol = max(2e-3, 10 * float(g["out_noise_fp64"].max()))
+                assert np.abs(a - b).max() <= rtol * np.abs(b).max() + 1e-5, k
+    finally:
+        hg.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script,factory,fixture", FAMILIES, ids=IDS)
+def test_family_bf16_train_step_runs_and_replays(script, factory, fixture):
+    """bf16 train mode at random init is chaos-dominated (Q13): finite results, losses near the reference's, the
+    first output within the band the reference's own bf16 autocast run shows; eager and CUDA-graph executions."""
+    import progressive_process_for_human_pose_estimation_b200 as hg
+
+    g = load(fixture, "train")
+    hg.set_compute_dtype(torch.bfloat16)
+    net = build(script, factory).cuda()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    for it in range(3):  # eager, graph forward, graph forward + backward
+        net.load_state_dict(sd0)
+        net.zero_grad(set_to_none=True)
+        out, losses = run_step(net, g)
+        for i, o in enumerate(out):
+            assert torch.isfinite(o).all()
+            assert abs(losses[i].item() - g["losses"][i]) <= 0.1 * abs(g["losses"][i]), (it, i)
+        err0 = rel(out[0].detach().cpu().numpy(), g["out0"])
+        assert err0 <= max(0.3, 2 * float(g["out_noise_bf16"][0])), err0  # reference's own bf16 run: 0.13 - 0.44
+        for n, p in net.named_parameters():
+            assert p.grad is None or torch.isfinite(p.grad).all(), n

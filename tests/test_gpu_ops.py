@@ -183,7 +183,7 @@ def test_batchnorm_train_fwd_bwd(shape, dtype, relu):
     daq = nhwc(da, dtype)
     ref.backward(nchw(daq, Cc))
     red = torch.zeros(2 * Cp, device=dev)
-    L.call("hg_bn_bwd_reduce", C.byref(d), L.ptr(daq), L.ptr(xq), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(red), st)
+    L.call("hg_bn_bwd_reduce", C.byref(d), L.ptr(daq), L.ptr(xq), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, L.ptr(red), st)
     addq = nhwc(torch.randn(N, Cc, H, W, device=dev), dtype)
     dx = torch.empty_like(xq)
     dgamma, dbeta, colsum = (torch.zeros(Cc, device=dev) for _ in range(3))
@@ -194,6 +194,36 @@ def test_batchnorm_train_fwd_bwd(shape, dtype, relu):
     close(dgamma, g_ref.grad, 1e-3 if dtype == torch.float32 else 2e-2, "bn dgamma")
     close(dbeta, b_ref.grad, 1e-3 if dtype == torch.float32 else 2e-2, "bn dbeta")
     assert colsum.abs().max().item() <= 1e-2 * (xr.grad.abs().sum((0, 2, 3)).max().item() + 1e-6), "sum(dx) ~ 0"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_batchnorm_eval_backward(dtype):
+    """eval(): running statistics are constants -> dx = gamma*invstd*g, dgamma = sum g*xhat(running), dbeta = sum g."""
+    torch.manual_seed(1)
+    dev = "cuda"
+    N, Cc, H, W = 3, 128, 8, 8
+    bn = torch.nn.BatchNorm2d(Cc).to(dev).eval()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.3)
+    x = torch.randn(N, Cc, H, W, device=dev)
+    da = torch.randn(N, Cc, H, W, device=dev)
+    xq, daq = nhwc(x, dtype), nhwc(da, dtype)
+    xr = nchw(xq, Cc).requires_grad_(True)
+    F.relu(bn(xr)).backward(nchw(daq, Cc))
+    st = L.stream_ptr()
+    d = L.HgBnDesc(N * H * W, Cc, L.hg_dtype(dtype), 1e-5, 1, 1)
+    red = torch.zeros(2 * Cc, device=dev)
+    dx = torch.empty_like(xq)
+    dg, db = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev)
+    L.call("hg_bn_bwd_reduce", C.byref(d), L.ptr(daq), L.ptr(xq), None, L.ptr(bn.weight), L.ptr(bn.bias),
+           L.ptr(bn.running_mean), L.ptr(bn.running_var), L.ptr(red), st)
+    L.call("hg_bn_bwd_apply", C.byref(d), L.ptr(daq), L.ptr(xq), None, L.ptr(bn.weight), L.ptr(bn.bias),
+           L.ptr(bn.running_mean), L.ptr(bn.running_var), L.ptr(red), None, L.ptr(dx), L.ptr(dg), L.ptr(db), None, st)
+    close(nchw(dx, Cc), xr.grad, tol(dtype), "bn eval dx")
+    close(dg, bn.weight.grad, 1e-4, "bn eval dgamma")
+    close(db, bn.bias.grad, 1e-4, "bn eval dbeta")
 
 
 def test_batchnorm_eval_and_running_update():

@@ -1,0 +1,99 @@
+"""In-graph latency of chains of DEPENDENT small kernels (the low-resolution hourglass levels are latency-bound:
+SURVEY 2.4).  Captures N back-to-back calls of one entry point into a CUDA graph and reports us per call."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from progressive_process_for_human_pose_estimation_b200 import _lib as L  # noqa: E402
+
+dev = torch.device("cuda")
+DT = torch.bfloat16
+
+
+def graph_time(body, reps=5):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        body()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            body()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(reps):
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def conv_chain(B, hw, cin, cout, k, n=100):
+    d = L.HgConvDesc(B, hw, hw, cin, cout, k, k, 1, k // 2, 1, L.HG_BF16)
+    x = torch.randn(B, hw, hw, cin, device=dev).to(DT)
+    y = torch.zeros(B, hw, hw, cout, device=dev, dtype=DT)
+    w = torch.randn(k * k, cout, cin, device=dev).to(DT) * 0.05
+    bias = torch.zeros(cout, device=dev)
+    stats = torch.zeros(2 * cout, device=dev)
+    # ping-pong so that every call depends on the previous one when cin == cout
+    bufs = [x, y] if cin == cout else None
+
+    def body():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for i in range(n):
+            if bufs:
+                a, b = bufs[i % 2], bufs[(i + 1) % 2]
+            else:
+                a, b = x, y
+            L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(a), L.ptr(w), L.ptr(bias), None, L.ptr(b), L.ptr(stats), None, st)
+
+    return graph_time(body) / n * 1e3
+
+
+def bn_chain(B, hw, c, n=100):
+    d = L.HgBnDesc(B * hw * hw, c, L.HG_BF16, 1e-5, 1, 0)
+    x = torch.randn(B, hw, hw, c, device=dev).to(DT)
+    y = torch.zeros_like(x)
+    stats = torch.zeros(2 * c, device=dev)
+    stats[:c] = 0.0
+    stats[c:] = float(B * hw * hw)
+    gam, bet = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+
+    def body():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for i in range(n):
+            a, b = (x, y) if i % 2 == 0 else (y, x)
+            L.call("hg_bn_apply", C.byref(d), L.ptr(a), L.ptr(stats), L.ptr(gam), L.ptr(bet), None, None, L.ptr(b), st)
+
+    return graph_time(body) / n * 1e3
+
+
+def empty_chain(n=200):
+    t = torch.zeros(64, device=dev, dtype=DT)
+
+    def body():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(n):
+            L.call("hg_add", L.HG_BF16, L.ptr(t), L.ptr(t), L.ptr(t), C.c_longlong(64), st)
+
+    return graph_time(body) / n * 1e3
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    print(f"trivial kernel chain (hg_add 64 elems): {empty_chain():.2f} us/call")
+    for hw in (4, 8, 16, 32, 64):
+        print(f"B=32 @{hw}x{hw}: conv3x3 128->128 {conv_chain(32, hw, 128, 128, 3):7.2f} us | "
+              f"conv1x1 256->128 {conv_chain(32, hw, 256, 128, 1):7.2f} us | "
+              f"conv1x1 128->256 {conv_chain(32, hw, 128, 256, 1):7.2f} us | "
+              f"conv1x1 256->256 {conv_chain(32, hw, 256, 256, 1):7.2f} us | "
+              f"bn_apply C256 {bn_chain(32, hw, 256):7.2f} us | bn_apply C128 {bn_chain(32, hw, 128):7.2f} us")

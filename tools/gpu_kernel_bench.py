@@ -83,7 +83,7 @@ def bn_case(H, Cc):
                                 None, None, L.ptr(ys[i % nrot]), st))
     out["apply"] = (t, 0, 2 * eb / t / 1e3)
     t = timeit(lambda i: L.call("hg_bn_bwd_reduce", C.byref(d), L.ptr(gs[i % nrot]), L.ptr(xs[i % nrot]), L.ptr(stats),
-                                L.ptr(gamma), L.ptr(beta), L.ptr(red), st))
+                                L.ptr(gamma), L.ptr(beta), None, None, L.ptr(red), st))
     out["bwd_reduce"] = (t, 0, 2 * eb / t / 1e3)
     t = timeit(lambda i: L.call("hg_bn_bwd_apply", C.byref(d), L.ptr(gs[i % nrot]), L.ptr(xs[i % nrot]), L.ptr(stats),
                                 L.ptr(gamma), L.ptr(beta), None, None, L.ptr(red), None, L.ptr(ys[i % nrot]), L.ptr(dg),

@@ -195,6 +195,28 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
 
+    # ---- where the step goes: forward / loss+backward / optimizer, CUDA events, same stream -------------
+    phases = None
+    if rank == 0:
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(3)]
+        for e in ev:
+            e[0].record()
+            out = model(x)
+            e[1].record()
+            loss = mse[0](out[0], y)
+            for k in range(1, NSTACK):
+                loss = loss + mse[k](out[k], y)
+            opt.zero_grad()
+            loss.backward()
+            e[2].record()
+            opt.step()
+            e[3].record()
+        torch.cuda.synchronize()
+        med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731
+        phases = {"forward_ms": round(med([e[0].elapsed_time(e[1]) for e in ev]), 3),
+                  "loss_backward_ms": round(med([e[1].elapsed_time(e[2]) for e in ev]), 3),
+                  "optimizer_ms": round(med([e[2].elapsed_time(e[3]) for e in ev]), 3)}
+
     # ---- end to end: pinned host batch -> device every step, loss read back every step ---------------
     xh = x_cpu.pin_memory()
     yh = y.cpu().pin_memory()
@@ -293,6 +315,7 @@ def run_ours(args):
             "frac_of_bf16_sustained_peak": round(value / world * TRAIN_GFLOP_PER_IMG / 1e3
                                                  / float(measured_peaks()[0]["bf16_tflops_sustained"]), 4),
             "loss_after_warmup": loss0,
+            "phases": phases,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -90,6 +90,41 @@ HG_API int hg_conv_wgrad(const HgConvDesc* d, const void* x, const void* dy, flo
 HG_API int hg_unpack_conv_wgrad(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int accumulate,
                          void* stream);
 
+/* ---- BatchNorm folded into the convolutions around it (tensor-core path only) -----------------------------
+ * The reference runs BN -> ReLU -> conv as three library kernels (try_with_torch.py:196-205).  Here the
+ * normalised activation a = [relu](gamma*(x-mean)*invstd + beta) is never written to HBM: the convolution reads the
+ * RAW tensor x and applies the transform to its operand tiles in shared memory (fprop, wgrad), and the data-gradient
+ * kernel applies the ReLU mask and accumulates the two BatchNorm-backward sums in its epilogue.
+ * HgBnFold describes that BatchNorm call site; `stats` = {sum, sum of squares} of x as accumulated by the kernel
+ * that produced x (training mode), or running statistics (eval mode, use_running = 1). */
+typedef struct HgBnFold {
+  const float* stats;
+  const float* gamma;
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  float eps;
+  int32_t relu;
+  int32_t use_running;
+  int32_t pad_;
+} HgBnFold;
+
+/* 1 when the tensor-core kernels take this geometry (stride 1, "same" padding, power-of-two maps, <= 256 padded
+ * channels, bf16); only then may the *_bn entry points be used. */
+HG_API int hg_conv_tc_eligible(const HgConvDesc* d);
+/* y = conv([relu](bn(x_raw))) + bias [+ residual]; stats / out_nchw as in hg_conv_fprop_ex. */
+HG_API int hg_conv_fprop_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* w_fprop,
+                            const float* bias, const void* residual, void* y, float* stats, float* out_nchw,
+                            void* stream);
+/* dw_packed += dy (x) [relu](bn(x_raw)); dbias += sum(dy). */
+HG_API int hg_conv_wgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* dy,
+                            float* dw_packed, float* dbias, void* stream);
+/* g = conv_transpose(dy, w) * [bn(x_raw) > 0]  (the mask only when bn->relu), stored in the layout of x_raw;
+ * red[0..Cp) += sum g, red[Cp..2Cp) += sum g * xhat  (caller zeroes red).  hg_bn_bwd_apply(da = g, ...) finishes
+ * the BatchNorm backward. */
+HG_API int hg_conv_dgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* dy, const void* w_dgrad,
+                            const void* x_raw, void* g, float* red, void* stream);
+
 /* Slices of a wider weight: the convolution over torch.cat([a, b, c], 1) is evaluated as three chained
  * convolutions (residual = previous partial sum) over the input-channel slices [cin_offset, cin_offset + d->Cin)
  * of the [Cout, cin_total, R, S] weight, so the concatenated tensor never exists

@@ -26,6 +26,12 @@ class HgBnDesc(C.Structure):
                 ("relu", C.c_int32), ("use_running", C.c_int32)]
 
 
+class HgBnFold(C.Structure):
+    _fields_ = [("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("eps", C.c_float), ("relu", C.c_int32), ("use_running", C.c_int32),
+                ("pad_", C.c_int32)]
+
+
 class HgBnRunningSite(C.Structure):
     _fields_ = [("stats", C.c_void_p), ("count", C.c_float), ("pad_", C.c_int32)]
 
@@ -59,6 +65,10 @@ SIGNATURES = {
     "hg_conv_fprop_ex": [C.POINTER(HgConvDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_conv_dgrad": [C.POINTER(HgConvDesc), _P, _P, _P, _P, _P],
     "hg_conv_wgrad": [C.POINTER(HgConvDesc), _P, _P, _P, _P, _P],
+    "hg_conv_tc_eligible": [C.POINTER(HgConvDesc)],
+    "hg_conv_fprop_bn": [C.POINTER(HgConvDesc), C.POINTER(HgBnFold), _P, _P, _P, _P, _P, _P, _P, _P],
+    "hg_conv_wgrad_bn": [C.POINTER(HgConvDesc), C.POINTER(HgBnFold), _P, _P, _P, _P, _P],
+    "hg_conv_dgrad_bn": [C.POINTER(HgConvDesc), C.POINTER(HgBnFold), _P, _P, _P, _P, _P, _P],
     "hg_unpack_conv_wgrad": [C.POINTER(HgConvDesc), _P, _P, _I, _P],
     "hg_bn_stats": [C.POINTER(HgBnDesc), _P, _P, _P],
     "hg_bn_apply": [C.POINTER(HgBnDesc), _P, _P, _P, _P, _P, _P, _P, _P],

@@ -59,10 +59,24 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
 }
 
 // implemented in conv_tc.cu / conv_ref.cu
+struct BnFoldDev {
+  const float* stats;
+  const float* gamma;
+  const float* beta;
+  const float* rmean;
+  const float* rvar;
+  float count;
+  float eps;
+  int relu;
+  int use_running;
+  int C, Cp;
+};
+BnFoldDev make_fold(const HgBnFold* f, int C, long long count);
 int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, int dil, int sign, const void* act,
                    const void* wpk, const float* bias, const void* res, void* out, float* stats, float* out_nchw,
-                   int c_real, cudaStream_t st);
-int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, cudaStream_t st);
+                   int c_real, int mode, const BnFoldDev* fold, cudaStream_t st);
+int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
+                    const BnFoldDev* fold, cudaStream_t st);
 template <typename T>
 int conv_ref_fprop(const HgConvDesc*, const void*, const void*, const float*, const void*, void*, float*,
                    cudaStream_t);
@@ -155,7 +169,7 @@ int hg_conv_fprop_ex(const HgConvDesc* d, const void* x, const void* w_fprop, co
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_eligible(d)) {
     return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cin), pad64(d->Cout), d->R, d->S, d->pad, d->dil, +1, x,
-                          w_fprop, bias, residual, y, stats, out_nchw, d->Cout, st);
+                          w_fprop, bias, residual, y, stats, out_nchw, d->Cout, 0, nullptr, st);
   }
   rc = d->dtype == HG_BF16 ? conv_ref_fprop<__nv_bfloat16>(d, x, w_fprop, bias, residual, y, out_nchw, st)
                            : conv_ref_fprop<float>(d, x, w_fprop, bias, residual, y, out_nchw, st);
@@ -181,10 +195,55 @@ int hg_conv_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_eligible(d)) {
     return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cout), pad64(d->Cin), d->R, d->S, d->pad, d->dil, -1, dy,
-                          w_dgrad, nullptr, addend, dx, nullptr, nullptr, 0, st);
+                          w_dgrad, nullptr, addend, dx, nullptr, nullptr, 0, 0, nullptr, st);
   }
   return d->dtype == HG_BF16 ? conv_ref_dgrad<__nv_bfloat16>(d, dy, w_dgrad, addend, dx, st)
                              : conv_ref_dgrad<float>(d, dy, w_dgrad, addend, dx, st);
+}
+
+static int check_fold(const HgConvDesc* d, const HgBnFold* bn, const char* who) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HG_REQUIRE(bn != nullptr && bn->gamma && bn->beta, "%s: HgBnFold / gamma / beta is NULL", who);
+  HG_REQUIRE(bn->use_running ? (bn->running_mean && bn->running_var) : (bn->stats != nullptr),
+             "%s: statistics missing for the selected BatchNorm mode", who);
+  if (!tc_eligible(d)) {
+    set_error("%s: geometry not taken by the tensor-core kernels (hg_conv_tc_eligible() == 0); run hg_bn_apply and "
+              "the plain convolution instead", who);
+    return HG_ERR_UNSUPPORTED;
+  }
+  return HG_OK;
+}
+
+int hg_conv_tc_eligible(const HgConvDesc* d) { return (d && check_desc(d) == HG_OK && tc_eligible(d)) ? 1 : 0; }
+
+int hg_conv_fprop_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* w_fprop,
+                     const float* bias, const void* residual, void* y, float* stats, float* out_nchw, void* stream) {
+  int rc = check_fold(d, bn, "hg_conv_fprop_bn");
+  if (rc) return rc;
+  HG_REQUIRE(x_raw && w_fprop && y, "hg_conv_fprop_bn: x_raw, w_fprop and y must be non-NULL");
+  const BnFoldDev f = make_fold(bn, d->Cin, (long long)d->N * d->H * d->W);
+  return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cin), pad64(d->Cout), d->R, d->S, d->pad, d->dil, +1, x_raw,
+                        w_fprop, bias, residual, y, stats, out_nchw, d->Cout, 1, &f, (cudaStream_t)stream);
+}
+
+int hg_conv_wgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* dy, float* dw_packed,
+                     float* dbias, void* stream) {
+  int rc = check_fold(d, bn, "hg_conv_wgrad_bn");
+  if (rc) return rc;
+  HG_REQUIRE(x_raw && dy, "hg_conv_wgrad_bn: x_raw and dy must be non-NULL");
+  const BnFoldDev f = make_fold(bn, d->Cin, (long long)d->N * d->H * d->W);
+  return conv_wgrad_bf16(d, x_raw, dy, dw_packed, dbias, &f, (cudaStream_t)stream);
+}
+
+int hg_conv_dgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* dy, const void* w_dgrad, const void* x_raw,
+                     void* g, float* red, void* stream) {
+  int rc = check_fold(d, bn, "hg_conv_dgrad_bn");
+  if (rc) return rc;
+  HG_REQUIRE(dy && w_dgrad && x_raw && g && red, "hg_conv_dgrad_bn: NULL pointer");
+  const BnFoldDev f = make_fold(bn, d->Cin, (long long)d->N * d->H * d->W);
+  return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cout), pad64(d->Cin), d->R, d->S, d->pad, d->dil, -1, dy, w_dgrad,
+                        nullptr, x_raw, g, red, nullptr, 0, 2, &f, (cudaStream_t)stream);
 }
 
 int hg_unpack_conv_wgrad_slice(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int cin_total,
@@ -205,7 +264,7 @@ int hg_conv_wgrad(const HgConvDesc* d, const void* x, const void* dy, float* dw_
   if (rc) return rc;
   HG_REQUIRE(x && dy, "hg_conv_wgrad: x and dy must be non-NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (tc_eligible(d)) return conv_wgrad_bf16(d, x, dy, dw_oihw, dbias, st);
+  if (tc_eligible(d)) return conv_wgrad_bf16(d, x, dy, dw_oihw, dbias, nullptr, st);
   return d->dtype == HG_BF16 ? conv_ref_wgrad<__nv_bfloat16>(d, x, dy, dw_oihw, dbias, st)
                              : conv_ref_wgrad<float>(d, x, dy, dw_oihw, dbias, st);
 }

@@ -20,6 +20,73 @@
 
 namespace hg {
 
+// Epilogue / prologue fusion modes of the GEMM kernel.
+//   kPlain : y = conv(x) [+bias][+residual][+stats]                                   (fprop, dgrad)
+//   kFold  : the A operand is a RAW tensor x that a BatchNorm(+ReLU) normalises: every A tile is rewritten in
+//            shared memory as a = [relu](scale_c * x + shift_c) before the tensor core reads it, so the normalised
+//            activation never exists in HBM (fprop of BN -> ReLU -> conv, reference try_with_torch.py:196-205)
+//   kMask  : dgrad whose result is the gradient of a BatchNorm(+ReLU) output: the epilogue applies the ReLU mask
+//            g = da * [bn(x) > 0], stores g and accumulates the two BatchNorm-backward sums (sum g, sum g*xhat)
+enum { kPlain = 0, kFold = 1, kMask = 2 };
+
+// BatchNorm folded into a convolution (device view of HgBnFold)
+struct BnFoldDev {
+  const float* stats;   // {sum, sum of squares}[2*Cp] of the raw tensor (training mode)
+  const float* gamma;
+  const float* beta;
+  const float* rmean;
+  const float* rvar;
+  float count;
+  float eps;
+  int relu;
+  int use_running;
+  int C, Cp;
+};
+
+__device__ __forceinline__ void bn_fold_coeffs(const BnFoldDev& f, int c, float& mean, float& invstd, float& scale,
+                                               float& shift) {
+  if (c < f.C) {
+    float mu, var;
+    if (f.use_running) {
+      mu = f.rmean[c];
+      var = f.rvar[c];
+    } else {
+      mu = f.stats[c] / f.count;
+      var = fmaxf(f.stats[f.Cp + c] / f.count - mu * mu, 0.f);
+    }
+    invstd = rsqrtf(var + f.eps);
+    mean = mu;
+    scale = f.gamma[c] * invstd;
+    shift = f.beta[c] - mu * scale;
+  } else {
+    mean = invstd = scale = shift = 0.f;
+  }
+}
+
+// a = [relu](scale * x + shift) on 8 consecutive channels held in one 16-byte register quad
+__device__ __forceinline__ uint4 bn_relu_chunk(uint4 u, const float (&sc)[8], const float (&sh)[8], bool relu) {
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __bfloat1622float2(h2[e]);
+    f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+    f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+    if (relu) {
+      f.x = fmaxf(f.x, 0.f);
+      f.y = fmaxf(f.y, 0.f);
+    }
+    h2[e] = __floats2bfloat162_rn(f.x, f.y);
+  }
+  return u;
+}
+
+__device__ __forceinline__ void load_coef8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 struct ConvGemmParams {
   int M_total;        // output pixels = N*H*W
   int H, W;           // spatial size (stride-1 "same" convolutions: in == out)
@@ -30,40 +97,58 @@ struct ConvGemmParams {
   int n_total;        // padded Cout (row pitch of bias / stats)
   int c_real;         // real Cout (for the NCHW fp32 side output)
   const float* bias;  // [n_total] or null
-  float* stats;       // [2*n_total] or null
+  float* stats;       // [2*n_total] or null;  kMask: the BatchNorm-backward sums {sum g, sum g*xhat}
   float* out_nchw;    // optional fp32 NCHW copy of the first c_real channels (heatmap heads)
-  int has_res;
+  int has_res;        // kPlain/kFold: residual added;  kMask: tmR is the raw BatchNorm input
   int n_tiles;        // padded Cout / BN
+  BnFoldDev fold;     // kFold: BatchNorm of the INPUT channels;  kMask: BatchNorm of the OUTPUT channels
 };
 
-template <int BN, int STAGES>
+// Shared-memory plan.  ALIAS = the epilogue staging buffers (output tile C; kMask: + the fp32 g*xhat tile Q) reuse the
+// pipeline stages, which are idle once the last MMA has retired: a 3-stage 3x3 kernel then needs ~100 KB and TWO CTAs
+// share an SM (one CTA's epilogue overlaps the other's main loop), a 2-stage 1x1 kernel ~70 KB (three CTAs).  A
+// residual / raw-BatchNorm-input tile that must be in C before the epilogue is then loaded after the main loop;
+// kernels with a residual and a short K keep a dedicated C buffer instead (ALIAS = false) and load it up front.
+template <int BN, int STAGES, int MODE, bool ALIAS>
 struct ConvGemmSmem {
   static constexpr int kABytes = 128 * 128;      // 128 pixels x 64 ch x 2 B
   static constexpr int kBBytes = BN * 128;       // BN out-channels x 64 ch x 2 B
   static constexpr int kCPanels = BN / 64;       // output staging: panels of 128 rows x 64 ch
   static constexpr int kCBytes = kCPanels * 128 * 128;
-  static constexpr int kBarBytes = 2048;
-  static constexpr int kTotal = STAGES * (kABytes + kBBytes) + kCBytes + kBarBytes + 1024 /*align slack*/;
+  static constexpr int kStageBytes = STAGES * (kABytes + kBBytes);
+  static constexpr int kEpiBytes = MODE == kMask ? 3 * kCBytes : kCBytes;
+  static constexpr int kMainBytes = ALIAS ? (kStageBytes > kEpiBytes ? kStageBytes : kEpiBytes)
+                                          : kStageBytes + kEpiBytes;
+  static constexpr int kCOffset = ALIAS ? 0 : kStageBytes;
+  static constexpr int kBarBytes = 256;          // mbarriers + TMEM slot
+  static constexpr int kBiasBytes = BN * 4;
+  static constexpr int kCoefBytes = 2048;        // kFold: scale/shift[256];  kMask: A/B/scale/shift[BN]
+  static constexpr int kTotal = kMainBytes + kBarBytes + kBiasBytes + kCoefBytes + 1024 /*align slack*/;
 };
 
-template <int BN, int STAGES, int MINB>
+template <int BN, int STAGES, int MINB, int MODE, bool ALIAS>
 __global__ void __launch_bounds__(192, MINB)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvGemmParams p) {
-  using L = ConvGemmSmem<BN, STAGES>;
+  using L = ConvGemmSmem<BN, STAGES, MODE, ALIAS>;
+  static_assert(2 * STAGES + 2 + STAGES <= 30, "barrier region too small");
+  static_assert(MODE != kMask || ALIAS, "the mask epilogue stages two tiles: it always aliases the pipeline stages");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array keeps the address space: LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * L::kABytes;
-  uint8_t* sC = sB + STAGES * L::kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + L::kCBytes);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tmem_full = bars + 2 * STAGES;   // accumulator ready
+  uint8_t* sC = smem + L::kCOffset;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kMainBytes);
+  uint64_t* full_bar = bars;                  // [STAGES] TMA landed
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES] MMAs done reading the slot
+  uint64_t* tmem_full = bars + 2 * STAGES;    // accumulator ready
   uint64_t* res_full = bars + 2 * STAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * STAGES + 4);  // [BN] (<= 256 floats = 1 KB - 64 B)
+  uint64_t* ready_bar = bars + 2 * STAGES + 2;  // [STAGES] kFold: A tile rewritten, MMA may read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [BN]
+  float* coef_s = bias_s + BN;                                                                // 512 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,6 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
     }
     mbar_init(tmem_full, 1);
     mbar_init(res_full, 1);
@@ -87,7 +173,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   if (warp >= 2) {
-    for (int c = threadIdx.x - 64; c < BN; c += 128) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
+    const int et = threadIdx.x - 64;
+    for (int c = et; c < BN; c += 128) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
+    if constexpr (MODE == kFold) {
+      // scale / shift of every INPUT channel (<= 256)
+      for (int c = et; c < p.kchunks * 64; c += 128) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
+        coef_s[c] = sc;
+        coef_s[256 + c] = sh;
+      }
+    }
+    if constexpr (MODE == kMask) {
+      for (int c = et; c < BN; c += 128) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, n_off + c, mu, is, sc, sh);
+        coef_s[c] = is;                 // xhat = y * A + B
+        coef_s[BN + c] = -mu * is;
+        coef_s[2 * BN + c] = sc;        // ReLU mask: scale * y + shift > 0 (the forward's own expression)
+        coef_s[3 * BN + c] = sh;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -102,7 +208,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rem = m0 - n0 * hw;
       const int h0 = rem / p.W;
       const int w0 = rem - h0 * p.W;
-      if (p.has_res) {
+      if (!ALIAS && p.has_res) {
         mbar_expect_tx(res_full, L::kCBytes);
         for (int pnl = 0; pnl < L::kCPanels; ++pnl)
           tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
@@ -122,6 +228,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (ALIAS && p.has_res) {
+        // C aliases the pipeline stages: the residual / raw BatchNorm input may only land once every MMA has read them
+        mbar_wait(tmem_full, 0);
+        mbar_expect_tx(res_full, L::kCBytes);
+        for (int pnl = 0; pnl < L::kCPanels; ++pnl)
+          tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -129,7 +242,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int kb = 0; kb < num_kb; ++kb) {
       const int st = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full_bar[st], ph);
+      if constexpr (MODE == kFold) mbar_wait(&ready_bar[st], ph);
+      else mbar_wait(&full_bar[st], ph);
       tc_fence_after();
       if (lane == 0) {
         const uint64_t adesc = make_smem_desc(smem_u32(sA + st * L::kABytes), 16, 1024);
@@ -145,16 +259,67 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== transform (kFold) + epilogue (warps 2..5) =====================
     const int sub = warp & 3;           // TMEM sub-partition this warp may read
     const int row = sub * 32 + lane;    // accumulator row == pixel within the tile
     const int et = threadIdx.x - 64;    // 0..127
+    const int m = m0 + row;
+    const bool row_ok = m < p.M_total;
+
+    if constexpr (MODE == kFold) {
+      // Rewrite every A tile in place: a = [relu](scale * x + shift).  Thread = one 16-byte channel chunk (8
+      // channels: its 16 coefficients live in registers) x 8 rows, so the eight shared-memory loads of a tile are
+      // issued back to back.  Rows that fall into the convolution padding (TMA zero fill) or past the end of the
+      // tensor must be zero AFTER the transform.
+      const int jch = et & 7;
+      const int rbase = et >> 3;                 // rows rbase + 16 * i
+      const int swz = (jch ^ (rbase & 7)) << 4;  // (row & 7) == (rbase & 7) for every row of this thread
+      const int hw = p.H * p.W;
+      int hrow[8], wrow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int mm = m0 + rbase + 16 * i;
+        const int rem = mm % hw;
+        hrow[i] = mm < p.M_total ? rem / p.W : -0x40000000;  // out-of-range rows never pass the bounds test
+        wrow[i] = rem % p.W;
+      }
+      const bool relu = p.fold.relu != 0;
+      int kb = 0;
+      for (int r = 0; r < p.taps_r; ++r) {
+        for (int s = 0; s < p.taps_s; ++s) {
+          const int dh = p.sign * (r * p.dil - p.pad);
+          const int dw = p.sign * (s * p.dil - p.pad);
+          uint32_t vmask = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if ((unsigned)(hrow[i] + dh) < (unsigned)p.H && (unsigned)(wrow[i] + dw) < (unsigned)p.W) vmask |= 1u << i;
+          for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
+            const int st = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            float sc[8], sh[8];
+            load_coef8(coef_s + kc * 64 + jch * 8, sc);
+            load_coef8(coef_s + 256 + kc * 64 + jch * 8, sh);
+            uint8_t* base = sA + st * L::kABytes + rbase * 128 + swz;
+            mbar_wait(&full_bar[st], ph);
+            uint4 u[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(base + i * 2048);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              u[i] = (vmask >> i) & 1u ? bn_relu_chunk(u[i], sc, sh, relu) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(base + i * 2048) = u[i];
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            mbar_arrive(&ready_bar[st]);
+          }
+        }
+      }
+    }
+
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     if (p.has_res) mbar_wait(res_full, 0);
     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-    const int m = m0 + row;
-    const bool row_ok = m < p.M_total;
     float* nchw_row = nullptr;
     int plane = 0;
     if (p.out_nchw != nullptr && row_ok) {
@@ -162,6 +327,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n = m / plane;
       nchw_row = p.out_nchw + (size_t)n * p.c_real * plane + (m - n * plane);
     }
+    // kMask: second staging buffer (g * xhat, fp32) right behind C, both inside the idle pipeline stages
+    uint8_t* sQ = sC + L::kCBytes;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       float v[32];
@@ -172,25 +339,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint8_t* rowp = sC + pnl * 16384 + row * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4* cp = reinterpret_cast<uint4*>(rowp + (((chunk0 + q) ^ (row & 7)) << 4));
+        const int swz = ((chunk0 + q) ^ (row & 7)) << 4;
+        uint4* cp = reinterpret_cast<uint4*>(rowp + swz);
         float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[j * 32 + q * 8 + e];
-        if (p.has_res) {
-          uint4 u = *cp;
+        if constexpr (MODE == kMask) {
+          // raw BatchNorm input of these 8 channels -> ReLU mask and xhat = y * A + B
+          const uint4 u = *cp;
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+          float y[8], qq[8], cA[8], cB[8], cS[8], cT[8];
+          const int c0 = j * 32 + q * 8;
+          load_coef8(coef_s + c0, cA);
+          load_coef8(coef_s + BN + c0, cB);
+          load_coef8(coef_s + 2 * BN + c0, cS);
+          load_coef8(coef_s + 3 * BN + c0, cT);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float2 f = __bfloat1622float2(h[e]);
-            o[2 * e] += f.x;
-            o[2 * e + 1] += f.y;
+            const float2 f = __bfloat1622float2(h[e]);
+            y[2 * e] = f.x;
+            y[2 * e + 1] = f.y;
           }
-        }
-        if (nchw_row != nullptr) {
+          const bool relu = p.fold.relu != 0;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int c = n_off + j * 32 + q * 8 + e;
-            if (c < p.c_real) nchw_row[(size_t)c * plane] = o[e];
+            float g = v[q * 8 + e];
+            if (relu && !(fmaf(y[e], cS[e], cT[e]) > 0.f)) g = 0.f;
+            // the sums are taken over the bf16 values bn_bwd_apply will read back
+            g = __bfloat162float(__float2bfloat16_rn(g));
+            o[e] = g;
+            qq[e] = g * fmaf(y[e], cA[e], cB[e]);
+          }
+          // q = g * xhat is staged in fp32: rows of 64 ch x 4 B = 256 B, one panel = 128 rows x 256 B
+          uint8_t* qrow = sQ + pnl * 32768 + row * 256;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int ch4 = ((chunk0 + q) * 2 + hlf);            // 16-byte chunk index within the 256 B row (0..15)
+            float4* qp = reinterpret_cast<float4*>(qrow + ((ch4 ^ (row & 15)) << 4));
+            *qp = make_float4(qq[hlf * 4], qq[hlf * 4 + 1], qq[hlf * 4 + 2], qq[hlf * 4 + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[j * 32 + q * 8 + e];
+          if (p.has_res) {
+            uint4 u = *cp;
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h[e]);
+              o[2 * e] += f.x;
+              o[2 * e + 1] += f.y;
+            }
+          }
+          if (nchw_row != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = n_off + j * 32 + q * 8 + e;
+              if (c < p.c_real) nchw_row[(size_t)c * plane] = o[e];
+            }
           }
         }
         uint4 w;
@@ -208,34 +412,60 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_store_commit();
     }
     if (p.stats != nullptr) {
-      // per-channel sum / sum of squares of the bf16 values just staged: thread = 2 adjacent channels x a slice
-      // of the 128 rows (fixed trip count so the loop unrolls and the LDS latencies overlap)
+      // Per-channel column sums of the values just staged (bf16, exactly what the consumers will read):
+      //   kPlain / kFold: sum y, sum y^2 (statistics for the BatchNorm that consumes this tensor)
+      //   kMask         : sum g, sum g*xhat (BatchNorm backward)
+      // thread = 4 adjacent channels x a slice of the rows; the slices are combined with shared-memory atomics and
+      // ONE vector reduction per 4 channels leaves the CTA (every CTA of the grid adds into the same 2*Cout floats:
+      // the L2 serialises per cache line, so the number of global atomics is what this costs).
       int valid = p.M_total - m0;
       valid = valid > 128 ? 128 : valid;
-      constexpr int kPairs = BN / 2;
-      constexpr int kGroups = 128 / kPairs > 0 ? 128 / kPairs : 1;
-      constexpr int kRows = 128 / kGroups;
-      for (int pi = et; pi < kPairs * kGroups; pi += 128) {
-        const int cpair = pi % kPairs, grp = pi / kPairs;
-        const int c = cpair * 2;
+      constexpr int kQuads = BN / 4;            // 32 or 16
+      constexpr int kGroups = 128 / kQuads;     // row slices: 4 or 8
+      constexpr int kRows = 128 / kGroups;      // 32 or 16
+      float* acc_s = coef_s;                    // [2 * BN] floats; the coefficients are dead by now
+      for (int i = et; i < 2 * BN; i += 128) acc_s[i] = 0.f;
+      named_bar_sync(1, 128);
+      {
+        const int quad = et % kQuads, grp = et / kQuads;
+        const int c = quad * 4;
         const uint8_t* colp = sC + (c >> 6) * 16384 + (c & 7) * 2;
         const int chunk = (c & 63) >> 3;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint8_t* qcol = sQ + (c >> 6) * 32768;
+        const int ch4 = (c & 63) >> 2;
 #pragma unroll 8
         for (int i = 0; i < kRows; ++i) {
           const int r = grp * kRows + i;
-          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4));
-          float2 f = __bfloat1622float2(h);
-          if (r >= valid) f = make_float2(0.f, 0.f);
-          s0 += f.x;
-          s1 += f.y;
-          q0 = fmaf(f.x, f.x, q0);
-          q1 = fmaf(f.y, f.y, q1);
+          const uint2 u = *reinterpret_cast<const uint2*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4));
+          float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+          float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+          float4 qv;
+          if constexpr (MODE == kMask) qv = *reinterpret_cast<const float4*>(qcol + r * 256 + ((ch4 ^ (r & 15)) << 4));
+          if (r < valid) {
+            s4[0] += f0.x; s4[1] += f0.y; s4[2] += f1.x; s4[3] += f1.y;
+            if constexpr (MODE == kMask) {
+              q4[0] += qv.x; q4[1] += qv.y; q4[2] += qv.z; q4[3] += qv.w;
+            } else {
+              q4[0] = fmaf(f0.x, f0.x, q4[0]); q4[1] = fmaf(f0.y, f0.y, q4[1]);
+              q4[2] = fmaf(f1.x, f1.x, q4[2]); q4[3] = fmaf(f1.y, f1.y, q4[3]);
+            }
+          }
         }
-        atomicAdd(p.stats + n_off + c, s0);
-        atomicAdd(p.stats + n_off + c + 1, s1);
-        atomicAdd(p.stats + p.n_total + n_off + c, q0);
-        atomicAdd(p.stats + p.n_total + n_off + c + 1, q1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          atomicAdd(acc_s + c + e, s4[e]);
+          atomicAdd(acc_s + BN + c + e, q4[e]);
+        }
+      }
+      named_bar_sync(1, 128);
+      if (et < 2 * kQuads) {
+        const int which = et / kQuads, quad = et % kQuads;
+        const float4 v4 = *reinterpret_cast<const float4*>(acc_s + which * BN + quad * 4);
+        float* dst = p.stats + which * p.n_total + n_off + quad * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v4.x), "f"(v4.y), "f"(v4.z),
+                     "f"(v4.w)
+                     : "memory");
       }
     }
     if (et == 0) tma_store_wait_read();
@@ -252,33 +482,68 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------------
 static inline int pad64(int c) { return (c + 63) & ~63; }
 
-template <int BN, int STAGES, int MINB>
+BnFoldDev make_fold(const HgBnFold* f, int C, long long count) {
+  BnFoldDev d;
+  d.stats = f->stats;
+  d.gamma = f->gamma;
+  d.beta = f->beta;
+  d.rmean = f->running_mean;
+  d.rvar = f->running_var;
+  d.count = (float)count;
+  d.eps = f->eps;
+  d.relu = f->relu;
+  d.use_running = f->use_running;
+  d.C = C;
+  d.Cp = pad64(C);
+  return d;
+}
+
+template <int BN, int STAGES, int MINB, int MODE, bool ALIAS>
 static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                             const CUtensorMap& tmR, const ConvGemmParams& p, cudaStream_t st) {
-  using L = ConvGemmSmem<BN, STAGES>;
+  using L = ConvGemmSmem<BN, STAGES, MODE, ALIAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    HG_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    L::kTotal));
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   dim3 grid(ceil_div(p.M_total, 128) * p.n_tiles);
-  conv_gemm_kernel<BN, STAGES, MINB><<<grid, 192, L::kTotal, st>>>(tmA, tmB, tmC, tmR, p);
+  conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS><<<grid, 192, L::kTotal, st>>>(tmA, tmB, tmC, tmR, p);
   HG_LAUNCH_OK("conv_gemm_kernel");
   count_launch();
   return HG_OK;
 }
 
+// Tile configuration: long K (3x3) = 3 stages, short K (1x1) = 2 stages; C aliases the stages unless a residual
+// has to be in C up front (then a dedicated buffer, still two CTAs per SM for the 1x1 kernels).
+template <int BN, int MODE>
+static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                              const CUtensorMap& tmC, const CUtensorMap& tmR, const ConvGemmParams& p,
+                              cudaStream_t st) {
+  if constexpr (MODE == kMask) {
+    return launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st);
+  } else {
+    constexpr int kShortMinB = MODE == kFold ? 2 : 3;  // the transform needs > 113 registers
+    if (has_res) return long_k ? launch_conv_gemm<BN, 3, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st)
+                               : launch_conv_gemm<BN, 2, 2, MODE, false>(tmA, tmB, tmC, tmR, p, st);
+    return long_k ? launch_conv_gemm<BN, 3, 2, MODE, true>(tmA, tmB, tmC, tmR, p, st)
+                  : launch_conv_gemm<BN, 2, kShortMinB, MODE, true>(tmA, tmB, tmC, tmR, p, st);
+  }
+}
+
 // act: [N,H,W,Kp] bf16 (A operand); wpk: [taps][Np][Kp] bf16; out/res: [N,H,W,Np] bf16.
+// mode kFold: `fold` describes the BatchNorm of act's channels (act is the raw tensor).
+// mode kMask: `fold` describes the BatchNorm of out's channels, `res` is its raw input, `stats` receives the sums.
 int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, int dil, int sign,
                    const void* act, const void* wpk, const float* bias, const void* res, void* out,
-                   float* stats, float* out_nchw, int c_real, cudaStream_t st) {
+                   float* stats, float* out_nchw, int c_real, int mode, const BnFoldDev* fold, cudaStream_t st) {
   if (!is_pow2(H) || !is_pow2(W) || W > 128) {
     set_error("conv_gemm_bf16: H and W must be powers of two with W <= 128 (got %dx%d)", H, W);
     return HG_ERR_UNSUPPORTED;
   }
-  if (Kp % 64 || Np % 64 || Np > 256) {
-    set_error("conv_gemm_bf16: padded channels must be multiples of 64, Cout <= 256 (got %d -> %d)", Kp, Np);
+  if (Kp % 64 || Np % 64 || Np > 256 || Kp > 256) {
+    set_error("conv_gemm_bf16: padded channels must be multiples of 64 and <= 256 (got %d -> %d)", Kp, Np);
     return HG_ERR_UNSUPPORTED;
   }
   const int bw = W < 128 ? W : 128;
@@ -325,6 +590,7 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
     if (rc) return rc;
   }
   ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
   p.M_total = (int)M;
   p.H = H;
   p.W = W;
@@ -341,11 +607,21 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   p.out_nchw = out_nchw;
   p.has_res = res != nullptr;
   p.n_tiles = Np / BN;
+  if (fold) p.fold = *fold;
   const bool long_k = R * S * (Kp / 64) > 4;
-  if (BN == 64) return long_k ? launch_conv_gemm<64, 4, 2>(tmA, tmB, tmC, tmR, p, st)
-                              : launch_conv_gemm<64, 2, 3>(tmA, tmB, tmC, tmR, p, st);
-  return long_k ? launch_conv_gemm<128, 4, 1>(tmA, tmB, tmC, tmR, p, st)
-                : launch_conv_gemm<128, 2, 2>(tmA, tmB, tmC, tmR, p, st);
+  const bool has_res = res != nullptr;
+  if (mode == kMask && (!res || !stats)) {
+    set_error("conv_gemm_bf16: mask mode needs the raw BatchNorm input and the reduction buffer");
+    return HG_ERR_BAD_ARG;
+  }
+  if (BN == 64) {
+    if (mode == kFold) return dispatch_conv_gemm<64, kFold>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
+    if (mode == kMask) return dispatch_conv_gemm<64, kMask>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
+    return dispatch_conv_gemm<64, kPlain>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
+  }
+  if (mode == kFold) return dispatch_conv_gemm<128, kFold>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
+  if (mode == kMask) return dispatch_conv_gemm<128, kMask>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
+  return dispatch_conv_gemm<128, kPlain>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
 }
 
 
@@ -358,9 +634,12 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
 // filter taps per CTA (their accumulators sit side by side in TMEM).  The pixel range is split across CTAs
 // and partial sums are reduced with vector fp32 atomics into the GEMM-layout gradient buffer (the same
 // buffer accumulates every call site of a shared weight, reference try_with_torch.py:217,224-237).
+//
+// FOLD = true: x is the RAW input of a BatchNorm(+ReLU) whose output the convolution consumed; the x tiles
+// are rewritten in shared memory as [relu](scale*x + shift) (zero in the padding) before the MMA reads them.
 // ======================================================================================================
 struct WgradParams {
-  int H, W;
+  int H, W, N;
   int taps_s;        // filter width S
   int dil, pad;
   int tap_rows;      // taps handled per CTA (T)
@@ -371,18 +650,23 @@ struct WgradParams {
   int stages;
   int stage_bytes;
   float* dw;         // [taps][Cout_p][Cin_p] fp32, accumulated
+  BnFoldDev fold;
 };
 
+template <bool FOLD>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
                   const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array keeps the address space: LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + 8;
   uint64_t* tmem_full = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* ready_bar = bars + 18;                             // [8]
+  float* coef_s = reinterpret_cast<float*>(bars + 32);         // scale[256], shift[256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -403,11 +687,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, cols);
+  if constexpr (FOLD) {
+    if (warp >= 2) {
+      for (int c = threadIdx.x - 64; c < p.Cin_p; c += 128) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
+        coef_s[c] = sc;
+        coef_s[256 + c] = sh;
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -446,7 +741,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       for (int i = 0; i < nkb; ++i) {
         const int st = i % p.stages;
         const uint32_t ph = (i / p.stages) & 1;
-        mbar_wait(&full_bar[st], ph);
+        if constexpr (FOLD) mbar_wait(&ready_bar[st], ph);
+        else mbar_wait(&full_bar[st], ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_u32(smem + st * p.stage_bytes);
@@ -466,6 +762,56 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       }
     } else {
       const int sub = warp & 3;
+      const int et = threadIdx.x - 64;
+      (void)et;
+      if constexpr (FOLD) {
+        // rewrite the x tiles of every stage (see conv_gemm_kernel): thread = one 16-byte channel chunk x 4 rows of
+        // each 64-row tile
+        const int jch = et & 7;
+        const int rbase = et >> 3;                 // rows rbase + 16 * i, i < 4
+        const int swz = (jch ^ (rbase & 7)) << 4;
+        const int hw = p.H * p.W;
+        const bool relu = p.fold.relu != 0;
+        for (int i = 0; i < nkb; ++i) {
+          const int st = i % p.stages;
+          const uint32_t ph = (i / p.stages) & 1;
+          int hrow[4], wrow[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int mm = (kb_beg + i) * 64 + rbase + 16 * k;
+            const int rem = mm % hw;
+            hrow[k] = mm / hw < p.N ? rem / p.W : -0x40000000;
+            wrow[k] = rem % p.W;
+          }
+          uint8_t* sB = smem + st * p.stage_bytes + a_bytes + rbase * 128 + swz;
+          mbar_wait(&full_bar[st], ph);
+          for (int t = 0; t < T; ++t) {
+            const int tap = tap0 + t;
+            const int r = tap / p.taps_s, s = tap - r * p.taps_s;
+            const int dh = r * p.dil - p.pad, dw = s * p.dil - p.pad;
+            uint32_t vmask = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if ((unsigned)(hrow[k] + dh) < (unsigned)p.H && (unsigned)(wrow[k] + dw) < (unsigned)p.W) vmask |= 1u << k;
+            for (int pn = 0; pn < p.n_panels; ++pn) {
+              float sc[8], sh[8];
+              load_coef8(coef_s + pn * 64 + jch * 8, sc);
+              load_coef8(coef_s + 256 + pn * 64 + jch * 8, sh);
+              uint8_t* base = sB + (t * p.n_panels + pn) * 8192;
+              uint4 u[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + k * 2048);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                u[k] = (vmask >> k) & 1u ? bn_relu_chunk(u[k], sc, sh, relu) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(base + k * 2048) = u[k];
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&ready_bar[st]);
+        }
+      }
       const int co = co_off + sub * 32 + lane;
       const bool row_ok = co < p.Cout_p;
       mbar_wait(tmem_full, 0);
@@ -510,7 +856,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 
 int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* out, cudaStream_t st);
 
-int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, cudaStream_t st) {
+int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
+                    const BnFoldDev* fold, cudaStream_t st) {
   const int Cin_p = pad64(d->Cin), Cout_p = pad64(d->Cout);
   const int H = d->H, W = d->W;
   const long long M = (long long)d->N * H * W;
@@ -542,8 +889,10 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
       if (rc) return rc;
     }
     WgradParams p;
+    memset(&p, 0, sizeof(p));
     p.H = H;
     p.W = W;
+    p.N = d->N;
     p.taps_s = d->S;
     p.dil = d->dil;
     p.pad = d->pad;
@@ -553,7 +902,7 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.Cout_p = Cout_p;
     p.total_kb = (int)((M + 63) / 64);
     p.stage_bytes = 2 * 8192 + T * p.n_panels * 8192;
-    p.stages = (200 * 1024) / p.stage_bytes;
+    p.stages = (196 * 1024) / p.stage_bytes;
     if (p.stages > 6) p.stages = 6;
     const int tap_groups = taps / T;
     const int mgroups = (Cout_p + 127) / 128;
@@ -565,14 +914,19 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.kb_per_cta = (p.total_kb + nsplit - 1) / nsplit;
     nsplit = (p.total_kb + p.kb_per_cta - 1) / p.kb_per_cta;
     p.dw = dw;
-    const int smem_bytes = p.stages * p.stage_bytes + 1024 + 1024;
+    if (fold) p.fold = *fold;
+    const int smem_bytes = p.stages * p.stage_bytes + 4096 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-      HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+      HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
       attr_set = true;
     }
     dim3 grid(nsplit, tap_groups, mgroups);
-    conv_wgrad_kernel<<<grid, 192, smem_bytes, st>>>(tmDy, tmX, p);
+    if (fold) conv_wgrad_kernel<true><<<grid, 192, smem_bytes, st>>>(tmDy, tmX, p);
+    else conv_wgrad_kernel<false><<<grid, 192, smem_bytes, st>>>(tmDy, tmX, p);
     HG_LAUNCH_OK("conv_wgrad_kernel");
     count_launch();
   }

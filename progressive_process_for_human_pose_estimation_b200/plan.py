@@ -20,6 +20,10 @@ from . import _lib as L
 
 _USE_GRAPHS = os.environ.get("HG_CUDA_GRAPHS", "1") != "0"
 _USE_LANES = os.environ.get("HG_STREAM_LANES", "1") != "0"
+_WGRAD_LANES = int(os.environ.get("HG_WGRAD_LANES", "1"))
+# 0: BatchNorm kernels stay separate; 1: only the data-gradient epilogue is fused (ReLU mask + BN-backward sums);
+# 2: additionally the forward / weight-gradient convolutions apply BN+ReLU to their operand tiles (no activation in HBM)
+_FOLD_BN = int(os.environ.get("HG_FOLD_BN", "1"))
 
 
 class Val:
@@ -194,6 +198,7 @@ class _LaneCtx:
 _WRITES = {
     "hg_nchw_f32_to_nhwc": (7,), "hg_nhwc_to_nchw_f32": (6,), "hg_stem_fwd": (8,), "hg_conv_fprop_ex": (5, 6, 7),
     "hg_conv_dgrad": (4,), "hg_bn_stats": (2,), "hg_bn_apply": (7,), "hg_bn_bwd_apply": (10,),
+    "hg_bn_bwd_reduce": (8,), "hg_conv_fprop_bn": (6, 7, 8), "hg_conv_dgrad_bn": (5, 6),
     "hg_maxpool2_fwd": (6,), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8,), "hg_upsample2x_bwd": (8,),
     "hg_add": (3,),
 }
@@ -249,6 +254,11 @@ class Plan:
         self._last_writer = {}      # data_ptr -> _Call that last wrote it (per call list)
         self._cur_lane = 0
         self.num_lanes = builder.num_lanes if _USE_LANES else 1
+        self.wgrad_lanes = []
+        self._wgrad_rr = 0
+        if _USE_LANES and _WGRAD_LANES > 0:
+            self.wgrad_lanes = list(range(self.num_lanes, self.num_lanes + _WGRAD_LANES))
+            self.num_lanes += _WGRAD_LANES
         self.lane_streams = None
         self.profile_records = None  # list while an instrumented (eager, event-timed) step is being recorded
         self.reducer = None        # set by parallel.DataParallel: all-reduces ranges of grad_arena
@@ -286,7 +296,8 @@ class Plan:
         i = self.param_index.get(id(p))
         return i is not None and p.requires_grad
 
-    def _emit(self, lst, name, *args, keep=()):
+    def _emit(self, lst, name, *args, keep=(), reads=()):
+        """reads: tensors the call reads through a struct (HgBnFold) rather than through a pointer argument."""
         c = _Call(name, args, keep)
         if lst is self.bwd_calls and self._pending_writes:
             c.writes = tuple(self._pending_writes)
@@ -302,6 +313,10 @@ class Plan:
                     deps.append(lw)
                 if i in wpos:
                     self._last_writer[a.value] = c
+        for t in reads:
+            lw = self._last_writer.get(t.data_ptr()) if t is not None else None
+            if lw is not None and lw.lane != c.lane and lw not in deps:
+                deps.append(lw)
         c.deps = tuple(deps)
         lst.append(c)
         return c
@@ -399,8 +414,26 @@ class Plan:
             else:
                 v.buf = self._act(v)
                 self.in_nchw = torch.zeros(v.N, v.C, v.H, v.W, device=dev, dtype=torch.float32)
+        # ---- BatchNorm folding: BN(+ReLU) whose only consumer is a tensor-core convolution is never materialised;
+        # the convolution transforms its operand tiles on the fly (hg_conv_fprop_bn / _wgrad_bn / _dgrad_bn)
+        self.n_folded = self.n_masked = 0
+        if _FOLD_BN and self.dt == torch.bfloat16:
+            lib = L.load()
+            for op in ops:
+                if op.kind != "bn" or op.out.needs_stats or len(op.out.consumers) != 1:
+                    continue
+                cons = op.out.consumers[0]
+                if cons.kind != "conv" or cons.ins[0] is not op.out or cons.ins[1] is op.out:
+                    continue
+                if not lib.hg_conv_tc_eligible(C.byref(self._conv_desc(cons.attrs["conv"], op.out))):
+                    continue
+                op.attrs["folded"] = _FOLD_BN >= 2   # activation not materialised
+                op.attrs["masked"] = True            # consumer's dgrad epilogue does the reduce
+                cons.attrs["fold"] = op
+                self.n_masked += 1
+                self.n_folded += 1 if op.attrs["folded"] else 0
         for op in ops:
-            if op.out is not None:
+            if op.out is not None and not op.attrs.get("folded"):
                 op.out.buf = self._act(op.out)
         all_vals = [v for v, _ in b.inputs] + [op.out for op in ops if op.out is not None]
         for v in all_vals:
@@ -418,6 +451,7 @@ class Plan:
         off = 0
         for op in bn_ops:
             op.attrs["red"] = self.red_arena[off:off + 2 * op.ins[0].Cp]
+            self._tracked.add(op.attrs["red"].data_ptr())
             off += 2 * op.ins[0].Cp
 
         # ---- outputs -------------------------------------------------------------------------------
@@ -447,6 +481,18 @@ class Plan:
         d = L.HgBnDesc(x.M, x.C, self.hdt, float(bn.eps), 1 if relu else 0, use_running)
         self._keep.append(d)
         return d
+
+    def _bn_fold(self, bnop):
+        """HgBnFold of a folded BatchNorm op + the tensors a call using it reads through the struct."""
+        bn, x = bnop.attrs["bn"], bnop.ins[0]
+        use_running = 0 if (self.training or not bn.track_running_stats) else 1
+        f = L.HgBnFold(x.stats.data_ptr() if x.stats is not None else None, self._p32(bn.weight).data_ptr(),
+                       self._p32(bn.bias).data_ptr(),
+                       bn.running_mean.data_ptr() if bn.running_mean is not None else None,
+                       bn.running_var.data_ptr() if bn.running_var is not None else None, float(bn.eps),
+                       1 if bnop.attrs["relu"] else 0, use_running, 0)
+        self._keep.append(f)
+        return f, (x.stats,)
 
     def _lower_forward(self, convs):
         f, st = self.fwd_calls, self.stream
@@ -489,18 +535,27 @@ class Plan:
                 info = self.conv_info[op.attrs["key"]]
                 d = self._conv_desc(cv, x)
                 nchw = self.out_static[self.out_index[id(out)]] if op.attrs["head"] else None
-                self._emit(f, "hg_conv_fprop_ex", C.byref(d), L.ptr(x.buf), L.ptr(info["wf"]),
-                           self._bias_ptr(cv, info) if op.attrs["use_bias"] else None,
-                           L.ptr(res.buf) if res else None,
-                           L.ptr(out.buf), L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw),
-                           st).tag = self._conv_tag(cv, x)
+                bias = self._bias_ptr(cv, info) if op.attrs["use_bias"] else None
+                if op.attrs.get("fold") is not None and op.attrs["fold"].attrs["folded"]:
+                    fold, reads = self._bn_fold(op.attrs["fold"])
+                    self._emit(f, "hg_conv_fprop_bn", C.byref(d), C.byref(fold), L.ptr(op.attrs["fold"].ins[0].buf),
+                               L.ptr(info["wf"]), bias, L.ptr(res.buf) if res else None, L.ptr(out.buf),
+                               L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw), st,
+                               reads=reads).tag = self._conv_tag(cv, x) + " +bn"
+                else:
+                    self._emit(f, "hg_conv_fprop_ex", C.byref(d), L.ptr(x.buf), L.ptr(info["wf"]), bias,
+                               L.ptr(res.buf) if res else None,
+                               L.ptr(out.buf), L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw),
+                               st).tag = self._conv_tag(cv, x)
             elif k == "bn":
                 bn, x, out = op.attrs["bn"], op.ins[0], op.out
                 d = self._bn_desc(bn, x, op.attrs["relu"])
-                self._emit(f, "hg_bn_apply", C.byref(d), L.ptr(x.buf), L.ptr(x.stats) if x.stats is not None else None,
-                           L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias)),
-                           L.ptr(bn.running_mean) if bn.running_mean is not None else None,
-                           L.ptr(bn.running_var) if bn.running_var is not None else None, L.ptr(out.buf), st)
+                if not op.attrs.get("folded"):
+                    self._emit(f, "hg_bn_apply", C.byref(d), L.ptr(x.buf),
+                               L.ptr(x.stats) if x.stats is not None else None,
+                               L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias)),
+                               L.ptr(bn.running_mean) if bn.running_mean is not None else None,
+                               L.ptr(bn.running_var) if bn.running_var is not None else None, L.ptr(out.buf), st)
                 if self.training and bn.track_running_stats:
                     running.setdefault(id(bn), (bn, []))[1].append((x.stats, float(x.M)))
                 if out.needs_stats:  # BN output feeding another BN directly (hourglass_compare.py:549-553)
@@ -590,6 +645,7 @@ class Plan:
                 cv, x, res = op.attrs["conv"], op.ins[0], op.ins[1]
                 info = self.conv_info[op.attrs["key"]]
                 d = self._conv_desc(cv, x)
+                foldop = op.attrs.get("fold")
                 if res is not None:
                     self._grad_passthrough(res, G)
                 wslot = self._gslot(cv.weight)
@@ -609,14 +665,35 @@ class Plan:
                     else:
                         dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
                         info["used"] = True
-                    self._emit(g, "hg_conv_wgrad", C.byref(d), L.ptr(x.buf), L.ptr(G), L.ptr(dwp), L.ptr(bslot),
-                               st).tag = self._conv_tag(cv, x)
+                    # Nothing downstream waits for a weight gradient until the very end of the pass, so the wgrad
+                    # kernels leave the critical dgrad -> BN-backward chain: they rotate over dedicated stream lanes
+                    # and fill the SMs the latency-bound low-resolution kernels of the main chain leave idle.
+                    keep_lane = self._cur_lane
+                    if self.wgrad_lanes:
+                        self._cur_lane = self.wgrad_lanes[self._wgrad_rr % len(self.wgrad_lanes)]
+                        self._wgrad_rr += 1
+                    if foldop is not None and foldop.attrs["folded"]:
+                        fold, reads = self._bn_fold(foldop)
+                        self._emit(g, "hg_conv_wgrad_bn", C.byref(d), C.byref(fold), L.ptr(foldop.ins[0].buf), L.ptr(G),
+                                   L.ptr(dwp), L.ptr(bslot), st).tag = self._conv_tag(cv, x) + " +bn"
+                    else:
+                        self._emit(g, "hg_conv_wgrad", C.byref(d), L.ptr(x.buf), L.ptr(G), L.ptr(dwp), L.ptr(bslot),
+                                   st).tag = self._conv_tag(cv, x)
+                    self._cur_lane = keep_lane
                     if wslot is not None and not info["direct"]:
                         info["last_wgrad"] = g[-1]
                 if x.requires_grad:
                     addend, dst = self._grad_target(x)
-                    self._emit(g, "hg_conv_dgrad", C.byref(d), L.ptr(G), L.ptr(info["wd"]), L.ptr(addend), L.ptr(dst),
-                               st).tag = self._conv_tag(cv, x)
+                    if foldop is not None:
+                        # epilogue = ReLU mask + the two BatchNorm-backward sums; dst holds g = da * [bn(x) > 0]
+                        assert addend is None, "a folded BatchNorm output has exactly one consumer"
+                        fold, reads = self._bn_fold(foldop)
+                        self._emit(g, "hg_conv_dgrad_bn", C.byref(d), C.byref(fold), L.ptr(G), L.ptr(info["wd"]),
+                                   L.ptr(foldop.ins[0].buf), L.ptr(dst), L.ptr(foldop.attrs["red"]),
+                                   st).tag = self._conv_tag(cv, x) + " +bn"
+                    else:
+                        self._emit(g, "hg_conv_dgrad", C.byref(d), L.ptr(G), L.ptr(info["wd"]), L.ptr(addend),
+                                   L.ptr(dst), st).tag = self._conv_tag(cv, x)
             elif k == "bn":
                 bn, x = op.attrs["bn"], op.ins[0]
                 d = self._bn_desc(bn, x, op.attrs["relu"])
@@ -625,7 +702,9 @@ class Plan:
                 stats = L.ptr(x.stats) if x.stats is not None else None
                 rmean = L.ptr(bn.running_mean) if bn.running_mean is not None else None
                 rvar = L.ptr(bn.running_var) if bn.running_var is not None else None
-                if not d.use_running or self._gslot_peek(bn.weight) or self._gslot_peek(bn.bias):
+                if op.attrs.get("masked"):
+                    pass  # the sums were accumulated by the consumer's hg_conv_dgrad_bn; G is already masked
+                elif not d.use_running or self._gslot_peek(bn.weight) or self._gslot_peek(bn.bias):
                     self._emit(g, "hg_bn_bwd_reduce", C.byref(d), L.ptr(G), L.ptr(x.buf), stats, gam, bet, rmean, rvar,
                                L.ptr(red), st)
                 colsum = None

@@ -66,11 +66,19 @@ def test_plan_lowering_structure(built):
         assert n_bn == 2 * (28 * 3 + 1) + 9
         plan = Plan(b, list(net.named_parameters()), torch.device("cpu"), torch.bfloat16)
         names = [c.name for c in plan.fwd_calls]
-        assert names.count("hg_conv_fprop_ex") == n_conv and names.count("hg_bn_apply") == n_bn
+        # BN(+ReLU) feeding a single tensor-core convolution: the consumer's data-gradient epilogue applies the ReLU
+        # mask and accumulates the BatchNorm-backward sums (HG_FOLD_BN >= 1); with HG_FOLD_BN = 2 the activation is
+        # not materialised at all (no hg_bn_apply launch, convolutions transform their operand tiles)
+        assert names.count("hg_conv_fprop_ex") + names.count("hg_conv_fprop_bn") == n_conv
+        assert names.count("hg_bn_apply") + plan.n_folded == n_bn and plan.n_folded == names.count("hg_conv_fprop_bn")
+        assert plan.n_masked >= 2 * 28 * 3 or os.environ.get("HG_FOLD_BN") == "0"
         assert names.count("hg_bn_update_running") == 1 and names.count("hg_stem_fwd") == 1
         bnames = [c.name for c in plan.bwd_calls]
         # the re-injection convs after the LAST stack receive no gradient (quirk Q5): 2 convs without backward
-        assert bnames.count("hg_conv_wgrad") == n_conv - 2
+        assert bnames.count("hg_conv_wgrad") + bnames.count("hg_conv_wgrad_bn") == n_conv - 2
+        assert bnames.count("hg_conv_wgrad_bn") == plan.n_folded
+        assert bnames.count("hg_conv_dgrad_bn") == plan.n_masked
+        assert bnames.count("hg_bn_bwd_reduce") + bnames.count("hg_conv_dgrad_bn") == bnames.count("hg_bn_bwd_apply")
         unused = [n for (n, _), u in zip(plan.params, plan.param_used) if not u]
         assert len(unused) == 12 and all(".conv4." in n for n in unused)  # quirk Q3
     finally:

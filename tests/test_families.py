@@ -87,7 +87,9 @@ def test_family_state_dict_matches_reference(script, factory, fixture, mode):
     sd = build(script, factory, mode).state_dict()
     assert list(sd.keys()) == [str(k) for k in g["keys"]]
     for i, k in enumerate(sd):
-        np.testing.assert_array_equal(digest(sd[k].float()), g["state_digest"][i], err_msg=k)
+        dg = digest(sd[k].float())
+        np.testing.assert_array_equal(dg[2:], g["state_digest"][i][2:], err_msg=k)
+        np.testing.assert_allclose(dg[:2], g["state_digest"][i][:2], rtol=1e-12, atol=1e-12, err_msg=k)
 
 
 def _check_grads(net, g, floor, mult, vacuous=0.25, noise_key="grad_noise_fp64"):
@@ -136,7 +138,9 @@ def test_family_fp32_eval_step_tight(script, factory, fixture):
         assert _check_grads(net, g, 2e-3, 10) > 20
         sd = net.state_dict()
         for i, k in enumerate(str(k) for k in g["keys"]):  # eval never touches the buffers
-            np.testing.assert_array_equal(digest(sd[k].float()), g["state_digest"][i], err_msg=k)
+            dg = digest(sd[k].float())  # (the two sums depend on the host's reduction order: last-bit tolerance)
+            np.testing.assert_array_equal(dg[2:], g["state_digest"][i][2:], err_msg=k)
+            np.testing.assert_allclose(dg[:2], g["state_digest"][i][:2], rtol=1e-12, atol=1e-12, err_msg=k)
     finally:
         hg.set_compute_dtype(torch.bfloat16)
 

@@ -125,6 +125,122 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     close(dbias, 2 * dyr.sum((0, 2, 3)), 1e-3, "dbias")
 
 
+FOLD_CASES = [
+    # N, H, W, Cin, Cout, k, dil, residual, relu, eval_mode
+    (2, 64, 64, 128, 128, 3, 1, False, True, False),
+    (2, 16, 16, 256, 128, 1, 1, False, True, False),
+    (4, 4, 4, 128, 128, 3, 1, False, True, False),
+    (3, 8, 8, 128, 256, 1, 1, True, True, False),
+    (2, 32, 32, 64, 64, 3, 1, False, False, False),
+    (2, 32, 32, 256, 256, 1, 1, True, True, True),
+    (5, 16, 16, 128, 128, 3, 1, False, True, True),
+    (2, 4, 4, 256, 256, 3, 6, False, True, False),   # dilated taps that only touch padding
+    (1, 8, 8, 256, 16, 1, 1, False, True, False),    # M = 64 < one tile, Cout padded to 64
+    (2, 128, 128, 64, 128, 1, 1, False, True, False),
+]
+
+
+@pytest.mark.parametrize("case", FOLD_CASES)
+def test_conv_with_folded_batchnorm(case):
+    """hg_conv_fprop_bn / hg_conv_wgrad_bn / hg_conv_dgrad_bn against the un-fused kernels of the same library
+    (hg_bn_apply -> conv, dgrad -> hg_bn_bwd_reduce) and against PyTorch fp32 ops."""
+    N, H, W, Cin, Cout, k, dil, res, relu, eval_mode = case
+    torch.manual_seed(3)
+    dev, dtype = "cuda", torch.bfloat16
+    pad = dil * (k // 2)
+    M = N * H * W
+    x = torch.randn(N, Cin, H, W, device=dev) * 1.7 + 0.3
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    gamma = torch.rand(Cin, device=dev) + 0.5
+    beta = torch.randn(Cin, device=dev) * 0.3
+    rmean = torch.randn(Cin, device=dev) * 0.2 + 0.3
+    rvar = torch.rand(Cin, device=dev) * 2 + 1.5
+    r = torch.randn(N, Cout, H, W, device=dev) if res else None
+    d = L.HgConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, dil, L.HG_BF16)
+    assert L.load().hg_conv_tc_eligible(C.byref(d)) == 1
+    Cin_p, Cout_p = L.pad64(Cin), L.pad64(Cout)
+    xq, rq = nhwc(x, dtype), (nhwc(r, dtype) if res else None)
+    wf = torch.empty(k * k, Cout_p, Cin_p, device=dev, dtype=dtype)
+    wd = torch.empty(k * k, Cin_p, Cout_p, device=dev, dtype=dtype)
+    bias_p = torch.zeros(Cout_p, device=dev)
+    bias_p[:Cout] = b
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
+    bnd = L.HgBnDesc(M, Cin, L.HG_BF16, 1e-5, 1 if relu else 0, 1 if eval_mode else 0)
+    xstats = torch.zeros(2 * Cin_p, device=dev)
+    L.call("hg_bn_stats", C.byref(bnd), L.ptr(xq), L.ptr(xstats), st)
+    fold = L.HgBnFold(xstats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr(), 1e-5,
+                      1 if relu else 0, 1 if eval_mode else 0, 0)
+    # ---- un-fused path of the same library
+    a = torch.empty_like(xq)
+    L.call("hg_bn_apply", C.byref(bnd), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta), L.ptr(rmean),
+           L.ptr(rvar), L.ptr(a), st)
+    y0 = torch.empty(N, H, W, Cout_p, device=dev, dtype=dtype)
+    s0 = torch.zeros(2 * Cout_p, device=dev)
+    L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(a), L.ptr(wf), L.ptr(bias_p), L.ptr(rq), L.ptr(y0), L.ptr(s0), None, st)
+    # ---- fused forward
+    y1 = torch.full((N, H, W, Cout_p), float("nan"), device=dev, dtype=dtype)
+    s1 = torch.zeros(2 * Cout_p, device=dev)
+    L.call("hg_conv_fprop_bn", C.byref(d), C.byref(fold), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), L.ptr(rq), L.ptr(y1),
+           L.ptr(s1), None, st)
+    assert torch.equal(y1, y0), f"fused fprop differs from bn_apply -> conv: {(y1.float() - y0.float()).abs().max()}"
+    close(s1, s0, 1e-5, "stats of the fused fprop")
+    # ---- PyTorch fp32 reference on the same bf16-representable inputs
+    xr = nchw(xq, Cin)
+    if eval_mode:
+        ar = F.batch_norm(xr, rmean, rvar, gamma, beta, False, 0.0, 1e-5)
+    else:
+        ar = F.batch_norm(xr, None, None, gamma, beta, True, 0.0, 1e-5)
+    if relu:
+        ar = F.relu(ar)
+    ref = F.conv2d(ar, w.to(dtype).float(), b, 1, pad, dil)
+    if res:
+        ref = ref + nchw(rq, Cout)
+    close(nchw(y1, Cout), ref, 2e-2, "fused fprop vs torch")
+    # ---- wgrad
+    dy = torch.randn(N, Cout, H, W, device=dev)
+    dyq = nhwc(dy, dtype)
+    dw0 = torch.zeros(k * k, Cout_p, Cin_p, device=dev)
+    dw1 = torch.zeros(k * k, Cout_p, Cin_p, device=dev)
+    db0, db1 = torch.zeros(Cout, device=dev), torch.zeros(Cout, device=dev)
+    L.call("hg_conv_wgrad", C.byref(d), L.ptr(a), L.ptr(dyq), L.ptr(dw0), L.ptr(db0), st)
+    L.call("hg_conv_wgrad_bn", C.byref(d), C.byref(fold), L.ptr(xq), L.ptr(dyq), L.ptr(dw1), L.ptr(db1), st)
+    close(dw1, dw0, 1e-5, "fused wgrad vs wgrad on the materialised activation")
+    close(db1, db0, 1e-5, "dbias")
+    # ---- dgrad with ReLU mask + BatchNorm-backward sums
+    da = torch.empty(N, H, W, Cin_p, device=dev, dtype=dtype)
+    L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), None, L.ptr(da), st)
+    red0 = torch.zeros(2 * Cin_p, device=dev)
+    L.call("hg_bn_bwd_reduce", C.byref(bnd), L.ptr(da), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta),
+           L.ptr(rmean), L.ptr(rvar), L.ptr(red0), st)
+    g1 = torch.full((N, H, W, Cin_p), float("nan"), device=dev, dtype=dtype)
+    red1 = torch.zeros(2 * Cin_p, device=dev)
+    L.call("hg_conv_dgrad_bn", C.byref(d), C.byref(fold), L.ptr(dyq), L.ptr(wd), L.ptr(xq), L.ptr(g1), L.ptr(red1), st)
+    mask = (a.float() > 0) if relu else torch.ones_like(a, dtype=torch.bool)
+    g0 = torch.where(mask, da.float(), torch.zeros((), device=dev))
+    assert torch.equal(g1.float(), g0), f"masked dgrad differs: {(g1.float() - g0).abs().max()}"
+    scale = red0.abs().max().item()
+    assert (red1 - red0).abs().max().item() <= 2e-3 * scale, ((red1 - red0).abs().max().item(), scale)
+    # finishing with hg_bn_bwd_apply(da = g) gives the same dx as the un-fused pair
+    dx0 = torch.empty_like(xq)
+    dx1 = torch.empty_like(xq)
+    for dsrc, redsrc, dst in ((da, red0, dx0), (g1, red1, dx1)):
+        L.call("hg_bn_bwd_apply", C.byref(bnd), L.ptr(dsrc), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta),
+               L.ptr(rmean), L.ptr(rvar), L.ptr(redsrc), None, L.ptr(dx1 if dst is dx1 else dx0), None, None, None, st)
+    close(dx1.float(), dx0.float(), 1e-2, "bn backward from the fused sums")
+
+
+def test_folded_entry_points_reject_unsupported_geometry():
+    d = L.HgConvDesc(2, 32, 32, 128, 128, 3, 3, 2, 1, 1, L.HG_BF16)  # stride 2: CUDA-core path only
+    assert L.load().hg_conv_tc_eligible(C.byref(d)) == 0
+    t = torch.zeros(4096, device="cuda")
+    fold = L.HgBnFold(t.data_ptr(), t.data_ptr(), t.data_ptr(), None, None, 1e-5, 1, 0, 0)
+    rc = L.load().hg_conv_fprop_bn(C.byref(d), C.byref(fold), L.ptr(t), L.ptr(t), None, None, L.ptr(t), None, None,
+                                   L.stream_ptr())
+    assert rc == -2 and "tensor-core" in L.last_error()
+
+
 def test_conv_tensor_core_matches_cuda_core_kernel():
     """The tcgen05 kernel and the FFMA kernel compute the same bf16 convolution."""
     torch.manual_seed(1)

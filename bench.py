@@ -197,7 +197,7 @@ def run_ours(args):
 
     # ---- where the step goes: forward / loss+backward / optimizer, CUDA events, same stream -------------
     phases = None
-    if rank == 0:
+    if True:  # every rank: the backward pass contains the gradient all-reduce
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(3)]
         for e in ev:
             e[0].record()

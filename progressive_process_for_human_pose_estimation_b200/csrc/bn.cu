@@ -59,6 +59,9 @@ __device__ __forceinline__ void bn_coeffs(const BnArgs& a, int c0, float (&mean)
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long long M, int Cp,
                                                        float* __restrict__ stats, int rows_per_block) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   __shared__ float red[2][256][9];
   const int vecs = Cp >> 3;            // 8-channel vectors per row (8, 16 or 32)
   const int vc = threadIdx.x % vecs;   // vector column
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 
 // rows per block: enough blocks to fill the machine, few enough that the per-channel atomics stay cheap
 static inline int rows_per_block_for(long long M, int rlanes) {
-  long long blocks = M / (rlanes * 8);
+  long long blocks = M / (rlanes * 2);  // small tensors are latency-bound: at most two dependent loads per thread
   if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
   if (blocks < 1) blocks = 1;
   return (int)((M + blocks - 1) / blocks);
@@ -117,9 +120,9 @@ int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats,
   const int rpb = rows_per_block_for(M, 256 / (Cp >> 3));
   const int blocks = ceil_div(M, rpb);
   if (dtype == HG_BF16)
-    bn_stats_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, M, Cp, stats, rpb);
+    launch_k(bn_stats_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, M, Cp, stats, rpb);
   else
-    bn_stats_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, M, Cp, stats, rpb);
+    launch_k(bn_stats_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)x, M, Cp, stats, rpb);
   HG_LAUNCH_OK("bn_stats_kernel");
   count_launch();
   return HG_OK;
@@ -129,6 +132,9 @@ int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats,
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long M, int Cp, int C,
                                                      float* __restrict__ out, int rows_per_block) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   __shared__ float red[256][9];
   const int vecs = Cp >> 3;
   const int vc = threadIdx.x % vecs;
@@ -164,9 +170,9 @@ int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* 
   const int rpb = rows_per_block_for(M, 256 / (Cp >> 3));
   const int blocks = ceil_div(M, rpb);
   if (dtype == HG_BF16)
-    colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, M, Cp, C, out, rpb);
+    launch_k(colsum_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)dy, M, Cp, C, out, rpb);
   else
-    colsum_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, M, Cp, C, out, rpb);
+    launch_k(colsum_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)dy, M, Cp, C, out, rpb);
   HG_LAUNCH_OK("colsum_kernel");
   count_launch();
   return HG_OK;
@@ -178,6 +184,9 @@ int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long M,
                                                        BnArgs a) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const int vecs = a.Cp >> 3;
   const int vc = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
@@ -204,6 +213,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ x,
                                                             long long M, BnArgs a, float* __restrict__ redout,
                                                             int rows_per_block) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   __shared__ float red[2][256][9];
   const int vecs = a.Cp >> 3;
   const int vc = threadIdx.x % vecs;
@@ -258,6 +270,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            long long M, BnArgs a, const float* __restrict__ redin,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            float* __restrict__ colsum, int rows_per_block) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   __shared__ float red[256][9];
   const int vecs = a.Cp >> 3;
   const int vc = threadIdx.x % vecs;
@@ -346,6 +361,9 @@ struct BnRunningModule {
 };
 
 __global__ void bn_running_kernel(const BnRunningModule* __restrict__ mods, const BnRunningSite* __restrict__ sites) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const BnRunningModule md = mods[blockIdx.x];
   for (int c = threadIdx.x; c < md.C; c += blockDim.x) {
     float rm = md.rmean[c], rv = md.rvar[c];
@@ -418,9 +436,9 @@ int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const floa
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == HG_BF16)
-    bn_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, d->M, a);
+    launch_k(bn_apply_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, d->M, a);
   else
-    bn_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, d->M, a);
+    launch_k(bn_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)x, (float*)y, d->M, a);
   HG_LAUNCH_OK("bn_apply_kernel");
   count_launch();
   return HG_OK;
@@ -439,10 +457,9 @@ int hg_bn_bwd_reduce(const HgBnDesc* d, const void* da, const void* x, const flo
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == HG_BF16)
-    bn_bwd_reduce_kernel<__nv_bfloat16>
-        <<<blocks, 256, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, d->M, a, red, rpb);
+    launch_k(bn_bwd_reduce_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)da, (const __nv_bfloat16*)x, d->M, a, red, rpb);
   else
-    bn_bwd_reduce_kernel<float><<<blocks, 256, 0, st>>>((const float*)da, (const float*)x, d->M, a, red, rpb);
+    launch_k(bn_bwd_reduce_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)da, (const float*)x, d->M, a, red, rpb);
   HG_LAUNCH_OK("bn_bwd_reduce_kernel");
   count_launch();
   return HG_OK;
@@ -461,11 +478,11 @@ int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const floa
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == HG_BF16)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+    launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, 
         (const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, d->M, a,
         red, dgamma, dbeta, colsum, rpb);
   else
-    bn_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)da, (const float*)x, (const float*)addend,
+    launch_k(bn_bwd_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)da, (const float*)x, (const float*)addend,
                                                         (float*)dx, d->M, a, red, dgamma, dbeta, colsum, rpb);
   HG_LAUNCH_OK("bn_bwd_apply_kernel");
   count_launch();
@@ -474,7 +491,7 @@ int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const floa
 
 int hg_bn_update_running(const void* modules_dev, const void* sites_dev, int num_modules, void* stream) {
   HG_REQUIRE(modules_dev && sites_dev && num_modules > 0, "hg_bn_update_running: bad arguments");
-  bn_running_kernel<<<num_modules, 256, 0, (cudaStream_t)stream>>>((const BnRunningModule*)modules_dev,
+  launch_k(bn_running_kernel, dim3(num_modules), dim3(256), 0, (cudaStream_t)stream, (const BnRunningModule*)modules_dev,
                                                                    (const BnRunningSite*)sites_dev);
   HG_LAUNCH_OK("bn_running_kernel");
   count_launch();

@@ -9,6 +9,7 @@ namespace hg {
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
+int g_use_pdl = 1;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -133,6 +134,10 @@ int hg_device_ok(void) {
 int hg_set_option(const char* name, int value) {
   if (strcmp(name, "force_ref_conv") == 0) {
     g_force_ref_conv = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "pdl") == 0) {
+    g_use_pdl = value;
     return HG_OK;
   }
   set_error("hg_set_option: unknown option '%s'", name);

@@ -132,7 +132,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvGemmParams p) {
   using L = ConvGemmSmem<BN, STAGES, MODE, ALIAS>;
-  static_assert(2 * STAGES + 2 + STAGES <= 30, "barrier region too small");
+  static_assert(3 * STAGES + 2 <= 30, "barrier region too small");
   static_assert(MODE != kMask || ALIAS, "the mask epilogue stages two tiles: it always aliases the pipeline stages");
   extern __shared__ uint8_t smem_raw[];
   // (pointer arithmetic on the shared array keeps the address space: LDS/STS instead of generic LD/ST)
@@ -172,6 +172,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail; global memory is ours from here
   if (warp >= 2) {
     const int et = threadIdx.x - 64;
     for (int c = et; c < BN; c += 128) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
@@ -236,6 +237,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
       }
     }
+    __syncwarp();
+    pdl_trigger();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
@@ -258,6 +261,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
     }
+    pdl_trigger();
   } else {
     // ===================== transform (kFold) + epilogue (warps 2..5) =====================
     const int sub = warp & 3;           // TMEM sub-partition this warp may read
@@ -318,6 +322,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    pdl_trigger();  // main loop done: the next kernel may start its prologue under our epilogue
     if (p.has_res) mbar_wait(res_full, 0);
     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
     float* nchw_row = nullptr;
@@ -509,26 +514,35 @@ static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     attr_set = true;
   }
   dim3 grid(ceil_div(p.M_total, 128) * p.n_tiles);
-  conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS><<<grid, 192, L::kTotal, st>>>(tmA, tmB, tmC, tmR, p);
+  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(192), L::kTotal, st, tmA, tmB, tmC, tmR, p);
   HG_LAUNCH_OK("conv_gemm_kernel");
   count_launch();
   return HG_OK;
 }
 
 // Tile configuration: long K (3x3) = 3 stages, short K (1x1) = 2 stages; C aliases the stages unless a residual
-// has to be in C up front (then a dedicated buffer, still two CTAs per SM for the 1x1 kernels).
+// has to be in C up front (then a dedicated buffer, still two CTAs per SM for the 1x1 kernels).  Grids of at most one
+// wave (the 4x4 .. 16x16 levels of the hourglass) are pure latency: one CTA per SM with every K block's TMA load in
+// flight at once (6 / 4 stages).
 template <int BN, int MODE>
 static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA, const CUtensorMap& tmB,
                               const CUtensorMap& tmC, const CUtensorMap& tmR, const ConvGemmParams& p,
                               cudaStream_t st) {
+  const bool single_wave = ceil_div(p.M_total, 128) * p.n_tiles <= kNumSMs;
   if constexpr (MODE == kMask) {
-    return launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st);
+    return single_wave ? launch_conv_gemm<BN, 6, 1, kMask, true>(tmA, tmB, tmC, tmR, p, st)
+                       : launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st);
   } else {
     constexpr int kShortMinB = MODE == kFold ? 2 : 3;  // the transform needs > 113 registers
-    if (has_res) return long_k ? launch_conv_gemm<BN, 3, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st)
-                               : launch_conv_gemm<BN, 2, 2, MODE, false>(tmA, tmB, tmC, tmR, p, st);
-    return long_k ? launch_conv_gemm<BN, 3, 2, MODE, true>(tmA, tmB, tmC, tmR, p, st)
-                  : launch_conv_gemm<BN, 2, kShortMinB, MODE, true>(tmA, tmB, tmC, tmR, p, st);
+    if (has_res) {
+      if (long_k) return launch_conv_gemm<BN, 3, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st);
+      return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st)
+                         : launch_conv_gemm<BN, 2, 2, MODE, false>(tmA, tmB, tmC, tmR, p, st);
+    }
+    if (long_k) return single_wave ? launch_conv_gemm<BN, 6, 1, MODE, true>(tmA, tmB, tmC, tmR, p, st)
+                                   : launch_conv_gemm<BN, 3, 2, MODE, true>(tmA, tmB, tmC, tmR, p, st);
+    return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, true>(tmA, tmB, tmC, tmR, p, st)
+                       : launch_conv_gemm<BN, 2, kShortMinB, MODE, true>(tmA, tmB, tmC, tmR, p, st);
   }
 }
 
@@ -693,6 +707,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, cols);
+  pdl_wait();
   if constexpr (FOLD) {
     if (warp >= 2) {
       for (int c = threadIdx.x - 64; c < p.Cin_p; c += 128) {
@@ -736,6 +751,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           }
         }
       }
+      __syncwarp();
+      pdl_trigger();
     } else if (warp == 1) {
       const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
       for (int i = 0; i < nkb; ++i) {
@@ -760,6 +777,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         }
         __syncwarp();
       }
+      pdl_trigger();
     } else {
       const int sub = warp & 3;
       const int et = threadIdx.x - 64;
@@ -816,6 +834,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       const bool row_ok = co < p.Cout_p;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
+      pdl_trigger();
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
       // All CTAs of a split finish together and add into the SAME tile: start each CTA at a different column so
       // that concurrent atomics hit different addresses (the L2 atomic unit serialises per address).
@@ -908,8 +927,10 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     const int mgroups = (Cout_p + 127) / 128;
     // one wave of CTAs, and at least 8 K-blocks (512 pixels) of work per CTA: the split-K partial sums are
     // reduced with atomics, so small problems must not be cut into many slices
+    // (small maps are latency-bound: there, two K blocks per CTA and more atomics beat a long serial loop)
+    const int min_kb = p.total_kb <= 256 ? 2 : 8;
     int nsplit = kNumSMs / (tap_groups * mgroups);
-    if (nsplit > p.total_kb / 8) nsplit = p.total_kb / 8;
+    if (nsplit > p.total_kb / min_kb) nsplit = p.total_kb / min_kb;
     if (nsplit < 1) nsplit = 1;
     p.kb_per_cta = (p.total_kb + nsplit - 1) / nsplit;
     nsplit = (p.total_kb + p.kb_per_cta - 1) / p.kb_per_cta;
@@ -925,8 +946,8 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
       attr_set = true;
     }
     dim3 grid(nsplit, tap_groups, mgroups);
-    if (fold) conv_wgrad_kernel<true><<<grid, 192, smem_bytes, st>>>(tmDy, tmX, p);
-    else conv_wgrad_kernel<false><<<grid, 192, smem_bytes, st>>>(tmDy, tmX, p);
+    if (fold) launch_k(conv_wgrad_kernel<true>, dim3(grid), dim3(192), smem_bytes, st, tmDy, tmX, p);
+    else launch_k(conv_wgrad_kernel<false>, dim3(grid), dim3(192), smem_bytes, st, tmDy, tmX, p);
     HG_LAUNCH_OK("conv_wgrad_kernel");
     count_launch();
   }

@@ -48,6 +48,12 @@ inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 constexpr int kNumSMs = 148;
 
+// Programmatic dependent launch (PDL): consecutive kernels of a stream are chained so that the next kernel's CTAs are
+// resident and through their prologue when the previous kernel drains.  Every kernel launched through launch_k()
+// executes pdl_wait() before its first access to global memory that an earlier kernel may produce (or still read),
+// and pdl_trigger() once its main work is issued.  hg_set_option("pdl", 0) falls back to plain stream order.
+extern int g_use_pdl;
+
 // ------------------------------------------------------------------------------------------
 // TMA descriptor encoding (driver entry point fetched at run time: no libcuda link needed).
 // ------------------------------------------------------------------------------------------
@@ -56,6 +62,26 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
                 const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swz);
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // Storage-type helpers: activations are bf16 (tensor-core path) or fp32 (CUDA-core path).
 // ------------------------------------------------------------------------------------------

@@ -15,6 +15,9 @@ namespace hg {
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H,
                                                            int W, int Cp) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const int vecs = Cp >> 3, Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * Ho * Wo * vecs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -42,6 +45,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                            const T* __restrict__ addend, T* __restrict__ dx, int N,
                                                            int H, int W, int Cp) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const int vecs = Cp >> 3, Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * Ho * Wo * vecs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -101,6 +107,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample2_add_fwd_kernel(const T* __restrict__ low, const T* __restrict__ skip,
                                                                 T* __restrict__ out, int N, int h, int w, int Cp,
                                                                 int mode) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const int vecs = Cp >> 3, H = 2 * h, W = 2 * w;
   const float sh = h > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sw = w > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
@@ -146,6 +155,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ addend,
                                                             T* __restrict__ dlow, int N, int h, int w, int Cp,
                                                             int mode) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const int vecs = Cp >> 3, H = 2 * h, W = 2 * w;
   const float sh = h > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sw = w > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
@@ -212,6 +224,9 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
                                                   long long nvec) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
@@ -228,6 +243,9 @@ __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, const T* __restrict__ addend,
                                                            T* __restrict__ dst, int N, int C, int HW, int Cp) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const int vecs = Cp >> 3;
   const long long total = (long long)N * HW * vecs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -258,6 +276,9 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N,
                                                            int C, int HW, int Cp) {
+  pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
+  pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
+
   const long long total = (long long)N * C * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -305,7 +326,7 @@ int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* 
   HG_REQUIRE(H % 2 == 0 && W % 2 == 0, "hg_maxpool2_fwd: odd spatial size %dx%d", H, W);
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * (H / 2) * (W / 2) * (Cp / 8);
-  HG_DISPATCH_T(dtype, (maxpool2_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  HG_DISPATCH_T(dtype, (launch_k(maxpool2_fwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
                            (const T*)x, (T*)y, N, H, W, Cp)));
   HG_LAUNCH_OK("maxpool2_fwd_kernel");
   count_launch();
@@ -320,7 +341,7 @@ int hg_maxpool2_bwd(int dtype, const void* x, const void* dy, const void* addend
   HG_REQUIRE(H % 2 == 0 && W % 2 == 0, "hg_maxpool2_bwd: odd spatial size %dx%d", H, W);
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * (H / 2) * (W / 2) * (Cp / 8);
-  HG_DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  HG_DISPATCH_T(dtype, (launch_k(maxpool2_bwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
                            (const T*)x, (const T*)dy, (const T*)addend, (T*)dx, N, H, W, Cp)));
   HG_LAUNCH_OK("maxpool2_bwd_kernel");
   count_launch();
@@ -335,7 +356,7 @@ int hg_upsample2x_add_fwd(int dtype, int mode, const void* low, const void* skip
   HG_REQUIRE(mode == 0 || mode == 1, "hg_upsample2x_add_fwd: mode must be 0 (bilinear_ac) or 1 (nearest)");
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * 4 * h * w * (Cp / 8);
-  HG_DISPATCH_T(dtype, (upsample2_add_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  HG_DISPATCH_T(dtype, (launch_k(upsample2_add_fwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
                            (const T*)low, (const T*)skip, (T*)out, N, h, w, Cp, mode)));
   HG_LAUNCH_OK("upsample2_add_fwd_kernel");
   count_launch();
@@ -350,7 +371,7 @@ int hg_upsample2x_bwd(int dtype, int mode, const void* dout, const void* addend,
   HG_REQUIRE(mode == 0 || mode == 1, "hg_upsample2x_bwd: mode must be 0 (bilinear_ac) or 1 (nearest)");
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * h * w * (Cp / 8);
-  HG_DISPATCH_T(dtype, (upsample2_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  HG_DISPATCH_T(dtype, (launch_k(upsample2_bwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
                            (const T*)dout, (const T*)addend, (T*)dlow, N, h, w, Cp, mode)));
   HG_LAUNCH_OK("upsample2_bwd_kernel");
   count_launch();
@@ -361,7 +382,7 @@ int hg_add(int dtype, const void* a, const void* b, void* out, long long n_elems
   HG_REQUIRE(dtype == HG_BF16 || dtype == HG_F32, "hg_add: bad dtype");
   HG_REQUIRE(a && b && out && n_elems > 0 && n_elems % 8 == 0, "hg_add: bad arguments");
   const long long nvec = n_elems / 8;
-  HG_DISPATCH_T(dtype, (add_kernel<T><<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b,
+  HG_DISPATCH_T(dtype, (launch_k(add_kernel<T>, dim3(grid_for(nvec)), dim3(256), 0, (cudaStream_t)stream, (const T*)a, (const T*)b,
                                                                                         (T*)out, nvec)));
   HG_LAUNCH_OK("add_kernel");
   count_launch();
@@ -375,7 +396,7 @@ int hg_nchw_f32_to_nhwc(int dtype, const float* src_nchw, const void* addend, in
   HG_REQUIRE(dst != nullptr, "hg_nchw_f32_to_nhwc: NULL dst");
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * H * W * (Cp / 8);
-  HG_DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  HG_DISPATCH_T(dtype, (launch_k(nchw_to_nhwc_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
                            src_nchw, (const T*)addend, (T*)dst, N, C, H * W, Cp)));
   HG_LAUNCH_OK("nchw_to_nhwc_kernel");
   count_launch();
@@ -388,7 +409,7 @@ int hg_nhwc_to_nchw_f32(int dtype, const void* src, int N, int C, int H, int W, 
   HG_REQUIRE(src && dst_nchw, "hg_nhwc_to_nchw_f32: NULL pointer");
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * C * H * W;
-  HG_DISPATCH_T(dtype, (nhwc_to_nchw_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  HG_DISPATCH_T(dtype, (launch_k(nhwc_to_nchw_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
                            (const T*)src, dst_nchw, N, C, H * W, Cp)));
   HG_LAUNCH_OK("nhwc_to_nchw_kernel");
   count_launch();

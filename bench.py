@@ -278,9 +278,16 @@ def run_ours(args):
             flops = 2.0 * B * 64 * 64 * 128 * 128 * 9
             ach = flops / (t / n * 1e-3) / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-            roofline = {"kernel": "conv_gemm_kernel<128,4> (fprop 3x3 128->128 @64x64, tcgen05)", "bound": "tensor",
-                        "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
-                        "traffic": None, "peak_source": f"{src} bf16_tflops_sustained",
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+            if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                if traffic is not None and B != 32:
+                    traffic = None  # captured at B=32 only
+            roofline = {"kernel": "conv_gemm_kernel<128,3,2,kPlain,alias> (fprop 3x3 128->128 @64x64, tcgen05 + TMA)",
+                        "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+                        "frac": round(ach / peak, 4), "traffic": traffic,
+                        "algorithmic_flops_per_launch": flops, "peak_source": f"{src} bf16_tflops_sustained",
                         "launches_per_step": n, "avg_us": round(t / n * 1e3, 2),
                         "share_of_step_kernel_time": round(t / total_ms, 4)}
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -53,6 +53,54 @@ __device__ __forceinline__ void bn_coeffs(const BnArgs& a, int c0, float (&mean)
   }
 }
 
+// Every block of a reduction kernel adds C per-channel partial sums into the same few cache lines, and the L2
+// serialises atomics per line: 4 channels per red.global.add.v4.f32 (dst 16-byte aligned), scalar tail.
+__device__ __forceinline__ void red_add_channels(float* dst, const float* src_smem, int C) {
+  const int c4n = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (C >> 2) : 0;
+  for (int q = threadIdx.x; q < c4n; q += blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src_smem + q * 4);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+  }
+  for (int c = c4n * 4 + threadIdx.x; c < C; c += blockDim.x) atomicAdd(dst + c, src_smem[c]);
+}
+
+// Block-wide version: thread c (< Cp <= 256) derives channel c once, the block shares the result through shared
+// memory (the per-thread version above costs 32 scalar global loads per thread, which dominates small tensors).
+// coef layout: [4][256] = mean, invstd, scale, shift.  Contains a __syncthreads().
+__device__ __forceinline__ void bn_coeffs_block(const BnArgs& a, float (*coef)[256], int vc, float (&mean)[8],
+                                                float (&invstd)[8], float (&scale)[8], float (&shift)[8]) {
+  for (int c = threadIdx.x; c < a.Cp; c += blockDim.x) {
+    float mu = 0.f, is = 0.f, sc = 0.f, sh = 0.f;
+    if (c < a.C) {
+      float var;
+      if (a.use_running) {
+        mu = a.rmean[c];
+        var = a.rvar[c];
+      } else {
+        mu = a.stats[c] / a.count;
+        var = fmaxf(a.stats[a.Cp + c] / a.count - mu * mu, 0.f);
+      }
+      is = rsqrtf(var + a.eps);
+      sc = a.gamma[c] * is;
+      sh = a.beta[c] - mu * sc;
+    }
+    coef[0][c] = mu;
+    coef[1][c] = is;
+    coef[2][c] = sc;
+    coef[3][c] = sh;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mean[e] = coef[0][vc * 8 + e];
+    invstd[e] = coef[1][vc * 8 + e];
+    scale[e] = coef[2][vc * 8 + e];
+    shift[e] = coef[3][vc * 8 + e];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // statistics: stats[c] += sum_m x[m,c]; stats[Cp+c] += sum_m x[m,c]^2
 // ------------------------------------------------------------------------------------------------------
@@ -103,7 +151,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 // rows per block: enough blocks to fill the machine, few enough that the per-channel atomics stay cheap
 static inline int rows_per_block_for(long long M, int rlanes) {
   long long blocks = M / (rlanes * 2);  // small tensors are latency-bound: at most two dependent loads per thread
-  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks > 6 * kNumSMs) blocks = 6 * kNumSMs;
   if (blocks < 1) blocks = 1;
   return (int)((M + blocks - 1) / blocks);
 }
@@ -154,12 +202,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = s[e];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
+  __shared__ float tot[256];
+  for (int c = threadIdx.x; c < Cp; c += 256) {
     const int v = c >> 3, e = c & 7;
     float a = 0.f;
     for (int r = 0; r < rlanes; ++r) a += red[r * vecs + v][e];
-    atomicAdd(out + c, a);
+    tot[c] = a;
   }
+  __syncthreads();
+  red_add_channels(out, tot, C);
 }
 
 int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* out, cudaStream_t st) {
@@ -187,22 +238,39 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
   pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
   pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
 
+  constexpr int U = 2;  // rows in flight per thread
   const int vecs = a.Cp >> 3;
   const int vc = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
   const int rlanes = 256 / vecs;
-  float mean[8], invstd[8], scale[8], shift[8];
-  bn_coeffs(a, vc * 8, mean, invstd, scale, shift);
-  for (long long m = (long long)blockIdx.x * rlanes + rl; m < M; m += (long long)gridDim.x * rlanes) {
-    float v[8];
-    load8(x + m * a.Cp + vc * 8, v);
+  const long long stride = (long long)gridDim.x * rlanes;
+  long long m = (long long)blockIdx.x * rlanes + rl;
+  // the first batch of rows is requested BEFORE the per-channel coefficients: one memory round trip instead of two
+  // (small tensors are pure latency)
+  float v[U][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float o = fmaf(v[e], scale[e], shift[e]);
-      if (a.relu) o = fmaxf(o, 0.f);
-      v[e] = o;
+  for (int u = 0; u < U; ++u)
+    if (m + u * stride < M) load8(x + (m + u * stride) * a.Cp + vc * 8, v[u]);
+  __shared__ float coef[4][256];
+  float mean[8], invstd[8], scale[8], shift[8];
+  bn_coeffs_block(a, coef, vc, mean, invstd, scale, shift);
+  while (m < M) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (m + u * stride < M) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float o = fmaf(v[u][e], scale[e], shift[e]);
+          if (a.relu) o = fmaxf(o, 0.f);
+          v[u][e] = o;
+        }
+        store8(y + (m + u * stride) * a.Cp + vc * 8, v[u]);
+      }
     }
-    store8(y + m * a.Cp + vc * 8, v);
+    m += U * stride;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (m + u * stride < M) load8(x + (m + u * stride) * a.Cp + vc * 8, v[u]);
   }
 }
 
@@ -278,65 +346,93 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   const int vc = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
   const int rlanes = 256 / vecs;
-  float mean[8], invstd[8], scale[8], shift[8];
-  bn_coeffs(a, vc * 8, mean, invstd, scale, shift);
-  float mg[8], mgx[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = vc * 8 + e;
-    if (a.use_running || c >= a.C) {
-      mg[e] = 0.f;
-      mgx[e] = 0.f;
-    } else {
-      mg[e] = redin[c] / a.count;
-      mgx[e] = redin[a.Cp + c] / a.count;
-    }
-  }
-  if (blockIdx.x == 0 && rl == 0) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = vc * 8 + e;
-      if (c < a.C) {
-        if (dgamma) atomicAdd(dgamma + c, redin[a.Cp + c]);
-        if (dbeta) atomicAdd(dbeta + c, redin[c]);
-      }
-    }
-  }
+  constexpr int U = 2;  // rows in flight per thread (three tensors each)
   const long long m0 = (long long)blockIdx.x * rows_per_block;
   long long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
+  long long m = m0 + rl;
+  // request the first rows before the coefficient / reduction loads (latency of small tensors)
+  float xv[U][8], gv[U][8], ad[U][8];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long mm = m + (long long)u * rlanes;
+    if (mm < m1) {
+      load8(x + mm * a.Cp + vc * 8, xv[u]);
+      load8(da + mm * a.Cp + vc * 8, gv[u]);
+      if (addend) load8(addend + mm * a.Cp + vc * 8, ad[u]);
+    }
+  }
+  __shared__ float coef[4][256];
+  __shared__ float mred[2][256];
+  for (int c = threadIdx.x; c < a.Cp; c += blockDim.x) {
+    float r0 = 0.f, r1 = 0.f;
+    if (c < a.C) {
+      r0 = redin[c];
+      r1 = redin[a.Cp + c];
+      if (blockIdx.x == 0) {
+        if (dgamma) atomicAdd(dgamma + c, r1);
+        if (dbeta) atomicAdd(dbeta + c, r0);
+      }
+    }
+    const bool stat = !a.use_running && c < a.C;
+    mred[0][c] = stat ? r0 / a.count : 0.f;
+    mred[1][c] = stat ? r1 / a.count : 0.f;
+  }
+  float mean[8], invstd[8], scale[8], shift[8];
+  bn_coeffs_block(a, coef, vc, mean, invstd, scale, shift);  // (its __syncthreads also publishes mred)
+  // dx = scale*(g - mg - xhat*mgx) = scale*g + cB*x + cC   (xhat = (x - mean)*invstd)
+  float cB[8], cC[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float mg = mred[0][vc * 8 + e], mgx = mred[1][vc * 8 + e];
+    cB[e] = -scale[e] * mgx * invstd[e];
+    cC[e] = -scale[e] * mg - cB[e] * mean[e];
+  }
   float cs[8] = {};
-#pragma unroll 2
-  for (long long m = m0 + rl; m < m1; m += rlanes) {
-    float xv[8], gv[8], o[8];
-    load8(x + m * a.Cp + vc * 8, xv);
-    load8(da + m * a.Cp + vc * 8, gv);
+  while (m < m1) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float g = gv[e];
-      if (a.relu && !(fmaf(xv[e], scale[e], shift[e]) > 0.f)) g = 0.f;
-      const float xh = (xv[e] - mean[e]) * invstd[e];
-      o[e] = scale[e] * (g - mg[e] - xh * mgx[e]);
-      cs[e] += o[e];
-    }
-    if (addend) {
-      float ad[8];
-      load8(addend + m * a.Cp + vc * 8, ad);
+    for (int u = 0; u < U; ++u) {
+      const long long mm = m + (long long)u * rlanes;
+      if (mm < m1) {
+        float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] += ad[e];
+        for (int e = 0; e < 8; ++e) {
+          float g = gv[u][e];
+          if (a.relu && !(fmaf(xv[u][e], scale[e], shift[e]) > 0.f)) g = 0.f;
+          o[e] = fmaf(scale[e], g, fmaf(cB[e], xv[u][e], cC[e]));
+          cs[e] += o[e];
+        }
+        if (addend) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += ad[u][e];
+        }
+        store8(dx + mm * a.Cp + vc * 8, o);
+      }
     }
-    store8(dx + m * a.Cp + vc * 8, o);
+    m += (long long)U * rlanes;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long mm = m + (long long)u * rlanes;
+      if (mm < m1) {
+        load8(x + mm * a.Cp + vc * 8, xv[u]);
+        load8(da + mm * a.Cp + vc * 8, gv[u]);
+        if (addend) load8(addend + mm * a.Cp + vc * 8, ad[u]);
+      }
+    }
   }
   if (colsum) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = cs[e];
     __syncthreads();
-    for (int c = threadIdx.x; c < a.C; c += 256) {
+    float* tot = &coef[0][0];  // coefficients are in registers by now
+    for (int c = threadIdx.x; c < a.Cp; c += 256) {
       const int v = c >> 3, e = c & 7;
       float p = 0.f;
       for (int r = 0; r < rlanes; ++r) p += red[r * vecs + v][e];
-      atomicAdd(colsum + c, p);
+      tot[c] = p;
     }
+    __syncthreads();
+    red_add_channels(colsum, tot, a.C);
   }
 }
 
@@ -432,7 +528,7 @@ int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const floa
              "hg_bn_apply: statistics missing for the selected mode");
   BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
   const int rlanes = 256 / (a.Cp >> 3);
-  int blocks = ceil_div(d->M, rlanes * 4);
+  int blocks = ceil_div(d->M, rlanes * 2);  // two rows in flight per thread; large tensors: 8 blocks per SM
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == HG_BF16)

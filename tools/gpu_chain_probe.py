@@ -77,6 +77,28 @@ def bn_chain(B, hw, c, n=100):
     return graph_time(body) / n * 1e3
 
 
+def bn_bwd_chain(B, hw, c, n=100, with_addend=False):
+    d = L.HgBnDesc(B * hw * hw, c, L.HG_BF16, 1e-5, 1, 0)
+    x = torch.randn(B, hw, hw, c, device=dev).to(DT)
+    g = torch.randn(B, hw, hw, c, device=dev).to(DT)
+    dx = torch.zeros_like(x)
+    add = torch.randn(B, hw, hw, c, device=dev).to(DT) if with_addend else None
+    stats = torch.zeros(2 * c, device=dev)
+    stats[c:] = float(B * hw * hw)
+    red = torch.zeros(2 * c, device=dev)
+    gam, bet = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    dg, db, cs = torch.zeros(c, device=dev), torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+
+    def body():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for i in range(n):
+            a, b = (g, dx) if i % 2 == 0 else (dx, g)
+            L.call("hg_bn_bwd_apply", C.byref(d), L.ptr(a), L.ptr(x), L.ptr(stats), L.ptr(gam), L.ptr(bet), None, None,
+                   L.ptr(red), L.ptr(add), L.ptr(b), L.ptr(dg), L.ptr(db), L.ptr(cs), st)
+
+    return graph_time(body) / n * 1e3
+
+
 def empty_chain(n=200):
     t = torch.zeros(64, device=dev, dtype=DT)
 
@@ -96,4 +118,6 @@ if __name__ == "__main__":
               f"conv1x1 256->128 {conv_chain(32, hw, 256, 128, 1):7.2f} us | "
               f"conv1x1 128->256 {conv_chain(32, hw, 128, 256, 1):7.2f} us | "
               f"conv1x1 256->256 {conv_chain(32, hw, 256, 256, 1):7.2f} us | "
-              f"bn_apply C256 {bn_chain(32, hw, 256):7.2f} us | bn_apply C128 {bn_chain(32, hw, 128):7.2f} us")
+              f"bn_apply C256 {bn_chain(32, hw, 256):7.2f} us | bn_apply C128 {bn_chain(32, hw, 128):7.2f} us | "
+              f"bn_bwd_apply C256+add {bn_bwd_chain(32, hw, 256, with_addend=True):7.2f} us | "
+              f"bn_bwd_apply C128 {bn_bwd_chain(32, hw, 128):7.2f} us")

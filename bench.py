@@ -247,6 +247,39 @@ def run_ours(args):
     h2d = xh.numel() * 4 + yh.numel() * 4
     # (the prefetch uploads one extra batch at the very end; bytes are counted per step as copied)
 
+    # ---- inference leg (BASELINE configs[4]): 4-stack / 17-joint network in eval(), heatmaps of the last stack
+    # decoded and scored by the PCKh threshold sweep, all on the device; images/s over all ranks ----------------
+    inference = None
+    if not args.no_inference:
+        import numpy as np
+
+        m.nStack, m.nOutChannels = 4, 17
+        torch.manual_seed(1)
+        inet = m.creatModel().to(dev).eval()
+        r = np.random.RandomState(7 + rank)
+        label = torch.zeros(B, 64, 64, dtype=torch.int64)
+        for b_ in range(B):
+            pos = r.choice(64 * 64, 17, replace=False)
+            for j, pp in enumerate(pos):
+                label[b_, pp // 64, pp % 64] = j + 1
+        label = label.to(dev)
+        x0 = r.uniform(5, 40, [B, 2]).astype("float32")
+        rect = torch.from_numpy(np.concatenate([x0, x0 + r.uniform(5, 20, [B, 2]).astype("float32")], 1)).to(dev)
+
+        def infer():
+            with torch.no_grad():
+                out = inet(x)
+                return hg.pckh_sweep_counts(out[-1], label, rect, 0)
+
+        for _ in range(3):
+            res = infer()
+        ms_inf = timed(infer, args.steps)
+        inference = {"metric": "inference images/sec, 4-stack hourglass 256x256 (17 joints) + argmax decode + PCKh sweep",
+                     "value": round(world * B * args.steps / (ms_inf / 1e3), 2), "unit": UNIT,
+                     "ms_per_step": round(ms_inf / args.steps, 3), "batch_per_gpu": B, "bn_mode": "eval",
+                     "pckh_total_joints": int(res["total"][:, 0].sum().item())}
+        m.nStack, m.nOutChannels = NSTACK, NJOINT
+
     # ---- per-kernel profile of one step (eager, CUDA events around every C-ABI call) ------------------
     roofline, table = None, None
     if rank == 0:
@@ -323,6 +356,7 @@ def run_ours(args):
                                                  / float(measured_peaks()[0]["bf16_tflops_sustained"]), 4),
             "loss_after_warmup": loss0,
             "phases": phases,
+            "inference": inference,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -393,6 +427,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

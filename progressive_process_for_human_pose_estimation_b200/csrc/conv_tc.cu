@@ -116,10 +116,14 @@ struct ConvGemmSmem {
   static constexpr int kCPanels = BN / 64;       // output staging: panels of 128 rows x 64 ch
   static constexpr int kCBytes = kCPanels * 128 * 128;
   static constexpr int kStageBytes = STAGES * (kABytes + kBBytes);
-  static constexpr int kEpiBytes = MODE == kMask ? 3 * kCBytes : kCBytes;
-  static constexpr int kMainBytes = ALIAS ? (kStageBytes > kEpiBytes ? kStageBytes : kEpiBytes)
-                                          : kStageBytes + kEpiBytes;
-  static constexpr int kCOffset = ALIAS ? 0 : kStageBytes;
+  static constexpr int kQBytes = MODE == kMask ? 2 * kCBytes : 0;   // fp32 g*xhat tile of the mask epilogue
+  // ALIAS: C (and Q) inside the stages.  !ALIAS: dedicated C behind the stages (loaded up front); Q still aliases
+  // the stages, which are idle by the time the epilogue writes it.
+  static constexpr int kMainBytes =
+      ALIAS ? (kStageBytes > kCBytes + kQBytes ? kStageBytes : kCBytes + kQBytes)
+            : (kStageBytes > kQBytes ? kStageBytes : kQBytes) + kCBytes;
+  static constexpr int kCOffset = ALIAS ? 0 : (kStageBytes > kQBytes ? kStageBytes : kQBytes);
+  static constexpr int kQOffset = ALIAS ? kCBytes : 0;
   static constexpr int kBarBytes = 256;          // mbarriers + TMEM slot
   static constexpr int kBiasBytes = BN * 4;
   static constexpr int kCoefBytes = 2048;        // kFold: scale/shift[256];  kMask: A/B/scale/shift[BN]
@@ -133,7 +137,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const ConvGemmParams p) {
   using L = ConvGemmSmem<BN, STAGES, MODE, ALIAS>;
   static_assert(3 * STAGES + 2 <= 30, "barrier region too small");
-  static_assert(MODE != kMask || ALIAS, "the mask epilogue stages two tiles: it always aliases the pipeline stages");
   extern __shared__ uint8_t smem_raw[];
   // (pointer arithmetic on the shared array keeps the address space: LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -332,8 +335,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n = m / plane;
       nchw_row = p.out_nchw + (size_t)n * p.c_real * plane + (m - n * plane);
     }
-    // kMask: second staging buffer (g * xhat, fp32) right behind C, both inside the idle pipeline stages
-    uint8_t* sQ = sC + L::kCBytes;
+    // kMask: second staging buffer (g * xhat, fp32) inside the idle pipeline stages
+    uint8_t* sQ = smem + L::kQOffset;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       float v[32];
@@ -530,8 +533,12 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
                               cudaStream_t st) {
   const bool single_wave = ceil_div(p.M_total, 128) * p.n_tiles <= kNumSMs;
   if constexpr (MODE == kMask) {
-    return single_wave ? launch_conv_gemm<BN, 6, 1, kMask, true>(tmA, tmB, tmC, tmR, p, st)
-                       : launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st);
+    // the raw BatchNorm input tile is prefetched into a dedicated C buffer wherever shared memory allows; only the
+    // multi-wave 3x3 kernel (two CTAs per SM) loads it after its (long) main loop
+    if (single_wave) return long_k ? launch_conv_gemm<BN, 5, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st)
+                                   : launch_conv_gemm<BN, 4, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st);
+    return long_k ? launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st)
+                  : launch_conv_gemm<BN, 2, 2, kMask, false>(tmA, tmB, tmC, tmR, p, st);
   } else {
     constexpr int kShortMinB = MODE == kFold ? 2 : 3;  // the transform needs > 113 registers
     if (has_res) {

@@ -265,3 +265,42 @@ def test_cpu_input_fails_loudly():
     net = m.creatModel()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net(torch.randn(1, 3, 256, 256))
+
+
+def test_full_size_train_steps_properties():
+    """BASELINE configs[1] at full size (8 stacks, 16 joints, B=32, bf16): properties that do not need an oracle --
+    finite decreasing loss over Adam steps, exact BatchNorm bookkeeping (a level's shared BN modules are updated
+    6-8 x nStack times per forward, quirk Q1), CUDA-graph replays, gradients only where the reference has them."""
+    hg.set_compute_dtype(torch.bfloat16)
+    m.nStack, m.nOutChannels = 8, 16
+    torch.manual_seed(0)
+    net = m.creatModel().cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(32, 3, 256, 256, generator=g).cuda()
+    import numpy as np
+    r = np.random.RandomState(4)
+    kp = np.zeros([32, 1, 16, 3])
+    kp[..., 0], kp[..., 1], kp[..., 2] = r.randint(0, 640, [32, 1, 16]), r.randint(0, 480, [32, 1, 16]), 2
+    y = hg.gaussian_heatmaps(kp, np.tile(np.array([[640.0, 480.0]]), (32, 1)))
+    losses = []
+    for it in range(6):
+        out = net(x)
+        assert len(out) == 8 and all(o.shape == (32, 16, 64, 64) for o in out)
+        loss = sum(torch.nn.MSELoss()(o, y) for o in out)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < 0.7 * losses[0], losses
+    sd = net.state_dict()
+    assert int(sd["hourglass1.residual_block.bn1.num_batches_tracked"]) == 6 * 8 * 6      # 6 calls x 8 stacks x 6 steps
+    assert int(sd["hourglass1.hourglass1.hourglass1.hourglass1.residual_block.bn1.num_batches_tracked"]) == 8 * 8 * 6
+    assert int(sd["residual4.bn2.num_batches_tracked"]) == 2 * 8 * 6
+    assert int(sd["residual1.bn1.num_batches_tracked"]) == 6
+    none = [n for n, p in net.named_parameters() if p.grad is None]
+    assert len(none) == 12 and all(".conv4." in n for n in none)   # identity blocks' unused projections (quirk Q3)
+    # decode of the (identical) targets is exact at full size
+    yx, mx = hg.decode_argmax(y)
+    assert torch.equal(yx[..., 0].long() * 64 + yx[..., 1].long(), y.flatten(2).argmax(-1))

@@ -217,6 +217,20 @@ HG_API int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, cons
 HG_API int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, int N, int H, int W, int relu,
                        float* dw_oihw, float* dbias, void* stream);
 
+/* ---- intermediate-supervision MSE loss (try_with_torch.py:305-308,333-341) --------------------------- */
+/* loss[s] += mean((pred_s - target)^2) for s < num_stacks (caller zeroes loss[num_stacks]); optionally
+ * dpred_s = 2 * grad_scale * (pred_s - target) / numel, the gradient `sum_s loss_s`.backward() sends into every
+ * returned heatmap.  preds_host / dpreds_host are HOST arrays of num_stacks DEVICE pointers (fp32 tensors of
+ * `numel` elements, 16-byte aligned); dpreds_host or any of its entries may be NULL. */
+#define HG_MSE_MAX_STACKS 8
+typedef struct HgMseDesc {
+  int64_t numel;
+  int32_t num_stacks;
+  float grad_scale;
+} HgMseDesc;
+HG_API int hg_mse_multi(const HgMseDesc* d, const float* const* preds_host, const float* target,
+                        float* const* dpreds_host, float* loss, void* stream);
+
 /* ---- target rendering ---------------------------------------------------------------------------- */
 /* Gaussian keypoint heatmaps, evaluated in float64 like the numpy code, stored as float32
  * (try_with_torch.py:107-132; variants try_with_torch_100.py:64-85, only_one_hourgless.py:112-132,

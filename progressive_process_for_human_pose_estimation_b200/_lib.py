@@ -47,6 +47,10 @@ class HgGaussDesc(C.Structure):
                [("pre_scale", C.c_double), ("sigma", C.c_double), ("amplitude", C.c_double)]
 
 
+class HgMseDesc(C.Structure):
+    _fields_ = [("numel", C.c_int64), ("num_stacks", C.c_int32), ("grad_scale", C.c_float)]
+
+
 class HgLabelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "P", "J", "L", "H", "W", "center_mode", "draw_points", "draw_lines",
                                          "line_value")]
@@ -87,6 +91,7 @@ SIGNATURES = {
     "hg_pack_conv_weight_slice": [C.POINTER(HgConvDesc), _P, _I, _I, _P, _P, _P],
     "hg_unpack_conv_wgrad_slice": [C.POINTER(HgConvDesc), _P, _P, _I, _I, _I, _P],
     "hg_mix_rows": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
     "hg_render_gauss": [C.POINTER(HgGaussDesc), _P, _P, _P, _P, _P],
     "hg_render_labels": [C.POINTER(HgLabelDesc), _P, _P, _P, _P, _P, _P],
     "hg_decode_argmax": [_P, _I, _I, _I, _I, _P, _P, _P],

@@ -48,6 +48,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.HgBnRunningModule) == 48
     assert ctypes.sizeof(L.HgGaussDesc) == 56
     assert ctypes.sizeof(L.HgLabelDesc) == 40
+    assert ctypes.sizeof(L.HgBnFold) == 56
+    assert ctypes.sizeof(L.HgMseDesc) == 16
 
 
 def test_plan_lowering_structure(built):

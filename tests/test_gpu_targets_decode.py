@@ -182,3 +182,32 @@ def test_render_decode_roundtrip_at_scale():
 def test_decode_requires_cuda_tensor():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         hg.decode_argmax(torch.zeros(1, 1, 64, 64))
+
+
+def test_fused_mse_losses_match_stock_modules():
+    """hg.mse_losses == sum of nn.MSELoss per stack (try_with_torch.py:333-341): values and gradients."""
+    torch.manual_seed(0)
+    S, shape = 8, (4, 16, 64, 64)
+    tgt = torch.rand(shape, device="cuda")
+    preds = [torch.randn(shape, device="cuda", requires_grad=True) for _ in range(S)]
+    ref = [torch.nn.MSELoss()(p, tgt) for p in preds]
+    sum(w * l for w, l in zip(range(1, S + 1), ref)).backward()
+    gref = [p.grad.clone() for p in preds]
+    for p in preds:
+        p.grad = None
+    losses = hg.mse_losses(preds, tgt)
+    assert losses.shape == (S,)
+    assert torch.allclose(losses, torch.stack(ref).detach(), rtol=1e-5, atol=0)
+    (losses * torch.arange(1, S + 1, device="cuda")).sum().backward()
+    for p, g in zip(preds, gref):
+        assert torch.allclose(p.grad, g, rtol=1e-6, atol=1e-9)
+    # odd element count (scalar tail) and a prediction that needs no gradient
+    a = torch.randn(3, 5, 7, device="cuda", requires_grad=True)
+    b = torch.randn(3, 5, 7, device="cuda")
+    t = torch.rand(3, 5, 7, device="cuda")
+    l2 = hg.mse_losses([a, b], t)
+    assert torch.allclose(l2, torch.stack([((a - t) ** 2).mean(), ((b - t) ** 2).mean()]).detach(), rtol=1e-5)
+    l2.sum().backward()
+    assert torch.allclose(a.grad, 2 * (a.detach() - t) / t.numel(), rtol=1e-6, atol=1e-9)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hg.mse_losses([a.detach().cpu()], t.cpu())

@@ -175,34 +175,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail; global memory is ours from here
-  if (warp >= 2) {
-    const int et = threadIdx.x - 64;
-    for (int c = et; c < BN; c += 128) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
-    if constexpr (MODE == kFold) {
-      // scale / shift of every INPUT channel (<= 256)
-      for (int c = et; c < p.kchunks * 64; c += 128) {
-        float mu, is, sc, sh;
-        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
-        coef_s[c] = sc;
-        coef_s[256 + c] = sh;
-      }
-    }
-    if constexpr (MODE == kMask) {
-      for (int c = et; c < BN; c += 128) {
-        float mu, is, sc, sh;
-        bn_fold_coeffs(p.fold, n_off + c, mu, is, sc, sh);
-        coef_s[c] = is;                 // xhat = y * A + B
-        coef_s[BN + c] = -mu * is;
-        coef_s[2 * BN + c] = sc;        // ReLU mask: scale * y + shift > 0 (the forward's own expression)
-        coef_s[3 * BN + c] = sh;
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; global memory is ours from here.  The producer warp
+  // starts its TMA loads at once; the per-channel coefficients are fetched by the epilogue warps meanwhile.
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -269,9 +248,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== transform (kFold) + epilogue (warps 2..5) =====================
     const int sub = warp & 3;           // TMEM sub-partition this warp may read
     const int row = sub * 32 + lane;    // accumulator row == pixel within the tile
-    const int et = threadIdx.x - 64;    // 0..127
     const int m = m0 + row;
     const bool row_ok = m < p.M_total;
+    {
+      const int et = threadIdx.x - 64;
+    for (int c = et; c < BN; c += 128) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
+    if constexpr (MODE == kFold) {
+      // scale / shift of every INPUT channel (<= 256)
+      for (int c = et; c < p.kchunks * 64; c += 128) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
+        coef_s[c] = sc;
+        coef_s[256 + c] = sh;
+      }
+    }
+    if constexpr (MODE == kMask) {
+      for (int c = et; c < BN; c += 128) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, n_off + c, mu, is, sc, sh);
+        coef_s[c] = is;                 // xhat = y * A + B
+        coef_s[BN + c] = -mu * is;
+        coef_s[2 * BN + c] = sc;        // ReLU mask: scale * y + shift > 0 (the forward's own expression)
+        coef_s[3 * BN + c] = sh;
+      }
+    }
+    }
+    const int et = threadIdx.x - 64;    // 0..127
+    named_bar_sync(1, 128);             // coefficients visible to the four epilogue warps
 
     if constexpr (MODE == kFold) {
       // Rewrite every A tile in place: a = [relu](scale * x + shift).  Thread = one 16-byte channel chunk (8
@@ -714,21 +717,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, cols);
-  pdl_wait();
-  if constexpr (FOLD) {
-    if (warp >= 2) {
-      for (int c = threadIdx.x - 64; c < p.Cin_p; c += 128) {
-        float mu, is, sc, sh;
-        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
-        coef_s[c] = sc;
-        coef_s[256 + c] = sh;
-      }
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const int a_bytes = 2 * 8192;
 
   if (nkb > 0) {
@@ -790,6 +783,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       const int et = threadIdx.x - 64;
       (void)et;
       if constexpr (FOLD) {
+        for (int c = et; c < p.Cin_p; c += 128) {
+          float mu, is, sc, sh;
+          bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
+          coef_s[c] = sc;
+          coef_s[256 + c] = sh;
+        }
+        named_bar_sync(1, 128);
         // rewrite the x tiles of every stage (see conv_gemm_kernel): thread = one 16-byte channel chunk x 4 rows of
         // each 64-row tile
         const int jch = et & 7;

@@ -24,6 +24,11 @@ _WGRAD_LANES = int(os.environ.get("HG_WGRAD_LANES", "1"))
 # 0: BatchNorm kernels stay separate; 1: only the data-gradient epilogue is fused (ReLU mask + BN-backward sums);
 # 2: additionally the forward / weight-gradient convolutions apply BN+ReLU to their operand tiles (no activation in HBM)
 _FOLD_BN = int(os.environ.get("HG_FOLD_BN", "1"))
+# Stream priority of the main lane in the FORWARD graph: it carries the latency-bound low-resolution chain, and when a
+# skip-branch lane's big kernel holds every SM the CTA scheduler must hand freed slots to the main lane first
+# (measured: forward 14.3 -> 13.1 ms).  In the backward graph any priority skew starves the wgrad lane into a tail
+# (32.1 -> 33.5 ms), so all backward lanes stay equal.
+_FWD_MAIN_PRIORITY = int(os.environ.get("HG_FWD_MAIN_PRIORITY", "-3"))
 
 
 class Val:
@@ -862,7 +867,9 @@ class Plan:
         captured).  Every lane is joined back into the main stream at the end."""
         main = torch.cuda.current_stream()
         if self.lane_streams is None:
-            self.lane_streams = [None] + [torch.cuda.Stream() for _ in range(self.num_lanes - 1)]
+            self.lane_streams = [None]
+            for lane in range(1, self.num_lanes):
+                self.lane_streams.append(torch.cuda.Stream())
         streams = [main] + self.lane_streams[1:]
         needed = set()
         for c in calls:
@@ -936,7 +943,7 @@ class Plan:
             self.prepare()
         if _USE_GRAPHS and self.n_fwd_runs >= 1 and self.profile_records is None:
             if self.fwd_graph is None:
-                self.fwd_graph = self._capture(self._fwd_body)
+                self.fwd_graph = self._capture(self._fwd_body, _FWD_MAIN_PRIORITY)
             self.fwd_graph.replay()
         else:
             self._fwd_body()
@@ -974,10 +981,10 @@ class Plan:
         gin = self.gin_static.clone() if self.gin_static is not None else None
         return gin, grads
 
-    def _capture(self, body):
+    def _capture(self, body, priority=0):
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
+        s = torch.cuda.Stream(priority=priority)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             with torch.cuda.graph(graph, stream=s):

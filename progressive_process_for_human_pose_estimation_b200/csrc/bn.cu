@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
 //   Block 0 adds dgamma += sum g*xhat, dbeta += sum g.  colsum (optional) += sum_m dx-without-addend,
 //   i.e. the bias gradient of the convolution that produced x.
 // ------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool ADD, bool CS>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ x,
                                                            const T* __restrict__ addend, T* __restrict__ dx,
                                                            long long M, BnArgs a, const float* __restrict__ redin,
@@ -346,20 +346,20 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   const int vc = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
   const int rlanes = 256 / vecs;
-  constexpr int U = 2;  // rows in flight per thread (three tensors each)
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;  // rows in flight per thread (three tensors each, kept unconverted)
   const long long m0 = (long long)blockIdx.x * rows_per_block;
   long long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
   long long m = m0 + rl;
   // request the first rows before the coefficient / reduction loads (latency of small tensors)
-  float xv[U][8], gv[U][8], ad[U][8];
+  Raw8<T> xr[U], gr[U], ar[ADD ? U : 1];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const long long mm = m + (long long)u * rlanes;
     if (mm < m1) {
-      load8(x + mm * a.Cp + vc * 8, xv[u]);
-      load8(da + mm * a.Cp + vc * 8, gv[u]);
-      if (addend) load8(addend + mm * a.Cp + vc * 8, ad[u]);
+      load_raw(x + mm * a.Cp + vc * 8, xr[u]);
+      load_raw(da + mm * a.Cp + vc * 8, gr[u]);
+      if (ADD) load_raw(addend + mm * a.Cp + vc * 8, ar[u]);
     }
   }
   __shared__ float coef[4][256];
@@ -394,17 +394,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     for (int u = 0; u < U; ++u) {
       const long long mm = m + (long long)u * rlanes;
       if (mm < m1) {
-        float o[8];
+        float xv[8], gv[8], o[8];
+        unpack(xr[u], xv);
+        unpack(gr[u], gv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float g = gv[u][e];
-          if (a.relu && !(fmaf(xv[u][e], scale[e], shift[e]) > 0.f)) g = 0.f;
-          o[e] = fmaf(scale[e], g, fmaf(cB[e], xv[u][e], cC[e]));
-          cs[e] += o[e];
+          float g = gv[e];
+          if (a.relu && !(fmaf(xv[e], scale[e], shift[e]) > 0.f)) g = 0.f;
+          o[e] = fmaf(scale[e], g, fmaf(cB[e], xv[e], cC[e]));
+          if (CS) cs[e] += o[e];
         }
-        if (addend) {
+        if (ADD) {
+          float ad[8];
+          unpack(ar[ADD ? u : 0], ad);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += ad[u][e];
+          for (int e = 0; e < 8; ++e) o[e] += ad[e];
         }
         store8(dx + mm * a.Cp + vc * 8, o);
       }
@@ -414,13 +418,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     for (int u = 0; u < U; ++u) {
       const long long mm = m + (long long)u * rlanes;
       if (mm < m1) {
-        load8(x + mm * a.Cp + vc * 8, xv[u]);
-        load8(da + mm * a.Cp + vc * 8, gv[u]);
-        if (addend) load8(addend + mm * a.Cp + vc * 8, ad[u]);
+        load_raw(x + mm * a.Cp + vc * 8, xr[u]);
+        load_raw(da + mm * a.Cp + vc * 8, gr[u]);
+        if (ADD) load_raw(addend + mm * a.Cp + vc * 8, ar[u]);
       }
     }
   }
-  if (colsum) {
+  if (CS) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = cs[e];
     __syncthreads();
@@ -573,13 +577,20 @@ int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const floa
   const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3));
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->dtype == HG_BF16)
-    launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, 
-        (const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, d->M, a,
-        red, dgamma, dbeta, colsum, rpb);
-  else
-    launch_k(bn_bwd_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)da, (const float*)x, (const float*)addend,
-                                                        (float*)dx, d->M, a, red, dgamma, dbeta, colsum, rpb);
+#define HG_BWD_APPLY(T, ADD, CS)                                                                                 \
+  launch_k(bn_bwd_apply_kernel<T, ADD, CS>, dim3(blocks), dim3(256), 0, st, (const T*)da, (const T*)x,            \
+           (const T*)addend, (T*)dx, d->M, a, red, dgamma, dbeta, colsum, rpb)
+#define HG_BWD_APPLY_T(T)                                   \
+  do {                                                      \
+    if (addend && colsum) HG_BWD_APPLY(T, true, true);      \
+    else if (addend) HG_BWD_APPLY(T, true, false);          \
+    else if (colsum) HG_BWD_APPLY(T, false, true);          \
+    else HG_BWD_APPLY(T, false, false);                     \
+  } while (0)
+  if (d->dtype == HG_BF16) HG_BWD_APPLY_T(__nv_bfloat16);
+  else HG_BWD_APPLY_T(float);
+#undef HG_BWD_APPLY_T
+#undef HG_BWD_APPLY
   HG_LAUNCH_OK("bn_bwd_apply_kernel");
   count_launch();
   return HG_OK;

@@ -116,7 +116,7 @@ struct ConvGemmSmem {
   static constexpr int kCPanels = BN / 64;       // output staging: panels of 128 rows x 64 ch
   static constexpr int kCBytes = kCPanels * 128 * 128;
   static constexpr int kStageBytes = STAGES * (kABytes + kBBytes);
-  static constexpr int kQBytes = MODE == kMask ? 2 * kCBytes : 0;   // fp32 g*xhat tile of the mask epilogue
+  static constexpr int kQBytes = MODE == kMask ? kCBytes : 0;   // kMask: masked gradient tile G (C holds the raw input)
   // ALIAS: C (and Q) inside the stages.  !ALIAS: dedicated C behind the stages (loaded up front); Q still aliases
   // the stages, which are idle by the time the epilogue writes it.
   static constexpr int kMainBytes =
@@ -126,7 +126,8 @@ struct ConvGemmSmem {
   static constexpr int kQOffset = ALIAS ? kCBytes : 0;
   static constexpr int kBarBytes = 256;          // mbarriers + TMEM slot
   static constexpr int kBiasBytes = BN * 4;
-  static constexpr int kCoefBytes = 2048;        // kFold: scale/shift[256];  kMask: A/B/scale/shift[BN]
+  static constexpr int kCoefBytes = 2048;        // kFold: scale/shift[256];  kMask: scale/shift/A/B[BN]
+  static constexpr int kAccBytes = 2 * BN * 4;   // per-channel column sums of the epilogue
   static constexpr int kTotal = kMainBytes + kBarBytes + kBiasBytes + kCoefBytes + 1024 /*align slack*/;
 };
 
@@ -152,6 +153,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [BN]
   float* coef_s = bias_s + BN;                                                                // 512 floats
+  float* acc_s = coef_s + 512;                                                                // [2 * BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -266,10 +268,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = et; c < BN; c += 128) {
         float mu, is, sc, sh;
         bn_fold_coeffs(p.fold, n_off + c, mu, is, sc, sh);
-        coef_s[c] = is;                 // xhat = y * A + B
-        coef_s[BN + c] = -mu * is;
-        coef_s[2 * BN + c] = sc;        // ReLU mask: scale * y + shift > 0 (the forward's own expression)
-        coef_s[3 * BN + c] = sh;
+        coef_s[c] = sc;                 // ReLU mask: scale * y + shift > 0 (the forward's own expression)
+        coef_s[BN + c] = sh;
+        coef_s[2 * BN + c] = is;        // xhat = y * A + B  ->  sum g*xhat = A * sum(g*y) + B * sum(g)
+        coef_s[3 * BN + c] = -mu * is;
       }
     }
     }
@@ -338,7 +340,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n = m / plane;
       nchw_row = p.out_nchw + (size_t)n * p.c_real * plane + (m - n * plane);
     }
-    // kMask: second staging buffer (g * xhat, fp32) inside the idle pipeline stages
+    // kMask: second staging buffer (masked gradient G, bf16) inside the idle pipeline stages
     uint8_t* sQ = smem + L::kQOffset;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
@@ -354,39 +356,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint4* cp = reinterpret_cast<uint4*>(rowp + swz);
         float o[8];
         if constexpr (MODE == kMask) {
-          // raw BatchNorm input of these 8 channels -> ReLU mask and xhat = y * A + B
+          // raw BatchNorm input of these 8 channels (stays in C) -> ReLU mask; the masked gradient goes to G
           const uint4 u = *cp;
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-          float y[8], qq[8], cA[8], cB[8], cS[8], cT[8];
+          float cS[8], cT[8];
           const int c0 = j * 32 + q * 8;
-          load_coef8(coef_s + c0, cA);
-          load_coef8(coef_s + BN + c0, cB);
-          load_coef8(coef_s + 2 * BN + c0, cS);
-          load_coef8(coef_s + 3 * BN + c0, cT);
+          load_coef8(coef_s + c0, cS);
+          load_coef8(coef_s + BN + c0, cT);
+          const bool relu = p.fold.relu != 0;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 f = __bfloat1622float2(h[e]);
-            y[2 * e] = f.x;
-            y[2 * e + 1] = f.y;
+            const bool k0 = !relu || fmaf(f.x, cS[2 * e], cT[2 * e]) > 0.f;
+            const bool k1 = !relu || fmaf(f.y, cS[2 * e + 1], cT[2 * e + 1]) > 0.f;
+            o[2 * e] = k0 ? v[q * 8 + 2 * e] : 0.f;
+            o[2 * e + 1] = k1 ? v[q * 8 + 2 * e + 1] : 0.f;
           }
-          const bool relu = p.fold.relu != 0;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float g = v[q * 8 + e];
-            if (relu && !(fmaf(y[e], cS[e], cT[e]) > 0.f)) g = 0.f;
-            // the sums are taken over the bf16 values bn_bwd_apply will read back
-            g = __bfloat162float(__float2bfloat16_rn(g));
-            o[e] = g;
-            qq[e] = g * fmaf(y[e], cA[e], cB[e]);
-          }
-          // q = g * xhat is staged in fp32: rows of 64 ch x 4 B = 256 B, one panel = 128 rows x 256 B
-          uint8_t* qrow = sQ + pnl * 32768 + row * 256;
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            const int ch4 = ((chunk0 + q) * 2 + hlf);            // 16-byte chunk index within the 256 B row (0..15)
-            float4* qp = reinterpret_cast<float4*>(qrow + ((ch4 ^ (row & 15)) << 4));
-            *qp = make_float4(qq[hlf * 4], qq[hlf * 4 + 1], qq[hlf * 4 + 2], qq[hlf * 4 + 3]);
-          }
+          cp = reinterpret_cast<uint4*>(sQ + pnl * 16384 + row * 128 + swz);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[j * 32 + q * 8 + e];
@@ -419,7 +405,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
     if (et == 0) {
-      for (int pnl = 0; pnl < L::kCPanels; ++pnl) tma_store_2d(&tmC, sC + pnl * 16384, n_off + pnl * 64, m0);
+      const uint8_t* src = MODE == kMask ? sQ : sC;
+      for (int pnl = 0; pnl < L::kCPanels; ++pnl) tma_store_2d(&tmC, src + pnl * 16384, n_off + pnl * 64, m0);
       tma_store_commit();
     }
     if (p.stats != nullptr) {
@@ -434,33 +421,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr int kQuads = BN / 4;            // 32 or 16
       constexpr int kGroups = 128 / kQuads;     // row slices: 4 or 8
       constexpr int kRows = 128 / kGroups;      // 32 or 16
-      float* acc_s = coef_s;                    // [2 * BN] floats; the coefficients are dead by now
       for (int i = et; i < 2 * BN; i += 128) acc_s[i] = 0.f;
       named_bar_sync(1, 128);
       {
         const int quad = et % kQuads, grp = et / kQuads;
         const int c = quad * 4;
-        const uint8_t* colp = sC + (c >> 6) * 16384 + (c & 7) * 2;
+        const int coff = (c >> 6) * 16384 + (c & 7) * 2;
         const int chunk = (c & 63) >> 3;
+        const uint8_t* vcol = (MODE == kMask ? sQ : sC) + coff;   // the values whose sum is taken
+        const uint8_t* ycol = sC + coff;                          // kMask: raw BatchNorm input
         float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint8_t* qcol = sQ + (c >> 6) * 32768;
-        const int ch4 = (c & 63) >> 2;
 #pragma unroll 8
         for (int i = 0; i < kRows; ++i) {
           const int r = grp * kRows + i;
-          const uint2 u = *reinterpret_cast<const uint2*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4));
+          const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+          const uint2 u = *reinterpret_cast<const uint2*>(vcol + off);
           float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
           float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-          float4 qv;
-          if constexpr (MODE == kMask) qv = *reinterpret_cast<const float4*>(qcol + r * 256 + ((ch4 ^ (r & 15)) << 4));
+          float2 y0 = f0, y1 = f1;
+          if constexpr (MODE == kMask) {
+            const uint2 uy = *reinterpret_cast<const uint2*>(ycol + off);
+            y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.x));
+            y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.y));
+          }
           if (r < valid) {
             s4[0] += f0.x; s4[1] += f0.y; s4[2] += f1.x; s4[3] += f1.y;
-            if constexpr (MODE == kMask) {
-              q4[0] += qv.x; q4[1] += qv.y; q4[2] += qv.z; q4[3] += qv.w;
-            } else {
-              q4[0] = fmaf(f0.x, f0.x, q4[0]); q4[1] = fmaf(f0.y, f0.y, q4[1]);
-              q4[2] = fmaf(f1.x, f1.x, q4[2]); q4[3] = fmaf(f1.y, f1.y, q4[3]);
-            }
+            q4[0] = fmaf(f0.x, y0.x, q4[0]); q4[1] = fmaf(f0.y, y0.y, q4[1]);
+            q4[2] = fmaf(f1.x, y1.x, q4[2]); q4[3] = fmaf(f1.y, y1.y, q4[3]);
           }
         }
 #pragma unroll
@@ -472,7 +459,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       named_bar_sync(1, 128);
       if (et < 2 * kQuads) {
         const int which = et / kQuads, quad = et % kQuads;
-        const float4 v4 = *reinterpret_cast<const float4*>(acc_s + which * BN + quad * 4);
+        float4 v4 = *reinterpret_cast<const float4*>(acc_s + which * BN + quad * 4);
+        if (MODE == kMask && which == 1) {
+          // sum g*xhat = A * sum(g*y) + B * sum(g)
+          const float4 sg = *reinterpret_cast<const float4*>(acc_s + quad * 4);
+          const float4 cA = *reinterpret_cast<const float4*>(coef_s + 2 * BN + quad * 4);
+          const float4 cB = *reinterpret_cast<const float4*>(coef_s + 3 * BN + quad * 4);
+          v4 = make_float4(fmaf(cA.x, v4.x, cB.x * sg.x), fmaf(cA.y, v4.y, cB.y * sg.y),
+                           fmaf(cA.z, v4.z, cB.z * sg.z), fmaf(cA.w, v4.w, cB.w * sg.w));
+        }
         float* dst = p.stats + which * p.n_total + n_off + quad * 4;
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v4.x), "f"(v4.y), "f"(v4.z),
                      "f"(v4.w)

@@ -323,6 +323,43 @@ def run_ours(args):
                         "algorithmic_flops_per_launch": flops, "peak_source": f"{src} bf16_tflops_sustained",
                         "launches_per_step": n, "avg_us": round(t / n * 1e3, 2),
                         "share_of_step_kernel_time": round(t / total_ms, 4)}
+        # secondary rooflines: the HBM-bound BatchNorm backward pass and the weight-gradient GEMM at 64x64
+        more = []
+        M64 = B * 64 * 64
+        k = ("hg_bn_bwd_apply", f"C256 M{M64} +addend")
+        if k in agg:
+            n, t = agg[k]
+            gbs = 4 * M64 * 256 * 2 / (t / n * 1e-3) / 1e9   # reads g, x, addend, writes dx (bf16)
+            more.append({"kernel": "bn_bwd_apply_kernel<bf16,ADD> C256 @64x64", "bound": "hbm",
+                         "achieved": round(gbs, 1), "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                         "frac": round(gbs / float(peaks["hbm_gbs"]), 4), "avg_us": round(t / n * 1e3, 2),
+                         "launches_per_step": n, "algorithmic_bytes_per_launch": 4 * M64 * 256 * 2})
+        k = ("hg_bn_apply", f"C256 M{M64}")
+        if k in agg:
+            n, t = agg[k]
+            gbs = 2 * M64 * 256 * 2 / (t / n * 1e-3) / 1e9
+            more.append({"kernel": "bn_apply_kernel<bf16> C256 @64x64", "bound": "hbm", "achieved": round(gbs, 1),
+                         "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": round(gbs / float(peaks["hbm_gbs"]), 4),
+                         "avg_us": round(t / n * 1e3, 2), "launches_per_step": n,
+                         "algorithmic_bytes_per_launch": 2 * M64 * 256 * 2})
+        k = ("hg_conv_wgrad", "128->128 k3 @64x64")
+        if k in agg:
+            n, t = agg[k]
+            tf = 2.0 * M64 * 128 * 128 * 9 / (t / n * 1e-3) / 1e12
+            pk = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+            more.append({"kernel": "conv_wgrad_kernel 3x3 128->128 @64x64", "bound": "tensor", "achieved": round(tf, 1),
+                         "peak": pk, "unit": "TFLOP/s", "frac": round(tf / pk, 4), "avg_us": round(t / n * 1e3, 2),
+                         "launches_per_step": n})
+        k = ("hg_conv_dgrad_bn", "128->128 k3 @64x64 +bn")
+        if k in agg:
+            n, t = agg[k]
+            tf = 2.0 * M64 * 128 * 128 * 9 / (t / n * 1e-3) / 1e12
+            pk = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+            more.append({"kernel": "conv_gemm_kernel<128,3,2,kMask> dgrad 3x3 128->128 @64x64 (+ReLU mask, BN sums)",
+                         "bound": "tensor", "achieved": round(tf, 1), "peak": pk, "unit": "TFLOP/s",
+                         "frac": round(tf / pk, 4), "avg_us": round(t / n * 1e3, 2), "launches_per_step": n})
+        if roofline is not None:
+            roofline["other_kernels"] = more
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "kernel_table.txt"), "w") as f:
             f.write(f"# per-call CUDA-event times of one eager step, B={B}/GPU, total {total_ms:.3f} ms\n")

@@ -192,14 +192,16 @@ typedef struct HgBnRunningModule {
 HG_API int hg_bn_update_running(const void* modules_dev, const void* sites_dev, int num_modules, void* stream);
 
 /* ---- spatial ops -------------------------------------------------------------------------------- */
-/* nn.MaxPool2d(2) (try_with_torch.py:220,226,265); backward routes to the first row-major maximum. */
-HG_API int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream);
+/* nn.MaxPool2d(2) (try_with_torch.py:220,226,265); backward routes to the first row-major maximum.
+ * stats (optional, here and in hg_upsample2x_add_fwd): {sum, sum of squares}[2*Cp] of the tensor just written,
+ * accumulated for the BatchNorm that reads it (caller zeroes), like hg_conv_fprop's `stats`. */
+HG_API int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, float* stats, void* stream);
 HG_API int hg_maxpool2_bwd(int dtype, const void* x, const void* dy, const void* addend, int N, int H, int W, int C,
                     void* dx, void* stream);
 /* out[N,2h,2w,C] = upsample_x2(low[N,h,w,C]) [+ skip]; mode 0 = bilinear align_corners=True
  * (try_with_torch.py:238-239), mode 1 = nearest (hourglass_compare.py:532-542). */
 HG_API int hg_upsample2x_add_fwd(int dtype, int mode, const void* low, const void* skip, int N, int h, int w, int C,
-                          void* out, void* stream);
+                          void* out, float* stats, void* stream);
 HG_API int hg_upsample2x_bwd(int dtype, int mode, const void* dout, const void* addend, int N, int h, int w, int C,
                       void* dlow, void* stream);
 HG_API int hg_add(int dtype, const void* a, const void* b, void* out, long long n_elems, void* stream);

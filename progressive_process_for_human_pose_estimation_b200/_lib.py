@@ -79,9 +79,9 @@ SIGNATURES = {
     "hg_bn_bwd_reduce": [C.POINTER(HgBnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_bn_bwd_apply": [C.POINTER(HgBnDesc)] + [_P] * 14,
     "hg_bn_update_running": [_P, _P, _I, _P],
-    "hg_maxpool2_fwd": [_I, _P, _I, _I, _I, _I, _P, _P],
+    "hg_maxpool2_fwd": [_I, _P, _I, _I, _I, _I, _P, _P, _P],
     "hg_maxpool2_bwd": [_I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
-    "hg_upsample2x_add_fwd": [_I, _I, _P, _P, _I, _I, _I, _I, _P, _P],
+    "hg_upsample2x_add_fwd": [_I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "hg_upsample2x_bwd": [_I, _I, _P, _P, _I, _I, _I, _I, _P, _P],
     "hg_add": [_I, _P, _P, _P, _LL, _P],
     "hg_nchw_f32_to_nhwc": [_I, _P, _P, _I, _I, _I, _I, _P, _P],

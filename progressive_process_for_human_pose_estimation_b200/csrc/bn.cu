@@ -53,19 +53,6 @@ __device__ __forceinline__ void bn_coeffs(const BnArgs& a, int c0, float (&mean)
   }
 }
 
-// Every block of a reduction kernel adds C per-channel partial sums into the same few cache lines, and the L2
-// serialises atomics per line: 4 channels per red.global.add.v4.f32 (dst 16-byte aligned), scalar tail.
-__device__ __forceinline__ void red_add_channels(float* dst, const float* src_smem, int C) {
-  const int c4n = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (C >> 2) : 0;
-  for (int q = threadIdx.x; q < c4n; q += blockDim.x) {
-    const float4 v = *reinterpret_cast<const float4*>(src_smem + q * 4);
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(v.x), "f"(v.y), "f"(v.z),
-                 "f"(v.w)
-                 : "memory");
-  }
-  for (int c = c4n * 4 + threadIdx.x; c < C; c += blockDim.x) atomicAdd(dst + c, src_smem[c]);
-}
-
 // Block-wide version: thread c (< Cp <= 256) derives channel c once, the block shares the result through shared
 // memory (the per-thread version above costs 32 scalar global loads per thread, which dominates small tensors).
 // coef layout: [4][256] = mean, invstd, scale, shift.  Contains a __syncthreads().

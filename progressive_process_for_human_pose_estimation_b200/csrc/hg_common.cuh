@@ -150,6 +150,48 @@ __device__ __forceinline__ void unpack(const Raw8<float>& r, float (&v)[8]) {
   v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
 }
 
+// Every block of a reduction kernel adds C per-channel partial sums into the same few cache lines, and the L2
+// serialises atomics per line: 4 channels per red.global.add.v4.f32 (dst 16-byte aligned), scalar tail.
+__device__ __forceinline__ void red_add_channels(float* dst, const float* src_smem, int C) {
+  const int c4n = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (C >> 2) : 0;
+  for (int q = threadIdx.x; q < c4n; q += blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src_smem + q * 4);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+  }
+  for (int c = c4n * 4 + threadIdx.x; c < C; c += blockDim.x) atomicAdd(dst + c, src_smem[c]);
+}
+
+// BatchNorm statistics fused into a streaming producer (256 threads, thread = 8 channels `vc*8..` of some rows):
+// stats[c] += sum, stats[Cp + c] += sum of squares over everything this block wrote.  Contains __syncthreads().
+__device__ __forceinline__ void block_channel_stats(const float (&s)[8], const float (&ss)[8], int Cp,
+                                                    float* __restrict__ stats) {
+  __shared__ float red[2][256][9];
+  __shared__ __align__(16) float tot[2][256];
+  const int vecs = Cp >> 3;
+  const int rlanes = 256 / vecs;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][threadIdx.x][e] = s[e];
+    red[1][threadIdx.x][e] = ss[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cp; c += 256) {
+    const int v = c >> 3, e = c & 7;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < rlanes; ++r) {
+      a += red[0][r * vecs + v][e];
+      b += red[1][r * vecs + v][e];
+    }
+    tot[0][c] = a;
+    tot[1][c] = b;
+  }
+  __syncthreads();
+  red_add_channels(stats, tot[0], Cp);
+  red_add_channels(stats + Cp, tot[1], Cp);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -14,12 +14,13 @@ namespace hg {
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H,
-                                                           int W, int Cp) {
+                                                           int W, int Cp, float* __restrict__ stats) {
   pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
   pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
 
   const int vecs = Cp >> 3, Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * Ho * Wo * vecs;
+  float st_s[8] = {}, st_q[8] = {};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int vc = (int)(i % vecs);
@@ -35,9 +36,15 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
     load8(p + (long long)W * Cp, c);
     load8(p + (long long)W * Cp + Cp, d);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
+    for (int e = 0; e < 8; ++e) {
+      o[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
+      const float r = to_f(from_f<T>(o[e]));  // statistics of the values as stored
+      st_s[e] += r;
+      st_q[e] = fmaf(r, r, st_q[e]);
+    }
     store8(y + i * 8, o);
   }
+  if (stats != nullptr) block_channel_stats(st_s, st_q, Cp, stats);  // (vc is the same for every row of a thread)
 }
 
 // dx[window] = dy routed to the FIRST row-major maximum of the window (PyTorch's tie-break), [+ addend]
@@ -106,7 +113,7 @@ __device__ __forceinline__ void bilin_coord(int o, int in_size, float scale, int
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2_add_fwd_kernel(const T* __restrict__ low, const T* __restrict__ skip,
                                                                 T* __restrict__ out, int N, int h, int w, int Cp,
-                                                                int mode) {
+                                                                int mode, float* __restrict__ stats) {
   pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
   pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
 
@@ -114,6 +121,7 @@ __global__ void __launch_bounds__(256) upsample2_add_fwd_kernel(const T* __restr
   const float sh = h > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sw = w > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
   const long long total = (long long)N * H * W * vecs;
+  float st_s[8] = {}, st_q[8] = {};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int vc = (int)(i % vecs);
@@ -145,8 +153,17 @@ __global__ void __launch_bounds__(256) upsample2_add_fwd_kernel(const T* __restr
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] += s[e];
     }
+    if (stats != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float r = to_f(from_f<T>(o[e]));
+        st_s[e] += r;
+        st_q[e] = fmaf(r, r, st_q[e]);
+      }
+    }
     store8(out + i * 8, o);
   }
+  if (stats != nullptr) block_channel_stats(st_s, st_q, Cp, stats);
 }
 
 // adjoint as a GATHER over the low-resolution pixels (deterministic, no atomics):
@@ -290,9 +307,10 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__
   }
 }
 
-static inline int grid_for(long long total) {
+// with_stats: every block ends with 2*Cp/4 vector atomics into the same cache lines -> fewer, fatter blocks
+static inline int grid_for(long long total, bool with_stats = false) {
   long long b = (total + 255) / 256;
-  const long long cap = (long long)kNumSMs * 16;
+  const long long cap = (long long)kNumSMs * (with_stats ? 4 : 16);
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
@@ -319,15 +337,15 @@ static int check_spatial(int dtype, int N, int H, int W, int C, const char* who)
   return HG_OK;
 }
 
-int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, void* stream) {
+int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, float* stats, void* stream) {
   int rc = check_spatial(dtype, N, H, W, C, "hg_maxpool2_fwd");
   if (rc) return rc;
   HG_REQUIRE(x && y, "hg_maxpool2_fwd: NULL pointer");
   HG_REQUIRE(H % 2 == 0 && W % 2 == 0, "hg_maxpool2_fwd: odd spatial size %dx%d", H, W);
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * (H / 2) * (W / 2) * (Cp / 8);
-  HG_DISPATCH_T(dtype, (launch_k(maxpool2_fwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
-                           (const T*)x, (T*)y, N, H, W, Cp)));
+  HG_DISPATCH_T(dtype, (launch_k(maxpool2_fwd_kernel<T>, dim3(grid_for(total, stats != nullptr)), dim3(256), 0,
+                                 (cudaStream_t)stream, (const T*)x, (T*)y, N, H, W, Cp, stats)));
   HG_LAUNCH_OK("maxpool2_fwd_kernel");
   count_launch();
   return HG_OK;
@@ -349,15 +367,16 @@ int hg_maxpool2_bwd(int dtype, const void* x, const void* dy, const void* addend
 }
 
 int hg_upsample2x_add_fwd(int dtype, int mode, const void* low, const void* skip, int N, int h, int w, int C,
-                          void* out, void* stream) {
+                          void* out, float* stats, void* stream) {
   int rc = check_spatial(dtype, N, h, w, C, "hg_upsample2x_add_fwd");
   if (rc) return rc;
   HG_REQUIRE(low && out, "hg_upsample2x_add_fwd: NULL pointer");
   HG_REQUIRE(mode == 0 || mode == 1, "hg_upsample2x_add_fwd: mode must be 0 (bilinear_ac) or 1 (nearest)");
   const int Cp = (C + 63) & ~63;
   const long long total = (long long)N * 4 * h * w * (Cp / 8);
-  HG_DISPATCH_T(dtype, (launch_k(upsample2_add_fwd_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
-                           (const T*)low, (const T*)skip, (T*)out, N, h, w, Cp, mode)));
+  HG_DISPATCH_T(dtype, (launch_k(upsample2_add_fwd_kernel<T>, dim3(grid_for(total, stats != nullptr)), dim3(256), 0,
+                                 (cudaStream_t)stream, (const T*)low, (const T*)skip, (T*)out, N, h, w, Cp, mode,
+                                 stats)));
   HG_LAUNCH_OK("upsample2_add_fwd_kernel");
   count_launch();
   return HG_OK;

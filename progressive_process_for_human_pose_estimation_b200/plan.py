@@ -204,7 +204,7 @@ _WRITES = {
     "hg_nchw_f32_to_nhwc": (7,), "hg_nhwc_to_nchw_f32": (6,), "hg_stem_fwd": (8,), "hg_conv_fprop_ex": (5, 6, 7),
     "hg_conv_dgrad": (4,), "hg_bn_stats": (2,), "hg_bn_apply": (7,), "hg_bn_bwd_apply": (10,),
     "hg_bn_bwd_reduce": (8,), "hg_conv_fprop_bn": (6, 7, 8), "hg_conv_dgrad_bn": (5, 6),
-    "hg_maxpool2_fwd": (6,), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8,), "hg_upsample2x_bwd": (8,),
+    "hg_maxpool2_fwd": (6, 7), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8, 9), "hg_upsample2x_bwd": (8,),
     "hg_add": (3,),
 }
 
@@ -469,6 +469,10 @@ class Plan:
         self._lower_forward(convs)
         if self.need_bwd:
             self._lower_backward(convs)
+        for c in self.fwd_calls + self.bwd_calls:   # shape tags of the BatchNorm calls (per-kernel profile)
+            if c.name in ("hg_bn_apply", "hg_bn_bwd_apply", "hg_bn_bwd_reduce", "hg_bn_stats") and not c.tag:
+                d = c.args[0]._obj
+                c.tag = f"C{d.C} M{d.M}" + (" +addend" if c.name == "hg_bn_bwd_apply" and c.args[9] is not None else "")
 
     # ------------------------------------------------------------------------------------------------
     def _conv_desc(self, cv, x):
@@ -567,15 +571,13 @@ class Plan:
                     self._stats_call(f, out)
             elif k == "pool":
                 x, out = op.ins[0], op.out
-                self._emit(f, "hg_maxpool2_fwd", self.hdt, L.ptr(x.buf), x.N, x.H, x.W, x.C, L.ptr(out.buf), st)
-                if out.needs_stats:
-                    self._stats_call(f, out)
+                self._emit(f, "hg_maxpool2_fwd", self.hdt, L.ptr(x.buf), x.N, x.H, x.W, x.C, L.ptr(out.buf),
+                           L.ptr(out.stats) if out.needs_stats else None, st)
             elif k == "up":
                 low, skip, out = op.ins[0], op.ins[1], op.out
                 self._emit(f, "hg_upsample2x_add_fwd", self.hdt, op.attrs["mode"], L.ptr(low.buf),
-                           L.ptr(skip.buf) if skip else None, low.N, low.H, low.W, low.C, L.ptr(out.buf), st)
-                if out.needs_stats:
-                    self._stats_call(f, out)
+                           L.ptr(skip.buf) if skip else None, low.N, low.H, low.W, low.C, L.ptr(out.buf),
+                           L.ptr(out.stats) if out.needs_stats else None, st)
             elif k == "add":
                 a, bb, out = op.ins[0], op.ins[1], op.out
                 self._emit(f, "hg_add", self.hdt, L.ptr(a.buf), L.ptr(bb.buf), L.ptr(out.buf),

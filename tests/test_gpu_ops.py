@@ -389,10 +389,14 @@ def test_maxpool_fwd_bwd_first_max_tiebreak(dtype):
     xq = nhwc(x, dtype)
     y = torch.empty(N, H // 2, W // 2, 64, device=dev, dtype=dtype)
     st = L.stream_ptr()
-    L.call("hg_maxpool2_fwd", L.hg_dtype(dtype), L.ptr(xq), N, H, W, Cc, L.ptr(y), st)
+    pstats = torch.zeros(2 * 64, device=dev)
+    L.call("hg_maxpool2_fwd", L.hg_dtype(dtype), L.ptr(xq), N, H, W, Cc, L.ptr(y), L.ptr(pstats), st)
     xr = x.clone().requires_grad_(True)
     ref = F.max_pool2d(xr, 2)
     assert torch.equal(nchw(y, Cc), ref.detach())
+    # fused BatchNorm statistics of the pooled tensor
+    close(pstats[:Cc], ref.detach().sum((0, 2, 3)), 1e-5, "pool stats sum")
+    close(pstats[64:64 + Cc], (ref.detach() ** 2).sum((0, 2, 3)), 1e-5, "pool stats sumsq")
     dy = torch.randn(N, Cc, H // 2, W // 2, device=dev)
     dyq = nhwc(dy, dtype)
     ref.backward(nchw(dyq, Cc))
@@ -417,7 +421,12 @@ def test_upsample_add_fwd_bwd(dtype, mode, hw):
     lq, sq = nhwc(low, dtype), nhwc(skip, dtype)
     out = torch.empty_like(sq)
     st = L.stream_ptr()
-    L.call("hg_upsample2x_add_fwd", L.hg_dtype(dtype), mode, L.ptr(lq), L.ptr(sq), N, hw, hw, Cc, L.ptr(out), st)
+    ustats = torch.zeros(2 * 64, device=dev)
+    L.call("hg_upsample2x_add_fwd", L.hg_dtype(dtype), mode, L.ptr(lq), L.ptr(sq), N, hw, hw, Cc, L.ptr(out),
+           L.ptr(ustats), st)
+    ov = nchw(out, Cc)
+    close(ustats[:Cc], ov.sum((0, 2, 3)), 1e-4, "upsample stats sum (of the stored values)")
+    close(ustats[64:64 + Cc], (ov * ov).sum((0, 2, 3)), 1e-4, "upsample stats sumsq")
     lr = nchw(lq, Cc).requires_grad_(True)
     if mode == 0:
         up = F.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=True)

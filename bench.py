@@ -137,6 +137,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L.load()
+    for opt in os.environ.get("HG_OPTIONS", "").split(","):   # e.g. HG_OPTIONS=single_wave_deep=0,wgrad_smem_kb=110
+        if "=" in opt:
+            k_, v_ = opt.split("=")
+            L.call("hg_set_option", k_.encode(), int(v_))
     if not L.load().hg_device_ok():
         raise SystemExit("bench.py: device is not compute capability 10.x")
     B = args.batch

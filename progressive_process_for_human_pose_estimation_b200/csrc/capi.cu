@@ -10,6 +10,7 @@ static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 int g_use_pdl = 1;
+extern int g_single_wave_deep, g_wgrad_smem_kb;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -134,6 +135,14 @@ int hg_device_ok(void) {
 int hg_set_option(const char* name, int value) {
   if (strcmp(name, "force_ref_conv") == 0) {
     g_force_ref_conv = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "single_wave_deep") == 0) {
+    g_single_wave_deep = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "wgrad_smem_kb") == 0) {
+    g_wgrad_smem_kb = value;
     return HG_OK;
   }
   if (strcmp(name, "pdl") == 0) {

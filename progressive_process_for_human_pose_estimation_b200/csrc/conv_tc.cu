@@ -20,6 +20,9 @@
 
 namespace hg {
 
+int g_single_wave_deep = 1;   // 1: one-wave grids use the deep (6/4-stage, ~190 KB) pipelines
+int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
+
 // Epilogue / prologue fusion modes of the GEMM kernel.
 //   kPlain : y = conv(x) [+bias][+residual][+stats]                                   (fprop, dgrad)
 //   kFold  : the A operand is a RAW tensor x that a BatchNorm(+ReLU) normalises: every A tile is rewritten in
@@ -529,7 +532,7 @@ template <int BN, int MODE>
 static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA, const CUtensorMap& tmB,
                               const CUtensorMap& tmC, const CUtensorMap& tmR, const ConvGemmParams& p,
                               cudaStream_t st) {
-  const bool single_wave = ceil_div(p.M_total, 128) * p.n_tiles <= kNumSMs;
+  const bool single_wave = g_single_wave_deep && ceil_div(p.M_total, 128) * p.n_tiles <= kNumSMs;
   if constexpr (MODE == kMask) {
     // the raw BatchNorm input tile is prefetched into a dedicated C buffer wherever shared memory allows; only the
     // multi-wave 3x3 kernel (two CTAs per SM) loads it after its (long) main loop
@@ -923,7 +926,8 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.Cout_p = Cout_p;
     p.total_kb = (int)((M + 63) / 64);
     p.stage_bytes = 2 * 8192 + T * p.n_panels * 8192;
-    p.stages = (196 * 1024) / p.stage_bytes;
+    p.stages = (g_wgrad_smem_kb * 1024) / p.stage_bytes;
+    if (p.stages < 2) p.stages = 2;
     if (p.stages > 6) p.stages = 6;
     const int tap_groups = taps / T;
     const int mgroups = (Cout_p + 127) / 128;

@@ -62,11 +62,6 @@ class HGModule(nn.Module):
             for _, p in params:
                 if p.device != x.device:
                     raise RuntimeError(f"{type(self).__name__}: parameters and input live on different devices")
-            if self.training:
-                for name, buf in self.named_buffers():
-                    if buf.is_floating_point() and buf.dtype != torch.float32:
-                        raise RuntimeError("training-mode BatchNorm needs fp32 running statistics "
-                                           f"(buffer {name} is {buf.dtype})")
             b = Builder(self.training, train_params)
             if self._is_model:
                 if x_rg:

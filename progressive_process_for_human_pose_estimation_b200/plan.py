@@ -291,6 +291,19 @@ class Plan:
             self._shadow[key] = (p, torch.empty_like(p.data, dtype=torch.float32))
         return self._shadow[key][1]
 
+    def _rstat(self, buf):
+        """fp32 tensor behind a BatchNorm running-statistics buffer: the buffer itself, or -- when the module was
+        cast with .half() as the reference's test paths do (try_with_torch.py:374-377) -- an fp32 shadow that is
+        refreshed before and written back after every forward."""
+        if buf is None:
+            return None
+        if buf.dtype == torch.float32:
+            return buf
+        key = id(buf)
+        if key not in self._shadow_buf:
+            self._shadow_buf[key] = (buf, torch.empty_like(buf, dtype=torch.float32))
+        return self._shadow_buf[key][1]
+
     def _gslot(self, p):
         """fp32 gradient slot of parameter p inside the flat gradient arena (None if p is frozen)."""
         i = self.param_index.get(id(p))
@@ -362,6 +375,7 @@ class Plan:
     def _lower(self):
         b, dev = self.b, self.device
         self._shadow = {}
+        self._shadow_buf = {}
         ops = b.ops
         # ---- parameters: flat gradient arena in named_parameters() order --------------------------
         # every slot starts on a 16-byte boundary: the wgrad kernel reduces straight into the slots of un-padded
@@ -501,8 +515,8 @@ class Plan:
         use_running = 0 if (self.training or not bn.track_running_stats) else 1
         f = L.HgBnFold(x.stats.data_ptr() if x.stats is not None else None, self._p32(bn.weight).data_ptr(),
                        self._p32(bn.bias).data_ptr(),
-                       bn.running_mean.data_ptr() if bn.running_mean is not None else None,
-                       bn.running_var.data_ptr() if bn.running_var is not None else None, float(bn.eps),
+                       self._rstat(bn.running_mean).data_ptr() if bn.running_mean is not None else None,
+                       self._rstat(bn.running_var).data_ptr() if bn.running_var is not None else None, float(bn.eps),
                        1 if bnop.attrs["relu"] else 0, use_running, 0)
         self._keep.append(f)
         return f, (x.stats,)
@@ -567,8 +581,8 @@ class Plan:
                     self._emit(f, "hg_bn_apply", C.byref(d), L.ptr(x.buf),
                                L.ptr(x.stats) if x.stats is not None else None,
                                L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias)),
-                               L.ptr(bn.running_mean) if bn.running_mean is not None else None,
-                               L.ptr(bn.running_var) if bn.running_var is not None else None, L.ptr(out.buf), st)
+                               L.ptr(self._rstat(bn.running_mean)),
+                               L.ptr(self._rstat(bn.running_var)), L.ptr(out.buf), st)
                 if self.training and bn.track_running_stats:
                     running.setdefault(id(bn), (bn, []))[1].append((x.stats, float(x.M)))
                 if out.needs_stats:  # BN output feeding another BN directly (hourglass_compare.py:549-553)
@@ -599,7 +613,8 @@ class Plan:
         if running:
             mods, sites = [], []
             for bn, lst in running.values():
-                mods.append(L.HgBnRunningModule(bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                mods.append(L.HgBnRunningModule(self._rstat(bn.running_mean).data_ptr(),
+                                                self._rstat(bn.running_var).data_ptr(),
                                                 bn.num_batches_tracked.data_ptr(), bn.num_features,
                                                 L.pad64(bn.num_features), len(sites), len(lst),
                                                 float(bn.momentum if bn.momentum is not None else 0.1), 0))
@@ -711,8 +726,8 @@ class Plan:
                 red = op.attrs["red"]
                 gam, bet = L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias))
                 stats = L.ptr(x.stats) if x.stats is not None else None
-                rmean = L.ptr(bn.running_mean) if bn.running_mean is not None else None
-                rvar = L.ptr(bn.running_var) if bn.running_var is not None else None
+                rmean = L.ptr(self._rstat(bn.running_mean))
+                rvar = L.ptr(self._rstat(bn.running_var))
                 if op.attrs.get("masked"):
                     pass  # the sums were accumulated by the consumer's hg_conv_dgrad_bn; G is already masked
                 elif not d.use_running or self._gslot_peek(bn.weight) or self._gslot_peek(bn.bias):
@@ -728,8 +743,8 @@ class Plan:
                 else:
                     addend, dst = None, self._scratch(x)
                 self._emit(g, "hg_bn_bwd_apply", C.byref(d), L.ptr(G), L.ptr(x.buf), stats, gam, bet,
-                           L.ptr(bn.running_mean) if bn.running_mean is not None else None,
-                           L.ptr(bn.running_var) if bn.running_var is not None else None, L.ptr(red), L.ptr(addend),
+                           L.ptr(self._rstat(bn.running_mean)),
+                           L.ptr(self._rstat(bn.running_var)), L.ptr(red), L.ptr(addend),
                            L.ptr(dst), L.ptr(self._gslot(bn.weight)), L.ptr(self._gslot(bn.bias)), L.ptr(colsum), st)
             elif k == "pool":
                 x = op.ins[0]
@@ -928,9 +943,14 @@ class Plan:
     def _fwd_body(self):
         for p, shadow in self._shadow.values():
             shadow.copy_(p.data)
+        for buf, shadow in self._shadow_buf.values():
+            shadow.copy_(buf)
         self._refresh_bias()
         self.stats_arena.zero_()
         self._run_calls(self.fwd_calls)
+        if self.training:
+            for buf, shadow in self._shadow_buf.values():
+                buf.copy_(shadow)
 
     def _refresh_bias(self):
         # padded fp32 bias vectors (device-to-device copies of the live parameters)

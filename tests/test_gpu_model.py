@@ -304,3 +304,34 @@ def test_full_size_train_steps_properties():
     # decode of the (identical) targets is exact at full size
     yx, mx = hg.decode_argmax(y)
     assert torch.equal(yx[..., 0].long() * 64 + yx[..., 1].long(), y.flatten(2).argmax(-1))
+
+
+def test_half_model_like_the_reference_test_mode():
+    """The reference's test branches run `model.half()` WITHOUT .eval() (try_with_torch.py:374-377, quirk Q10): fp16
+    parameters and BN buffers, batch statistics at batch 1.  The drop-in takes the same calls; results against the
+    fp32 oracle at bf16-path tolerance, BN bookkeeping carried by the (half) buffers."""
+    hg.set_compute_dtype(torch.bfloat16)
+    net, sd0, x, tgt, cfg = _model_and_oracle(2, 17, 1, True)
+    net = net.half().cuda()
+    sdh = {k: (v.half().float() if v.is_floating_point() else v.clone()) for k, v in sd0.items()}  # fp16-rounded weights
+    sd = ho.clone_state(sdh)
+    with torch.no_grad():
+        oo = ho.creat_model_s(sd, x.half().float(), cfg)
+        out = net(x.half().cuda())
+        out_again = net(x.half().cuda())  # CUDA-graph replay
+    assert all(o.dtype == torch.float16 for o in out)
+    assert rel(out[0].float().cpu(), oo[0]) <= 0.3        # train-mode BN at batch 1, random init: chaotic (Q13)
+    assert torch.isfinite(out_again[1].float()).all()
+    st = net.state_dict()
+    assert st["residual1.bn1.running_mean"].dtype == torch.float16
+    assert int(st["residual1.bn1.num_batches_tracked"]) == 2
+    assert not torch.equal(st["residual1.bn1.running_mean"].float().cpu(), sd0["residual1.bn1.running_mean"])
+    # eval() on the same half model: well conditioned
+    net.load_state_dict({k: v for k, v in sdh.items()})
+    net.eval()
+    cfg.training = False
+    with torch.no_grad():
+        oe = ho.creat_model_s(ho.clone_state(sdh), x.half().float(), cfg)
+        oute = net(x.half().cuda())
+    for k in range(2):
+        assert rel(oute[k].float().cpu(), oe[k]) <= 3e-2 * (1 + k), (k, rel(oute[k].float().cpu(), oe[k]))

@@ -10,7 +10,8 @@ static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 int g_use_pdl = 1;
-extern int g_single_wave_deep, g_wgrad_smem_kb;
+extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles;
+extern long long* g_dbg_ts;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -135,6 +136,33 @@ int hg_device_ok(void) {
 int hg_set_option(const char* name, int value) {
   if (strcmp(name, "force_ref_conv") == 0) {
     g_force_ref_conv = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "dbg_ts") == 0) {   // 1: start stamping conv_gemm CTA 0 phases; 2: print the last kernel's stamps
+    if (value == 1 && !g_dbg_ts) {
+      if (cudaMalloc(&g_dbg_ts, 32 * sizeof(long long)) != cudaSuccess) return HG_ERR_CUDA;
+      cudaMemset(g_dbg_ts, 0, 32 * sizeof(long long));
+    } else if (value == 2 && g_dbg_ts) {
+      long long h[32];
+      cudaDeviceSynchronize();
+      cudaMemcpy(h, g_dbg_ts, sizeof(h), cudaMemcpyDeviceToHost);
+      static const char* nm[11] = {"entry", "prologue done", "pdl_wait done", "first TMA issued", "first tile landed",
+                                   "last MMA committed", "accumulator ready", "row pass done", "stats+store issued",
+                                   "store read done", "exit"};
+      for (int i = 1; i < 11; ++i)
+        fprintf(stderr, "  %-20s +%6lld cycles (%.2f us)\n", nm[i], h[i] - h[0], (h[i] - h[0]) / 1965.0);
+      fprintf(stderr, "  producer loop entry +%lld; TMA pair issued at:", h[15] - h[0]);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[16 + i] - h[0]);
+      fprintf(stderr, "\n  MMA warp saw tile k at:");
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[24 + i] - h[0]);
+      fprintf(stderr, "\n");
+    } else if (value == 0) {
+      g_dbg_ts = nullptr;
+    }
+    return HG_OK;
+  }
+  if (strcmp(name, "small_n_tiles") == 0) {
+    g_small_n_tiles = value;
     return HG_OK;
   }
   if (strcmp(name, "single_wave_deep") == 0) {

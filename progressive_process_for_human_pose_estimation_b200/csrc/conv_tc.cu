@@ -20,6 +20,8 @@
 
 namespace hg {
 
+int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
+long long* g_dbg_ts = nullptr;  // debug: per-phase clock64 stamps of CTA 0 (hg_set_option dbg_ts)
 int g_single_wave_deep = 1;   // 1: one-wave grids use the deep (6/4-stage, ~190 KB) pipelines
 int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
 
@@ -105,6 +107,7 @@ struct ConvGemmParams {
   int has_res;        // kPlain/kFold: residual added;  kMask: tmR is the raw BatchNorm input
   int n_tiles;        // padded Cout / BN
   BnFoldDev fold;     // kFold: BatchNorm of the INPUT channels;  kMask: BatchNorm of the OUTPUT channels
+  long long* ts;      // debug timestamps or null
 };
 
 // Shared-memory plan.  ALIAS = the epilogue staging buffers (output tile C; kMask: + the fp32 g*xhat tile Q) reuse the
@@ -160,6 +163,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[0] = clock64();
   // 1-D grid, N tile fastest: the CTAs that share an activation tile run back to back (second read hits L2)
   const int m0 = (blockIdx.x / p.n_tiles) * 128;
   const int n_off = (blockIdx.x % p.n_tiles) * BN;
@@ -184,9 +188,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[1] = clock64();
   // PDL: everything above overlapped the previous kernel's tail; global memory is ours from here.  The producer warp
   // starts its TMA loads at once; the per-channel coefficients are fetched by the epilogue warps meanwhile.
   pdl_wait();
+  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[2] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -201,6 +207,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int pnl = 0; pnl < L::kCPanels; ++pnl)
           tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
       }
+      if (p.ts && blockIdx.x == 0) p.ts[15] = clock64();
       int kb = 0;
       for (int r = 0; r < p.taps_r; ++r) {
         for (int s = 0; s < p.taps_s; ++s) {
@@ -213,6 +220,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_expect_tx(&full_bar[st], L::kABytes + L::kBBytes);
             tma_load_4d(sA + st * L::kABytes, &tmA, &full_bar[st], kc * 64, w0 + dw, h0 + dh, n0);
             tma_load_3d(sB + st * L::kBBytes, &tmB, &full_bar[st], kc * 64, n_off, r * p.taps_s + s);
+            if (p.ts && blockIdx.x == 0 && kb == 0) p.ts[3] = clock64();
+            if (p.ts && blockIdx.x == 0 && kb < 8) p.ts[16 + kb] = clock64();
           }
         }
       }
@@ -235,6 +244,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (MODE == kFold) mbar_wait(&ready_bar[st], ph);
       else mbar_wait(&full_bar[st], ph);
       tc_fence_after();
+      if (p.ts && blockIdx.x == 0 && lane == 0 && kb == 0) p.ts[4] = clock64();
+      if (p.ts && blockIdx.x == 0 && lane == 0 && kb < 8) p.ts[24 + kb] = clock64();
       if (lane == 0) {
         const uint64_t adesc = make_smem_desc(smem_u32(sA + st * L::kABytes), 16, 1024);
         const uint64_t bdesc = make_smem_desc(smem_u32(sB + st * L::kBBytes), 16, 1024);
@@ -248,6 +259,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
     }
+    if (p.ts && blockIdx.x == 0 && lane == 0) p.ts[5] = clock64();
     pdl_trigger();
   } else {
     // ===================== transform (kFold) + epilogue (warps 2..5) =====================
@@ -333,6 +345,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[6] = clock64();
     pdl_trigger();  // main loop done: the next kernel may start its prologue under our epilogue
     if (p.has_res) mbar_wait(res_full, 0);
     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
@@ -404,6 +417,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         *cp = w;
       }
     }
+    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[7] = clock64();
     tc_fence_before();
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
@@ -477,13 +491,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      : "memory");
       }
     }
+    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[8] = clock64();
     if (et == 0) tma_store_wait_read();
+    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[9] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[10] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -575,7 +592,10 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   const long long M = (long long)N * H * W;
   // N tile of at most 128 channels: short-K (1x1) kernels then fit two CTAs per SM (one CTA's epilogue overlaps
   // the other's TMA/MMA phase); 256 output channels = two N tiles that share the activation tile through L2.
-  const int BN = Np > 128 ? 128 : Np;
+  // One-wave grids (4x4 .. 16x16 levels) are pure latency: 64-channel N tiles double the CTA count, which halves
+  // the per-CTA epilogue and weight-load time (the activation tile is then read by two SMs in parallel).
+  int BN = Np > 128 ? 128 : Np;
+  if (g_small_n_tiles && BN == 128 && ceil_div(M, 128) * (Np / 64) <= kNumSMs) BN = 64;
   if (BN != 64 && BN != 128) {
     set_error("conv_gemm_bf16: unsupported padded Cout %d", Np);
     return HG_ERR_UNSUPPORTED;
@@ -630,6 +650,7 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   p.has_res = res != nullptr;
   p.n_tiles = Np / BN;
   if (fold) p.fold = *fold;
+  p.ts = g_dbg_ts;
   const bool long_k = R * S * (Kp / 64) > 4;
   const bool has_res = res != nullptr;
   if (mode == kMask && (!res || !stats)) {

@@ -112,6 +112,16 @@ def empty_chain(n=200):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    if os.environ.get("SMALL_N"):
+        L.call("hg_set_option", b"small_n_tiles", int(os.environ["SMALL_N"]))
+    if os.environ.get("DBG_TS"):
+        L.call("hg_set_option", b"dbg_ts", 1)
+        for hw, cin, cout, k in ((4, 256, 128, 1), (4, 128, 128, 3), (64, 128, 128, 3)):
+            t = conv_chain(32, hw, cin, cout, k, n=20)
+            print(f"phases of CTA 0, conv {k}x{k} {cin}->{cout} @{hw}x{hw} (chain: {t:.2f} us/call)", flush=True)
+            L.call("hg_set_option", b"dbg_ts", 2)
+        L.call("hg_set_option", b"dbg_ts", 0)
+        sys.exit(0)
     print(f"trivial kernel chain (hg_add 64 elems): {empty_chain():.2f} us/call")
     for hw in (4, 8, 16, 32, 64):
         print(f"B=32 @{hw}x{hw}: conv3x3 128->128 {conv_chain(32, hw, 128, 128, 3):7.2f} us | "

@@ -233,6 +233,35 @@ typedef struct HgMseDesc {
 HG_API int hg_mse_multi(const HgMseDesc* d, const float* const* preds_host, const float* target,
                         float* const* dpreds_host, float* loss, void* stream);
 
+/* ---- per-pixel class cross-entropy heads --------------------------------------------------------- */
+/* nn.CrossEntropyLoss (mean over labels != ignore_index) on fp32 NCHW logits with int64 [B,H,W] labels
+ * (only_one_hourgless.py:348,370; try_different_stack.py:360-361,388-389; the [:, :18] / [:, 18:] slices of every
+ * stack's output in try_skeleton_and_keypoints.py:390-397,423-435).  Every term of a training step goes through one
+ * call: term t reads `channels` consecutive channel planes starting at `logits` (point it at the first channel of
+ * the slice; images are `logits_bstride` floats apart), adds its loss to loss[t] (caller zeroes loss[T] and count[T])
+ * and, when dlogits != NULL, writes grad_scale * (softmax - onehot) / count into the same planes of the gradient
+ * tensor (0 for ignored pixels).  *bad_label (may be NULL) is set to 1 if a label is outside [0, channels) and is
+ * not ignore_index; such pixels are treated as ignored. */
+#define HG_CE_MAX_TERMS 16
+typedef struct HgCeTerm {
+  const float* logits;
+  float* dlogits;
+  const int64_t* target;
+  int64_t logits_bstride;
+  int64_t dlogits_bstride;
+  int32_t channels;
+  int32_t pad_;
+} HgCeTerm;
+typedef struct HgCeDesc {
+  int32_t num_terms;
+  int32_t B;
+  int32_t HW;
+  int32_t ignore_index;
+  float grad_scale;
+} HgCeDesc;
+HG_API int hg_ce_multi(const HgCeDesc* d, const HgCeTerm* terms_host, float* loss, int32_t* count, int32_t* bad_label,
+                       void* stream);
+
 /* ---- target rendering ---------------------------------------------------------------------------- */
 /* Gaussian keypoint heatmaps, evaluated in float64 like the numpy code, stored as float32
  * (try_with_torch.py:107-132; variants try_with_torch_100.py:64-85, only_one_hourgless.py:112-132,
@@ -271,6 +300,11 @@ HG_API int hg_decode_argmax(const void* heatmaps, int dtype, int num_maps, int H
 HG_API int hg_pckh_sweep(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
                   int chan_offset, int njoints, const float* thresholds, int nthr, int32_t* correct, int32_t* total,
                   int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream);
+/* PCKh "D" (calculate_parameters.py:906-937): same decode and label lookup as hg_pckh_sweep, but a joint is correct
+ * when  sqrt(d2) < standard * factors[s]  (the reference uses the single factor 0.5; float32 throughout). */
+HG_API int hg_pckh_abs(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
+                int chan_offset, int njoints, const float* factors, int nfac, int32_t* correct, int32_t* total,
+                int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream);
 /* PCKh "A" (only_one_hourgless.py:285-313): counts[0] += correct, counts[1] += total. */
 HG_API int hg_pckh_a(const void* x, int x_dtype, const void* target, int t_dtype, int B, int Cx, int Ct, int H, int W,
               int njoints, int head_ch, int neck_ch, int32_t* counts, void* stream);

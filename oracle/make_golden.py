@@ -169,6 +169,21 @@ def golden_pckh():
                         std_b=np.array([float(s) for s in std_b], dtype=np.float32), acc_a=np.float64(acc_a))
 
 
+def golden_pckh_d():
+    """PCKh D (calculate_parameters.py:906-937) and, on the same near-label inputs, PCKh B of the reference."""
+    cp = refload.load("calculate_parameters")
+    pc = refload.load("performance_compare")
+    pc.nKeypoint_MPII = 16
+    from oracle.synth import pckh_near_inputs
+
+    d = pckh_near_inputs(0)
+    x, tgt, rect = torch.from_numpy(d["x17"]), torch.from_numpy(d["target"]), torch.from_numpy(d["rect"])
+    acc_d, pred_d, lab_d = cp.PCKh().forward(x, tgt, rect)
+    acc_b, pred_b, lab_b, _ = pc.PCKh().forward(x, tgt, rect)
+    np.savez_compressed(os.path.join(GOLDEN, "pckh_d.npz"), seed=0, acc_d=np.array(acc_d, dtype=np.float64),
+                        pred_d=np.stack(pred_d), lab_d=np.stack(lab_d), acc_b=acc_b, pred_b=np.stack(pred_b))
+
+
 # (reference script, model factory attribute, drop-in module name)
 FAMILIES = [
     ("try_different_stack", "creatModel"),
@@ -265,6 +280,7 @@ def main():
     golden_model_c1()
     golden_targets()
     golden_pckh()
+    golden_pckh_d()
     golden_families()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))

@@ -65,6 +65,37 @@ def pckh_sweep(x, target, rect, chan_offset=0, njoints=None):
                 accuracy=accuracy)
 
 
+def pckh_d(x, target, rect):
+    """PCKh 'D' (calculate_parameters.py:906-937): prediction channel j+1, single test
+    sqrt(float32(d2)) < standard * 0.5 with standard = sqrt(...) * 0.6, all float32.
+    Returns (correct[B], total[B], predict[B,C,2] (x,y), label[B,C,2]); rows of absent joints stay zero."""
+    x = np.asarray(x)
+    target = np.asarray(target)
+    rect = np.asarray(rect, dtype=np.float32)
+    B, C = x.shape[:2]
+    correct = np.zeros([B], dtype=np.int64)
+    total = np.zeros([B], dtype=np.int64)
+    predict = np.zeros([B, C, 2], dtype=np.float64)
+    label = np.zeros([B, C, 2], dtype=np.float64)
+    for i in range(B):
+        dx = np.float32(rect[i, 0] - rect[i, 2])
+        dy = np.float32(rect[i, 1] - rect[i, 3])
+        std = np.float32(np.sqrt(np.float32(np.float32(dx * dx) + np.float32(dy * dy)))) * np.float32(0.6)
+        for j in range(C - 1):
+            pos = np.argwhere(target[i] == (j + 1))
+            if pos.shape[0] == 0:
+                continue
+            ly, lx = int(pos[0, 0]), int(pos[0, 1])
+            py, px = argmax_first(x[i, j + 1].astype(np.float32))
+            d2 = (ly - py) ** 2 + (lx - px) ** 2
+            if np.float32(np.sqrt(np.float32(d2))) < np.float32(np.float32(std) * np.float32(0.5)):
+                correct[i] += 1
+            total[i] += 1
+            predict[i, j] = (px, py)
+            label[i, j] = (lx, ly)
+    return correct, total, predict, label
+
+
 def pckh_a(x, target, batch_size, njoints=14, head_ch=13, neck_ch=1):
     """PCKh 'A' (only_one_hourgless.py:285-313 = try_with_torch_100.py:283-311), quirk Q8 kept: label_xs and
     predict_xs are both the arg-max of the LABEL map's row `head_ys`, so only the y error counts.

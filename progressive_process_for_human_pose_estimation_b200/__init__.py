@@ -6,9 +6,10 @@ keys): try_with_torch, try_with_torch_100, only_one_hourgless.  Kernels live in 
 (include/hg_sm100a.h); see DESIGN.md.
 """
 from ._modules import get_compute_dtype, set_compute_dtype  # noqa: F401
-from .evaluate import PCKh_hourglass, PCKh_softmax, decode_argmax, pckh_sweep_counts  # noqa: F401
-from .losses import mse_losses  # noqa: F401
+from .evaluate import (PCKh_half_standard, PCKh_hourglass, PCKh_softmax, decode_argmax,  # noqa: F401
+                       pckh_sweep_counts)
+from .losses import cross_entropy_losses, mse_losses  # noqa: F401
 from .targets import gaussian_heatmaps, label_maps  # noqa: F401
 
 __all__ = ["set_compute_dtype", "get_compute_dtype", "gaussian_heatmaps", "label_maps", "decode_argmax",
-           "pckh_sweep_counts", "PCKh_hourglass", "PCKh_softmax", "mse_losses"]
+           "pckh_sweep_counts", "PCKh_hourglass", "PCKh_softmax", "PCKh_half_standard", "mse_losses", "cross_entropy_losses"]

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libhg_sm100a.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 HG_BF16, HG_F32, HG_F16 = 0, 1, 2
+HG_CE_MAX_TERMS = 16
 
 
 class HgConvDesc(C.Structure):
@@ -49,6 +50,16 @@ class HgGaussDesc(C.Structure):
 
 class HgMseDesc(C.Structure):
     _fields_ = [("numel", C.c_int64), ("num_stacks", C.c_int32), ("grad_scale", C.c_float)]
+
+
+class HgCeTerm(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("dlogits", C.c_void_p), ("target", C.c_void_p), ("logits_bstride", C.c_int64),
+                ("dlogits_bstride", C.c_int64), ("channels", C.c_int32), ("pad_", C.c_int32)]
+
+
+class HgCeDesc(C.Structure):
+    _fields_ = [("num_terms", C.c_int32), ("B", C.c_int32), ("HW", C.c_int32), ("ignore_index", C.c_int32),
+                ("grad_scale", C.c_float)]
 
 
 class HgLabelDesc(C.Structure):
@@ -92,10 +103,12 @@ SIGNATURES = {
     "hg_unpack_conv_wgrad_slice": [C.POINTER(HgConvDesc), _P, _P, _I, _I, _I, _P],
     "hg_mix_rows": [_P, _P, _P, _I, _I, _I, _I, _P],
     "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
+    "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
     "hg_render_gauss": [C.POINTER(HgGaussDesc), _P, _P, _P, _P, _P],
     "hg_render_labels": [C.POINTER(HgLabelDesc), _P, _P, _P, _P, _P, _P],
     "hg_decode_argmax": [_P, _I, _I, _I, _I, _P, _P, _P],
     "hg_pckh_sweep": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "hg_pckh_abs": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "hg_pckh_a": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
 }
 _SPECIAL = {"hg_last_error_string": ([], C.c_char_p), "hg_launch_count": ([], C.c_ulonglong)}

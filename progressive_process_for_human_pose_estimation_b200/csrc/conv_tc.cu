@@ -18,6 +18,13 @@
 // (reference try_with_torch.py:186-193,199-207,248,253,271-273,291-297).
 #include "hg_common.cuh"
 
+// -DHG_DBG_TS=1 compiles per-phase clock64() stamps of CTA 0 into conv_gemm_kernel (hg_set_option("dbg_ts", 1|2));
+// even an untaken `if (p.ts)` per phase costs ~8 % on the 64x64 kernels, so the production build has none.
+#ifndef HG_DBG_TS
+#define HG_DBG_TS 0
+#endif
+#define HG_TS (HG_DBG_TS && p.ts)
+
 namespace hg {
 
 int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
@@ -163,7 +170,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[0] = clock64();
+  if (HG_TS && blockIdx.x == 0 && threadIdx.x == 0) p.ts[0] = clock64();
   // 1-D grid, N tile fastest: the CTAs that share an activation tile run back to back (second read hits L2)
   const int m0 = (blockIdx.x / p.n_tiles) * 128;
   const int n_off = (blockIdx.x % p.n_tiles) * BN;
@@ -188,11 +195,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[1] = clock64();
+  if (HG_TS && blockIdx.x == 0 && threadIdx.x == 0) p.ts[1] = clock64();
   // PDL: everything above overlapped the previous kernel's tail; global memory is ours from here.  The producer warp
   // starts its TMA loads at once; the per-channel coefficients are fetched by the epilogue warps meanwhile.
   pdl_wait();
-  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[2] = clock64();
+  if (HG_TS && blockIdx.x == 0 && threadIdx.x == 0) p.ts[2] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -207,7 +214,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int pnl = 0; pnl < L::kCPanels; ++pnl)
           tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
       }
-      if (p.ts && blockIdx.x == 0) p.ts[15] = clock64();
+      if (HG_TS && blockIdx.x == 0) p.ts[15] = clock64();
       int kb = 0;
       for (int r = 0; r < p.taps_r; ++r) {
         for (int s = 0; s < p.taps_s; ++s) {
@@ -220,8 +227,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_expect_tx(&full_bar[st], L::kABytes + L::kBBytes);
             tma_load_4d(sA + st * L::kABytes, &tmA, &full_bar[st], kc * 64, w0 + dw, h0 + dh, n0);
             tma_load_3d(sB + st * L::kBBytes, &tmB, &full_bar[st], kc * 64, n_off, r * p.taps_s + s);
-            if (p.ts && blockIdx.x == 0 && kb == 0) p.ts[3] = clock64();
-            if (p.ts && blockIdx.x == 0 && kb < 8) p.ts[16 + kb] = clock64();
+            if (HG_TS && blockIdx.x == 0 && kb == 0) p.ts[3] = clock64();
+            if (HG_TS && blockIdx.x == 0 && kb < 8) p.ts[16 + kb] = clock64();
           }
         }
       }
@@ -244,8 +251,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (MODE == kFold) mbar_wait(&ready_bar[st], ph);
       else mbar_wait(&full_bar[st], ph);
       tc_fence_after();
-      if (p.ts && blockIdx.x == 0 && lane == 0 && kb == 0) p.ts[4] = clock64();
-      if (p.ts && blockIdx.x == 0 && lane == 0 && kb < 8) p.ts[24 + kb] = clock64();
+      if (HG_TS && blockIdx.x == 0 && lane == 0 && kb == 0) p.ts[4] = clock64();
+      if (HG_TS && blockIdx.x == 0 && lane == 0 && kb < 8) p.ts[24 + kb] = clock64();
       if (lane == 0) {
         const uint64_t adesc = make_smem_desc(smem_u32(sA + st * L::kABytes), 16, 1024);
         const uint64_t bdesc = make_smem_desc(smem_u32(sB + st * L::kBBytes), 16, 1024);
@@ -259,7 +266,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
     }
-    if (p.ts && blockIdx.x == 0 && lane == 0) p.ts[5] = clock64();
+    if (HG_TS && blockIdx.x == 0 && lane == 0) p.ts[5] = clock64();
     pdl_trigger();
   } else {
     // ===================== transform (kFold) + epilogue (warps 2..5) =====================
@@ -345,7 +352,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[6] = clock64();
+    if (HG_TS && blockIdx.x == 0 && et == 0) p.ts[6] = clock64();
     pdl_trigger();  // main loop done: the next kernel may start its prologue under our epilogue
     if (p.has_res) mbar_wait(res_full, 0);
     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
@@ -417,7 +424,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         *cp = w;
       }
     }
-    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[7] = clock64();
+    if (HG_TS && blockIdx.x == 0 && et == 0) p.ts[7] = clock64();
     tc_fence_before();
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
@@ -491,16 +498,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      : "memory");
       }
     }
-    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[8] = clock64();
+    if (HG_TS && blockIdx.x == 0 && et == 0) p.ts[8] = clock64();
     if (et == 0) tma_store_wait_read();
-    if (p.ts && blockIdx.x == 0 && et == 0) p.ts[9] = clock64();
+    if (HG_TS && blockIdx.x == 0 && et == 0) p.ts[9] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-  if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) p.ts[10] = clock64();
+  if (HG_TS && blockIdx.x == 0 && threadIdx.x == 0) p.ts[10] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------------

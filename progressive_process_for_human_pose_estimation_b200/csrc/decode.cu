@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) decode_argmax_kernel(const void* __restri
 __global__ void __launch_bounds__(256) pckh_sweep_kernel(const void* __restrict__ x, int dtype, int C, int H, int W,
                                                          const long long* __restrict__ target,
                                                          const float* __restrict__ rect, int chan_offset, int njoints,
-                                                         const float* __restrict__ thr, int nthr,
+                                                         const float* __restrict__ thr, int nthr, int rule,
                                                          int* __restrict__ correct, int* __restrict__ total,
                                                          int* __restrict__ predict_xy, int* __restrict__ label_xy,
                                                          int* __restrict__ found, float* __restrict__ standard_out) {
@@ -115,9 +115,13 @@ __global__ void __launch_bounds__(256) pckh_sweep_kernel(const void* __restrict_
   if (threadIdx.x == 0) {
     const int ly = li / W, lx = li % W, py = pi / W, px = pi % W;
     const int dy = ly - py, dx = lx - px;
-    const float dist = __fdiv_rn(__fsqrt_rn((float)(dy * dy + dx * dx)), standard);
+    // rule 0 (PCKh B/C): sqrt(d2) / standard < k;  rule 1 (PCKh D, calculate_parameters.py:927-929):
+    // sqrt(d2) < standard * k -- the two roundings differ, so each evaluator keeps its own float32 expression
+    const float root = __fsqrt_rn((float)(dy * dy + dx * dx));
+    const float dist = __fdiv_rn(root, standard);
     for (int s = 0; s < nthr; ++s) {
-      if (dist < thr[s]) atomicAdd(correct + b * nthr + s, 1);
+      const bool hit = rule == 0 ? dist < thr[s] : root < __fmul_rn(standard, thr[s]);
+      if (hit) atomicAdd(correct + b * nthr + s, 1);
       atomicAdd(total + b * nthr + s, 1);
     }
     predict_xy[(b * njoints + j) * 2] = px;
@@ -192,21 +196,36 @@ int hg_decode_argmax(const void* heatmaps, int dtype, int num_maps, int H, int W
   return HG_OK;
 }
 
-int hg_pckh_sweep(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
-                  int chan_offset, int njoints, const float* thresholds, int nthr, int32_t* correct, int32_t* total,
-                  int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream) {
+static int pckh_launch(const char* who, int rule, const void* x, int dtype, int B, int C, int H, int W,
+                       const int64_t* target, const float* rect, int chan_offset, int njoints, const float* thresholds,
+                       int nthr, int32_t* correct, int32_t* total, int32_t* predict_xy, int32_t* label_xy,
+                       int32_t* found, float* standard, void* stream) {
   HG_REQUIRE(x && target && rect && thresholds && correct && total && predict_xy && label_xy && found,
-             "hg_pckh_sweep: NULL pointer");
-  HG_REQUIRE(dtype >= 0 && dtype <= 2, "hg_pckh_sweep: bad dtype");
-  HG_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && njoints > 0 && nthr > 0, "hg_pckh_sweep: non-positive size");
-  HG_REQUIRE(chan_offset >= 0 && njoints + chan_offset <= C, "hg_pckh_sweep: joints exceed channels");
+             "%s: NULL pointer", who);
+  HG_REQUIRE(dtype >= 0 && dtype <= 2, "%s: bad dtype", who);
+  HG_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && njoints > 0 && nthr > 0, "%s: non-positive size", who);
+  HG_REQUIRE(chan_offset >= 0 && njoints + chan_offset <= C, "%s: joints exceed channels", who);
   dim3 grid(njoints, B);
   pckh_sweep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dtype, C, H, W, (const long long*)target, rect,
-                                                             chan_offset, njoints, thresholds, nthr, correct, total,
-                                                             predict_xy, label_xy, found, standard);
+                                                             chan_offset, njoints, thresholds, nthr, rule, correct,
+                                                             total, predict_xy, label_xy, found, standard);
   HG_LAUNCH_OK("pckh_sweep_kernel");
   count_launch();
   return HG_OK;
+}
+
+int hg_pckh_sweep(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
+                  int chan_offset, int njoints, const float* thresholds, int nthr, int32_t* correct, int32_t* total,
+                  int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream) {
+  return pckh_launch("hg_pckh_sweep", 0, x, dtype, B, C, H, W, target, rect, chan_offset, njoints, thresholds, nthr,
+                     correct, total, predict_xy, label_xy, found, standard, stream);
+}
+
+int hg_pckh_abs(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
+                int chan_offset, int njoints, const float* factors, int nfac, int32_t* correct, int32_t* total,
+                int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream) {
+  return pckh_launch("hg_pckh_abs", 1, x, dtype, B, C, H, W, target, rect, chan_offset, njoints, factors, nfac, correct,
+                     total, predict_xy, label_xy, found, standard, stream);
 }
 
 int hg_pckh_a(const void* x, int x_dtype, const void* target, int t_dtype, int B, int Cx, int Ct, int H, int W,

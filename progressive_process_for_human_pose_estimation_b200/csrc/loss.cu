@@ -72,6 +72,78 @@ __global__ void __launch_bounds__(256) mse_multi_kernel(const MseArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Per-pixel class cross-entropy heads (nn.CrossEntropyLoss on [B,C,64,64] logits with [B,64,64] int64 labels:
+// only_one_hourgless.py:348,370; try_different_stack.py:360-361,388-389; and on the channel slices [:, :18] /
+// [:, 18:] of every stack's output, try_skeleton_and_keypoints.py:390-397,423-435).  The reference runs one
+// log-softmax + NLL + mean (and their backward kernels, plus a slice-gradient zero-fill) per term; here ALL terms
+// of a step go through one launch: blockIdx.y = term, one thread per pixel, channels strided by H*W (coalesced
+// across the warp), max / sum-exp / gradient in three sweeps of which only the first misses L1.
+// mean reduction over the labels != ignore_index, like the module's defaults.
+struct CeArgs {
+  HgCeTerm term[HG_CE_MAX_TERMS];
+  float* loss;         // [T]  += sum nll / count
+  int* count;          // [T]  valid labels (written by ce_count_kernel)
+  int* bad;            // != NULL: set to 1 when a label is outside [0, C) and not ignore_index
+  int B, HW, ignore_index;
+  float gscale;
+};
+
+__global__ void __launch_bounds__(256) ce_count_kernel(const CeArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const HgCeTerm& t = a.term[blockIdx.y];
+  const long long n = (long long)a.B * a.HW;
+  int c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long y = t.target[i];
+    if (y >= 0 && y < t.channels) ++c;
+    else if (y != a.ignore_index && a.bad) *a.bad = 1;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(a.count + blockIdx.y, c);
+}
+
+__global__ void __launch_bounds__(256) ce_multi_kernel(const CeArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[8];
+  const HgCeTerm& t = a.term[blockIdx.y];
+  const long long n = (long long)a.B * a.HW;
+  const float inv = 1.f / (float)a.count[blockIdx.y];  // inf when every label is ignored: loss = 0 * inf = NaN
+  const float k = a.gscale * inv;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / a.HW), p = (int)(i % a.HW);
+    const float* x = t.logits + (long long)b * t.logits_bstride + p;
+    const long long y = t.target[i];
+    const bool valid = y >= 0 && y < t.channels;
+    float m = -INFINITY;
+    for (int c = 0; c < t.channels; ++c) m = fmaxf(m, __ldg(x + (long long)c * a.HW));
+    float s = 0.f;
+    for (int c = 0; c < t.channels; ++c) s += expf(__ldg(x + (long long)c * a.HW) - m);
+    const float lse = m + logf(s);
+    if (valid) acc += lse - __ldg(x + y * a.HW);
+    if (t.dlogits) {
+      float* g = t.dlogits + (long long)b * t.dlogits_bstride + p;
+      for (int c = 0; c < t.channels; ++c) {
+        const float sm = expf(__ldg(x + (long long)c * a.HW) - lse);
+        g[(long long)c * a.HW] = valid ? k * (sm - (c == y ? 1.f : 0.f)) : 0.f;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float v = warp_sum(acc);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    atomicAdd(a.loss + blockIdx.y, tot * inv);
+  }
+}
+
 }  // namespace hg
 
 using namespace hg;
@@ -103,6 +175,43 @@ int hg_mse_multi(const HgMseDesc* d, const float* const* preds_host, const float
   if (blocks < 1) blocks = 1;
   launch_k(mse_multi_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
   HG_LAUNCH_OK("mse_multi_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_ce_multi(const HgCeDesc* d, const HgCeTerm* terms_host, float* loss, int32_t* count, int32_t* bad_label,
+                void* stream) {
+  HG_REQUIRE(d && terms_host && loss && count, "hg_ce_multi: NULL pointer");
+  HG_REQUIRE(d->num_terms > 0 && d->num_terms <= HG_CE_MAX_TERMS, "hg_ce_multi: 1..%d terms supported",
+             HG_CE_MAX_TERMS);
+  HG_REQUIRE(d->B > 0 && d->HW > 0, "hg_ce_multi: empty tensors");
+  CeArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int t = 0; t < d->num_terms; ++t) {
+    const HgCeTerm& h = terms_host[t];
+    HG_REQUIRE(h.logits && h.target, "hg_ce_multi: term %d has a NULL tensor", t);
+    HG_REQUIRE(h.channels > 0, "hg_ce_multi: term %d has no channels", t);
+    HG_REQUIRE(h.logits_bstride >= (long long)h.channels * d->HW &&
+                   (!h.dlogits || h.dlogits_bstride >= (long long)h.channels * d->HW),
+               "hg_ce_multi: term %d: batch stride smaller than channels * H * W", t);
+    a.term[t] = h;
+  }
+  a.loss = loss;
+  a.count = count;
+  a.bad = bad_label;
+  a.B = d->B;
+  a.HW = d->HW;
+  a.ignore_index = d->ignore_index;
+  a.gscale = d->grad_scale;
+  const long long n = (long long)d->B * d->HW;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  dim3 grid((unsigned)blocks, (unsigned)d->num_terms);
+  launch_k(ce_count_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a);
+  HG_LAUNCH_OK("ce_count_kernel");
+  count_launch();
+  launch_k(ce_multi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a);
+  HG_LAUNCH_OK("ce_multi_kernel");
   count_launch();
   return HG_OK;
 }

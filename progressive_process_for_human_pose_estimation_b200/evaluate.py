@@ -32,15 +32,17 @@ def decode_argmax(heatmaps):
     return yx.view(*hm.shape[:-2], 2), mx.view(hm.shape[:-2])
 
 
-def pckh_sweep_counts(x, target, rect, chan_offset=0, njoints=None):
-    """Integer results of the PCKh threshold sweep, all on the device (no host sync)."""
+def pckh_sweep_counts(x, target, rect, chan_offset=0, njoints=None, thresholds=None, absolute=False):
+    """Integer results of the PCKh threshold sweep, all on the device (no host sync).
+    absolute=False: correct when sqrt(d2)/standard < k (evaluators B/C); absolute=True: sqrt(d2) < standard*k
+    (evaluator D, calculate_parameters.py:927-929)."""
     x = _as_cuda(x, "x")
     target = _as_cuda(target, "target").to(torch.int64)
     rect = _as_cuda(rect, "rect").to(torch.float32)
     B, Cx, H, W = x.shape
     nj = Cx - chan_offset if njoints is None else njoints
     dev = x.device
-    thr = torch.from_numpy(_THRESHOLDS).to(dev)
+    thr = torch.from_numpy(_THRESHOLDS if thresholds is None else np.asarray(thresholds, dtype=np.float32)).to(dev)
     nthr = thr.numel()
     correct = torch.zeros(B, nthr, device=dev, dtype=torch.int32)
     total = torch.zeros(B, nthr, device=dev, dtype=torch.int32)
@@ -49,8 +51,8 @@ def pckh_sweep_counts(x, target, rect, chan_offset=0, njoints=None):
     found = torch.zeros(B, nj, device=dev, dtype=torch.int32)
     standard = torch.zeros(B, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        L.call("hg_pckh_sweep", L.ptr(x), L.hg_dtype(x.dtype), B, Cx, H, W, L.ptr(target), L.ptr(rect), chan_offset, nj,
-               L.ptr(thr), nthr, L.ptr(correct), L.ptr(total), L.ptr(predict), L.ptr(label), L.ptr(found),
+        L.call("hg_pckh_abs" if absolute else "hg_pckh_sweep", L.ptr(x), L.hg_dtype(x.dtype), B, Cx, H, W,
+               L.ptr(target), L.ptr(rect), chan_offset, nj, L.ptr(thr), nthr, L.ptr(correct), L.ptr(total), L.ptr(predict), L.ptr(label), L.ptr(found),
                L.ptr(standard), L.stream_ptr())
     return dict(correct=correct, total=total, predict=predict, label=label, found=found, standard=standard)
 
@@ -81,6 +83,26 @@ class PCKh_softmax(nn.Module):
         r = pckh_sweep_counts(x, target, rect, 1)
         acc, pred, lab = _sweep_result(r)
         return acc, pred, lab, [s for s in r["standard"].cpu()]
+
+
+class PCKh_half_standard(nn.Module):
+    """PCKh 'D' (calculate_parameters.py:906-937 `PCKh`): class-probability input (channel j+1 <-> label value j+1),
+    ONE threshold: correct when sqrt(d2) < standard * 0.5 with standard = 0.6 * head-box diagonal, float32.
+    Returns (accuracy: list of B python floats correct/total, predicts, labels).  Like the reference it raises
+    ZeroDivisionError for an image without any annotated joint, and label value C (= x.shape[1]) cannot be
+    evaluated (the reference indexes channel C and fails)."""
+
+    def forward(self, x, target, rect):
+        nj = x.shape[1] - 1
+        r = pckh_sweep_counts(x, target, rect, 1, nj, thresholds=[0.5], absolute=True)
+        correct = r["correct"].cpu().numpy()[:, 0]
+        total = r["total"].cpu().numpy()[:, 0]
+        accuracy = [int(c) / int(t) for c, t in zip(correct, total)]  # ZeroDivisionError when total == 0
+        # the reference's predict / label arrays have x.shape[1] rows (row C-1 is never filled)
+        pad = np.zeros([x.shape[0], 1, 2])
+        pred = np.concatenate([r["predict"].cpu().numpy().astype(np.float64), pad], 1)
+        lab = np.concatenate([r["label"].cpu().numpy().astype(np.float64), pad], 1)
+        return accuracy, [p for p in pred], [l for l in lab]
 
 
 def make_pckh_a(g):

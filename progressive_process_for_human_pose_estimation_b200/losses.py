@@ -1,4 +1,4 @@
-"""Fused intermediate-supervision MSE loss (csrc/loss.cu).
+"""Fused intermediate-supervision losses (csrc/loss.cu): per-stack MSE and per-pixel class cross-entropy heads.
 
 The reference sums one `nn.MSELoss` per stack (try_with_torch.py:305-308,333-341); those stock modules keep working
 on the heatmaps the drop-in models return.  `mse_losses(result, target)` is the optional fast path: one kernel reads
@@ -48,3 +48,101 @@ def mse_losses(result, target):
     """Per-stack MSE losses as one tensor [nStack]; `mse_losses(result, y).sum().backward()` is the training
     objective of try_with_torch.py:333-342."""
     return _MseMulti.apply(target, *result)
+
+
+def _plane_view(t):
+    """True when `t` [B,C,H,W] can be read in place: channel planes contiguous and H*W apart (a channel slice of a
+    contiguous NCHW tensor qualifies)."""
+    B, C, H, W = t.shape
+    sb, sc, sh, sw = t.stride()
+    return sw == 1 and sh == W and sc == H * W and sb >= C * H * W
+
+
+class _CeMulti(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, *logits):
+        # spec: (terms, ignore_index, check_labels); terms[t] = (index into logits, c0, c1, target)
+        terms, ignore_index, check = spec
+        T = len(terms)
+        if T < 1 or T > L.HG_CE_MAX_TERMS:
+            raise RuntimeError(f"cross_entropy_losses: 1..{L.HG_CE_MAX_TERMS} terms supported")
+        B, _, H, W = logits[0].shape
+        HW = H * W
+        dev = logits[0].device
+        srcs, grads = [], []
+        for i, x in enumerate(logits):
+            if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or x.shape[0] != B or x.shape[2:] != (H, W):
+                raise RuntimeError("cross_entropy_losses: logits must be fp32 CUDA tensors [B,C,H,W] of one batch / "
+                                   "map size (there is no CPU fallback)")
+            srcs.append(x if _plane_view(x) else x.contiguous())
+            if ctx.needs_input_grad[i + 1]:
+                covered = sorted((c0, c1) for k, c0, c1, _ in terms if k == i)
+                full = covered[0][0] == 0 and covered[-1][1] == x.shape[1] and all(
+                    a[1] == b[0] for a, b in zip(covered, covered[1:]))
+                grads.append((torch.empty if full else torch.zeros)(x.shape, device=dev, dtype=torch.float32))
+            else:
+                grads.append(None)
+        arr = (L.HgCeTerm * T)()
+        keep = []
+        for t, (k, c0, c1, target) in enumerate(terms):
+            x, g = srcs[k], grads[k]
+            if not (0 <= c0 < c1 <= x.shape[1]):
+                raise RuntimeError(f"cross_entropy_losses: channel slice [{c0}, {c1}) outside {x.shape[1]} channels")
+            if not target.is_cuda or tuple(target.shape) != (B, H, W):
+                raise RuntimeError("cross_entropy_losses: labels must be a CUDA tensor [B,H,W]")
+            tg = target.contiguous().to(torch.int64)
+            keep.append(tg)
+            arr[t].logits = x.data_ptr() + 4 * c0 * HW
+            arr[t].dlogits = (g.data_ptr() + 4 * c0 * HW) if g is not None else None
+            arr[t].target = tg.data_ptr()
+            arr[t].logits_bstride = x.stride(0)
+            arr[t].dlogits_bstride = g.stride(0) if g is not None else 0
+            arr[t].channels = c1 - c0
+        loss = torch.zeros(T, device=dev, dtype=torch.float32)
+        count = torch.zeros(T + 1, device=dev, dtype=torch.int32)  # [T] = bad-label flag
+        d = L.HgCeDesc(T, B, HW, ignore_index, 1.0)
+        with torch.cuda.device(dev):
+            L.call("hg_ce_multi", C.byref(d), arr, L.ptr(loss), L.ptr(count), C.c_void_p(count.data_ptr() + 4 * T),
+                   L.stream_ptr())
+        if check and int(count[T]) != 0:
+            raise IndexError("cross_entropy_losses: a label is outside [0, C) and is not ignore_index")
+        ctx.grads, ctx.terms = grads, [(k, c0, c1) for k, c0, c1, _ in terms]
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        out = [None]
+        for i, g in enumerate(ctx.grads):
+            if g is not None:
+                for t, (k, c0, c1) in enumerate(ctx.terms):
+                    if k == i:
+                        g[:, c0:c1].mul_(gloss[t])
+            out.append(g)
+        ctx.grads = None
+        return tuple(out)
+
+
+def cross_entropy_losses(terms, ignore_index=-100, check_labels=False):
+    """All `nn.CrossEntropyLoss` heads of a training step in one launch.  terms: list of `(logits, target)` or
+    `(logits, target, (c0, c1))`; logits fp32 [B,C,64,64] (a model output), target int64 [B,64,64], (c0, c1) a channel
+    slice of logits.  Returns a tensor with one mean-reduced loss per term, e.g. the objective of
+    try_skeleton_and_keypoints.py:423-435:
+
+        terms = [(r, by_keypoints, (0, 18)) for r in result] + [(r, by_skeleton, (18, 38)) for r in result]
+        cross_entropy_losses(terms).sum().backward()
+
+    Passing the slice explicitly lets every term of one output write into the same gradient tensor (no
+    zero-padded slice gradients); `(result[k][:, :18], target)` on views works too.
+    check_labels=True synchronises and raises IndexError on labels outside [0, C) (PyTorch's device assert)."""
+    uniq, spec = [], []
+    for term in terms:
+        x, target = term[0], term[1]
+        c0, c1 = term[2] if len(term) > 2 else (0, x.shape[1])
+        for k, u in enumerate(uniq):
+            if u is x:
+                break
+        else:
+            uniq.append(x)
+            k = len(uniq) - 1
+        spec.append((k, int(c0), int(c1), target))
+    return _CeMulti.apply((spec, int(ignore_index), bool(check_labels)), *uniq)

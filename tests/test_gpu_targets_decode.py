@@ -2,11 +2,14 @@
 oracle/pckh_np.py, both pinned to the reference / Pillow by the `not gpu` tests).  Integer results (label maps,
 decoded indices, PCKh counts) must be bit-exact; Gaussians are float64-evaluated and must match to the last
 float32 bit except for the documented <= 1 ulp allowance of the device exp()."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 import progressive_process_for_human_pose_estimation_b200 as hg  # noqa: E402
 import progressive_process_for_human_pose_estimation_b200.only_one_hourgless as ooh  # noqa: E402
@@ -143,6 +146,29 @@ def test_pckh_sweep_bit_exact(dtype, chan_offset):
         assert np.isnan(acc[4]).all()
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_pckh_d_bit_exact(dtype):
+    """PCKh D (calculate_parameters.py:906-937) against the numpy oracle and the reference-generated golden."""
+    from oracle.synth import pckh_inputs, pckh_near_inputs
+
+    for seed in range(5):
+        d = pckh_near_inputs(seed)
+        x = torch.from_numpy(d["x17"]).to(dtype)
+        tgt, rect = torch.from_numpy(d["target"]), torch.from_numpy(d["rect"])
+        acc, pred, lab = hg.PCKh_half_standard()(x.cuda(), tgt.cuda(), rect.cuda())
+        c, t, p, l = pckh_np.pckh_d(x.float().numpy(), d["target"], d["rect"])
+        assert acc == [int(a) / int(b) for a, b in zip(c, t)], seed
+        assert np.array_equal(np.stack(pred), p) and np.array_equal(np.stack(lab), l)
+        if seed == 0 and dtype == torch.float32:
+            g = np.load(os.path.join(GOLDEN, "pckh_d.npz"))
+            assert np.array_equal(np.array(acc), g["acc_d"])
+            assert np.array_equal(np.stack(pred), g["pred_d"]) and np.array_equal(np.stack(lab), g["lab_d"])
+    d = pckh_inputs(0)  # image 4 has no annotated joint: correct / total is 0 / 0 in the reference too
+    with pytest.raises(ZeroDivisionError):
+        hg.PCKh_half_standard()(torch.from_numpy(d["x17"]).cuda(), torch.from_numpy(d["target"]).cuda(),
+                                torch.from_numpy(d["rect"]).cuda())
+
+
 def test_pckh_a_bit_exact_counts():
     for seed in range(4):
         r = np.random.RandomState(seed)
@@ -211,3 +237,67 @@ def test_fused_mse_losses_match_stock_modules():
     assert torch.allclose(a.grad, 2 * (a.detach() - t) / t.numel(), rtol=1e-6, atol=1e-9)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         hg.mse_losses([a.detach().cpu()], t.cpu())
+
+
+def test_fused_cross_entropy_heads_match_stock_modules():
+    """hg.cross_entropy_losses == the nn.CrossEntropyLoss heads of try_skeleton_and_keypoints.py:423-435 (channel
+    slices [:, :18] / [:, 18:] of 4 stack outputs), only_one_hourgless.py:370 and try_different_stack.py:388-389,
+    evaluated by the stock module on the CPU in fp32 (the reference's implementation); rtol 1e-5 (north_star fp32)."""
+    def close(got, want):
+        # rtol 1e-5 plus an absolute term at 1e-5 of the gradient scale: softmax - onehot cancels near sm = 1
+        return torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-5 * want.abs().max().item())
+
+    torch.manual_seed(0)
+    B, S = 4, 4
+    outs = [(3 * torch.randn(B, 38, 64, 64)).requires_grad_() for _ in range(S)]
+    yk = torch.randint(0, 18, (B, 64, 64))
+    ys = torch.randint(0, 20, (B, 64, 64))
+    ce = torch.nn.CrossEntropyLoss()
+    ref = [ce(o[:, :18], yk) for o in outs] + [ce(o[:, 18:], ys) for o in outs]
+    w = torch.arange(1, 2 * S + 1, dtype=torch.float32)
+    sum(wi * li for wi, li in zip(w, ref)).backward()
+    gref = [o.grad.clone() for o in outs]
+    dev = [o.detach().cuda().requires_grad_() for o in outs]
+    terms = [(o, yk.cuda(), (0, 18)) for o in dev] + [(o, ys.cuda(), (18, 38)) for o in dev]
+    n0 = hg._lib.launch_count()
+    losses = hg.cross_entropy_losses(terms)
+    assert hg._lib.launch_count() - n0 == 2  # label count + fused loss/gradient: 8 terms in 2 launches
+    assert torch.allclose(losses.cpu(), torch.stack(ref).detach(), rtol=1e-5, atol=0)
+    (losses * w.cuda()).sum().backward()
+    for o, g in zip(dev, gref):
+        assert close(o.grad, g)
+    # the same heads called on channel-slice VIEWS (how the reference script passes them), no explicit slices
+    dev2 = [o.detach().cuda().requires_grad_() for o in outs]
+    l2 = hg.cross_entropy_losses([(o[:, :18], yk.cuda()) for o in dev2] + [(o[:, 18:], ys.cuda()) for o in dev2])
+    assert torch.allclose(l2, losses, rtol=1e-6)  # block partial sums are added with atomics: order varies
+    (l2 * w.cuda()).sum().backward()
+    for o, g in zip(dev2, gref):
+        assert close(o.grad, g)
+    # single 18-class head (only_one_hourgless.py:370); a partial slice leaves the other channels' gradient at zero
+    x = torch.randn(2, 18, 64, 64, requires_grad=True)
+    y = torch.randint(0, 18, (2, 64, 64))
+    r = ce(x, y)
+    r.backward()
+    xd = x.detach().cuda().requires_grad_()
+    l = hg.cross_entropy_losses([(xd, y.cuda())])
+    l.sum().backward()
+    assert torch.allclose(l.cpu()[0], r.detach(), rtol=1e-5) and close(xd.grad, x.grad)
+    xd2 = x.detach().cuda().requires_grad_()
+    hg.cross_entropy_losses([(xd2, (y % 5).cuda(), (3, 8))]).sum().backward()
+    assert (xd2.grad[:, :3] == 0).all() and (xd2.grad[:, 8:] == 0).all() and (xd2.grad[:, 3:8] != 0).any()
+    # ignore_index (module default -100): mean over the remaining labels; all ignored -> NaN like PyTorch
+    yi = y.clone()
+    yi[0, :32] = -100
+    x.grad = None
+    ri = ce(x, yi)
+    ri.backward()
+    xd3 = x.detach().cuda().requires_grad_()
+    li = hg.cross_entropy_losses([(xd3, yi.cuda())])
+    li.sum().backward()
+    assert torch.allclose(li.cpu()[0], ri.detach(), rtol=1e-5)
+    assert close(xd3.grad, x.grad) and (xd3.grad[0, :, :32] == 0).all()
+    assert torch.isnan(hg.cross_entropy_losses([(xd3.detach(), torch.full_like(yi, -100).cuda())])).all()
+    with pytest.raises(IndexError):
+        hg.cross_entropy_losses([(xd3.detach(), (y + 1).cuda())], check_labels=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hg.cross_entropy_losses([(x.detach(), y)])

@@ -92,6 +92,38 @@ def test_pckh_oracle_reproduces_reference_golden():
     assert np.isnan(c["accuracy"][4]).all()  # image without annotated joints
 
 
+def test_pckh_d_oracle_reproduces_reference_golden():
+    from oracle.synth import pckh_near_inputs
+
+    g = np.load(os.path.join(GOLDEN, "pckh_d.npz"))
+    d = pckh_near_inputs(int(g["seed"]))
+    c, t, pred, lab = pckh_np.pckh_d(d["x17"], d["target"], d["rect"])
+    np.testing.assert_array_equal(c.astype(np.float64) / t, g["acc_d"])
+    assert 0 < c.sum() < t.sum()  # both outcomes of the threshold test occur
+    np.testing.assert_array_equal(pred, g["pred_d"])
+    np.testing.assert_array_equal(lab, g["lab_d"])
+    b = pckh_np.pckh_sweep(d["x17"], d["target"], d["rect"], 1)
+    np.testing.assert_array_equal(b["accuracy"], g["acc_b"])
+    np.testing.assert_array_equal(b["predict"].astype(np.float64), g["pred_b"])
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_pckh_d_oracle_vs_reference_class_many_seeds():
+    from oracle.synth import pckh_near_inputs
+
+    cp = refload.load("calculate_parameters")
+    for seed in range(1, 5):
+        d = pckh_near_inputs(seed)
+        acc, pred, lab = cp.PCKh().forward(torch.from_numpy(d["x17"]), torch.from_numpy(d["target"]),
+                                           torch.from_numpy(d["rect"]))
+        c, t, p, l = pckh_np.pckh_d(d["x17"], d["target"], d["rect"])
+        assert acc == [int(a) / int(b) for a, b in zip(c, t)]
+        assert np.array_equal(np.stack(pred), p) and np.array_equal(np.stack(lab), l)
+    d = pckh_inputs(0)  # image 4 has no annotated joint: the reference divides 0 / 0
+    with pytest.raises(ZeroDivisionError):
+        cp.PCKh().forward(torch.from_numpy(d["x17"]), torch.from_numpy(d["target"]), torch.from_numpy(d["rect"]))
+
+
 def test_thresholds_are_float32_rounded():
     want = [0, 0.05000000075, 0.10000000149, 0.15000000596, 0.20000000298, 0.25, 0.30000001192, 0.34999999404,
             0.40000000596, 0.44999998808, 0.5]

@@ -114,6 +114,33 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     if os.environ.get("SMALL_N"):
         L.call("hg_set_option", b"small_n_tiles", int(os.environ["SMALL_N"]))
+    if os.environ.get("SPLIT_AB"):
+        # A/B in one process: weight tiles issued by a second thread (split_producer) vs. one producer thread
+        def one(B, hw, cin, cout, k, flag):
+            L.call("hg_set_option", b"split_producer", flag)
+            torch.manual_seed(0)
+            d = L.HgConvDesc(B, hw, hw, cin, cout, k, k, 1, k // 2, 1, L.HG_BF16)
+            x = torch.randn(B, hw, hw, cin, device=dev).to(DT)
+            y = torch.zeros(B, hw, hw, cout, device=dev, dtype=DT)
+            w = (torch.randn(k * k, cout, cin, device=dev) * 0.05).to(DT)
+            bias = torch.zeros(cout, device=dev)
+            stats = torch.zeros(2 * cout, device=dev)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(x), L.ptr(w), L.ptr(bias), None, L.ptr(y), L.ptr(stats), None, st)
+            torch.cuda.synchronize()
+            return y, stats
+        for hw in (4, 8, 16, 32, 64):
+            for cin, cout, k in ((128, 128, 3), (256, 128, 1), (128, 256, 1)):
+                y0, s0 = one(32, hw, cin, cout, k, 0)
+                y1, s1 = one(32, hw, cin, cout, k, 1)
+                same = torch.equal(y0, y1) and torch.allclose(s0, s1, rtol=1e-4)
+                t = []
+                for flag in (0, 1, 0, 1):
+                    L.call("hg_set_option", b"split_producer", flag)
+                    t.append(conv_chain(32, hw, cin, cout, k))
+                print(f"@{hw}x{hw} conv{k}x{k} {cin}->{cout}: one producer {t[0]:.2f}/{t[2]:.2f} us, split {t[1]:.2f}/{t[3]:.2f} us, "
+                      f"identical output: {same}", flush=True)
+        sys.exit(0)
     if os.environ.get("DBG_TS"):
         L.call("hg_set_option", b"dbg_ts", 1)
         for hw, cin, cout, k in ((4, 256, 128, 1), (4, 128, 128, 3), (64, 128, 128, 3)):

@@ -116,6 +116,12 @@ HG_API int hg_conv_tc_eligible(const HgConvDesc* d);
 HG_API int hg_conv_fprop_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* w_fprop,
                             const float* bias, const void* residual, void* y, float* stats, float* out_nchw,
                             void* stream);
+/* Inference: convolution followed by an eval-mode BatchNorm(+ReLU) of its OUTPUT channels in one kernel,
+ * y = [relu](gamma * (conv(x) + bias - running_mean) / sqrt(running_var + eps) + beta): the nn.Conv2d -> nn.BatchNorm2d
+ * -> nn.ReLU runs inside every ResidualBlock (try_with_torch.py:196-205) and `lin` (:243-256) under model.eval().
+ * bn_out->use_running must be 1; tensor-core geometries only (hg_conv_tc_eligible). */
+HG_API int hg_conv_fprop_bnout(const HgConvDesc* d, const HgBnFold* bn_out, const void* x, const void* w_fprop,
+                               const float* bias, void* y, float* out_nchw, void* stream);
 /* dw_packed += dy (x) [relu](bn(x_raw)); dbias += sum(dy). */
 HG_API int hg_conv_wgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* dy,
                             float* dw_packed, float* dbias, void* stream);

@@ -269,6 +269,25 @@ int hg_conv_fprop_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw,
                         w_fprop, bias, residual, y, stats, out_nchw, d->Cout, 1, &f, (cudaStream_t)stream);
 }
 
+int hg_conv_fprop_bnout(const HgConvDesc* d, const HgBnFold* bn_out, const void* x, const void* w_fprop,
+                        const float* bias, void* y, float* out_nchw, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HG_REQUIRE(bn_out && bn_out->gamma && bn_out->beta && bn_out->use_running && bn_out->running_mean &&
+                 bn_out->running_var,
+             "hg_conv_fprop_bnout: an inference-mode BatchNorm (use_running = 1, running_mean / running_var / gamma / "
+             "beta) is required");
+  HG_REQUIRE(x && w_fprop && y, "hg_conv_fprop_bnout: x, w_fprop and y must be non-NULL");
+  if (!tc_eligible(d)) {
+    set_error("hg_conv_fprop_bnout: geometry not taken by the tensor-core kernels (hg_conv_tc_eligible() == 0); run "
+              "the plain convolution and hg_bn_apply instead");
+    return HG_ERR_UNSUPPORTED;
+  }
+  const BnFoldDev f = make_fold(bn_out, d->Cout, (long long)d->N * d->H * d->W);
+  return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cin), pad64(d->Cout), d->R, d->S, d->pad, d->dil, +1, x, w_fprop,
+                        bias, nullptr, y, nullptr, out_nchw, d->Cout, 3, &f, (cudaStream_t)stream);
+}
+
 int hg_conv_wgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* dy, float* dw_packed,
                      float* dbias, void* stream) {
   int rc = check_fold(d, bn, "hg_conv_wgrad_bn");

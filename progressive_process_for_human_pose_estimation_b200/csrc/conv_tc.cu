@@ -39,7 +39,9 @@ int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
 //            activation never exists in HBM (fprop of BN -> ReLU -> conv, reference try_with_torch.py:196-205)
 //   kMask  : dgrad whose result is the gradient of a BatchNorm(+ReLU) output: the epilogue applies the ReLU mask
 //            g = da * [bn(x) > 0], stores g and accumulates the two BatchNorm-backward sums (sum g, sum g*xhat)
-enum { kPlain = 0, kFold = 1, kMask = 2 };
+//   kPlainBnOut : kPlain whose epilogue also applies an inference-mode BatchNorm(+ReLU) to the OUTPUT channels,
+//            y = [relu](scale_c * (conv + bias_c) + shift_c) with running statistics (no residual, no statistics)
+enum { kPlain = 0, kFold = 1, kMask = 2, kPlainBnOut = 3 };
 
 // BatchNorm folded into a convolution (device view of HgBnFold)
 struct BnFoldDev {
@@ -277,6 +279,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       const int et = threadIdx.x - 64;
     for (int c = et; c < BN; c += 128) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
+    if constexpr (MODE == kPlainBnOut) {   // y = scale * acc + (scale * bias + shift)
+      for (int c = et; c < BN; c += 128) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, n_off + c, mu, is, sc, sh);
+        coef_s[c] = sc;
+        bias_s[c] = fmaf(bias_s[c], sc, sh);
+      }
+    }
     if constexpr (MODE == kFold) {
       // scale / shift of every INPUT channel (<= 256)
       for (int c = et; c < p.kchunks * 64; c += 128) {
@@ -397,8 +407,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           cp = reinterpret_cast<uint4*>(sQ + pnl * 16384 + row * 128 + swz);
         } else {
+          if constexpr (MODE == kPlainBnOut) {
+            const bool relu = p.fold.relu != 0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[j * 32 + q * 8 + e];
+            for (int e = 0; e < 8; ++e) {
+              const float t = fmaf(v[q * 8 + e], coef_s[j * 32 + q * 8 + e], bias_s[j * 32 + q * 8 + e]);
+              o[e] = relu ? fmaxf(t, 0.f) : t;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[j * 32 + q * 8 + e];
+          }
           if (p.has_res) {
             uint4 u = *cp;
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -566,7 +585,7 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
                   : launch_conv_gemm<BN, 2, 2, kMask, false>(tmA, tmB, tmC, tmR, p, st);
   } else {
     constexpr int kShortMinB = MODE == kFold ? 2 : 3;  // the transform needs > 113 registers
-    if (has_res) {
+    if constexpr (MODE != kPlainBnOut) if (has_res) {
       if (long_k) return launch_conv_gemm<BN, 3, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st);
       return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st)
                          : launch_conv_gemm<BN, 2, 2, MODE, false>(tmA, tmB, tmC, tmR, p, st);
@@ -658,6 +677,12 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   p.n_tiles = Np / BN;
   if (fold) p.fold = *fold;
   p.ts = g_dbg_ts;
+  if (mode == kPlainBnOut) {
+    if (!fold || !fold->use_running || res || stats) {
+      set_error("conv_gemm_bf16: output BatchNorm needs running statistics and takes no residual / statistics");
+      return HG_ERR_BAD_ARG;
+    }
+  }
   const bool long_k = R * S * (Kp / 64) > 4;
   const bool has_res = res != nullptr;
   if (mode == kMask && (!res || !stats)) {
@@ -667,10 +692,12 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   if (BN == 64) {
     if (mode == kFold) return dispatch_conv_gemm<64, kFold>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
     if (mode == kMask) return dispatch_conv_gemm<64, kMask>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
+    if (mode == kPlainBnOut) return dispatch_conv_gemm<64, kPlainBnOut>(long_k, false, tmA, tmB, tmC, tmR, p, st);
     return dispatch_conv_gemm<64, kPlain>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
   }
   if (mode == kFold) return dispatch_conv_gemm<128, kFold>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
   if (mode == kMask) return dispatch_conv_gemm<128, kMask>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
+  if (mode == kPlainBnOut) return dispatch_conv_gemm<128, kPlainBnOut>(long_k, false, tmA, tmB, tmC, tmR, p, st);
   return dispatch_conv_gemm<128, kPlain>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
 }
 

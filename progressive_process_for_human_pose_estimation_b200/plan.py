@@ -24,6 +24,9 @@ _WGRAD_LANES = int(os.environ.get("HG_WGRAD_LANES", "4"))
 # 0: BatchNorm kernels stay separate; 1: only the data-gradient epilogue is fused (ReLU mask + BN-backward sums);
 # 2: additionally the forward / weight-gradient convolutions apply BN+ReLU to their operand tiles (no activation in HBM)
 _FOLD_BN = int(os.environ.get("HG_FOLD_BN", "1"))
+# inference (eval mode, no gradients): a BatchNorm(+ReLU) whose producer is a tensor-core convolution runs in that
+# convolution's epilogue (hg_conv_fprop_bnout)
+_FUSE_EVAL_BN = os.environ.get("HG_FUSE_EVAL_BN", "1") != "0"
 # Stream priority of the main lane in the FORWARD graph: it carries the latency-bound low-resolution chain, and when a
 # skip-branch lane's big kernel holds every SM the CTA scheduler must hand freed slots to the main lane first
 # (measured: forward 14.3 -> 13.1 ms).  In the backward graph any priority skew starves the wgrad lane into a tail
@@ -206,7 +209,7 @@ class _LaneCtx:
 # argument is a read.  Parameter / weight-gradient pointers are not tracked (read-only or commutative atomics).
 _WRITES = {
     "hg_nchw_f32_to_nhwc": (7,), "hg_nhwc_to_nchw_f32": (6,), "hg_stem_fwd": (8,), "hg_conv_fprop_ex": (5, 6, 7),
-    "hg_conv_dgrad": (4,), "hg_bn_stats": (2,), "hg_bn_apply": (7,), "hg_bn_bwd_apply": (10,),
+    "hg_conv_dgrad": (4,), "hg_conv_fprop_bnout": (5, 6), "hg_bn_stats": (2,), "hg_bn_apply": (7,), "hg_bn_bwd_apply": (10,),
     "hg_bn_bwd_reduce": (8,), "hg_conv_fprop_bn": (6, 7, 8), "hg_conv_dgrad_bn": (5, 6),
     "hg_maxpool2_fwd": (6, 7), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8, 9), "hg_upsample2x_bwd": (8,),
     "hg_add": (3,),
@@ -455,8 +458,29 @@ class Plan:
                 cons.attrs["fold"] = op
                 self.n_masked += 1
                 self.n_folded += 1 if op.attrs["folded"] else 0
+        # ---- inference: conv -> eval-mode BN(+ReLU) in ONE kernel (hg_conv_fprop_bnout): the BatchNorm is a per-channel
+        # affine with known coefficients, applied in the convolution's epilogue; the raw conv output never exists
+        self.n_bn_out = 0
+        if _FUSE_EVAL_BN and self.dt == torch.bfloat16 and not self.need_bwd and not self.training:
+            lib = L.load()
+            for op in ops:
+                if op.kind != "conv" or op.ins[1] is not None or op.attrs["head"] or op.attrs["mix"] is not None:
+                    continue
+                out = op.out
+                if out.needs_stats or len(out.consumers) != 1 or any(out is v for v, _ in b.outputs):
+                    continue
+                cons = out.consumers[0]
+                if cons.kind != "bn" or cons.attrs.get("folded") or not cons.attrs["bn"].track_running_stats:
+                    continue
+                if op.attrs.get("fold") is not None and op.attrs["fold"].attrs.get("folded"):
+                    continue
+                if not lib.hg_conv_tc_eligible(C.byref(self._conv_desc(op.attrs["conv"], op.ins[0]))):
+                    continue
+                op.attrs["bn_out"] = cons
+                cons.attrs["in_producer"] = True
+                self.n_bn_out += 1
         for op in ops:
-            if op.out is not None and not op.attrs.get("folded"):
+            if op.out is not None and not op.attrs.get("folded") and op.attrs.get("bn_out") is None:
                 op.out.buf = self._act(op.out)
         all_vals = [v for v, _ in b.inputs] + [op.out for op in ops if op.out is not None]
         for v in all_vals:
@@ -563,7 +587,12 @@ class Plan:
                 d = self._conv_desc(cv, x)
                 nchw = self.out_static[self.out_index[id(out)]] if op.attrs["head"] else None
                 bias = self._bias_ptr(cv, info) if op.attrs["use_bias"] else None
-                if op.attrs.get("fold") is not None and op.attrs["fold"].attrs["folded"]:
+                if op.attrs.get("bn_out") is not None:
+                    bnop = op.attrs["bn_out"]
+                    fold, _ = self._bn_fold(bnop)
+                    self._emit(f, "hg_conv_fprop_bnout", C.byref(d), C.byref(fold), L.ptr(x.buf), L.ptr(info["wf"]),
+                               bias, L.ptr(bnop.out.buf), None, st).tag = self._conv_tag(cv, x) + " +bn_out"
+                elif op.attrs.get("fold") is not None and op.attrs["fold"].attrs["folded"]:
                     fold, reads = self._bn_fold(op.attrs["fold"])
                     self._emit(f, "hg_conv_fprop_bn", C.byref(d), C.byref(fold), L.ptr(op.attrs["fold"].ins[0].buf),
                                L.ptr(info["wf"]), bias, L.ptr(res.buf) if res else None, L.ptr(out.buf),
@@ -577,7 +606,7 @@ class Plan:
             elif k == "bn":
                 bn, x, out = op.attrs["bn"], op.ins[0], op.out
                 d = self._bn_desc(bn, x, op.attrs["relu"])
-                if not op.attrs.get("folded"):
+                if not op.attrs.get("folded") and not op.attrs.get("in_producer"):
                     self._emit(f, "hg_bn_apply", C.byref(d), L.ptr(x.buf),
                                L.ptr(x.stats) if x.stats is not None else None,
                                L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias)),

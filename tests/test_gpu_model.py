@@ -210,6 +210,9 @@ def test_model_eval_mode_4stack_vs_oracle(dtype, tol):
         out = net(x.cuda())
         out2 = net(x.cuda())  # CUDA-graph replay
     assert len(out) == 4
+    plan = next(iter(net._plans.values()))
+    if dtype == torch.bfloat16:  # inference: BN2/BN3 of every residual block and lin.bn run in their producer conv
+        assert plan.n_bn_out > 0 and any(c.name == "hg_conv_fprop_bnout" for c in plan.fwd_calls)
     for k in range(4):
         assert rel(out[k].cpu(), oo[k]) <= tol * (1 + k), (k, rel(out[k].cpu(), oo[k]))
         assert torch.equal(out[k], out2[k])
@@ -284,7 +287,8 @@ def test_full_size_train_steps_properties():
     kp[..., 0], kp[..., 1], kp[..., 2] = r.randint(0, 640, [32, 1, 16]), r.randint(0, 480, [32, 1, 16]), 2
     y = hg.gaussian_heatmaps(kp, np.tile(np.array([[640.0, 480.0]]), (32, 1)))
     losses = []
-    for it in range(6):
+    steps = 10  # the first Adam steps at lr 1e-3 overshoot (the loss rises before it falls); atomics make runs differ
+    for it in range(steps):
         out = net(x)
         assert len(out) == 8 and all(o.shape == (32, 16, 64, 64) for o in out)
         loss = sum(torch.nn.MSELoss()(o, y) for o in out)
@@ -295,10 +299,10 @@ def test_full_size_train_steps_properties():
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < 0.7 * losses[0], losses
     sd = net.state_dict()
-    assert int(sd["hourglass1.residual_block.bn1.num_batches_tracked"]) == 6 * 8 * 6      # 6 calls x 8 stacks x 6 steps
-    assert int(sd["hourglass1.hourglass1.hourglass1.hourglass1.residual_block.bn1.num_batches_tracked"]) == 8 * 8 * 6
-    assert int(sd["residual4.bn2.num_batches_tracked"]) == 2 * 8 * 6
-    assert int(sd["residual1.bn1.num_batches_tracked"]) == 6
+    assert int(sd["hourglass1.residual_block.bn1.num_batches_tracked"]) == 6 * 8 * steps  # 6 calls x 8 stacks x steps
+    assert int(sd["hourglass1.hourglass1.hourglass1.hourglass1.residual_block.bn1.num_batches_tracked"]) == 8 * 8 * steps
+    assert int(sd["residual4.bn2.num_batches_tracked"]) == 2 * 8 * steps
+    assert int(sd["residual1.bn1.num_batches_tracked"]) == steps
     none = [n for n, p in net.named_parameters() if p.grad is None]
     assert len(none) == 12 and all(".conv4." in n for n in none)   # identity blocks' unused projections (quirk Q3)
     # decode of the (identical) targets is exact at full size

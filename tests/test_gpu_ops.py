@@ -480,3 +480,56 @@ def test_layout_roundtrip_and_add():
         s = torch.empty_like(q)
         L.call("hg_add", L.hg_dtype(dtype), L.ptr(q), L.ptr(q), L.ptr(s), C.c_longlong(q.numel()), st)
         assert torch.equal(s.float(), (q.float() * 2).to(dtype).float())
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W, Cin, Cout, k, relu
+    (4, 64, 64, 256, 128, 1, True), (4, 32, 32, 128, 128, 3, True), (32, 4, 4, 128, 256, 1, False),
+    (2, 16, 16, 256, 256, 1, True), (3, 8, 8, 64, 38, 1, True),
+])
+def test_conv_with_output_batchnorm_eval(case):
+    """hg_conv_fprop_bnout (conv -> eval-mode BN -> ReLU in one kernel, the inference form of
+    try_with_torch.py:196-205,243-256) against PyTorch fp32 ops on the same bf16-representable inputs and against
+    the un-fused kernels of the same library."""
+    N, H, W, Cin, Cout, k, relu = case
+    torch.manual_seed(5)
+    dev, dtype = "cuda", torch.bfloat16
+    pad = k // 2
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    gamma = torch.rand(Cout, device=dev) + 0.5
+    beta = torch.randn(Cout, device=dev) * 0.3
+    rmean = torch.randn(Cout, device=dev) * 0.2
+    rvar = torch.rand(Cout, device=dev) * 2 + 0.5
+    d = L.HgConvDesc(N, H, W, Cin, Cout, k, k, 1, pad, 1, L.HG_BF16)
+    assert L.load().hg_conv_tc_eligible(C.byref(d)) == 1
+    Cin_p, Cout_p = L.pad64(Cin), L.pad64(Cout)
+    xq = nhwc(x, dtype)
+    wf = torch.empty(k * k, Cout_p, Cin_p, device=dev, dtype=dtype)
+    bias_p = torch.zeros(Cout_p, device=dev)
+    bias_p[:Cout] = b
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), None, st)
+    fold = L.HgBnFold(None, gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr(), 1e-5,
+                      1 if relu else 0, 1, 0)
+    y1 = torch.full((N, H, W, Cout_p), float("nan"), device=dev, dtype=dtype)
+    L.call("hg_conv_fprop_bnout", C.byref(d), C.byref(fold), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), L.ptr(y1), None, st)
+    ref = F.batch_norm(F.conv2d(nchw(xq, Cin), w.to(dtype).float(), b, 1, pad), rmean, rvar, gamma, beta, False, 0.0,
+                       1e-5)
+    if relu:
+        ref = F.relu(ref)
+    close(nchw(y1, Cout), ref, 2e-2, "conv + output BN vs torch")
+    assert (y1[..., Cout:] == 0).all()  # padded channels stay zero
+    # un-fused: conv (bf16 store) -> hg_bn_apply; the fused kernel skips one bf16 rounding, so only close
+    y0 = torch.empty_like(y1)
+    L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), None, L.ptr(y0), None, None, st)
+    bnd = L.HgBnDesc(N * H * W, Cout, L.HG_BF16, 1e-5, 1 if relu else 0, 1)
+    a0 = torch.empty_like(y0)
+    L.call("hg_bn_apply", C.byref(bnd), L.ptr(y0), None, L.ptr(gamma), L.ptr(beta), L.ptr(rmean), L.ptr(rvar),
+           L.ptr(a0), st)
+    close(y1.float(), a0.float(), 2e-2, "fused vs un-fused")
+    # a training-mode BatchNorm cannot be folded into its producer: loud error, no fallback
+    bad = L.HgBnFold(None, gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr(), 1e-5, 1, 0, 0)
+    with pytest.raises(RuntimeError, match="inference-mode"):
+        L.call("hg_conv_fprop_bnout", C.byref(d), C.byref(bad), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), L.ptr(y1), None, st)

@@ -10,7 +10,7 @@ static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 int g_use_pdl = 1;
-extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles;
+extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce;
 extern long long* g_dbg_ts;
 
 void set_error(const char* fmt, ...) {
@@ -159,6 +159,14 @@ int hg_set_option(const char* name, int value) {
     } else if (value == 0) {
       g_dbg_ts = nullptr;
     }
+    return HG_OK;
+  }
+  if (strcmp(name, "wgrad_bulk_reduce") == 0) {
+    g_wgrad_bulk_reduce = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "wgrad_dbg") == 0) {
+    g_wgrad_dbg = value;
     return HG_OK;
   }
   if (strcmp(name, "small_n_tiles") == 0) {

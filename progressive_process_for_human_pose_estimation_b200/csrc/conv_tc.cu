@@ -28,6 +28,8 @@
 namespace hg {
 
 int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
+int g_wgrad_bulk_reduce = 0;    // 1: wgrad epilogue through shared memory + cp.reduce.async.bulk (measured: no faster)
+int g_wgrad_dbg = 0;            // HG_DBG_TS builds only: 1 = wgrad epilogue without the atomics, 2 = no epilogue at all
 long long* g_dbg_ts = nullptr;  // debug: per-phase clock64 stamps of CTA 0 (hg_set_option dbg_ts)
 int g_single_wave_deep = 1;   // 1: one-wave grids use the deep (6/4-stage, ~190 KB) pipelines
 int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
@@ -725,6 +727,8 @@ struct WgradParams {
   int total_kb;      // ceil(M / 64)
   int kb_per_cta;
   int stages;
+  int dbg;
+  int bulk_reduce;   // epilogue: partial tile -> shared memory -> cp.reduce.async.bulk (else per-thread red.v4)
   int stage_bytes;
   float* dw;         // [taps][Cout_p][Cin_p] fp32, accumulated
   BnFoldDev fold;
@@ -896,29 +900,67 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       tc_fence_after();
       pdl_trigger();
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-      // All CTAs of a split finish together and add into the SAME tile: start each CTA at a different column so
-      // that concurrent atomics hit different addresses (the L2 atomic unit serialises per address).
-      const int nchunk = N / 32;
-      for (int tt = 0; tt < T; ++tt) {
-        const int t = (tt + blockIdx.x) % T;
-        float* dst = p.dw + ((size_t)(tap0 + t) * p.Cout_p + co) * p.Cin_p;
-        for (int jj = 0; jj < nchunk; ++jj) {
-          const int j = (jj + blockIdx.x) % nchunk;
-          float v[32];
-          tmem_ld32(taddr + t * N + j * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            const int rot = (blockIdx.x / nchunk) & 7;
+      if (p.bulk_reduce) {
+        // The partial tile goes through shared memory (the pipeline stages are idle: every MMA has completed) as a
+        // linear [128 co][N ci] fp32 image per tap and is added to the gradient by ONE bulk reduce per tap: the
+        // per-thread red.global.add.v4 of a TMEM row touch 32 different 512-byte-apart rows per warp instruction
+        // (12288 scattered 16-byte atomics per CTA; measured 5-9 us of every wgrad launch).
+        float* stage = reinterpret_cast<float*>(smem);
+        const int rloc = sub * 32 + lane;
+        const int nchunk = N / 32;
+        for (int t = 0; t < ((HG_DBG_TS && p.dbg == 2) ? 0 : T); ++t) {
+          float* rowp = stage + ((size_t)t * 128 + rloc) * N;
+          for (int j = 0; j < nchunk; ++j) {
+            float v[32];
+            tmem_ld32(taddr + t * N + j * 32, v);
+            tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const int qq = (q + rot) & 7;
+              const int qq = (q + lane) & 7;   // a quarter warp stores 8 different 16-byte columns: no bank conflict
               float a = v[0], b = v[1], c = v[2], d = v[3];
 #pragma unroll
               for (int z = 1; z < 8; ++z)
                 if (qq == z) { a = v[z * 4]; b = v[z * 4 + 1]; c = v[z * 4 + 2]; d = v[z * 4 + 3]; }
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 32 + qq * 4), "f"(a),
-                           "f"(b), "f"(c), "f"(d)
-                           : "memory");
+              *reinterpret_cast<float4*>(rowp + j * 32 + qq * 4) = make_float4(a, b, c, d);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0 && !(HG_DBG_TS && p.dbg)) {
+          int rows = p.Cout_p - co_off;
+          if (rows > 128) rows = 128;
+          for (int t = 0; t < T; ++t)
+            bulk_reduce_add_f32(p.dw + ((size_t)(tap0 + t) * p.Cout_p + co_off) * p.Cin_p, stage + (size_t)t * 128 * N,
+                                (uint32_t)rows * N * 4);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+      } else {
+        // All CTAs of a split finish together and add into the SAME tile: start each CTA at a different column so
+        // that concurrent atomics hit different addresses (the L2 atomic unit serialises per address).
+        const int nchunk = N / 32;
+        for (int tt = 0; tt < ((HG_DBG_TS && p.dbg == 2) ? 0 : T); ++tt) {
+          const int t = (tt + blockIdx.x) % T;
+          float* dst = p.dw + ((size_t)(tap0 + t) * p.Cout_p + co) * p.Cin_p;
+          for (int jj = 0; jj < nchunk; ++jj) {
+            const int j = (jj + blockIdx.x) % nchunk;
+            float v[32];
+            tmem_ld32(taddr + t * N + j * 32, v);
+            tmem_ld_wait();
+            if (row_ok && !(HG_DBG_TS && p.dbg == 1)) {
+              const int rot = (blockIdx.x / nchunk) & 7;
+  #pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int qq = (q + rot) & 7;
+                float a = v[0], b = v[1], c = v[2], d = v[3];
+  #pragma unroll
+                for (int z = 1; z < 8; ++z)
+                  if (qq == z) { a = v[z * 4]; b = v[z * 4 + 1]; c = v[z * 4 + 2]; d = v[z * 4 + 3]; }
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 32 + qq * 4), "f"(a),
+                             "f"(b), "f"(c), "f"(d)
+                             : "memory");
+              }
             }
           }
         }
@@ -996,7 +1038,15 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.kb_per_cta = (p.total_kb + nsplit - 1) / nsplit;
     nsplit = (p.total_kb + p.kb_per_cta - 1) / p.kb_per_cta;
     p.dw = dw;
+    p.dbg = g_wgrad_dbg;
+    p.bulk_reduce = g_wgrad_bulk_reduce;
     if (fold) p.fold = *fold;
+    if (p.bulk_reduce && p.stages * p.stage_bytes < T * Cin_p * 512) {
+      // room for the fp32 staging image [T][128][Cin_p]: more stages if they fit, else the per-thread atomics
+      const int need = (T * Cin_p * 512 + p.stage_bytes - 1) / p.stage_bytes;
+      if (need <= 8 && need * p.stage_bytes <= 220 * 1024) p.stages = need;
+      else p.bulk_reduce = 0;
+    }
     const int smem_bytes = p.stages * p.stage_bytes + 4096 + 1024;
     static bool attr_set = false;
     if (!attr_set) {

@@ -277,6 +277,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// dst[0..bytes) += src[0..bytes) as fp32, reduced in L2 by the bulk-copy engine (both 16-byte aligned, bytes % 16 == 0)
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst_global, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                   reinterpret_cast<uint64_t>(dst_global)),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

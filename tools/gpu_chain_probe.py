@@ -99,6 +99,20 @@ def bn_bwd_chain(B, hw, c, n=100, with_addend=False):
     return graph_time(body) / n * 1e3
 
 
+def wgrad_chain(B, hw, cin, cout, k, n=50):
+    d = L.HgConvDesc(B, hw, hw, cin, cout, k, k, 1, k // 2, 1, L.HG_BF16)
+    x = torch.randn(B, hw, hw, cin, device=dev).to(DT)
+    dy = torch.randn(B, hw, hw, cout, device=dev).to(DT)
+    dw = torch.zeros(k * k, cout, cin, device=dev)
+
+    def body():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for i in range(n):
+            L.call("hg_conv_wgrad", C.byref(d), L.ptr(x), L.ptr(dy), L.ptr(dw), None, st)
+
+    return graph_time(body) / n * 1e3
+
+
 def empty_chain(n=200):
     t = torch.zeros(64, device=dev, dtype=DT)
 
@@ -140,6 +154,32 @@ if __name__ == "__main__":
                     t.append(conv_chain(32, hw, cin, cout, k))
                 print(f"@{hw}x{hw} conv{k}x{k} {cin}->{cout}: one producer {t[0]:.2f}/{t[2]:.2f} us, split {t[1]:.2f}/{t[3]:.2f} us, "
                       f"identical output: {same}", flush=True)
+        sys.exit(0)
+    if os.environ.get("WGRAD"):
+        # wgrad epilogue: per-thread red.v4 atomics vs shared-memory staging + cp.reduce.async.bulk (A/B in one process)
+        def once(B, hw, cin, cout, k, bulk):
+            L.call("hg_set_option", b"wgrad_bulk_reduce", bulk)
+            torch.manual_seed(0)
+            d = L.HgConvDesc(B, hw, hw, cin, cout, k, k, 1, k // 2, 1, L.HG_BF16)
+            x = torch.randn(B, hw, hw, cin, device=dev).to(DT)
+            dy = torch.randn(B, hw, hw, cout, device=dev).to(DT)
+            dw = torch.zeros(k * k, cout, cin, device=dev)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            L.call("hg_conv_wgrad", C.byref(d), L.ptr(x), L.ptr(dy), L.ptr(dw), None, st)
+            torch.cuda.synchronize()
+            return dw
+        for hw in (4, 8, 16, 32, 64):
+            for cin, cout, k in ((128, 128, 3), (256, 128, 1), (128, 256, 1), (256, 256, 1), (256, 64, 1)):
+                d0, d1 = once(32, hw, cin, cout, k, 0), once(32, hw, cin, cout, k, 1)
+                err = ((d0 - d1).abs().max() / d0.abs().max()).item()
+                t = []
+                for bulk, dbg in ((0, 0), (1, 0), (1, 1), (1, 2)):
+                    L.call("hg_set_option", b"wgrad_bulk_reduce", bulk)
+                    L.call("hg_set_option", b"wgrad_dbg", dbg)
+                    t.append(wgrad_chain(32, hw, cin, cout, k))
+                L.call("hg_set_option", b"wgrad_dbg", 0)
+                print(f"wgrad @{hw}x{hw} {k}x{k} {cin}->{cout}: atomics {t[0]:.2f} us | bulk reduce {t[1]:.2f} | staged, no reduce "
+                      f"{t[2]:.2f} | no epilogue {t[3]:.2f} | rel diff {err:.1e}", flush=True)
         sys.exit(0)
     if os.environ.get("DBG_TS"):
         L.call("hg_set_option", b"dbg_ts", 1)

@@ -28,6 +28,9 @@
 namespace hg {
 
 int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
+int g_wgrad_small_n_panels = 0; // small maps (see g_wgrad_t1_max_kb): input-channel panels (of 64) per CTA; 0 = policy
+                                // (1x1 or <= 32 K blocks: 1 panel, else 2), -1 = never split the input channels
+int g_wgrad_t1_max_kb = 128;    // "small map": at most this many 64-pixel K blocks (16x16 at batch 32); 3x3: one tap per CTA     // 3x3 wgrad: one tap per CTA when the map has at most this many 64-pixel K blocks
 int g_wgrad_bulk_reduce = 0;    // 1: wgrad epilogue through shared memory + cp.reduce.async.bulk (measured: no faster)
 int g_wgrad_dbg = 0;            // HG_DBG_TS builds only: 1 = wgrad epilogue without the atomics, 2 = no epilogue at all
 long long* g_dbg_ts = nullptr;  // debug: per-phase clock64 stamps of CTA 0 (hg_set_option dbg_ts)
@@ -722,7 +725,8 @@ struct WgradParams {
   int taps_s;        // filter width S
   int dil, pad;
   int tap_rows;      // taps handled per CTA (T)
-  int n_panels;      // Cin_p / 64
+  int n_panels;      // 64-channel input panels per CTA (Cin_p / 64 / n_groups)
+  int n_groups;      // CTAs that split the input channels
   int Cin_p, Cout_p;
   int total_kb;      // ceil(M / 64)
   int kb_per_cta;
@@ -753,7 +757,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int N = p.n_panels * 64;
   const int T = p.tap_rows;
-  const int tap0 = blockIdx.y * T;
+  const int tap0 = (blockIdx.y / p.n_groups) * T;
+  const int pn0 = (blockIdx.y % p.n_groups) * p.n_panels;   // first input-channel panel of this CTA
   const int co_off = blockIdx.z * 128;
   const int kb_beg = blockIdx.x * p.kb_per_cta;
   int kb_end = kb_beg + p.kb_per_cta;
@@ -804,7 +809,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             const int r = tap / p.taps_s, s = tap - r * p.taps_s;
             const int dh = r * p.dil - p.pad, dw = s * p.dil - p.pad;
             for (int pn = 0; pn < p.n_panels; ++pn)
-              tma_load_4d(sB + (t * p.n_panels + pn) * 8192, &tmX, &full_bar[st], pn * 64, w0 + dw, h0 + dh, n0);
+              tma_load_4d(sB + (t * p.n_panels + pn) * 8192, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 + dw, h0 + dh,
+                          n0);
           }
         }
       }
@@ -877,8 +883,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
               if ((unsigned)(hrow[k] + dh) < (unsigned)p.H && (unsigned)(wrow[k] + dw) < (unsigned)p.W) vmask |= 1u << k;
             for (int pn = 0; pn < p.n_panels; ++pn) {
               float sc[8], sh[8];
-              load_coef8(coef_s + pn * 64 + jch * 8, sc);
-              load_coef8(coef_s + 256 + pn * 64 + jch * 8, sh);
+              load_coef8(coef_s + (pn0 + pn) * 64 + jch * 8, sc);
+              load_coef8(coef_s + 256 + (pn0 + pn) * 64 + jch * 8, sh);
               uint8_t* base = sB + (t * p.n_panels + pn) * 8192;
               uint4 u[4];
 #pragma unroll
@@ -942,7 +948,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         const int nchunk = N / 32;
         for (int tt = 0; tt < ((HG_DBG_TS && p.dbg == 2) ? 0 : T); ++tt) {
           const int t = (tt + blockIdx.x) % T;
-          float* dst = p.dw + ((size_t)(tap0 + t) * p.Cout_p + co) * p.Cin_p;
+          float* dst = p.dw + ((size_t)(tap0 + t) * p.Cout_p + co) * p.Cin_p + pn0 * 64;
           for (int jj = 0; jj < nchunk; ++jj) {
             const int j = (jj + blockIdx.x) % nchunk;
             float v[32];
@@ -984,8 +990,11 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
   const long long M = (long long)d->N * H * W;
   if (dw) {
     const int taps = d->R * d->S;
+    // Three taps per CTA share one dy tile (fewer loads), but the CTA then pushes 3 x 64 KB of fp32 adds through its
+    // SM's L2 port (~20 B/clk: the epilogue atomics are 5-9 us of a launch).  Small maps cannot fill the SMs with
+    // K slices anyway: there one tap per CTA triples the CTAs that share the atomics.
     int T = 1;
-    if (taps == 9 && Cin_p <= 128) T = 3;
+    if (taps == 9 && Cin_p <= 128 && (M + 63) / 64 > g_wgrad_t1_max_kb) T = 3;
     const int bw = W < 64 ? W : 64;
     int bh = 64 / bw;
     if (bh > H) bh = H;
@@ -1018,7 +1027,16 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.dil = d->dil;
     p.pad = d->pad;
     p.tap_rows = T;
-    p.n_panels = Cin_p / 64;
+    // small maps: split the input channels over CTAs as well (same reason as one tap per CTA: the fp32 adds a CTA
+    // pushes through its SM's L2 port are what a small wgrad launch costs)
+    // (B200, batch 32, us per launch: 3x3 128->128 @4x4 11.5 -> 4.5, 1x1 256->128 8.1 -> 4.5, 3x3 @16x16 15.8 -> 10.7)
+    p.n_groups = 1;
+    if ((M + 63) / 64 <= g_wgrad_t1_max_kb && g_wgrad_small_n_panels >= 0) {
+      int per_cta = g_wgrad_small_n_panels;
+      if (per_cta == 0) per_cta = (taps == 1 || (M + 63) / 64 <= 32) ? 1 : 2;
+      if (Cin_p / 64 > per_cta && (Cin_p / 64) % per_cta == 0) p.n_groups = Cin_p / 64 / per_cta;
+    }
+    p.n_panels = Cin_p / 64 / p.n_groups;
     p.Cin_p = Cin_p;
     p.Cout_p = Cout_p;
     p.total_kb = (int)((M + 63) / 64);
@@ -1032,7 +1050,7 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     // reduced with atomics, so small problems must not be cut into many slices
     // (small maps are latency-bound: there, two K blocks per CTA and more atomics beat a long serial loop)
     const int min_kb = p.total_kb <= 256 ? 2 : 8;
-    int nsplit = kNumSMs / (tap_groups * mgroups);
+    int nsplit = kNumSMs / (tap_groups * mgroups * p.n_groups);
     if (nsplit > p.total_kb / min_kb) nsplit = p.total_kb / min_kb;
     if (nsplit < 1) nsplit = 1;
     p.kb_per_cta = (p.total_kb + nsplit - 1) / nsplit;
@@ -1041,6 +1059,7 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.dbg = g_wgrad_dbg;
     p.bulk_reduce = g_wgrad_bulk_reduce;
     if (fold) p.fold = *fold;
+    if (p.n_groups > 1) p.bulk_reduce = 0;   // the CTA's rows are not contiguous in dw
     if (p.bulk_reduce && p.stages * p.stage_bytes < T * Cin_p * 512) {
       // room for the fp32 staging image [T][128][Cin_p]: more stages if they fit, else the per-thread atomics
       const int need = (T * Cin_p * 512 + p.stage_bytes - 1) / p.stage_bytes;
@@ -1056,7 +1075,7 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
                                       227 * 1024));
       attr_set = true;
     }
-    dim3 grid(nsplit, tap_groups, mgroups);
+    dim3 grid(nsplit, tap_groups * p.n_groups, mgroups);
     if (fold) launch_k(conv_wgrad_kernel<true>, dim3(grid), dim3(192), smem_bytes, st, tmDy, tmX, p);
     else launch_k(conv_wgrad_kernel<false>, dim3(grid), dim3(192), smem_bytes, st, tmDy, tmX, p);
     HG_LAUNCH_OK("conv_wgrad_kernel");

@@ -155,6 +155,29 @@ if __name__ == "__main__":
                 print(f"@{hw}x{hw} conv{k}x{k} {cin}->{cout}: one producer {t[0]:.2f}/{t[2]:.2f} us, split {t[1]:.2f}/{t[3]:.2f} us, "
                       f"identical output: {same}", flush=True)
         sys.exit(0)
+    if os.environ.get("WGRAD_T1"):
+        def once(hw, cin, cout, k):
+            torch.manual_seed(0)
+            d = L.HgConvDesc(32, hw, hw, cin, cout, k, k, 1, k // 2, 1, L.HG_BF16)
+            x = torch.randn(32, hw, hw, cin, device=dev).to(DT)
+            dy = torch.randn(32, hw, hw, cout, device=dev).to(DT)
+            dw = torch.zeros(k * k, cout, cin, device=dev)
+            L.call("hg_conv_wgrad", C.byref(d), L.ptr(x), L.ptr(dy), L.ptr(dw), None,
+                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            return dw
+        for hw in (4, 8, 16, 32):
+            for cin, cout, k in ((128, 128, 3), (256, 128, 1), (128, 256, 1), (256, 256, 1)):
+                t, outs = [], []
+                for thr, npan in ((0, 0), (128, 0), (128, 2), (128, 1)):
+                    L.call("hg_set_option", b"wgrad_t1_max_kb", thr)
+                    L.call("hg_set_option", b"wgrad_small_n_panels", npan)
+                    outs.append(once(hw, cin, cout, k))
+                    t.append(wgrad_chain(32, hw, cin, cout, k))
+                err = max(((o - outs[0]).abs().max() / outs[0].abs().max()).item() for o in outs[1:])
+                print(f"wgrad {k}x{k} {cin}->{cout} @{hw}x{hw}: base {t[0]:.2f} us | 1 tap/CTA {t[1]:.2f} | + 128-ch N tiles "
+                      f"{t[2]:.2f} | + 64-ch N tiles {t[3]:.2f} | max rel diff {err:.1e}", flush=True)
+        sys.exit(0)
     if os.environ.get("WGRAD"):
         # wgrad epilogue: per-thread red.v4 atomics vs shared-memory staging + cp.reduce.async.bulk (A/B in one process)
         def once(B, hw, cin, cout, k, bulk):

@@ -268,6 +268,35 @@ typedef struct HgCeDesc {
 HG_API int hg_ce_multi(const HgCeDesc* d, const HgCeTerm* terms_host, float* loss, int32_t* count, int32_t* bad_label,
                        void* stream);
 
+/* ---- input pipeline tail (next row N1) ---------------------------------------------------------- */
+/* transforms.ToTensor() + transforms.Normalize(mean, std) (try_with_torch.py:310-313) on the GPU:
+ * dst[n,c,h,w] = (src[n,h,w,c] / 255 - mean[c]) / std[c] in torchvision's fp32 operation order (bit-exact).
+ * src uint8 NHWC (device), mean_host / std_host HOST arrays of C floats, C <= 4. */
+HG_API int hg_image_u8_to_nchw_f32(const uint8_t* src_nhwc, int N, int H, int W, int C, const float* mean_host,
+                                   const float* std_host, float* dst_nchw, void* stream);
+
+/* ---- optimizer step (next row N4) ------------------------------------------------------------------ */
+/* torch.optim.Adam (amsgrad = False) on every parameter tensor in one launch (try_with_torch.py:317,342-344).
+ * chunks_dev is a DEVICE array: thread block b updates chunks_dev[b] (a slice of at most a few thousand elements of
+ * one tensor; fp32 param / grad / exp_avg / exp_avg_sq).  `step` is the 1-based step count AFTER the increment;
+ * lr_d / beta1_d / beta2_d carry the double-precision hyper-parameters python passes (bias corrections are evaluated
+ * in double like the reference), lr / beta1 / beta2 their float copies (validation only). */
+typedef struct HgAdamChunk {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} HgAdamChunk;
+typedef struct HgAdamDesc {
+  double lr_d, beta1_d, beta2_d;
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;
+  int32_t num_chunks;
+  int32_t pad_;
+} HgAdamDesc;
+HG_API int hg_adam_multi(const HgAdamDesc* d, const HgAdamChunk* chunks_dev, void* stream);
+
 /* ---- target rendering ---------------------------------------------------------------------------- */
 /* Gaussian keypoint heatmaps, evaluated in float64 like the numpy code, stored as float32
  * (try_with_torch.py:107-132; variants try_with_torch_100.py:64-85, only_one_hourgless.py:112-132,
@@ -311,6 +340,16 @@ HG_API int hg_pckh_sweep(const void* x, int dtype, int B, int C, int H, int W, c
 HG_API int hg_pckh_abs(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
                 int chan_offset, int njoints, const float* factors, int nfac, int32_t* correct, int32_t* total,
                 int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream);
+/* Fused `softmax over channels -> PCKh` (next row N3: pckh.forward(softmax(result[2]), y_keypoints, rect),
+ * hourglass_compare.py:1160, performance_compare.py:646-647): the probabilities are never written.
+ * hg_softmax_stats: max_sum[b,h,w] = {max_c x, sum_c exp(x - max)} (float2 per pixel, fp32 NCHW logits);
+ * hg_pckh_logits: hg_pckh_sweep (absolute = 0) / hg_pckh_abs (absolute = 1) whose decoded value is
+ * exp(x - max) / sum, PyTorch's softmax expression, evaluated while the logits are scanned. */
+HG_API int hg_softmax_stats(const float* logits, int B, int C, int H, int W, float* max_sum, void* stream);
+HG_API int hg_pckh_logits(const float* logits, const float* max_sum, int absolute, int B, int C, int H, int W,
+                   const int64_t* target, const float* rect, int chan_offset, int njoints, const float* thresholds,
+                   int nthr, int32_t* correct, int32_t* total, int32_t* predict_xy, int32_t* label_xy, int32_t* found,
+                   float* standard, void* stream);
 /* PCKh "A" (only_one_hourgless.py:285-313): counts[0] += correct, counts[1] += total. */
 HG_API int hg_pckh_a(const void* x, int x_dtype, const void* target, int t_dtype, int B, int Cx, int Ct, int H, int W,
               int njoints, int head_ch, int neck_ch, int32_t* counts, void* stream);

@@ -6,10 +6,11 @@ keys): try_with_torch, try_with_torch_100, only_one_hourgless.  Kernels live in 
 (include/hg_sm100a.h); see DESIGN.md.
 """
 from ._modules import get_compute_dtype, set_compute_dtype  # noqa: F401
-from .evaluate import (PCKh_half_standard, PCKh_hourglass, PCKh_softmax, decode_argmax,  # noqa: F401
+from .evaluate import (PCKh_from_logits, PCKh_half_standard, PCKh_hourglass, PCKh_softmax, decode_argmax,  # noqa: F401
                        pckh_sweep_counts)
 from .losses import cross_entropy_losses, mse_losses  # noqa: F401
-from .targets import gaussian_heatmaps, label_maps  # noqa: F401
+from .optim import Adam  # noqa: F401
+from .targets import gaussian_heatmaps, label_maps, to_tensor_normalize  # noqa: F401
 
 __all__ = ["set_compute_dtype", "get_compute_dtype", "gaussian_heatmaps", "label_maps", "decode_argmax",
-           "pckh_sweep_counts", "PCKh_hourglass", "PCKh_softmax", "PCKh_half_standard", "mse_losses", "cross_entropy_losses"]
+           "pckh_sweep_counts", "PCKh_hourglass", "PCKh_softmax", "PCKh_half_standard", "PCKh_from_logits", "mse_losses", "cross_entropy_losses", "Adam", "to_tensor_normalize"]

@@ -62,6 +62,17 @@ class HgCeDesc(C.Structure):
                 ("grad_scale", C.c_float)]
 
 
+class HgAdamChunk(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64)]
+
+
+class HgAdamDesc(C.Structure):
+    _fields_ = [("lr_d", C.c_double), ("beta1_d", C.c_double), ("beta2_d", C.c_double), ("lr", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("step", C.c_int32), ("num_chunks", C.c_int32), ("pad_", C.c_int32)]
+
+
 class HgLabelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "P", "J", "L", "H", "W", "center_mode", "draw_points", "draw_lines",
                                          "line_value")]
@@ -105,11 +116,15 @@ SIGNATURES = {
     "hg_mix_rows": [_P, _P, _P, _I, _I, _I, _I, _P],
     "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
     "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
+    "hg_image_u8_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "hg_adam_multi": [C.POINTER(HgAdamDesc), _P, _P],
     "hg_render_gauss": [C.POINTER(HgGaussDesc), _P, _P, _P, _P, _P],
     "hg_render_labels": [C.POINTER(HgLabelDesc), _P, _P, _P, _P, _P, _P],
     "hg_decode_argmax": [_P, _I, _I, _I, _I, _P, _P, _P],
     "hg_pckh_sweep": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "hg_pckh_abs": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "hg_softmax_stats": [_P, _I, _I, _I, _I, _P, _P],
+    "hg_pckh_logits": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "hg_pckh_a": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
 }
 _SPECIAL = {"hg_last_error_string": ([], C.c_char_p), "hg_launch_count": ([], C.c_ulonglong)}

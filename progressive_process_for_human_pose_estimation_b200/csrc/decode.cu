@@ -21,13 +21,14 @@ __device__ __forceinline__ float ld_val(const void* p, int dtype, long long i) {
 
 // first row-major index of the maximum of n values (block-wide). NaN is never "greater", like torch.max's
 // comparison on well-formed heatmaps. Result valid in every thread.
-__device__ int block_argmax(const void* base, int dtype, long long off, int n, float* out_max) {
+template <class F>
+__device__ int block_argmax_f(F value, int n, float* out_max) {
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = ld_val(base, dtype, off + i);
+    const float v = value(i);
     if (v > bv || (v == bv && i < bi)) {
       bv = v;
       bi = i;
@@ -62,6 +63,36 @@ __device__ int block_argmax(const void* base, int dtype, long long off, int n, f
   if (out_max) *out_max = bv;
   if (bi == 0x7fffffff) bi = 0;  // all-NaN map
   return bi;
+}
+
+__device__ int block_argmax(const void* base, int dtype, long long off, int n, float* out_max) {
+  return block_argmax_f([=](int i) { return ld_val(base, dtype, off + i); }, n, out_max);
+}
+
+// Channel softmax evaluated on the fly (fused `softmax(result[2])` -> PCKh of hourglass_compare.py:1160 /
+// performance_compare.py:646-647): ms[pixel] = {max_c x, sum_c exp(x - max)} from softmax_stats_kernel; the value is
+// exp(x - max) / sum, the expression (and channel order of the sum) of PyTorch's softmax kernels.
+__device__ int block_argmax_softmax(const float* x, long long off, const float2* ms, int n, float* out_max) {
+  return block_argmax_f(
+      [=](int i) {
+        const float2 c = ms[i];
+        return __fdiv_rn(expf(x[off + i] - c.x), c.y);
+      },
+      n, out_max);
+}
+
+__global__ void __launch_bounds__(256) softmax_stats_kernel(const float* __restrict__ x, int C, int HW, long long npix,
+                                                            float2* __restrict__ ms) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW;
+    const float* p = x + b * (long long)C * HW + (i - b * HW);
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, __ldg(p + (long long)c * HW));
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(__ldg(p + (long long)c * HW) - m);
+    ms[i] = make_float2(m, sum);
+  }
 }
 
 // first row-major index i with lab[i] == value, or -1
@@ -100,7 +131,8 @@ __global__ void __launch_bounds__(256) pckh_sweep_kernel(const void* __restrict_
                                                          const float* __restrict__ thr, int nthr, int rule,
                                                          int* __restrict__ correct, int* __restrict__ total,
                                                          int* __restrict__ predict_xy, int* __restrict__ label_xy,
-                                                         int* __restrict__ found, float* __restrict__ standard_out) {
+                                                         int* __restrict__ found, float* __restrict__ standard_out,
+                                                         const float2* __restrict__ ms) {
   const int j = blockIdx.x, b = blockIdx.y, HW = H * W;
   const int li = block_first_equal(target + (long long)b * HW, HW, (long long)(j + 1));
   // standard = sqrt((x1-x2)^2 + (y1-y2)^2) * 0.6, all in float32 (rect is a float32 tensor)
@@ -111,7 +143,9 @@ __global__ void __launch_bounds__(256) pckh_sweep_kernel(const void* __restrict_
     if (threadIdx.x == 0) found[b * njoints + j] = 0;
     return;
   }
-  const int pi = block_argmax(x, dtype, ((long long)b * C + j + chan_offset) * HW, HW, nullptr);
+  const long long xoff = ((long long)b * C + j + chan_offset) * HW;
+  const int pi = ms ? block_argmax_softmax(reinterpret_cast<const float*>(x), xoff, ms + (long long)b * HW, HW, nullptr)
+                    : block_argmax(x, dtype, xoff, HW, nullptr);
   if (threadIdx.x == 0) {
     const int ly = li / W, lx = li % W, py = pi / W, px = pi % W;
     const int dy = ly - py, dx = lx - px;
@@ -196,7 +230,7 @@ int hg_decode_argmax(const void* heatmaps, int dtype, int num_maps, int H, int W
   return HG_OK;
 }
 
-static int pckh_launch(const char* who, int rule, const void* x, int dtype, int B, int C, int H, int W,
+static int pckh_launch(const char* who, int rule, const float2* ms, const void* x, int dtype, int B, int C, int H, int W,
                        const int64_t* target, const float* rect, int chan_offset, int njoints, const float* thresholds,
                        int nthr, int32_t* correct, int32_t* total, int32_t* predict_xy, int32_t* label_xy,
                        int32_t* found, float* standard, void* stream) {
@@ -208,7 +242,7 @@ static int pckh_launch(const char* who, int rule, const void* x, int dtype, int 
   dim3 grid(njoints, B);
   pckh_sweep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dtype, C, H, W, (const long long*)target, rect,
                                                              chan_offset, njoints, thresholds, nthr, rule, correct,
-                                                             total, predict_xy, label_xy, found, standard);
+                                                             total, predict_xy, label_xy, found, standard, ms);
   HG_LAUNCH_OK("pckh_sweep_kernel");
   count_launch();
   return HG_OK;
@@ -217,15 +251,39 @@ static int pckh_launch(const char* who, int rule, const void* x, int dtype, int 
 int hg_pckh_sweep(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
                   int chan_offset, int njoints, const float* thresholds, int nthr, int32_t* correct, int32_t* total,
                   int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream) {
-  return pckh_launch("hg_pckh_sweep", 0, x, dtype, B, C, H, W, target, rect, chan_offset, njoints, thresholds, nthr,
+  return pckh_launch("hg_pckh_sweep", 0, nullptr, x, dtype, B, C, H, W, target, rect, chan_offset, njoints, thresholds, nthr,
                      correct, total, predict_xy, label_xy, found, standard, stream);
 }
 
 int hg_pckh_abs(const void* x, int dtype, int B, int C, int H, int W, const int64_t* target, const float* rect,
                 int chan_offset, int njoints, const float* factors, int nfac, int32_t* correct, int32_t* total,
                 int32_t* predict_xy, int32_t* label_xy, int32_t* found, float* standard, void* stream) {
-  return pckh_launch("hg_pckh_abs", 1, x, dtype, B, C, H, W, target, rect, chan_offset, njoints, factors, nfac, correct,
+  return pckh_launch("hg_pckh_abs", 1, nullptr, x, dtype, B, C, H, W, target, rect, chan_offset, njoints, factors, nfac, correct,
                      total, predict_xy, label_xy, found, standard, stream);
+}
+
+int hg_softmax_stats(const float* logits, int B, int C, int H, int W, float* max_sum, void* stream) {
+  HG_REQUIRE(logits && max_sum, "hg_softmax_stats: NULL pointer");
+  HG_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "hg_softmax_stats: non-positive size");
+  HG_REQUIRE((reinterpret_cast<uintptr_t>(max_sum) & 7) == 0, "hg_softmax_stats: max_sum must be 8-byte aligned");
+  const long long npix = (long long)B * H * W;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  softmax_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(logits, C, H * W, npix,
+                                                                            reinterpret_cast<float2*>(max_sum));
+  HG_LAUNCH_OK("softmax_stats_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_pckh_logits(const float* logits, const float* max_sum, int absolute, int B, int C, int H, int W,
+                   const int64_t* target, const float* rect, int chan_offset, int njoints, const float* thresholds,
+                   int nthr, int32_t* correct, int32_t* total, int32_t* predict_xy, int32_t* label_xy, int32_t* found,
+                   float* standard, void* stream) {
+  HG_REQUIRE(max_sum != nullptr, "hg_pckh_logits: max_sum (hg_softmax_stats) is NULL");
+  return pckh_launch("hg_pckh_logits", absolute ? 1 : 0, reinterpret_cast<const float2*>(max_sum), logits, HG_F32, B, C,
+                     H, W, target, rect, chan_offset, njoints, thresholds, nthr, correct, total, predict_xy, label_xy,
+                     found, standard, stream);
 }
 
 int hg_pckh_a(const void* x, int x_dtype, const void* target, int t_dtype, int B, int Cx, int Ct, int H, int W,

@@ -314,6 +314,34 @@ static inline int grid_for(long long total, bool with_stats = false) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Input pipeline tail (next row N1): transforms.ToTensor() + transforms.Normalize(mean, std) of the reference's
+// datasets (try_with_torch.py:310-313: mean = std = 0.5) on the GPU -- uint8 HWC pixels in, fp32 NCHW planes out,
+// the exact fp32 operations of torchvision: t = u / 255;  y = (t - mean[c]) / std[c].  The host then ships one byte
+// per sample instead of four.
+// ------------------------------------------------------------------------------------------------------
+struct U8Norm {
+  float mean[4], stdv[4];
+};
+
+__global__ void __launch_bounds__(256) image_u8_to_nchw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                               long long npix_total, int HW, int C, U8Norm nm) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix_total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW;
+    const int p = (int)(i - n * HW);
+    const uint8_t* s = src + i * C;
+    float* d = dst + n * (long long)C * HW + p;
+    for (int c = 0; c < C; ++c) {
+      const float t = __fdiv_rn((float)s[c], 255.f);
+      d[(long long)c * HW] = __fdiv_rn(__fsub_rn(t, nm.mean[c]), nm.stdv[c]);
+    }
+  }
+}
+
 }  // namespace hg
 
 using namespace hg;
@@ -431,6 +459,26 @@ int hg_nhwc_to_nchw_f32(int dtype, const void* src, int N, int C, int H, int W, 
   HG_DISPATCH_T(dtype, (launch_k(nhwc_to_nchw_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
                            (const T*)src, dst_nchw, N, C, H * W, Cp)));
   HG_LAUNCH_OK("nhwc_to_nchw_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_image_u8_to_nchw_f32(const uint8_t* src_nhwc, int N, int H, int W, int C, const float* mean_host,
+                            const float* std_host, float* dst_nchw, void* stream) {
+  HG_REQUIRE(src_nhwc && dst_nchw && mean_host && std_host, "hg_image_u8_to_nchw_f32: NULL pointer");
+  HG_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 4, "hg_image_u8_to_nchw_f32: 1..4 channels, positive sizes");
+  U8Norm nm;
+  for (int c = 0; c < 4; ++c) {
+    nm.mean[c] = c < C ? mean_host[c] : 0.f;
+    nm.stdv[c] = c < C ? std_host[c] : 1.f;
+    HG_REQUIRE(nm.stdv[c] != 0.f, "hg_image_u8_to_nchw_f32: std must be non-zero");
+  }
+  const long long npix = (long long)N * H * W;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  launch_k(image_u8_to_nchw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src_nhwc, dst_nchw, npix,
+           H * W, C, nm);
+  HG_LAUNCH_OK("image_u8_to_nchw_kernel");
   count_launch();
   return HG_OK;
 }

@@ -32,10 +32,12 @@ def decode_argmax(heatmaps):
     return yx.view(*hm.shape[:-2], 2), mx.view(hm.shape[:-2])
 
 
-def pckh_sweep_counts(x, target, rect, chan_offset=0, njoints=None, thresholds=None, absolute=False):
+def pckh_sweep_counts(x, target, rect, chan_offset=0, njoints=None, thresholds=None, absolute=False, logits=False):
     """Integer results of the PCKh threshold sweep, all on the device (no host sync).
     absolute=False: correct when sqrt(d2)/standard < k (evaluators B/C); absolute=True: sqrt(d2) < standard*k
-    (evaluator D, calculate_parameters.py:927-929)."""
+    (evaluator D, calculate_parameters.py:927-929).
+    logits=True: x holds the network's raw fp32 class scores and the evaluator sees softmax(x, dim=1) -- the
+    `pckh.forward(softmax(result[2]), ...)` call of hourglass_compare.py:1160 without writing the probabilities."""
     x = _as_cuda(x, "x")
     target = _as_cuda(target, "target").to(torch.int64)
     rect = _as_cuda(rect, "rect").to(torch.float32)
@@ -50,6 +52,16 @@ def pckh_sweep_counts(x, target, rect, chan_offset=0, njoints=None, thresholds=N
     label = torch.zeros(B, nj, 2, device=dev, dtype=torch.int32)
     found = torch.zeros(B, nj, device=dev, dtype=torch.int32)
     standard = torch.zeros(B, device=dev, dtype=torch.float32)
+    if logits:
+        if x.dtype != torch.float32:
+            raise RuntimeError("pckh_sweep_counts(logits=True): fp32 class scores expected")
+        ms = torch.empty(B, H, W, 2, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.call("hg_softmax_stats", L.ptr(x), B, Cx, H, W, L.ptr(ms), L.stream_ptr())
+            L.call("hg_pckh_logits", L.ptr(x), L.ptr(ms), 1 if absolute else 0, B, Cx, H, W, L.ptr(target), L.ptr(rect),
+                   chan_offset, nj, L.ptr(thr), nthr, L.ptr(correct), L.ptr(total), L.ptr(predict), L.ptr(label),
+                   L.ptr(found), L.ptr(standard), L.stream_ptr())
+        return dict(correct=correct, total=total, predict=predict, label=label, found=found, standard=standard)
     with torch.cuda.device(dev):
         L.call("hg_pckh_abs" if absolute else "hg_pckh_sweep", L.ptr(x), L.hg_dtype(x.dtype), B, Cx, H, W,
                L.ptr(target), L.ptr(rect), chan_offset, nj, L.ptr(thr), nthr, L.ptr(correct), L.ptr(total), L.ptr(predict), L.ptr(label), L.ptr(found),
@@ -81,6 +93,17 @@ class PCKh_softmax(nn.Module):
 
     def forward(self, x, target, rect):
         r = pckh_sweep_counts(x, target, rect, 1)
+        acc, pred, lab = _sweep_result(r)
+        return acc, pred, lab, [s for s in r["standard"].cpu()]
+
+
+class PCKh_from_logits(nn.Module):
+    """PCKh 'B' on raw class scores: `PCKh_from_logits()(result[2], y, rect)` returns what the reference's
+    `pckh.forward(nn.functional.softmax(result[2]), y, rect)` returns (hourglass_compare.py:1160,
+    performance_compare.py:646-647), the softmax being evaluated inside the decode."""
+
+    def forward(self, x, target, rect):
+        r = pckh_sweep_counts(x, target, rect, 1, logits=True)
         acc, pred, lab = _sweep_result(r)
         return acc, pred, lab, [s for s in r["standard"].cpu()]
 

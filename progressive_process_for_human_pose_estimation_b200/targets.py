@@ -70,3 +70,25 @@ def label_maps(persons, img_wh, limbs, H=64, W=64, num_persons=None, center_mode
         L.call("hg_render_labels", C.byref(d), L.ptr(persons), L.ptr(num_persons), L.ptr(img_wh), L.ptr(limbs_t),
                L.ptr(out), L.stream_ptr())
     return out
+
+
+def to_tensor_normalize(images_u8, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    """transforms.ToTensor() + transforms.Normalize(mean, std) of the reference datasets (try_with_torch.py:310-313)
+    for a whole batch on the GPU: uint8 [B,H,W,C] (what PIL hands over after resize) -> fp32 [B,C,H,W], bit-exact
+    with torchvision.  The host ships 1 byte per sample instead of 4."""
+    import ctypes as C
+
+    if not torch.is_tensor(images_u8) or images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
+        raise TypeError("to_tensor_normalize: expected a uint8 tensor [B,H,W,C]")
+    if not images_u8.is_cuda:
+        raise RuntimeError("to_tensor_normalize: the batch must live on the GPU (there is no CPU fallback)")
+    x = images_u8.contiguous()
+    B, H, W, Ch = x.shape
+    if len(mean) != Ch or len(std) != Ch:
+        raise ValueError("to_tensor_normalize: one mean / std per channel")
+    out = torch.empty(B, Ch, H, W, device=x.device, dtype=torch.float32)
+    m = (C.c_float * Ch)(*[float(v) for v in mean])
+    s = (C.c_float * Ch)(*[float(v) for v in std])
+    with torch.cuda.device(x.device):
+        L.call("hg_image_u8_to_nchw_f32", L.ptr(x), B, H, W, Ch, m, s, L.ptr(out), L.stream_ptr())
+    return out

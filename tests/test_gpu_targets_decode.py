@@ -301,3 +301,53 @@ def test_fused_cross_entropy_heads_match_stock_modules():
         hg.cross_entropy_losses([(xd3.detach(), (y + 1).cuda())], check_labels=True)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         hg.cross_entropy_losses([(x.detach(), y)])
+
+
+def test_to_tensor_normalize_bit_exact():
+    """hg.to_tensor_normalize == transforms.ToTensor() + Normalize(0.5, 0.5) of try_with_torch.py:310-313 evaluated
+    on the CPU (torchvision when importable, else the same two torch expressions), every uint8 value, bit for bit."""
+    r = np.random.RandomState(0)
+    img = r.randint(0, 256, size=(5, 64, 48, 3)).astype(np.uint8)
+    img[0, 0, :, 0] = np.arange(48) * 5 % 256
+    img[1].reshape(-1)[:256] = np.arange(256)          # all 256 values
+    for mean, std in (((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
+        try:
+            from PIL import Image
+            from torchvision import transforms
+            tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=mean, std=std)])
+            ref = torch.stack([tf(Image.fromarray(im)) for im in img])
+        except ImportError:
+            t = torch.from_numpy(img).permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+            ref = t.sub_(torch.tensor(mean).view(1, 3, 1, 1)).div_(torch.tensor(std).view(1, 3, 1, 1))
+        got = hg.to_tensor_normalize(torch.from_numpy(img).cuda(), mean, std)
+        assert got.shape == (5, 3, 64, 48) and got.dtype == torch.float32
+        assert torch.equal(got.cpu(), ref)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hg.to_tensor_normalize(torch.from_numpy(img))
+
+
+def test_pckh_from_logits_equals_softmax_then_pckh():
+    """Fused softmax -> PCKh B (hourglass_compare.py:1160: pckh.forward(softmax(result[2]), y, rect)): identical
+    counts and decoded positions to (a) PyTorch's softmax on the GPU followed by the un-fused evaluator and (b) the
+    numpy oracle on the CPU softmax, on peaked and on random class scores."""
+    from oracle.synth import pckh_near_inputs
+
+    for seed in range(4):
+        d = pckh_near_inputs(seed)
+        r = np.random.RandomState(50 + seed)
+        z = r.randn(*d["x17"].shape).astype(np.float32) * 2
+        if seed % 2 == 0:   # peaked scores: the labelled joints' neighbourhoods win
+            z += 6 * np.log(np.maximum(d["x17"], 1e-6)).astype(np.float32).clip(-3, 0)
+        zt = torch.from_numpy(z)
+        tgt, rect = torch.from_numpy(d["target"]), torch.from_numpy(d["rect"])
+        fused = hg.pckh_sweep_counts(zt.cuda(), tgt.cuda(), rect.cuda(), 1, logits=True)
+        plain = hg.pckh_sweep_counts(torch.softmax(zt.cuda(), 1), tgt.cuda(), rect.cuda(), 1)
+        for k in ("correct", "total", "predict", "label", "found"):
+            assert torch.equal(fused[k], plain[k]), (seed, k)
+        ref = pckh_np.pckh_sweep(torch.softmax(zt, 1).numpy(), d["target"], d["rect"], 1)
+        for k in ("correct", "total", "predict", "label", "found"):
+            assert np.array_equal(fused[k].cpu().numpy(), ref[k]), (seed, k)
+        acc, pred, lab, std = hg.PCKh_from_logits()(zt.cuda(), tgt.cuda(), rect.cuda())
+        assert np.array_equal(acc, ref["accuracy"]) and np.array_equal(np.stack(pred), ref["predict"].astype(np.float64))
+    with pytest.raises(RuntimeError, match="fp32"):
+        hg.pckh_sweep_counts(zt.cuda().half(), tgt.cuda(), rect.cuda(), 1, logits=True)

@@ -155,6 +155,10 @@ if __name__ == "__main__":
                 print(f"@{hw}x{hw} conv{k}x{k} {cin}->{cout}: one producer {t[0]:.2f}/{t[2]:.2f} us, split {t[1]:.2f}/{t[3]:.2f} us, "
                       f"identical output: {same}", flush=True)
         sys.exit(0)
+    if os.environ.get("BN64"):   # the four BatchNorm streaming kernels at 64x64 only (ncu --set full capture)
+        print(bn_chain(32, 64, 256, n=4), bn_chain(32, 64, 128, n=4), bn_bwd_chain(32, 64, 256, n=4, with_addend=True),
+              bn_bwd_chain(32, 64, 128, n=4))
+        sys.exit(0)
     if os.environ.get("WGRAD_T1"):
         def once(hw, cin, cout, k):
             torch.manual_seed(0)

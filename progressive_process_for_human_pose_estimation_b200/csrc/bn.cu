@@ -136,9 +136,22 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 }
 
 // rows per block: enough blocks to fill the machine, few enough that the per-channel atomics stay cheap
-static inline int rows_per_block_for(long long M, int rlanes) {
+int g_bn_blocks_per_sm = 6;       // grid cap of bn_apply (no per-block atomics) (hg_set_option "bn_blocks_per_sm")
+// Kernels whose blocks end with per-channel atomics into the SAME 2*C floats (bn_bwd_apply's bias-gradient column
+// sums, bn_stats, colsum, bn_bwd_reduce): the L2 serialises those per cache line, so their grid is ONE wave.  Measured
+// (B200, batch 32, bn_bwd_apply C128): 6 blocks/SM 24.4 us @64x64, 12.4 us @32x32;  2 blocks/SM 18.5 / 7.0 us;
+// C256+addend @16x16: 9.7 us (6/SM) -> 6.0 us (1/SM).  0 = policy below, > 0 = fixed blocks per SM.
+int g_bn_bwd_blocks_per_sm = 0;
+
+static inline int atomic_grid_per_sm(long long M) {
+  if (g_bn_bwd_blocks_per_sm > 0) return g_bn_bwd_blocks_per_sm;
+  return M >= 32768 ? 2 : 1;
+}
+
+static inline int rows_per_block_for(long long M, int rlanes, int per_sm = 0) {
   long long blocks = M / (rlanes * 2);  // small tensors are latency-bound: at most two dependent loads per thread
-  if (blocks > 6 * kNumSMs) blocks = 6 * kNumSMs;
+  if (per_sm <= 0) per_sm = g_bn_blocks_per_sm;
+  if (blocks > (long long)per_sm * kNumSMs) blocks = (long long)per_sm * kNumSMs;
   if (blocks < 1) blocks = 1;
   return (int)((M + blocks - 1) / blocks);
 }
@@ -152,7 +165,7 @@ int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats,
     set_error("bn_stats: Cp > 256 unsupported");
     return HG_ERR_UNSUPPORTED;
   }
-  const int rpb = rows_per_block_for(M, 256 / (Cp >> 3));
+  const int rpb = rows_per_block_for(M, 256 / (Cp >> 3), atomic_grid_per_sm(M));
   const int blocks = ceil_div(M, rpb);
   if (dtype == HG_BF16)
     launch_k(bn_stats_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, M, Cp, stats, rpb);
@@ -205,7 +218,7 @@ int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* 
     set_error("colsum: padded channel count %d unsupported", Cp);
     return HG_ERR_UNSUPPORTED;
   }
-  const int rpb = rows_per_block_for(M, 256 / (Cp >> 3));
+  const int rpb = rows_per_block_for(M, 256 / (Cp >> 3), atomic_grid_per_sm(M));
   const int blocks = ceil_div(M, rpb);
   if (dtype == HG_BF16)
     launch_k(colsum_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)dy, M, Cp, C, out, rpb);
@@ -540,7 +553,7 @@ int hg_bn_bwd_reduce(const HgBnDesc* d, const void* da, const void* x, const flo
   HG_REQUIRE(d->use_running ? (running_mean && running_var) : (stats != nullptr),
              "hg_bn_bwd_reduce: statistics missing for the selected mode");
   BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
-  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3));
+  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3), atomic_grid_per_sm(d->M));
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == HG_BF16)
@@ -561,7 +574,7 @@ int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const floa
   HG_REQUIRE(d->use_running ? (running_mean && running_var) : (stats && red),
              "hg_bn_bwd_apply: statistics missing for the selected mode");
   BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
-  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3));
+  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3), atomic_grid_per_sm(d->M));
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
 #define HG_BWD_APPLY(T, ADD, CS)                                                                                 \

@@ -37,7 +37,7 @@ def graph_time(body, reps=5):
     return best
 
 
-def conv_chain(B, hw, cin, cout, k, n=100):
+def conv_chain(B, hw, cin, cout, k, n=100, with_stats=True):
     d = L.HgConvDesc(B, hw, hw, cin, cout, k, k, 1, k // 2, 1, L.HG_BF16)
     x = torch.randn(B, hw, hw, cin, device=dev).to(DT)
     y = torch.zeros(B, hw, hw, cout, device=dev, dtype=DT)
@@ -54,7 +54,8 @@ def conv_chain(B, hw, cin, cout, k, n=100):
                 a, b = bufs[i % 2], bufs[(i + 1) % 2]
             else:
                 a, b = x, y
-            L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(a), L.ptr(w), L.ptr(bias), None, L.ptr(b), L.ptr(stats), None, st)
+            L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(a), L.ptr(w), L.ptr(bias), None, L.ptr(b),
+                   L.ptr(stats) if with_stats else None, None, st)
 
     return graph_time(body) / n * 1e3
 
@@ -154,6 +155,28 @@ if __name__ == "__main__":
                     t.append(conv_chain(32, hw, cin, cout, k))
                 print(f"@{hw}x{hw} conv{k}x{k} {cin}->{cout}: one producer {t[0]:.2f}/{t[2]:.2f} us, split {t[1]:.2f}/{t[3]:.2f} us, "
                       f"identical output: {same}", flush=True)
+        sys.exit(0)
+    if os.environ.get("CONV_STATS"):   # cost of the per-channel statistics (smem column pass + global atomics) in fprop
+        for hw in (4, 16, 32, 64):
+            for cin, cout, k in ((128, 128, 3), (256, 128, 1), (128, 256, 1)):
+                a, b = conv_chain(32, hw, cin, cout, k), conv_chain(32, hw, cin, cout, k, with_stats=False)
+                print(f"@{hw}x{hw} conv{k}x{k} {cin}->{cout}: with statistics {a:.2f} us, without {b:.2f} us", flush=True)
+        sys.exit(0)
+    if os.environ.get("BN_GRID"):   # grid cap (blocks per SM) of the streaming BatchNorm kernels
+        for hw in (8, 16):
+            for per_sm in (1, 2, 6):
+                L.call("hg_set_option", b"bn_bwd_blocks_per_sm", per_sm)
+                print(f"@{hw} blocks/SM {per_sm}: bwd256+add {bn_bwd_chain(32, hw, 256, n=50, with_addend=True):.2f} "
+                      f"bwd128 {bn_bwd_chain(32, hw, 128, n=50):.2f} us", flush=True)
+        for per_sm in (1, 2, 6):
+            L.call("hg_set_option", b"bn_blocks_per_sm", per_sm)
+            L.call("hg_set_option", b"bn_bwd_blocks_per_sm", per_sm)
+            r = []
+            for hw in (32, 64):
+                r += [bn_chain(32, hw, 256, n=20), bn_chain(32, hw, 128, n=20), bn_bwd_chain(32, hw, 256, n=20, with_addend=True),
+                      bn_bwd_chain(32, hw, 128, n=20)]
+            print(f"blocks/SM {per_sm:2d}: @32 apply256 {r[0]:.2f} apply128 {r[1]:.2f} bwd256+add {r[2]:.2f} bwd128 {r[3]:.2f} | "
+                  f"@64 apply256 {r[4]:.2f} apply128 {r[5]:.2f} bwd256+add {r[6]:.2f} bwd128 {r[7]:.2f} us", flush=True)
         sys.exit(0)
     if os.environ.get("BN64"):   # the four BatchNorm streaming kernels at 64x64 only (ncu --set full capture)
         print(bn_chain(32, 64, 256, n=4), bn_chain(32, 64, 128, n=4), bn_bwd_chain(32, 64, 256, n=4, with_addend=True),

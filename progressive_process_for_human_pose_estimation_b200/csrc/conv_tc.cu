@@ -27,7 +27,10 @@
 
 namespace hg {
 
+int g_short_alias = 1;         // 1: multi-wave 1x1 kernels with a residual / raw BN input load it AFTER the (short) main loop
+                               // into the aliased staging tile: 64 KB per CTA, 3 CTAs/SM instead of 2
 int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
+int g_wgrad_big_n_panels = 0;   // larger maps: input-channel panels per CTA (0 = all): fewer K splits, fewer atomics
 int g_wgrad_small_n_panels = 0; // small maps (see g_wgrad_t1_max_kb): input-channel panels (of 64) per CTA; 0 = policy
                                 // (1x1 or <= 32 K blocks: 1 panel, else 2), -1 = never split the input channels
 int g_wgrad_t1_max_kb = 128;    // "small map": at most this many 64-pixel K blocks (16x16 at batch 32); 3x3: one tap per CTA     // 3x3 wgrad: one tap per CTA when the map has at most this many 64-pixel K blocks
@@ -586,12 +589,14 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
     // multi-wave 3x3 kernel (two CTAs per SM) loads it after its (long) main loop
     if (single_wave) return long_k ? launch_conv_gemm<BN, 5, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st)
                                    : launch_conv_gemm<BN, 4, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st);
+    if (!long_k && g_short_alias) return launch_conv_gemm<BN, 2, 3, kMask, true>(tmA, tmB, tmC, tmR, p, st);
     return long_k ? launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st)
                   : launch_conv_gemm<BN, 2, 2, kMask, false>(tmA, tmB, tmC, tmR, p, st);
   } else {
     constexpr int kShortMinB = MODE == kFold ? 2 : 3;  // the transform needs > 113 registers
     if constexpr (MODE != kPlainBnOut) if (has_res) {
       if (long_k) return launch_conv_gemm<BN, 3, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st);
+      if (!single_wave && g_short_alias) return launch_conv_gemm<BN, 2, kShortMinB, MODE, true>(tmA, tmB, tmC, tmR, p, st);
       return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st)
                          : launch_conv_gemm<BN, 2, 2, MODE, false>(tmA, tmB, tmC, tmR, p, st);
     }
@@ -1031,6 +1036,9 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     // pushes through its SM's L2 port are what a small wgrad launch costs)
     // (B200, batch 32, us per launch: 3x3 128->128 @4x4 11.5 -> 4.5, 1x1 256->128 8.1 -> 4.5, 3x3 @16x16 15.8 -> 10.7)
     p.n_groups = 1;
+    if ((M + 63) / 64 > g_wgrad_t1_max_kb && g_wgrad_big_n_panels > 0 && Cin_p / 64 > g_wgrad_big_n_panels &&
+        (Cin_p / 64) % g_wgrad_big_n_panels == 0)
+      p.n_groups = Cin_p / 64 / g_wgrad_big_n_panels;
     if ((M + 63) / 64 <= g_wgrad_t1_max_kb && g_wgrad_small_n_panels >= 0) {
       int per_cta = g_wgrad_small_n_panels;
       if (per_cta == 0) per_cta = (taps == 1 || (M + 63) / 64 <= 32) ? 1 : 2;

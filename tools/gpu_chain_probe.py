@@ -156,6 +156,16 @@ if __name__ == "__main__":
                 print(f"@{hw}x{hw} conv{k}x{k} {cin}->{cout}: one producer {t[0]:.2f}/{t[2]:.2f} us, split {t[1]:.2f}/{t[3]:.2f} us, "
                       f"identical output: {same}", flush=True)
         sys.exit(0)
+    if os.environ.get("WGRAD_BIG"):   # larger maps: input-channel split (fewer K splits -> fewer atomics, more dy re-reads)
+        for hw in (32, 64):
+            for cin, cout, k in ((128, 128, 3), (256, 128, 1), (128, 256, 1), (256, 256, 1)):
+                t = []
+                for npan in (0, 2, 1):
+                    L.call("hg_set_option", b"wgrad_big_n_panels", npan)
+                    t.append(wgrad_chain(32, hw, cin, cout, k))
+                print(f"wgrad {k}x{k} {cin}->{cout} @{hw}x{hw}: all channels/CTA {t[0]:.2f} us | 128 ch/CTA {t[1]:.2f} | 64 ch/CTA {t[2]:.2f}",
+                      flush=True)
+        sys.exit(0)
     if os.environ.get("CONV_STATS"):   # cost of the per-channel statistics (smem column pass + global atomics) in fprop
         for hw in (4, 16, 32, 64):
             for cin, cout, k in ((128, 128, 3), (256, 128, 1), (128, 256, 1)):

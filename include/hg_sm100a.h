@@ -210,6 +210,13 @@ HG_API int hg_upsample2x_add_fwd(int dtype, int mode, const void* low, const voi
                           void* out, float* stats, void* stream);
 HG_API int hg_upsample2x_bwd(int dtype, int mode, const void* dout, const void* addend, int N, int h, int w, int C,
                       void* dlow, void* stream);
+/* Image-level branch of ASPP (train.py:476-479,488-489): y[n,c] = scale * sum_hw x[n,h,w,c] [+ addend[n,c]]
+ * (nn.AdaptiveAvgPool2d((1,1)) with scale = 1/(H*W)) and its transpose x[n,h,w,c] = scale * y[n,c] [+ addend[n,h,w,c]]
+ * (F.interpolate of a 1x1 map, bilinear align_corners=True, = broadcast); each is the other's backward. */
+HG_API int hg_spatial_mean(int dtype, const void* x, int N, int H, int W, int C, float scale, const void* addend, void* y,
+                           void* stream);
+HG_API int hg_spatial_broadcast(int dtype, const void* y, int N, int H, int W, int C, float scale, const void* addend,
+                                void* x, void* stream);
 HG_API int hg_add(int dtype, const void* a, const void* b, void* out, long long n_elems, void* stream);
 /* layout changes at the module boundary (NCHW fp32 tensors of the training loop <-> NHWC activations) */
 HG_API int hg_nchw_f32_to_nhwc(int dtype, const float* src_nchw, const void* addend, int N, int C, int H, int W, void* dst,

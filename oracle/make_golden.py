@@ -184,6 +184,60 @@ def golden_pckh_d():
                         pred_d=np.stack(pred_d), lab_d=np.stack(lab_d), acc_b=acc_b, pred_b=np.stack(pred_b))
 
 
+def golden_aspp():
+    """train.ASPP_Block / train._ASPPModule of the reference (train.py:449-495): seeded weights, train-mode forward +
+    backward and eval-mode forward on [4,256,8,8]."""
+    tr = refload.load("train")
+    torch.manual_seed(0)
+    net = tr.ASPP_Block()
+    with torch.no_grad():   # non-trivial BatchNorm parameters / running statistics
+        g = torch.Generator().manual_seed(5)
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
+                m.running_mean.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.bias.shape, generator=g) + 0.5)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(4, 256, 8, 8, generator=g).requires_grad_()
+    w = torch.randn(4, 256, 8, 8, generator=g)
+    net.train()
+    out = net(x)
+    (out * w).sum().backward()
+    # yardstick: how far the reference's OWN bf16-autocast run is from its fp32 run on this input (BatchNorm over the
+    # 4 samples of the image-level branch amplifies rounding in the backward pass)
+    net_ac = tr.ASPP_Block()
+    net_ac.load_state_dict(sd0)
+    net_ac.train()
+    x_ac = x.detach().clone().requires_grad_()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out_ac = net_ac(x_ac)
+    (out_ac.float() * w).sum().backward()
+    noise = np.array([((out_ac.float() - out).norm() / out.norm()).item(), ((x_ac.grad - x.grad).norm() / x.grad.norm()).item()])
+    named = list(net.named_parameters())
+    # per-parameter gradient digests (norm and a seeded random projection) keep the fixture small
+    gp = torch.Generator().manual_seed(7)
+    arrays = {"grad_names": np.array([k for k, _ in named]),
+              "grad_norm": np.array([p.grad.double().norm().item() for _, p in named]),
+              "grad_proj": np.array([(p.grad.double().flatten() * torch.randn(p.numel(), generator=gp).double()).sum().item()
+                                     for _, p in named])}
+    sd1 = {k: v.clone() for k, v in net.state_dict().items()}
+    net.load_state_dict(sd0)
+    net.eval()
+    with torch.no_grad():
+        out_eval = net(x.detach())
+    torch.manual_seed(1)
+    am = tr._ASPPModule(256, 256, 3, padding=6, dilation=6)
+    am.train()
+    out_am = am(x.detach())
+    f16 = lambda t: t.detach().numpy().astype(np.float16)  # noqa: E731  (reference values to 1e-3: tolerance is 1e-2)
+    np.savez_compressed(os.path.join(GOLDEN, "aspp_block.npz"), out_train=out.detach().numpy(), gx=x.grad.numpy(),
+                        out_eval=f16(out_eval), out_module=f16(out_am), noise_bf16_autocast=noise,
+                        running_mean_after=sd1["conv1.1.running_mean"].numpy(),
+                        gap_running_var_after=sd1["global_avg_pool.2.running_var"].numpy(), **arrays)
+
+
 # (reference script, model factory attribute, drop-in module name)
 FAMILIES = [
     ("try_different_stack", "creatModel"),
@@ -281,6 +335,7 @@ def main():
     golden_targets()
     golden_pckh()
     golden_pckh_d()
+    golden_aspp()
     golden_families()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))

@@ -241,6 +241,57 @@ def make_s_family(g):
     return ResidualBlock, hourglass, lin, creatModel
 
 
+def make_aspp_block(g=None):
+    """`_ASPPModule` (try_with_aspp.py:193-205 = train.py:449-461: dilated conv, no bias -> BN -> ReLU) and `ASPP_Block`
+    (train.py:465-495: 1x1 + three dilated 3x3 branches (6 / 12 / 18) + image-level branch (global average pool ->
+    1x1 -> BN -> ReLU -> broadcast), concatenated (1280 ch) -> 1x1 -> BN -> ReLU) as executable drop-in modules."""
+
+    class _ASPPModule(HGModule):
+        def __init__(self, inplanes, planes, kernel_size, padding, dilation):
+            super(_ASPPModule, self).__init__()
+            self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, stride=1, padding=padding,
+                                         dilation=dilation, bias=False)
+            self.bn = nn.BatchNorm2d(planes)
+            self.relu = nn.ReLU()
+
+        def _emit(self, b, x):
+            return b.bn_relu(self.bn, b.conv(self.atrous_conv, x))
+
+    class ASPP_Block(HGModule):
+        def __init__(self):
+            super(ASPP_Block, self).__init__()
+            inplanes = 256
+            dilations = [1, 6, 12, 18]
+            self.aspp1 = _ASPPModule(inplanes, 256, 1, padding=0, dilation=dilations[0])
+            self.aspp2 = _ASPPModule(inplanes, 256, 3, padding=dilations[1], dilation=dilations[1])
+            self.aspp3 = _ASPPModule(inplanes, 256, 3, padding=dilations[2], dilation=dilations[2])
+            self.aspp4 = _ASPPModule(inplanes, 256, 3, padding=dilations[3], dilation=dilations[3])
+            self.global_avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)),
+                                                 nn.Conv2d(inplanes, 256, 1, stride=1, bias=False),
+                                                 nn.BatchNorm2d(256),
+                                                 nn.ReLU())
+            self.conv1 = nn.Sequential(nn.Conv2d(1280, 256, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU())
+
+        def _emit(self, b, x):
+            # the five branches only share their input: one stream lane each
+            xs = []
+            for i, m in enumerate((self.aspp1, self.aspp2, self.aspp3, self.aspp4)):
+                with b.on_lane(i):
+                    xs.append(m._emit(b, x))
+            with b.on_lane(4):
+                x5 = b.global_avg_pool(x)
+                x5 = b.bn_relu(self.global_avg_pool[2], b.conv(self.global_avg_pool[1], x5))
+                xs.append(b.broadcast_to(x5, x.H, x.W))
+            # torch.cat + 1x1 conv as five chained convolutions over slices of the 1280-channel weight
+            return b.bn_relu(self.conv1[1], b.conv_cat(self.conv1[0], xs))
+
+    for cls in (_ASPPModule, ASPP_Block):
+        if g is not None:
+            cls.__module__ = g.get("__name__", cls.__module__)
+        cls.__qualname__ = cls.__name__
+    return _ASPPModule, ASPP_Block
+
+
 def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4):
     """Shared body of the multi-head creatModel variants: per-stack heads conv2_k and re-injection conv4_k over a
     concatenation (try_different_stack.py:300-329; try_with_aspp_remove_max_pool.py:277-304)."""
@@ -277,15 +328,8 @@ def make_multihead_family(g, aspp_members=False, num_heads=3):
     bottom level has no extra residual blocks, try_with_aspp.py:250-279)."""
     ResidualBlock, hourglass_s, lin, _ = make_s_family(g)
 
-    class _ASPPModule(nn.Module):
-        """Parameter container only: never called by the reference's forward (quirk Q6)."""
-
-        def __init__(self, inplanes, planes, kernel_size, padding, dilation):
-            super(_ASPPModule, self).__init__()
-            self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, stride=1, padding=padding,
-                                         dilation=dilation, bias=False)
-            self.bn = nn.BatchNorm2d(planes)
-            self.relu = nn.ReLU()
+    # never called by this family's forward (quirk Q6) but executable on its own, like the reference class
+    _ASPPModule, _ = make_aspp_block(g)
 
     if aspp_members:
         class hourglass(HGModule):
@@ -482,13 +526,7 @@ def make_nopool_family(g):
     ResidualBlock = make_q4_block(g)
     _, _, lin, _ = make_s_family(g)
 
-    class _ASPPModule(nn.Module):
-        def __init__(self, inplanes, planes, kernel_size, padding, dilation):
-            super(_ASPPModule, self).__init__()
-            self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, stride=1, padding=padding,
-                                         dilation=dilation, bias=False)
-            self.bn = nn.BatchNorm2d(planes)
-            self.relu = nn.ReLU()
+    _ASPPModule, _ = make_aspp_block(g)
 
     class hourglass(HGModule):
         def __init__(self, n, f):

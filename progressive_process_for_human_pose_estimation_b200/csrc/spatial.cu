@@ -316,6 +316,77 @@ static inline int grid_for(long long total, bool with_stats = false) {
 
 
 // ------------------------------------------------------------------------------------------------------
+// Global average pooling and its transpose, the image-level branch of ASPP (train.py:476-479,488-489:
+// nn.AdaptiveAvgPool2d((1, 1)) ... F.interpolate(x5, size, mode='bilinear', align_corners=True) of a 1x1 map, i.e. a
+// broadcast).  y[n, c] = scale * sum_hw x[n, hw, c] [+ addend[n, c]];   x[n, hw, c] = scale * y[n, c] [+ addend].
+// Each is the other's backward.  Block = (n, 32 channel vectors) x 8 row lanes.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) spatial_sum_kernel(const T* __restrict__ x, const T* __restrict__ addend,
+                                                          T* __restrict__ y, int HW, int Cp, float scale) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[8][32][9];
+  const int vecs = Cp >> 3;
+  const int vl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int vc = blockIdx.x * 32 + vl;
+  const long long n = blockIdx.y;
+  float acc[8] = {};
+  if (vc < vecs) {
+    for (int r = rl; r < HW; r += 8) {
+      float v[8];
+      load8(x + (n * HW + r) * Cp + vc * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][vl][e] = acc[e];
+  __syncthreads();
+  if (rl == 0 && vc < vecs) {
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += red[k][vl][e];
+      o[e] = t * scale;
+    }
+    if (addend) {
+      float a[8];
+      load8(addend + n * Cp + vc * 8, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += a[e];
+    }
+    store8(y + n * Cp + vc * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) spatial_bcast_kernel(const T* __restrict__ y, const T* __restrict__ addend,
+                                                            T* __restrict__ x, long long total, int HW, int Cp,
+                                                            float scale) {
+  pdl_wait();
+  pdl_trigger();
+  const int vecs = Cp >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vecs);
+    const long long n = i / vecs / HW;
+    float v[8];
+    load8(y + n * Cp + vc * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= scale;
+    if (addend) {
+      float a[8];
+      load8(addend + i * 8, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += a[e];
+    }
+    store8(x + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Input pipeline tail (next row N1): transforms.ToTensor() + transforms.Normalize(mean, std) of the reference's
 // datasets (try_with_torch.py:310-313: mean = std = 0.5) on the GPU -- uint8 HWC pixels in, fp32 NCHW planes out,
 // the exact fp32 operations of torchvision: t = u / 255;  y = (t - mean[c]) / std[c].  The host then ships one byte
@@ -479,6 +550,34 @@ int hg_image_u8_to_nchw_f32(const uint8_t* src_nhwc, int N, int H, int W, int C,
   launch_k(image_u8_to_nchw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src_nhwc, dst_nchw, npix,
            H * W, C, nm);
   HG_LAUNCH_OK("image_u8_to_nchw_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_spatial_mean(int dtype, const void* x, int N, int H, int W, int C, float scale, const void* addend, void* y,
+                    void* stream) {
+  int rc = check_spatial(dtype, N, H, W, C, "hg_spatial_mean");
+  if (rc) return rc;
+  HG_REQUIRE(x && y, "hg_spatial_mean: NULL pointer");
+  const int Cp = (C + 63) & ~63;
+  dim3 grid((Cp / 8 + 31) / 32, N);
+  HG_DISPATCH_T(dtype, (launch_k(spatial_sum_kernel<T>, grid, dim3(256), 0, (cudaStream_t)stream, (const T*)x,
+                                 (const T*)addend, (T*)y, H * W, Cp, scale)));
+  HG_LAUNCH_OK("spatial_sum_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_spatial_broadcast(int dtype, const void* y, int N, int H, int W, int C, float scale, const void* addend,
+                         void* x, void* stream) {
+  int rc = check_spatial(dtype, N, H, W, C, "hg_spatial_broadcast");
+  if (rc) return rc;
+  HG_REQUIRE(x && y, "hg_spatial_broadcast: NULL pointer");
+  const int Cp = (C + 63) & ~63;
+  const long long total = (long long)N * H * W * (Cp / 8);
+  HG_DISPATCH_T(dtype, (launch_k(spatial_bcast_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream,
+                                 (const T*)y, (const T*)addend, (T*)x, total, H * W, Cp, scale)));
+  HG_LAUNCH_OK("spatial_bcast_kernel");
   count_launch();
   return HG_OK;
 }

@@ -167,6 +167,19 @@ class Builder:
         self.ops.append(Op("up", [low, skip], out, mode=0 if mode == "bilinear" else 1))
         return out
 
+    def global_avg_pool(self, x):
+        """nn.AdaptiveAvgPool2d((1, 1)) (train.py:476)."""
+        out = Val(x.N, 1, 1, x.C, self._rg(x), "gap")
+        self.ops.append(Op("gap", [x], out))
+        return out
+
+    def broadcast_to(self, y, H, W):
+        """F.interpolate of a 1x1 map to HxW (bilinear, align_corners=True: a constant map; train.py:489)."""
+        assert y.H == 1 and y.W == 1
+        out = Val(y.N, H, W, y.C, self._rg(y), "bcast")
+        self.ops.append(Op("bcast", [y], out))
+        return out
+
     def add(self, a, b):
         out = Val(a.N, a.H, a.W, a.C, self._rg(a, b), "add")
         self.ops.append(Op("add", [a, b], out))
@@ -212,7 +225,7 @@ _WRITES = {
     "hg_conv_dgrad": (4,), "hg_conv_fprop_bnout": (5, 6), "hg_bn_stats": (2,), "hg_bn_apply": (7,), "hg_bn_bwd_apply": (10,),
     "hg_bn_bwd_reduce": (8,), "hg_conv_fprop_bn": (6, 7, 8), "hg_conv_dgrad_bn": (5, 6),
     "hg_maxpool2_fwd": (6, 7), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8, 9), "hg_upsample2x_bwd": (8,),
-    "hg_add": (3,),
+    "hg_add": (3,), "hg_spatial_mean": (8,), "hg_spatial_broadcast": (8,),
 }
 
 
@@ -631,6 +644,18 @@ class Plan:
                            C.c_longlong(out.numel_padded()), st)
                 if out.needs_stats:
                     self._stats_call(f, out)
+            elif k == "gap":
+                x, out = op.ins[0], op.out
+                self._emit(f, "hg_spatial_mean", self.hdt, L.ptr(x.buf), x.N, x.H, x.W, x.C,
+                           C.c_float(1.0 / (x.H * x.W)), None, L.ptr(out.buf), st)
+                if out.needs_stats:
+                    self._stats_call(f, out)
+            elif k == "bcast":
+                y, out = op.ins[0], op.out
+                self._emit(f, "hg_spatial_broadcast", self.hdt, L.ptr(y.buf), out.N, out.H, out.W, out.C,
+                           C.c_float(1.0), None, L.ptr(out.buf), st)
+                if out.needs_stats:
+                    self._stats_call(f, out)
             elif k == "export":
                 v = op.ins[0]
                 self._emit(f, "hg_nhwc_to_nchw_f32", self.hdt, L.ptr(v.buf), v.N, v.C, v.H, v.W,
@@ -792,6 +817,18 @@ class Plan:
             elif k == "add":
                 self._grad_passthrough(op.ins[0], G)
                 self._grad_passthrough(op.ins[1], G)
+            elif k == "gap":
+                x = op.ins[0]
+                if x.requires_grad:
+                    addend, dst = self._grad_target(x)
+                    self._emit(g, "hg_spatial_broadcast", self.hdt, L.ptr(G), x.N, x.H, x.W, x.C,
+                               C.c_float(1.0 / (x.H * x.W)), L.ptr(addend), L.ptr(dst), st)
+            elif k == "bcast":
+                y = op.ins[0]
+                if y.requires_grad:
+                    addend, dst = self._grad_target(y)
+                    self._emit(g, "hg_spatial_mean", self.hdt, L.ptr(G), out.N, out.H, out.W, out.C, C.c_float(1.0),
+                               L.ptr(addend), L.ptr(dst), st)
             elif k == "stem":
                 cv, x = op.attrs["conv"], op.ins[0]
                 self._emit(g, "hg_stem_bwd", self.hdt, L.ptr(x.buf), L.ptr(out.buf), L.ptr(G), x.N, x.H, x.W,

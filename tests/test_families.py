@@ -215,3 +215,79 @@ def test_family_bf16_train_step_runs_and_replays(script, factory, fixture):
         assert err0 <= max(0.3, 2 * float(g["out_noise_bf16"][0])), err0  # reference's own bf16 run: 0.13 - 0.44
         for n, p in net.named_parameters():
             assert p.grad is None or torch.isfinite(p.grad).all(), n
+
+
+def _aspp_net(mod_cls):
+    torch.manual_seed(0)
+    net = mod_cls()
+    with torch.no_grad():   # the BatchNorm parameters / running statistics of oracle/make_golden.py::golden_aspp
+        g = torch.Generator().manual_seed(5)
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
+                m.running_mean.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.bias.shape, generator=g) + 0.5)
+    return net
+
+
+def test_aspp_block_state_dict_matches_reference():
+    """Same keys, shapes and seeded values as train.ASPP_Block (train.py:465-495)."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference tree not present (GPU box)")
+    import progressive_process_for_human_pose_estimation_b200.train as tr
+    ref = refload.load("train")
+    torch.manual_seed(0)
+    a = tr.ASPP_Block().state_dict()
+    torch.manual_seed(0)
+    b = ref.ASPP_Block().state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-4), (torch.bfloat16, 3e-2)])
+def test_aspp_block_matches_reference_golden(dtype, tol):
+    """Executed ASPP: dilated 3x3 branches (6/12/18), image-level branch (global average pool -> 1x1 ->
+    BN over [B,256,1,1] -> broadcast), virtual cat 1280 -> 256; train-mode forward/backward and eval-mode forward
+    against the reference's own train.ASPP_Block run on the CPU (tests/golden/aspp_block.npz)."""
+    import progressive_process_for_human_pose_estimation_b200 as hg
+    import progressive_process_for_human_pose_estimation_b200.train as tr
+    g = np.load(os.path.join(GOLDEN, "aspp_block.npz"))
+    hg.set_compute_dtype(dtype)
+    try:
+        gen = torch.Generator().manual_seed(6)
+        x = torch.randn(4, 256, 8, 8, generator=gen)
+        w = torch.randn(4, 256, 8, 8, generator=gen)
+        net = _aspp_net(tr.ASPP_Block).cuda().train()
+        xc = x.cuda().requires_grad_()
+        out = net(xc)
+        (out * w.cuda()).sum().backward()
+        # bf16: the reference's own autocast(bf16) run is 6e-2 away from its fp32 run in the input gradient (BatchNorm
+        # over the 4 samples of the image-level branch); the yardstick is part of the fixture (parity protocol iv)
+        ac_out, ac_gx = (float(v) for v in g["noise_bf16_autocast"]) if dtype == torch.bfloat16 else (0.0, 0.0)
+        gtol = max(2 * tol, 1.5 * ac_gx)
+        assert rel(out.detach().cpu(), torch.from_numpy(g["out_train"])) <= max(tol, 1.5 * ac_out)
+        assert rel(xc.grad.cpu(), torch.from_numpy(g["gx"])) <= gtol
+        gp = torch.Generator().manual_seed(7)
+        for (k, p), name, norm, proj in zip(net.named_parameters(), g["grad_names"], g["grad_norm"], g["grad_proj"]):
+            assert k == str(name)
+            r = torch.randn(p.numel(), generator=gp).double()
+            got = p.grad.detach().double().cpu().flatten()
+            scale = max(float(norm), 1e-3 * float(np.max(g["grad_norm"])))   # bias-like gradients that are ~0
+            assert abs(got.norm().item() - norm) <= 2 * gtol * scale, k
+            assert abs((got * r).sum().item() - proj) <= 4 * gtol * scale, k
+        sd = net.state_dict()
+        assert rel(sd["conv1.1.running_mean"].cpu(), torch.from_numpy(g["running_mean_after"])) <= 2 * tol
+        assert rel(sd["global_avg_pool.2.running_var"].cpu(), torch.from_numpy(g["gap_running_var_after"])) <= 2 * tol
+        net = _aspp_net(tr.ASPP_Block).cuda().eval()
+        with torch.no_grad():
+            oe = net(x.cuda())
+        assert rel(oe.cpu(), torch.from_numpy(g["out_eval"].astype(np.float32))) <= tol + 1e-3
+        torch.manual_seed(1)
+        am = tr._ASPPModule(256, 256, 3, padding=6, dilation=6).cuda().train()
+        om = am(x.cuda())
+        assert rel(om.detach().cpu(), torch.from_numpy(g["out_module"].astype(np.float32))) <= tol + 1e-3
+    finally:
+        hg.set_compute_dtype(torch.bfloat16)

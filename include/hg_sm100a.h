@@ -325,7 +325,8 @@ HG_API int hg_render_gauss(const HgGaussDesc* d, const double* keypoints, const 
 typedef struct HgLabelDesc {
   int32_t B, P, J, L, H, W;
   int32_t center_mode;
-  int32_t draw_points; /* draw.point value k+1 for visible joints */
+  int32_t draw_points; /* 1: draw.point value k+1 for visible joints; 2: MPII draw.ellipse on the float centre +-0.5
+                          (train.py:681-686) */
   int32_t draw_lines;  /* draw.line for limbs whose both ends are visible */
   int32_t line_value;  /* 0: limb index + 1, otherwise this constant (background map = 1) */
 } HgLabelDesc;

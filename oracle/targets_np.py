@@ -114,7 +114,19 @@ def label_map(persons, img_wh, J, limbs, H=64, W=64, center_mode=0, draw_points=
         x = centres(persons[p, :, 0], img_wh[0], W, center_mode, True)
         y = centres(persons[p, :, 1], img_wh[1], H, center_mode, True)
         v = persons[p, :, 2]
-        if draw_points:
+        if draw_points == 2:
+            # MPII keypoint map (train.py:681-686): ellipse((x-.5, y-.5, x+.5, y+.5)) of the float centre; Pillow
+            # (12.2, Draw.c) truncates the box toward zero and fills it, except a box collapsed to a single point
+            fx = centres(persons[p, :, 0], img_wh[0], W, center_mode, False)
+            fy = centres(persons[p, :, 1], img_wh[1], H, center_mode, False)
+            for k in range(J):
+                if v[k] > 0:
+                    x0, y0, x1, y1 = int(fx[k] - 0.5), int(fy[k] - 0.5), int(fx[k] + 0.5), int(fy[k] + 0.5)
+                    if x1 > x0 or y1 > y0:
+                        for yy in range(y0, y1 + 1):
+                            for xx in range(x0, x1 + 1):
+                                _put(canvas, xx, yy, k + 1)
+        elif draw_points:
             for k in range(J):
                 if v[k] > 0:
                     draw_point(canvas, x[k], y[k], k + 1)

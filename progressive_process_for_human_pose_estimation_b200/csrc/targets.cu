@@ -108,6 +108,18 @@ __global__ void __launch_bounds__(128) render_labels_kernel(HgLabelDesc d, const
       if (d.draw_points) {
         for (int j = 0; j < d.J; ++j) {
           if (!(k[3 * j + 2] > 0.0)) continue;
+          if (d.draw_points == 2) {
+            // MPII keypoint map (train.py:681-686): ImageDraw.ellipse((x-.5, y-.5, x+.5, y+.5)) of the FLOAT centre.
+            // Pillow truncates the four box coordinates toward zero; a 1x1 / 1x2 / 2x1 / 2x2 box is filled
+            // completely, a box that collapses to one point (both extents 0) draws nothing (Pillow 12.2 Draw.c).
+            const double fx = centre_of(k[3 * j], iw, (double)d.W, d.center_mode, 0);
+            const double fy = centre_of(k[3 * j + 1], ih, (double)d.H, d.center_mode, 0);
+            const int x0 = (int)(fx - 0.5), y0 = (int)(fy - 0.5), x1 = (int)(fx + 0.5), y1 = (int)(fy + 0.5);
+            if (x1 > x0 || y1 > y0)
+              for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) put8(canvas, d.W, d.H, xx, yy, j + 1);
+            continue;
+          }
           const int x = (int)centre_of(k[3 * j], iw, (double)d.W, d.center_mode, 1);
           const int y = (int)centre_of(k[3 * j + 1], ih, (double)d.H, d.center_mode, 1);
           put8(canvas, d.W, d.H, x, y, j + 1);

@@ -58,13 +58,16 @@ def label_maps(persons, img_wh, limbs, H=64, W=64, num_persons=None, center_mode
                draw_lines=True, line_value=0, device="cuda"):
     """Integer label maps [B, H, W] int64 drawn like PIL's ImageDraw.point / ImageDraw.line
     (try_different_stack.py:146-155: skeleton map = limbs with value i+1, background map = limbs with value 1;
-    try_skeleton_and_keypoints.py:104-111: keypoint map = points with value k+1)."""
+    try_skeleton_and_keypoints.py:104-111: keypoint map = points with value k+1).
+    draw_points="ellipse" (with center_mode=1): the MPII keypoint map of train.py:668-690, ImageDraw.ellipse on the
+    float centre +-0.5; its skeleton map is draw_lines with center_mode=1."""
     persons, img_wh, num_persons, B, P, J = _prep(persons, img_wh, num_persons, device)
     limbs_t = torch.as_tensor(np.asarray(limbs, dtype=np.int32).reshape(-1, 2)).to(persons.device).contiguous()
     if limbs_t.numel() and (int(limbs_t.max()) >= J or int(limbs_t.min()) < 0):
         raise ValueError("limb end point index out of range")
     out = torch.empty(B, H, W, device=persons.device, dtype=torch.int64)
-    d = L.HgLabelDesc(B, P, J, limbs_t.shape[0], H, W, center_mode, 1 if draw_points else 0, 1 if draw_lines else 0,
+    d = L.HgLabelDesc(B, P, J, limbs_t.shape[0], H, W, center_mode,
+                      2 if draw_points == "ellipse" else (1 if draw_points else 0), 1 if draw_lines else 0,
                       int(line_value))
     with torch.cuda.device(persons.device):
         L.call("hg_render_labels", C.byref(d), L.ptr(persons), L.ptr(num_persons), L.ptr(img_wh), L.ptr(limbs_t),

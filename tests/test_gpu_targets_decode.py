@@ -93,6 +93,30 @@ def test_label_maps_bit_exact(mode):
     assert int(got[0].abs().sum()) == 0
 
 
+def test_mpii_label_maps_bit_exact():
+    """MPII keypoint (ImageDraw.ellipse on the float centre) and skeleton maps of train.py:668-690 against the numpy
+    oracle (pinned to Pillow by tests/test_oracle_targets_pckh.py::test_mpii_label_maps_match_pillow)."""
+    sks = [[0, 1], [1, 2], [2, 6], [6, 3], [3, 4], [4, 5], [6, 7], [7, 8], [8, 9], [10, 11], [11, 12], [12, 7], [7, 13],
+           [13, 14], [14, 15]]
+    r = np.random.RandomState(4)
+    B = 16
+    wh = np.stack([r.randint(150, 900, B), r.randint(150, 900, B)], 1).astype(np.float64)
+    kp = np.zeros([B, 1, 16, 3])
+    kp[:, 0, :, 0] = r.uniform(-6, 1, [B, 16]) + r.rand(B, 16) * wh[:, :1]
+    kp[:, 0, :, 1] = r.uniform(-6, 1, [B, 16]) + r.rand(B, 16) * wh[:, 1:]
+    kp[0, 0, :4, 0] = np.array([0.1, 0.49, 0.5, 63.6]) * wh[0, 0] / 64      # collapsed / clipped ellipse boxes
+    kp[0, 0, :4, 1] = np.array([0.2, 0.3, 63.9, 0.4]) * wh[0, 1] / 64
+    kp[..., 2] = r.rand(B, 1, 16) < 0.8
+    gk = hg.label_maps(kp, wh, sks, center_mode=1, draw_points="ellipse", draw_lines=False)
+    gs = hg.label_maps(kp, wh, sks, center_mode=1, draw_lines=True)
+    for b in range(B):
+        rk = targets_np.label_map(kp[b], wh[b], 16, sks, center_mode=1, draw_points=2, draw_lines=False)
+        rs = targets_np.label_map(kp[b], wh[b], 16, sks, center_mode=1, draw_lines=True)
+        assert np.array_equal(gk[b].cpu().numpy(), rk), b
+        assert np.array_equal(gs[b].cpu().numpy(), rs), b
+    assert int((gk > 0).sum()) > 0
+
+
 def _heatmaps(seed, B, C, dtype):
     r = np.random.RandomState(seed)
     x = torch.from_numpy(r.randn(B, C, 64, 64).astype(np.float32))

@@ -52,6 +52,43 @@ def test_rasteriser_matches_pillow():
         assert np.array_equal(np.array(im), cv), c
 
 
+def test_mpii_label_maps_match_pillow():
+    """MPII keypoint / skeleton label maps (train.py:668-690): the oracle against the reference's own statements run
+    with Pillow (the third-party rasteriser of this path; 12.2.0 in this image): ImageDraw.ellipse on the float
+    centre +-0.5 and ImageDraw.line on float end points, including centres on and beyond the canvas border."""
+    from PIL import Image, ImageDraw
+    sks = [[0, 1], [1, 2], [2, 6], [6, 3], [3, 4], [4, 5], [6, 7], [7, 8], [8, 9], [10, 11], [11, 12], [12, 7], [7, 13],
+           [13, 14], [14, 15]]
+    r = np.random.RandomState(3)
+    for trial in range(40):
+        w, h = r.randint(150, 900), r.randint(150, 900)
+        pts = np.zeros([16, 3])
+        pts[:, 0] = r.uniform(-6, w + 6, 16)
+        pts[:, 1] = r.uniform(-6, h + 6, 16)
+        if trial % 5 == 0:
+            pts[:4, 0] = [0.1 * w / 64, 0.49 * w / 64, 0.5 * w / 64, 63.6 * w / 64]   # box collapses / clips
+            pts[:4, 1] = [0.2 * h / 64, 0.3 * h / 64, 63.9 * h / 64, 0.4 * h / 64]
+        pts[:, 2] = r.rand(16) < 0.8
+        inputsize = 256
+        kmap = Image.fromarray(np.zeros([64, 64], dtype=np.uint8))
+        smap = Image.fromarray(np.zeros([64, 64], dtype=np.uint8))
+        dk, ds = ImageDraw.Draw(kmap), ImageDraw.Draw(smap)
+        xs = pts[:, 0] * inputsize / w / 4
+        ys = pts[:, 1] * inputsize / h / 4
+        v = pts[:, 2]
+        for i in range(16):
+            if v[i] > 0:
+                size = 1
+                dk.ellipse((xs[i] - size / 2, ys[i] - size / 2, xs[i] + size / 2, ys[i] + size / 2), fill=i + 1)
+        for i, sk in enumerate(sks):
+            if np.all(v[sk]) > 0:
+                ds.line(np.stack([xs[sk], ys[sk]], axis=1).reshape([-1]).tolist(), i + 1)
+        got_k = targets_np.label_map(pts[None], (w, h), 16, sks, center_mode=1, draw_points=2, draw_lines=False)
+        got_s = targets_np.label_map(pts[None], (w, h), 16, sks, center_mode=1, draw_points=False, draw_lines=True)
+        assert np.array_equal(got_k, np.array(kmap).astype(np.int64)), trial
+        assert np.array_equal(got_s, np.array(smap).astype(np.int64)), trial
+
+
 def test_gauss_variants_against_reference_expressions():
     """Float-centre / x100 / accumulate variants evaluated with the reference's own numpy expressions."""
     import numpy.matlib  # noqa: F401

@@ -154,12 +154,23 @@ struct ConvGemmSmem {
   static constexpr int kTotal = kMainBytes + kBarBytes + kBiasBytes + kCoefBytes + 1024 /*align slack*/;
 };
 
+// Epilogue warps.  One-wave grids (MINB == 1: one CTA per SM, pure latency): two warps per TMEM lane quarter, each takes
+// half of the tile's columns -- a single warp per SM sub-partition has nothing to hide its tcgen05.ld / shared-memory
+// latencies behind (3x3 @4x4 9.2 -> 8.8 us, 1x1 5.2 -> 5.0 us).  Multi-wave grids keep four warps: the co-resident
+// CTAs already interleave, and the extra threads only cost (1x1 @64x64 24.6 -> 25.7 us with eight).
+template <int MINB>
+struct ConvThreads {
+  static constexpr int kEpi = MINB == 1 ? 256 : 128;
+  static constexpr int kAll = 64 + kEpi;
+};
+
 template <int BN, int STAGES, int MINB, int MODE, bool ALIAS>
-__global__ void __launch_bounds__(192, MINB)
+__global__ void __launch_bounds__(ConvThreads<MINB>::kAll, MINB)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvGemmParams p) {
   using L = ConvGemmSmem<BN, STAGES, MODE, ALIAS>;
+  constexpr int kEpiThreads = ConvThreads<MINB>::kEpi;
   static_assert(3 * STAGES + 2 <= 30, "barrier region too small");
   extern __shared__ uint8_t smem_raw[];
   // (pointer arithmetic on the shared array keeps the address space: LDS/STS instead of generic LD/ST)
@@ -194,7 +205,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&ready_bar[s], 128);
+      mbar_init(&ready_bar[s], kEpiThreads);
     }
     mbar_init(tmem_full, 1);
     mbar_init(res_full, 1);
@@ -286,9 +297,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool row_ok = m < p.M_total;
     {
       const int et = threadIdx.x - 64;
-    for (int c = et; c < BN; c += 128) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
+    for (int c = et; c < BN; c += kEpiThreads) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
     if constexpr (MODE == kPlainBnOut) {   // y = scale * acc + (scale * bias + shift)
-      for (int c = et; c < BN; c += 128) {
+      for (int c = et; c < BN; c += kEpiThreads) {
         float mu, is, sc, sh;
         bn_fold_coeffs(p.fold, n_off + c, mu, is, sc, sh);
         coef_s[c] = sc;
@@ -297,7 +308,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if constexpr (MODE == kFold) {
       // scale / shift of every INPUT channel (<= 256)
-      for (int c = et; c < p.kchunks * 64; c += 128) {
+      for (int c = et; c < p.kchunks * 64; c += kEpiThreads) {
         float mu, is, sc, sh;
         bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
         coef_s[c] = sc;
@@ -305,7 +316,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if constexpr (MODE == kMask) {
-      for (int c = et; c < BN; c += 128) {
+      for (int c = et; c < BN; c += kEpiThreads) {
         float mu, is, sc, sh;
         bn_fold_coeffs(p.fold, n_off + c, mu, is, sc, sh);
         coef_s[c] = sc;                 // ReLU mask: scale * y + shift > 0 (the forward's own expression)
@@ -315,22 +326,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     }
-    const int et = threadIdx.x - 64;    // 0..127
-    named_bar_sync(1, 128);             // coefficients visible to the four epilogue warps
+    const int et = threadIdx.x - 64;    // 0..kEpiThreads-1
+    named_bar_sync(1, kEpiThreads);     // coefficients visible to the epilogue warps
 
     if constexpr (MODE == kFold) {
       // Rewrite every A tile in place: a = [relu](scale * x + shift).  Thread = one 16-byte channel chunk (8
-      // channels: its 16 coefficients live in registers) x 8 rows, so the eight shared-memory loads of a tile are
+      // channels: its 16 coefficients live in registers) x kR rows, so the shared-memory loads of a tile are
       // issued back to back.  Rows that fall into the convolution padding (TMA zero fill) or past the end of the
       // tensor must be zero AFTER the transform.
       const int jch = et & 7;
-      const int rbase = et >> 3;                 // rows rbase + 16 * i
+      constexpr int kRB = kEpiThreads / 8;       // row bases (32)
+      constexpr int kR = 128 / kRB;              // rows per thread (4)
+      const int rbase = et >> 3;                 // rows rbase + kRB * i
       const int swz = (jch ^ (rbase & 7)) << 4;  // (row & 7) == (rbase & 7) for every row of this thread
       const int hw = p.H * p.W;
-      int hrow[8], wrow[8];
+      int hrow[kR], wrow[kR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int mm = m0 + rbase + 16 * i;
+      for (int i = 0; i < kR; ++i) {
+        const int mm = m0 + rbase + kRB * i;
         const int rem = mm % hw;
         hrow[i] = mm < p.M_total ? rem / p.W : -0x40000000;  // out-of-range rows never pass the bounds test
         wrow[i] = rem % p.W;
@@ -343,7 +356,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int dw = p.sign * (s * p.dil - p.pad);
           uint32_t vmask = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < kR; ++i)
             if ((unsigned)(hrow[i] + dh) < (unsigned)p.H && (unsigned)(wrow[i] + dw) < (unsigned)p.W) vmask |= 1u << i;
           for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
             const int st = kb % STAGES;
@@ -353,14 +366,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             load_coef8(coef_s + 256 + kc * 64 + jch * 8, sh);
             uint8_t* base = sA + st * L::kABytes + rbase * 128 + swz;
             mbar_wait(&full_bar[st], ph);
-            uint4 u[8];
+            uint4 u[kR];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(base + i * 2048);
+            for (int i = 0; i < kR; ++i) u[i] = *reinterpret_cast<const uint4*>(base + i * kRB * 128);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < kR; ++i)
               u[i] = (vmask >> i) & 1u ? bn_relu_chunk(u[i], sc, sh, relu) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(base + i * 2048) = u[i];
+            for (int i = 0; i < kR; ++i) *reinterpret_cast<uint4*>(base + i * kRB * 128) = u[i];
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
             mbar_arrive(&ready_bar[st]);
           }
@@ -383,8 +396,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     // kMask: second staging buffer (masked gradient G, bf16) inside the idle pipeline stages
     uint8_t* sQ = smem + L::kQOffset;
+    constexpr int kColSplit = kEpiThreads / 128;          // warps per TMEM lane quarter (1 or 2)
+    const int chalf = (warp - 2) >> 2;                    // which part of the tile's columns this warp stages
 #pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
+    for (int j = chalf * (BN / 32 / kColSplit); j < (chalf + 1) * (BN / 32 / kColSplit); ++j) {
       float v[32];
       tmem_ld32(taddr + j * 32, v);
       tmem_ld_wait();
@@ -454,7 +469,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (HG_TS && blockIdx.x == 0 && et == 0) p.ts[7] = clock64();
     tc_fence_before();
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, kEpiThreads);
     if (et == 0) {
       const uint8_t* src = MODE == kMask ? sQ : sC;
       for (int pnl = 0; pnl < L::kCPanels; ++pnl) tma_store_2d(&tmC, src + pnl * 16384, n_off + pnl * 64, m0);
@@ -470,10 +485,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int valid = p.M_total - m0;
       valid = valid > 128 ? 128 : valid;
       constexpr int kQuads = BN / 4;            // 32 or 16
-      constexpr int kGroups = 128 / kQuads;     // row slices: 4 or 8
-      constexpr int kRows = 128 / kGroups;      // 32 or 16
-      for (int i = et; i < 2 * BN; i += 128) acc_s[i] = 0.f;
-      named_bar_sync(1, 128);
+      constexpr int kGroups = kEpiThreads / kQuads;   // row slices: 8 or 16
+      constexpr int kRows = 128 / kGroups;            // 16 or 8
+      for (int i = et; i < 2 * BN; i += kEpiThreads) acc_s[i] = 0.f;
+      named_bar_sync(1, kEpiThreads);
       {
         const int quad = et % kQuads, grp = et / kQuads;
         const int c = quad * 4;
@@ -507,7 +522,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           atomicAdd(acc_s + BN + c + e, q4[e]);
         }
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (et < 2 * kQuads) {
         const int which = et / kQuads, quad = et % kQuads;
         float4 v4 = *reinterpret_cast<const float4*>(acc_s + which * BN + quad * 4);
@@ -569,7 +584,8 @@ static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     attr_set = true;
   }
   dim3 grid(ceil_div(p.M_total, 128) * p.n_tiles);
-  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(192), L::kTotal, st, tmA, tmB, tmC, tmR, p);
+  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB>::kAll), L::kTotal, st, tmA,
+           tmB, tmC, tmR, p);
   HG_LAUNCH_OK("conv_gemm_kernel");
   count_launch();
   return HG_OK;

@@ -24,6 +24,9 @@
 #define HG_DBG_TS 0
 #endif
 #define HG_TS (HG_DBG_TS && p.ts)
+#ifndef HG_EPI_ONEWAVE
+#define HG_EPI_ONEWAVE 256
+#endif
 
 namespace hg {
 
@@ -158,19 +161,19 @@ struct ConvGemmSmem {
 // half of the tile's columns -- a single warp per SM sub-partition has nothing to hide its tcgen05.ld / shared-memory
 // latencies behind (3x3 @4x4 9.2 -> 8.8 us, 1x1 5.2 -> 5.0 us).  Multi-wave grids keep four warps: the co-resident
 // CTAs already interleave, and the extra threads only cost (1x1 @64x64 24.6 -> 25.7 us with eight).
-template <int MINB>
+template <int MINB, int BN>
 struct ConvThreads {
-  static constexpr int kEpi = MINB == 1 ? 256 : 128;
+  static constexpr int kEpi = MINB == 1 ? (BN >= 128 ? HG_EPI_ONEWAVE : 256) : 128;
   static constexpr int kAll = 64 + kEpi;
 };
 
 template <int BN, int STAGES, int MINB, int MODE, bool ALIAS>
-__global__ void __launch_bounds__(ConvThreads<MINB>::kAll, MINB)
+__global__ void __launch_bounds__(ConvThreads<MINB, BN>::kAll, MINB)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvGemmParams p) {
   using L = ConvGemmSmem<BN, STAGES, MODE, ALIAS>;
-  constexpr int kEpiThreads = ConvThreads<MINB>::kEpi;
+  constexpr int kEpiThreads = ConvThreads<MINB, BN>::kEpi;
   static_assert(3 * STAGES + 2 <= 30, "barrier region too small");
   extern __shared__ uint8_t smem_raw[];
   // (pointer arithmetic on the shared array keeps the address space: LDS/STS instead of generic LD/ST)
@@ -584,7 +587,7 @@ static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     attr_set = true;
   }
   dim3 grid(ceil_div(p.M_total, 128) * p.n_tiles);
-  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB>::kAll), L::kTotal, st, tmA,
+  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB, BN>::kAll), L::kTotal, st, tmA,
            tmB, tmC, tmR, p);
   HG_LAUNCH_OK("conv_gemm_kernel");
   count_launch();

@@ -217,6 +217,11 @@ HG_API int hg_spatial_mean(int dtype, const void* x, int N, int H, int W, int C,
                            void* stream);
 HG_API int hg_spatial_broadcast(int dtype, const void* y, int N, int H, int W, int C, float scale, const void* addend,
                                 void* x, void* stream);
+/* Channel-window copy between NHWC tensors of `rows` pixels (channels padded to 64 in memory):
+ * dst[r, dst_c0 + c] = src[r, src_c0 + c] [+ addend[r, dst_c0 + c]], c < channels (rounded up to 8).  One call per
+ * input of a materialised torch.cat(xs, 1) (train.py:528-538,570-583); with the roles swapped, its backward. */
+HG_API int hg_channel_copy(int dtype, const void* src, int src_channels, int src_c0, const void* addend, void* dst,
+                           int dst_channels, int dst_c0, int channels, long long rows, void* stream);
 HG_API int hg_add(int dtype, const void* a, const void* b, void* out, long long n_elems, void* stream);
 /* layout changes at the module boundary (NCHW fp32 tensors of the training loop <-> NHWC activations) */
 HG_API int hg_nchw_f32_to_nhwc(int dtype, const float* src_nchw, const void* addend, int N, int C, int H, int W, void* dst,

@@ -246,6 +246,7 @@ FAMILIES = [
     ("try_with_aspp_remove_max_pool", "creatModel"),
     ("try_skeleton_and_keypoints", "creatModel"),
     ("hourglass_compare", "creatModel"),  # = performance_compare.creatModel_hourglass (same network, same fixture)
+    ("train", "creatModel"),              # progressive model: Q4 blocks, stride-2 down-sampling, ASPP bottom, cat skips
 ]
 
 
@@ -263,13 +264,15 @@ def randomize_running_stats(net, seed=5):
             mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
 
 
-def golden_families():
+def golden_families(only=None):
     """One seeded fp32 step (forward, sum of per-output MSE against uniform random targets, backward) of every
     other model family the drop-in mirrors, executed by the REFERENCE classes: outputs, losses, digests of every
     gradient and of the state_dict before / after (BN running statistics).  B=2, 128x128 input.  Two variants:
     `train` (batch statistics: chaotic at random init, SURVEY Q13 -- checked against the fp64 yardstick stored with
     it) and `eval` (seeded running statistics: well conditioned, so forward AND backward parity are tight)."""
     for script, factory in FAMILIES:
+        if only is not None and script not in only:
+            continue
         for mode in ("train", "eval"):
             ref = refload.load(script)
             torch.manual_seed(0)

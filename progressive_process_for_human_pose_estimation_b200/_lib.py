@@ -108,6 +108,7 @@ SIGNATURES = {
     "hg_upsample2x_bwd": [_I, _I, _P, _P, _I, _I, _I, _I, _P, _P],
     "hg_spatial_mean": [_I, _P, _I, _I, _I, _I, C.c_float, _P, _P, _P],
     "hg_spatial_broadcast": [_I, _P, _I, _I, _I, _I, C.c_float, _P, _P, _P],
+    "hg_channel_copy": [_I, _P, _I, _I, _P, _P, _I, _I, _I, _LL, _P],
     "hg_add": [_I, _P, _P, _P, _LL, _P],
     "hg_nchw_f32_to_nhwc": [_I, _P, _P, _I, _I, _I, _I, _P, _P],
     "hg_nhwc_to_nchw_f32": [_I, _P, _I, _I, _I, _I, _P, _P],

@@ -292,6 +292,91 @@ def make_aspp_block(g=None):
     return _ASPPModule, ASPP_Block
 
 
+def make_train_family(g):
+    """train.py:411-601, the progressive multi-branch model: Q4 residual blocks, an un-shared hourglass
+    whose four down-sampling steps are stride-2 blocks, whose bottom is the executed ASPP block and whose up path is
+    nearest x2 -> block(f -> f/2) -> cat with the skip branch; three stages with bias-free heads (2 / 16 / 17 channels
+    by default) re-injected as cat[conv(head), conv(ll), conv(inter)]."""
+    ResidualBlock = make_q4_block(g)
+    _ASPPModule, ASPP_Block = make_aspp_block(g)
+
+    class hourglass(HGModule):
+        def __init__(self, f):
+            super(hourglass, self).__init__()
+            self.f = f
+            self.downsample1 = ResidualBlock(f, f, stride=2)
+            self.downsample2 = ResidualBlock(f, f, stride=2)
+            self.downsample3 = ResidualBlock(f, f, stride=2)
+            self.downsample4 = ResidualBlock(f, f, stride=2)
+            self.residual1 = ResidualBlock(f, int(f / 2))
+            self.residual2 = ResidualBlock(f, int(f / 2))
+            self.residual3 = ResidualBlock(f, int(f / 2))
+            self.residual4 = ResidualBlock(f, int(f / 2))
+            self.upsample1 = ResidualBlock(f, int(f / 2))
+            self.upsample2 = ResidualBlock(f, int(f / 2))
+            self.upsample3 = ResidualBlock(f, int(f / 2))
+            self.upsample4 = ResidualBlock(f, int(f / 2))
+            self.aspp = ASPP_Block()
+
+        def _emit(self, b, x):
+            ups, down = [], x
+            for lvl, (res, ds) in enumerate(((self.residual1, self.downsample1), (self.residual2, self.downsample2),
+                                             (self.residual3, self.downsample3), (self.residual4, self.downsample4))):
+                with b.on_lane(lvl + 1):           # skip branches are independent of the deeper path
+                    ups.append(res._emit(b, down))
+                down = ds._emit(b, down)
+            out = self.aspp._emit(b, down)
+            for up_block, skip in ((self.upsample4, ups[3]), (self.upsample3, ups[2]), (self.upsample2, ups[1]),
+                                   (self.upsample1, ups[0])):
+                out = b.upsample2x_add(out, None, mode="nearest")   # F.interpolate(out, scale_factor=2)
+                out = up_block._emit(b, out)
+                out = b.cat([out, skip])
+            return out
+
+    class creatModel(HGModule):
+        _is_model = True
+
+        def __init__(self):
+            super(creatModel, self).__init__()
+            nFeats = g["nFeats"]
+            self.preprocess1 = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3), nn.ReLU(), ResidualBlock(64, 128, stride=2),
+                                             ResidualBlock(128, 128), ResidualBlock(128, nFeats))
+            self.stage1 = hourglass(nFeats)
+            self.stage1_out = nn.Conv2d(nFeats, g["nOutChannels_0"], 1, 1, 0, bias=False)
+            self.stage1_return = nn.Conv2d(g["nOutChannels_0"], int(nFeats / 2), 1, 1, 0, bias=False)
+            self.stage1_retuen_2 = nn.Conv2d(nFeats, int(nFeats / 4), 1, 1, 0, bias=False)
+            self.stage1_down_feature = nn.Conv2d(nFeats, int(nFeats / 4), 1, 1, 0, bias=False)
+            self.stage2 = hourglass(nFeats)
+            self.stage2_out = nn.Conv2d(nFeats, g["nOutChannels_1"], 1, 1, 0, bias=False)
+            self.stage2_return = nn.Conv2d(g["nOutChannels_1"], int(nFeats / 2), 1, 1, 0, bias=False)
+            self.stage2_retuen_2 = nn.Conv2d(nFeats, int(nFeats / 4), 1, 1, 0, bias=False)
+            self.stage2_down_feature = nn.Conv2d(nFeats, int(nFeats / 4), 1, 1, 0, bias=False)
+            self.stage3 = hourglass(nFeats)
+            self.stage3_out = nn.Conv2d(nFeats, g["nOutChannels_2"], 1, 1, 0, bias=False)
+
+        def _emit(self, b, x):
+            pre = self.preprocess1
+            inter = b.stem(pre[0], x)
+            for blk in (pre[2], pre[3], pre[4]):
+                inter = blk._emit(b, inter)
+            out = []
+            for i, (stage, head, ret, ret2, down) in enumerate((
+                    (self.stage1, self.stage1_out, self.stage1_return, self.stage1_retuen_2, self.stage1_down_feature),
+                    (self.stage2, self.stage2_out, self.stage2_return, self.stage2_retuen_2, self.stage2_down_feature),
+                    (self.stage3, self.stage3_out, None, None, None))):
+                ll = stage._emit(b, inter)
+                tmpOut = b.conv(head, ll, head=True)
+                out.insert(i, tmpOut)
+                if ret is not None:
+                    inter = b.cat([b.conv(ret, tmpOut), b.conv(ret2, ll), b.conv(down, inter)])
+            return out
+
+    for cls in (hourglass, creatModel):
+        cls.__module__ = g.get("__name__", cls.__module__)
+        cls.__qualname__ = cls.__name__
+    return ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel
+
+
 def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4):
     """Shared body of the multi-head creatModel variants: per-stack heads conv2_k and re-injection conv4_k over a
     concatenation (try_different_stack.py:300-329; try_with_aspp_remove_max_pool.py:277-304)."""

@@ -387,6 +387,33 @@ __global__ void __launch_bounds__(256) spatial_bcast_kernel(const T* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Channel-window copy: dst[r, dst_c0 + c] = src[r, src_c0 + c] [+ addend[r, dst_c0 + c]] for c < 8 * vecs.
+// torch.cat(xs, dim=1) whose result feeds a BatchNorm (train.py:528-538,570-583) is one call per input; its backward
+// (a channel slice of the gradient, accumulated into the input's gradient) is the same kernel with the roles swapped.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) channel_copy_kernel(const T* __restrict__ src, int src_Cp, int src_c0,
+                                                           const T* __restrict__ addend, T* __restrict__ dst, int dst_Cp,
+                                                           int dst_c0, int vecs, long long total) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vecs;
+    const int v = (int)(i - r * vecs);
+    float x[8];
+    load8(src + r * src_Cp + src_c0 + v * 8, x);
+    if (addend) {
+      float a[8];
+      load8(addend + r * dst_Cp + dst_c0 + v * 8, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] += a[e];
+    }
+    store8(dst + r * dst_Cp + dst_c0 + v * 8, x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Input pipeline tail (next row N1): transforms.ToTensor() + transforms.Normalize(mean, std) of the reference's
 // datasets (try_with_torch.py:310-313: mean = std = 0.5) on the GPU -- uint8 HWC pixels in, fp32 NCHW planes out,
 // the exact fp32 operations of torchvision: t = u / 255;  y = (t - mean[c]) / std[c].  The host then ships one byte
@@ -578,6 +605,22 @@ int hg_spatial_broadcast(int dtype, const void* y, int N, int H, int W, int C, f
   HG_DISPATCH_T(dtype, (launch_k(spatial_bcast_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream,
                                  (const T*)y, (const T*)addend, (T*)x, total, H * W, Cp, scale)));
   HG_LAUNCH_OK("spatial_bcast_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_channel_copy(int dtype, const void* src, int src_channels, int src_c0, const void* addend, void* dst,
+                    int dst_channels, int dst_c0, int channels, long long rows, void* stream) {
+  HG_REQUIRE(dtype == HG_BF16 || dtype == HG_F32, "hg_channel_copy: bad dtype");
+  HG_REQUIRE(src && dst && rows > 0 && channels > 0, "hg_channel_copy: bad arguments");
+  const int sCp = (src_channels + 63) & ~63, dCp = (dst_channels + 63) & ~63;
+  const int vecs = (channels + 7) / 8;
+  HG_REQUIRE(src_c0 % 8 == 0 && dst_c0 % 8 == 0, "hg_channel_copy: channel offsets must be multiples of 8");
+  HG_REQUIRE(src_c0 + vecs * 8 <= sCp && dst_c0 + vecs * 8 <= dCp, "hg_channel_copy: window exceeds the padded tensor");
+  const long long total = rows * vecs;
+  HG_DISPATCH_T(dtype, (launch_k(channel_copy_kernel<T>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream,
+                                 (const T*)src, sCp, src_c0, (const T*)addend, (T*)dst, dCp, dst_c0, vecs, total)));
+  HG_LAUNCH_OK("channel_copy_kernel");
   count_launch();
   return HG_OK;
 }

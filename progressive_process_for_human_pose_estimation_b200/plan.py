@@ -180,6 +180,15 @@ class Builder:
         self.ops.append(Op("bcast", [y], out))
         return out
 
+    def cat(self, xs):
+        """torch.cat(xs, dim=1) as a real tensor (its consumer is a BatchNorm: train.py:528-538,570-583).  Every
+        input but the last needs a channel count that is a multiple of 8."""
+        assert all(v.C % 8 == 0 for v in xs[:-1]), [v.C for v in xs]
+        assert all((v.N, v.H, v.W) == (xs[0].N, xs[0].H, xs[0].W) for v in xs)
+        out = Val(xs[0].N, xs[0].H, xs[0].W, sum(v.C for v in xs), self._rg(*xs), "cat")
+        self.ops.append(Op("cat", list(xs), out))
+        return out
+
     def add(self, a, b):
         out = Val(a.N, a.H, a.W, a.C, self._rg(a, b), "add")
         self.ops.append(Op("add", [a, b], out))
@@ -226,6 +235,7 @@ _WRITES = {
     "hg_bn_bwd_reduce": (8,), "hg_conv_fprop_bn": (6, 7, 8), "hg_conv_dgrad_bn": (5, 6),
     "hg_maxpool2_fwd": (6, 7), "hg_maxpool2_bwd": (8,), "hg_upsample2x_add_fwd": (8, 9), "hg_upsample2x_bwd": (8,),
     "hg_add": (3,), "hg_spatial_mean": (8,), "hg_spatial_broadcast": (8,),
+    "hg_channel_copy": (5,),
 }
 
 
@@ -644,6 +654,14 @@ class Plan:
                            C.c_longlong(out.numel_padded()), st)
                 if out.needs_stats:
                     self._stats_call(f, out)
+            elif k == "cat":
+                out, off = op.out, 0
+                for v in op.ins:
+                    self._emit(f, "hg_channel_copy", self.hdt, L.ptr(v.buf), v.C, 0, None, L.ptr(out.buf), out.C, off,
+                               v.C, C.c_longlong(v.M), st)
+                    off += v.C
+                if out.needs_stats:
+                    self._stats_call(f, out)
             elif k == "gap":
                 x, out = op.ins[0], op.out
                 self._emit(f, "hg_spatial_mean", self.hdt, L.ptr(x.buf), x.N, x.H, x.W, x.C,
@@ -817,6 +835,14 @@ class Plan:
             elif k == "add":
                 self._grad_passthrough(op.ins[0], G)
                 self._grad_passthrough(op.ins[1], G)
+            elif k == "cat":
+                off = 0
+                for v in op.ins:
+                    if v.requires_grad:
+                        addend, dst = self._grad_target(v)
+                        self._emit(g, "hg_channel_copy", self.hdt, L.ptr(G), out.C, off, L.ptr(addend), L.ptr(dst), v.C,
+                                   0, v.C, C.c_longlong(v.M), st)
+                    off += v.C
             elif k == "gap":
                 x = op.ins[0]
                 if x.requires_grad:

@@ -1,18 +1,35 @@
-"""Drop-in for the building blocks of train.py that lie on the hot path: the executed ASPP modules
-(`_ASPPModule` reference train.py:449-461, `ASPP_Block` :465-495) and the Q4 residual block (:411-447).
+"""Drop-in for train.py, the progressive multi-branch model of the repository (reference train.py:411-601): Q4
+residual blocks (:411-447), the executed ASPP modules (`_ASPPModule` :449-461, `ASPP_Block` :465-495), the un-shared
+hourglass with stride-2 down-sampling, ASPP bottom and cat skips (:498-540) and the three-stage `creatModel` with
+bias-free heads re-injected through torch.cat (:543-601).  Module-global configuration as in the reference.
 
-train.py's `creatModel` (the progressive multi-branch model, :498-601) and its bootstrapped losses are the next
-row N2 of SURVEY 8(f) and are not built; everything here is what that model is assembled from.
+    import progressive_process_for_human_pose_estimation_b200.train as m
+    model = m.creatModel().cuda()
+    result = model(images)      # [B,2,64,64] background, [B,16,64,64] limbs, [B,17,64,64] keypoints (autograd-enabled)
 
-    from progressive_process_for_human_pose_estimation_b200.train import ASPP_Block
-    aspp = ASPP_Block().cuda()
-    y = aspp(x)            # x [B,256,h,w] fp32 NCHW -> [B,256,h,w]; autograd-enabled, same state_dict keys
+The bootstrapped / masked losses of train.py:343-391 are NOT built (they remain stock PyTorch on the returned maps).
 """
-from ._modules import make_aspp_block, make_q4_block
+from ._modules import make_train_family
+from .evaluate import PCKh_softmax as _PCKhB
 
 nModules = 2
 nFeats = 256
 nStack = 3
+nKeypoint_COCO = 17
+nSkeleton_COCO = 19
+nKeypoint_MPII = 16
+nSkeleton_MPII = 15
+nOutChannels_0 = 2
+nOutChannels_1 = nSkeleton_MPII + 1
+nOutChannels_2 = nKeypoint_MPII + 1
+batch_size = 48
+keypoints = 17
+skeleton = 20
+inputsize = 256
+threshold = 1
 
-ResidualBlock = make_q4_block(globals())
-_ASPPModule, ASPP_Block = make_aspp_block(globals())
+ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel = make_train_family(globals())
+
+
+class PCKh(_PCKhB):
+    """train.py:759-791: class-probability input, channel j+1 <-> label value j+1 (evaluator B)."""

@@ -33,6 +33,7 @@ FAMILIES = [
     ("try_skeleton_and_keypoints", "creatModel", "try_skeleton_and_keypoints"),
     ("hourglass_compare", "creatModel", "hourglass_compare"),
     ("performance_compare", "creatModel_hourglass", "hourglass_compare"),  # same network as hourglass_compare
+    ("train", "creatModel", "train"),
 ]
 IDS = [f[0] for f in FAMILIES]
 

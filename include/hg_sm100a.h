@@ -268,7 +268,9 @@ typedef struct HgCeTerm {
   int64_t logits_bstride;
   int64_t dlogits_bstride;
   int32_t channels;
-  int32_t pad_;
+  float norm;                /* > 0: loss and gradient are divided by this instead of the valid-label count */
+  const float* pixel_weight; /* optional [B,H,W]: per-pixel weight of loss and gradient (selection mask / mask input) */
+  float* nll_out;            /* optional [B,H,W]: the per-pixel negative log-likelihood (0 for ignored labels) */
 } HgCeTerm;
 typedef struct HgCeDesc {
   int32_t num_terms;
@@ -279,6 +281,11 @@ typedef struct HgCeDesc {
 } HgCeDesc;
 HG_API int hg_ce_multi(const HgCeDesc* d, const HgCeTerm* terms_host, float* loss, int32_t* count, int32_t* bad_label,
                        void* stream);
+/* Bootstrapping of train.py:343-362,394-408 (torch.topk(loss.view(B, -1), k) then mean): mask[r, i] = 1 for the k
+ * largest of the n values of row r (ties at the k-th value: lowest indices), else 0; kth_value[r] (optional) receives
+ * the k-th largest value.  Bootstrapped cross-entropy = hg_ce_multi (nll_out) -> hg_topk_mask -> hg_ce_multi with
+ * pixel_weight = mask and norm = B * k. */
+HG_API int hg_topk_mask(const float* values, int rows, int n, int k, float* mask, float* kth_value, void* stream);
 
 /* ---- input pipeline tail (next row N1) ---------------------------------------------------------- */
 /* transforms.ToTensor() + transforms.Normalize(mean, std) (try_with_torch.py:310-313) on the GPU:
@@ -308,6 +315,12 @@ typedef struct HgAdamDesc {
   int32_t pad_;
 } HgAdamDesc;
 HG_API int hg_adam_multi(const HgAdamDesc* d, const HgAdamChunk* chunks_dev, void* stream);
+
+/* Weighted / bootstrapped MSE (train.py:379-408): sq_out[i] = (pred - target)^2 (optional; input of hg_topk_mask);
+ * loss += sum w * (pred - target)^2 / norm and dpred = 2 * grad_scale * w * (pred - target) / norm (each optional),
+ * w = weight[i] (per element) or weight[b, hw] broadcast over the C channels (weight_per_pixel = 1), 1 when NULL. */
+HG_API int hg_mse_weighted(const float* pred, const float* target, const float* weight, int weight_per_pixel, int B, int C,
+                           int HW, float norm, float grad_scale, float* sq_out, float* dpred, float* loss, void* stream);
 
 /* ---- target rendering ---------------------------------------------------------------------------- */
 /* Gaussian keypoint heatmaps, evaluated in float64 like the numpy code, stored as float32

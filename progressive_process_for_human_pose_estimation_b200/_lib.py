@@ -54,7 +54,8 @@ class HgMseDesc(C.Structure):
 
 class HgCeTerm(C.Structure):
     _fields_ = [("logits", C.c_void_p), ("dlogits", C.c_void_p), ("target", C.c_void_p), ("logits_bstride", C.c_int64),
-                ("dlogits_bstride", C.c_int64), ("channels", C.c_int32), ("pad_", C.c_int32)]
+                ("dlogits_bstride", C.c_int64), ("channels", C.c_int32), ("norm", C.c_float),
+                ("pixel_weight", C.c_void_p), ("nll_out", C.c_void_p)]
 
 
 class HgCeDesc(C.Structure):
@@ -121,6 +122,8 @@ SIGNATURES = {
     "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
     "hg_image_u8_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "hg_adam_multi": [C.POINTER(HgAdamDesc), _P, _P],
+    "hg_mse_weighted": [_P, _P, _P, _I, _I, _I, _I, C.c_float, C.c_float, _P, _P, _P, _P],
+    "hg_topk_mask": [_P, _I, _I, _I, _P, _P, _P],
     "hg_render_gauss": [C.POINTER(HgGaussDesc), _P, _P, _P, _P, _P],
     "hg_render_labels": [C.POINTER(HgLabelDesc), _P, _P, _P, _P, _P, _P],
     "hg_decode_argmax": [_P, _I, _I, _I, _I, _P, _P, _P],

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(256) ce_multi_kernel(const CeArgs a) {
   __shared__ float red[8];
   const HgCeTerm& t = a.term[blockIdx.y];
   const long long n = (long long)a.B * a.HW;
-  const float inv = 1.f / (float)a.count[blockIdx.y];  // inf when every label is ignored: loss = 0 * inf = NaN
+  // normaliser: the valid-label count (nn.CrossEntropyLoss, mean) or the caller's (bootstrapped / masked variants)
+  const float inv = 1.f / (t.norm > 0.f ? t.norm : (float)a.count[blockIdx.y]);  // inf when every label is ignored
   const float k = a.gscale * inv;
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -124,12 +125,16 @@ __global__ void __launch_bounds__(256) ce_multi_kernel(const CeArgs a) {
     float s = 0.f;
     for (int c = 0; c < t.channels; ++c) s += expf(__ldg(x + (long long)c * a.HW) - m);
     const float lse = m + logf(s);
-    if (valid) acc += lse - __ldg(x + y * a.HW);
+    const float nll = valid ? lse - __ldg(x + y * a.HW) : 0.f;
+    const float w = t.pixel_weight ? t.pixel_weight[i] : 1.f;
+    acc += w * nll;
+    if (t.nll_out) t.nll_out[i] = nll;
     if (t.dlogits) {
       float* g = t.dlogits + (long long)b * t.dlogits_bstride + p;
+      const float kw = k * w;
       for (int c = 0; c < t.channels; ++c) {
         const float sm = expf(__ldg(x + (long long)c * a.HW) - lse);
-        g[(long long)c * a.HW] = valid ? k * (sm - (c == y ? 1.f : 0.f)) : 0.f;
+        g[(long long)c * a.HW] = valid ? kw * (sm - (c == y ? 1.f : 0.f)) : 0.f;
       }
     }
   }
@@ -141,6 +146,122 @@ __global__ void __launch_bounds__(256) ce_multi_kernel(const CeArgs a) {
     float tot = 0.f;
     for (int w = 0; w < 8; ++w) tot += red[w];
     atomicAdd(a.loss + blockIdx.y, tot * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Bootstrapping (train.py:343-362 Costomer_CrossEntropyLoss, :394-408 Costomer_MSELoss): the mean of the k largest
+// per-pixel losses of every image, torch.topk(loss.view(B, -1), k).  One block per image: 4-pass radix select (8-bit
+// digits, MSB first) of the k-th largest value, then mask[i] = 1 for the k selected elements (values above the
+// threshold, and the lowest-index ties at the threshold) -- the mask is the per-pixel weight of the loss kernels.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int order_key(float v) {
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // larger float <=> larger key
+}
+
+__global__ void __launch_bounds__(1024) topk_mask_kernel(const float* __restrict__ v, int n, int k,
+                                                         float* __restrict__ mask, float* __restrict__ kth) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ int hist[256];
+  __shared__ unsigned int s_prefix;
+  __shared__ int s_need;
+  __shared__ int s_scan[1024];
+  const float* row = v + (long long)blockIdx.x * n;
+  float* mrow = mask + (long long)blockIdx.x * n;
+  if (threadIdx.x == 0) {
+    s_prefix = 0u;
+    s_need = k;
+  }
+  for (int d = 3; d >= 0; --d) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const unsigned int himask = d == 3 ? 0u : (0xffffffffu << (8 * (d + 1)));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int key = order_key(row[i]);
+      if ((key & himask) == prefix) atomicAdd(&hist[(key >> (8 * d)) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int need = s_need, b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= need) break;
+        need -= hist[b];
+      }
+      s_need = need;
+      s_prefix = prefix | ((unsigned int)b << (8 * d));
+    }
+    __syncthreads();
+  }
+  const unsigned int T = s_prefix;   // key of the k-th largest value
+  const int need = s_need;           // how many elements equal to it belong to the top k
+  // ties at the threshold: the lowest indices win (contiguous chunk per thread + block scan of the tie counts)
+  const int chunk = (n + blockDim.x - 1) / blockDim.x;
+  const int lo = threadIdx.x * chunk, hi = min(n, lo + chunk);
+  int eq = 0;
+  for (int i = lo; i < hi; ++i) eq += order_key(row[i]) == T;
+  s_scan[threadIdx.x] = eq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+      const int c = s_scan[t];
+      s_scan[t] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  int before = s_scan[threadIdx.x];
+  for (int i = lo; i < hi; ++i) {
+    const unsigned int key = order_key(row[i]);
+    float m = key > T ? 1.f : 0.f;
+    if (key == T) {
+      m = before < need ? 1.f : 0.f;
+      ++before;
+    }
+    mrow[i] = m;
+  }
+  if (kth && threadIdx.x == 0) {
+    const unsigned int u = (T & 0x80000000u) ? (T & 0x7fffffffu) : ~T;
+    kth[blockIdx.x] = __uint_as_float(u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Weighted / bootstrapped MSE (train.py:379-408 Costomer_MSELoss_with_mask, Costomer_MSELoss): one element-wise pass
+//   sq_out[i] = (p - t)^2                      (feeds hg_topk_mask)            and / or
+//   loss += sum w * (p - t)^2 / norm,  dpred[i] = 2 * gscale * w * (p - t) / norm
+// with w per element (top-k mask over C*H*W) or per pixel, broadcast over the channels (mask input [B,H,W]).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mse_weighted_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                           const float* __restrict__ w, int w_per_pixel, int C, int HW,
+                                                           long long numel, float norm, float gscale,
+                                                           float* __restrict__ sq_out, float* __restrict__ dpred,
+                                                           float* __restrict__ loss) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[8];
+  float acc = 0.f;
+  const float k = 2.f * gscale / norm;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float d = pred[i] - tgt[i];
+    const float sq = d * d;
+    if (sq_out) sq_out[i] = sq;
+    float wi = 1.f;
+    if (w) wi = w_per_pixel ? w[(i / ((long long)C * HW)) * HW + i % HW] : w[i];
+    acc += wi * sq;
+    if (dpred) dpred[i] = k * wi * d;
+  }
+  const float v = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    atomicAdd(loss, tot / norm);
   }
 }
 
@@ -212,6 +333,29 @@ int hg_ce_multi(const HgCeDesc* d, const HgCeTerm* terms_host, float* loss, int3
   count_launch();
   launch_k(ce_multi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a);
   HG_LAUNCH_OK("ce_multi_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_topk_mask(const float* values, int rows, int n, int k, float* mask, float* kth_value, void* stream) {
+  HG_REQUIRE(values && mask, "hg_topk_mask: NULL pointer");
+  HG_REQUIRE(rows > 0 && n > 0 && k > 0 && k <= n, "hg_topk_mask: need 0 < k <= n");
+  launch_k(topk_mask_kernel, dim3((unsigned)rows), dim3(1024), 0, (cudaStream_t)stream, values, n, k, mask, kth_value);
+  HG_LAUNCH_OK("topk_mask_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_mse_weighted(const float* pred, const float* target, const float* weight, int weight_per_pixel, int B, int C,
+                    int HW, float norm, float grad_scale, float* sq_out, float* dpred, float* loss, void* stream) {
+  HG_REQUIRE(pred && target, "hg_mse_weighted: NULL pointer");
+  HG_REQUIRE(B > 0 && C > 0 && HW > 0 && norm > 0.f, "hg_mse_weighted: bad sizes / normaliser");
+  const long long numel = (long long)B * C * HW;
+  long long blocks = (numel + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  launch_k(mse_weighted_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, pred, target, weight,
+           weight_per_pixel, C, HW, numel, norm, grad_scale, sq_out, dpred, loss);
+  HG_LAUNCH_OK("mse_weighted_kernel");
   count_launch();
   return HG_OK;
 }

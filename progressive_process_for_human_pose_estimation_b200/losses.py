@@ -146,3 +146,120 @@ def cross_entropy_losses(terms, ignore_index=-100, check_labels=False):
             k = len(uniq) - 1
         spec.append((k, int(c0), int(c1), target))
     return _CeMulti.apply((spec, int(ignore_index), bool(check_labels)), *uniq)
+
+
+def _ce_call(x, tgt, nll_out=None, weight=None, norm=0.0, grad=None):
+    """One hg_ce_multi term over all channels of x; returns the [1] loss tensor."""
+    B, Cx, H, W = x.shape
+    arr = (L.HgCeTerm * 1)()
+    arr[0].logits, arr[0].target = x.data_ptr(), tgt.data_ptr()
+    arr[0].dlogits = grad.data_ptr() if grad is not None else None
+    arr[0].logits_bstride = x.stride(0)
+    arr[0].dlogits_bstride = grad.stride(0) if grad is not None else 0
+    arr[0].channels = Cx
+    arr[0].norm = float(norm)
+    arr[0].pixel_weight = weight.data_ptr() if weight is not None else None
+    arr[0].nll_out = nll_out.data_ptr() if nll_out is not None else None
+    loss = torch.zeros(1, device=x.device, dtype=torch.float32)
+    count = torch.zeros(2, device=x.device, dtype=torch.int32)
+    d = L.HgCeDesc(1, B, H * W, -100, 1.0)
+    L.call("hg_ce_multi", C.byref(d), arr, L.ptr(loss), L.ptr(count), C.c_void_p(count.data_ptr() + 4), L.stream_ptr())
+    return loss
+
+
+def _check_ce_inputs(input, target, who):
+    if not input.is_cuda or input.dtype != torch.float32 or input.dim() != 4:
+        raise RuntimeError(f"{who}: fp32 CUDA logits [B,C,H,W] expected (there is no CPU fallback)")
+    if not target.is_cuda or tuple(target.shape) != (input.shape[0],) + tuple(input.shape[2:]):
+        raise RuntimeError(f"{who}: labels must be a CUDA tensor [B,H,W]")
+    x = input if _plane_view(input) else input.contiguous()
+    return x, target.contiguous().to(torch.int64)
+
+
+class _CeWeighted(torch.autograd.Function):
+    """mean-of-top-k (mask=None) or mask-weighted per-pixel cross entropy."""
+
+    @staticmethod
+    def forward(ctx, input, target, k, mask):
+        x, tgt = _check_ce_inputs(input, target, "bootstrapped / masked cross entropy")
+        B, Cx, H, W = x.shape
+        grad = torch.empty(x.shape, device=x.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(x.device):
+            if mask is None:
+                nll = torch.empty(B, H * W, device=x.device, dtype=torch.float32)
+                _ce_call(x, tgt, nll_out=nll, norm=1.0)
+                sel = torch.empty_like(nll)
+                L.call("hg_topk_mask", L.ptr(nll), B, H * W, int(k), L.ptr(sel), None, L.stream_ptr())
+                loss = _ce_call(x, tgt, weight=sel, norm=float(B * k), grad=grad)
+            else:
+                w = mask.contiguous().to(torch.float32)
+                loss = _ce_call(x, tgt, weight=w, norm=float(B * H * W), grad=grad)
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gloss):
+        g, ctx.grad = ctx.grad, None
+        return (g * gloss if g is not None else None), None, None, None
+
+
+def bootstrapped_cross_entropy(input, target, fraction):
+    """Costomer_CrossEntropyLoss.forward of train.py:350-362: per-pixel NLL of log_softmax(input, dim=1), the
+    k = int(H * W * max(fraction, 0.1)) largest of every image, their mean."""
+    if fraction < 0.1:
+        fraction = 0.1
+    k = int(input.shape[2] * input.shape[3] * fraction)
+    return _CeWeighted.apply(input, target, k, None)
+
+
+def masked_cross_entropy(input, target, mask):
+    """Costomer_CrossEntropyLoss_with_mask.forward of train.py:372-376: mean over ALL pixels of nll * mask."""
+    return _CeWeighted.apply(input, target, 0, mask)
+
+
+class _MseWeighted(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, target, k, mask):
+        if not input.is_cuda or input.dtype != torch.float32 or input.dim() != 4 or input.shape != target.shape:
+            raise RuntimeError("bootstrapped / masked MSE: fp32 CUDA tensors [B,C,H,W] of one shape expected "
+                               "(there is no CPU fallback)")
+        x, t = input.contiguous(), target.contiguous().to(torch.float32)
+        B, Cx, H, W = x.shape
+        HW = H * W
+        grad = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        loss = torch.zeros(1, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            if mask is None:   # mean of the k largest squared errors of every image (over C*H*W elements)
+                sq = torch.empty(B, Cx * HW, device=x.device, dtype=torch.float32)
+                L.call("hg_mse_weighted", L.ptr(x), L.ptr(t), None, 0, B, Cx, HW, C.c_float(1.0), C.c_float(1.0),
+                       L.ptr(sq), None, None, L.stream_ptr())
+                sel = torch.empty_like(sq)
+                L.call("hg_topk_mask", L.ptr(sq), B, Cx * HW, int(k), L.ptr(sel), None, L.stream_ptr())
+                L.call("hg_mse_weighted", L.ptr(x), L.ptr(t), L.ptr(sel), 0, B, Cx, HW, C.c_float(float(B * k)),
+                       C.c_float(1.0), None, L.ptr(grad), L.ptr(loss), L.stream_ptr())
+            else:
+                w = mask.contiguous().to(torch.float32)
+                L.call("hg_mse_weighted", L.ptr(x), L.ptr(t), L.ptr(w), 1, B, Cx, HW, C.c_float(float(x.numel())),
+                       C.c_float(1.0), None, L.ptr(grad), L.ptr(loss), L.stream_ptr())
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gloss):
+        g, ctx.grad = ctx.grad, None
+        return (g * gloss if g is not None else None), None, None, None
+
+
+def bootstrapped_mse(input, target, fraction):
+    """Costomer_MSELoss.forward of train.py:401-408: squared errors, the k = int(H * W * max(fraction, 0.25)) largest
+    of every image (over all C*H*W elements), their mean."""
+    if fraction < 0.25:
+        fraction = 0.25
+    k = int(input.shape[2] * input.shape[3] * fraction)
+    return _MseWeighted.apply(input, target, k, None)
+
+
+def masked_mse(input, target, mask):
+    """Costomer_MSELoss_with_mask.forward of train.py:386-391: mean over all elements of (input - target)^2 * mask,
+    mask [B,H,W] broadcast over the channels."""
+    return _MseWeighted.apply(input, target, 0, mask)

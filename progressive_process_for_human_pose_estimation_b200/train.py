@@ -7,8 +7,13 @@ bias-free heads re-injected through torch.cat (:543-601).  Module-global configu
     model = m.creatModel().cuda()
     result = model(images)      # [B,2,64,64] background, [B,16,64,64] limbs, [B,17,64,64] keypoints (autograd-enabled)
 
-The bootstrapped / masked losses of train.py:343-391 are NOT built (they remain stock PyTorch on the returned maps).
+The bootstrapped / masked losses of train.py:343-408 keep their class names and `forward(input, target, fraction | mask)`
+signatures; each is a few kernel launches (per-pixel NLL / squared error -> radix-select top-k mask -> weighted loss +
+gradient) instead of log_softmax + nll_loss + topk + mean and their autograd graph.
 """
+import torch.nn as nn
+
+from . import losses as _losses
 from ._modules import make_train_family
 from .evaluate import PCKh_softmax as _PCKhB
 
@@ -33,3 +38,31 @@ ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel = make_train_famil
 
 class PCKh(_PCKhB):
     """train.py:759-791: class-probability input, channel j+1 <-> label value j+1 (evaluator B)."""
+
+
+class Costomer_CrossEntropyLoss(nn.Module):
+    """train.py:343-362: mean of the k = int(H*W*max(fraction, 0.1)) largest per-pixel NLLs of every image."""
+
+    def forward(self, input, target, fraction):
+        return _losses.bootstrapped_cross_entropy(input, target, fraction)
+
+
+class Costomer_CrossEntropyLoss_with_mask(nn.Module):
+    """train.py:365-376: mean over all pixels of nll * mask."""
+
+    def forward(self, input, target, mask):
+        return _losses.masked_cross_entropy(input, target, mask)
+
+
+class Costomer_MSELoss_with_mask(nn.Module):
+    """train.py:379-391: mean over all elements of (input - target)^2 * mask[B,H,W]."""
+
+    def forward(self, input, target, mask):
+        return _losses.masked_mse(input, target, mask)
+
+
+class Costomer_MSELoss(nn.Module):
+    """train.py:394-408: mean of the k = int(H*W*max(fraction, 0.25)) largest squared errors of every image."""
+
+    def forward(self, input, target, fraction):
+        return _losses.bootstrapped_mse(input, target, fraction)

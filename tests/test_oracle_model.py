@@ -109,3 +109,33 @@ def test_dropin_state_dict_layout_matches_reference():
     # module-global configuration is read at call time, like the reference (try_with_torch.py:224,285)
     twt.nStack = 8
     assert twt.creatModel()._config_key() == (8, 2)
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_custom_losses_restate_reference():
+    """oracle/losses_torch.py == the Costomer_* loss classes of train.py:343-408 (values and gradients, bit for bit)."""
+    import warnings
+
+    from oracle import losses_torch as lt
+    tr = refload.load("train")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 17, 16, 16, generator=g)
+    y = torch.randint(0, 17, (3, 16, 16), generator=g)
+    t = torch.rand(3, 17, 16, 16, generator=g)
+    mask = (torch.rand(3, 16, 16, generator=g) < 0.4)
+    cases = [(tr.Costomer_CrossEntropyLoss(), lt.bootstrapped_cross_entropy, (y, 0.3)),
+             (tr.Costomer_CrossEntropyLoss(), lt.bootstrapped_cross_entropy, (y, 0.01)),
+             (tr.Costomer_CrossEntropyLoss_with_mask(), lt.masked_cross_entropy, (y, mask)),
+             (tr.Costomer_MSELoss_with_mask(), lt.masked_mse, (t, mask)),
+             (tr.Costomer_MSELoss(), lt.bootstrapped_mse, (t, 0.5)),
+             (tr.Costomer_MSELoss(), lt.bootstrapped_mse, (t, 0.1))]
+    for ref_mod, fn, args in cases:
+        a = x.clone().requires_grad_()
+        b = x.clone().requires_grad_()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            la = ref_mod.forward(a, *args)
+        lb = fn(b, *args)
+        la.backward()
+        lb.backward()
+        assert torch.equal(la, lb) and torch.equal(a.grad, b.grad), fn.__name__

@@ -180,12 +180,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()   # still inside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -241,6 +243,16 @@ def run_ours(args):
             bufs[slot][0].copy_(xh, non_blocking=True)
             bufs[slot][1].copy_(yh, non_blocking=True)
 
+    # every step's loss is copied device -> host (pinned, asynchronously) and read by the host one step later, so the
+    # host keeps launching ahead like the reference loop (which prints the loss every 50 iterations); the last loss is
+    # read inside the timed region by `drain`
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
+    def read_loss(i):
+        loss_ready[i % 2].synchronize()
+        state["last"] = float(loss_host[i % 2][0])
+
     def e2e_step():
         i = state["i"]
         if i == 0:
@@ -249,12 +261,20 @@ def run_ours(args):
         xb, yb = bufs[i % 2]
         copy_stream.wait_stream(torch.cuda.current_stream())  # the other slot is free once the previous step is queued
         upload((i + 1) % 2)  # next step's batch travels while this step computes
-        state["last"] = step(xb, yb).item()  # device -> host read of the loss
+        loss = step(xb, yb)
+        if i > 0:
+            read_loss(i - 1)                                   # host read of the previous step's loss
+        loss_host[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)   # device -> host copy of this step's loss
+        loss_ready[i % 2].record()
         state["i"] = i + 1
 
+    def drain():
+        read_loss(state["i"] - 1)
+
     e2e_step()
+    drain()
     state["i"] = 0
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = timed(e2e_step, args.steps, finish=drain)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = xh.numel() * 4 + yh.numel() * 4
     # (the prefetch uploads one extra batch at the very end; bytes are counted per step as copied)
@@ -279,12 +299,20 @@ def run_ours(args):
             torch.cuda.current_stream().wait_stream(copy_stream)
             copy_stream.wait_stream(torch.cuda.current_stream())
             upload_u8((i + 1) % 2)
-            step(hg.to_tensor_normalize(ubufs[i % 2]), bufs[i % 2][1]).item()
+            loss = step(hg.to_tensor_normalize(ubufs[i % 2]), bufs[i % 2][1])
+            if i > 0:
+                read_loss(i - 1)
+            loss_host[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ready[i % 2].record()
             ustate["i"] = i + 1
 
+        def drain_u8():
+            read_loss(ustate["i"] - 1)
+
         e2e_u8_step()
+        drain_u8()
         ustate["i"] = 0
-        ms_u8 = timed(e2e_u8_step, args.steps)
+        ms_u8 = timed(e2e_u8_step, args.steps, finish=drain_u8)
         e2e_u8 = {"value": round(world * B * args.steps / (ms_u8 / 1e3), 2), "unit": UNIT,
                   "h2d_bytes_per_step": xu8.numel() + yh.numel() * 4, "d2h_bytes_per_step": 4,
                   "ms_per_step": round(ms_u8 / args.steps, 3),

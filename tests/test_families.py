@@ -211,7 +211,11 @@ def test_family_bf16_train_step_runs_and_replays(script, factory, fixture):
         out, losses = run_step(net, g)
         for i, o in enumerate(out):
             assert torch.isfinite(o).all()
-            assert abs(losses[i].item() - g["losses"][i]) <= 0.1 * abs(g["losses"][i]), (it, i)
+            # band: 10 %, wider where the reference's own bf16-autocast outputs are further from its fp64 run (an MSE
+            # moves by about the output's relative error; atomics make our runs differ from each other as well --
+            # worst deviation seen over 18 runs per family: 0.10 for try_skeleton_and_keypoints, <= 0.04 elsewhere)
+            band = max(0.1, 0.6 * float(g["out_noise_bf16"][i]))
+            assert abs(losses[i].item() - g["losses"][i]) <= band * abs(g["losses"][i]), (it, i)
         err0 = rel(out[0].detach().cpu().numpy(), g["out0"])
         assert err0 <= max(0.3, 2 * float(g["out_noise_bf16"][0])), err0  # reference's own bf16 run: 0.13 - 0.44
         for n, p in net.named_parameters():

@@ -294,6 +294,25 @@ HG_API int hg_topk_mask(const float* values, int rows, int n, int k, float* mask
 HG_API int hg_image_u8_to_nchw_f32(const uint8_t* src_nhwc, int N, int H, int W, int C, const float* mean_host,
                                    const float* std_host, float* dst_nchw, void* stream);
 
+/* PIL's `image.resize([256, 256])` (try_with_torch.py:99; default filter BICUBIC) for a batch of variable-size RGB
+ * images, bit-exact with Pillow's Resample.c on 8-bit data (two passes, horizontal first, 22-bit fixed-point
+ * coefficients, uint8 intermediate).  images_dev: DEVICE array of descriptors (src = uint8 HWC RGB pixels of one
+ * image; *_off = offsets, in ints, of its coefficient [out x ksize] and bounds [out x 2] tables inside coef_dev /
+ * bounds_dev; tmp_off = byte offset of its [h, out_w, 3] intermediate image inside tmp).  The tables are Pillow's
+ * precompute_coeffs + normalize_coeffs_8bpc, computed by the host.  Outputs (either may be NULL): out_nhwc uint8
+ * [B, out_h, out_w, 3] and out_nchw_norm fp32 [B, 3, out_h, out_w] = ToTensor + Normalize(mean, std) of it. */
+typedef struct HgResizeImage {
+  const uint8_t* src;
+  int32_t w, h;
+  int32_t kx_off, ky_off;
+  int32_t bx_off, by_off;
+  int32_t ksize_x, ksize_y;
+  int64_t tmp_off;
+} HgResizeImage;
+HG_API int hg_resize_bicubic_u8(const HgResizeImage* images_dev, int num_images, int max_h, int out_w, int out_h,
+                                const int32_t* coef_dev, const int32_t* bounds_dev, uint8_t* tmp, uint8_t* out_nhwc,
+                                float* out_nchw_norm, const float* mean_host, const float* std_host, void* stream);
+
 /* ---- optimizer step (next row N4) ------------------------------------------------------------------ */
 /* torch.optim.Adam (amsgrad = False) on every parameter tensor in one launch (try_with_torch.py:317,342-344).
  * chunks_dev is a DEVICE array: thread block b updates chunks_dev[b] (a slice of at most a few thousand elements of

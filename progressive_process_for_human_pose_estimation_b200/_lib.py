@@ -74,6 +74,12 @@ class HgAdamDesc(C.Structure):
                 ("step", C.c_int32), ("num_chunks", C.c_int32), ("pad_", C.c_int32)]
 
 
+class HgResizeImage(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("kx_off", C.c_int32), ("ky_off", C.c_int32),
+                ("bx_off", C.c_int32), ("by_off", C.c_int32), ("ksize_x", C.c_int32), ("ksize_y", C.c_int32),
+                ("tmp_off", C.c_int64)]
+
+
 class HgLabelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "P", "J", "L", "H", "W", "center_mode", "draw_points", "draw_lines",
                                          "line_value")]
@@ -121,6 +127,7 @@ SIGNATURES = {
     "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
     "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
     "hg_image_u8_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "hg_resize_bicubic_u8": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_adam_multi": [C.POINTER(HgAdamDesc), _P, _P],
     "hg_mse_weighted": [_P, _P, _P, _I, _I, _I, _I, C.c_float, C.c_float, _P, _P, _P, _P],
     "hg_topk_mask": [_P, _I, _I, _I, _P, _P, _P],

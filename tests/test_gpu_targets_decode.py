@@ -375,3 +375,31 @@ def test_pckh_from_logits_equals_softmax_then_pckh():
         assert np.array_equal(acc, ref["accuracy"]) and np.array_equal(np.stack(pred), ref["predict"].astype(np.float64))
     with pytest.raises(RuntimeError, match="fp32"):
         hg.pckh_sweep_counts(zt.cuda().half(), tgt.cuda(), rect.cuda(), 1, logits=True)
+
+
+def test_resize_bicubic_bit_exact_with_pillow():
+    """hg.resize_bicubic == [Image.resize([256, 256]) ...] of try_with_torch.py:99 run by Pillow itself on the host, for a
+    ragged batch; the fused variant == transforms.ToTensor + Normalize(0.5, 0.5) of the resized image (:310-313)."""
+    from PIL import Image
+    r = np.random.RandomState(1)
+    sizes = [(480, 640), (427, 640), (640, 480), (256, 256), (100, 37), (333, 500), (64, 300), (257, 255), (3, 5), (1, 1),
+             (720, 1280)]
+    imgs = []
+    for h, w in sizes:
+        im = r.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        if h > 300:
+            im[: h // 2] = np.linspace(0, 255, w)[None, :, None].astype(np.uint8)
+        imgs.append(im)
+    want = np.stack([np.array(Image.fromarray(im).convert("RGB").resize([256, 256])) for im in imgs])
+    n0 = hg._lib.launch_count()
+    got = hg.resize_bicubic([torch.from_numpy(im).cuda() for im in imgs])
+    assert hg._lib.launch_count() - n0 == 2          # horizontal + vertical pass for the whole ragged batch
+    assert got.dtype == torch.uint8 and got.shape == (len(sizes), 256, 256, 3)
+    assert np.array_equal(got.cpu().numpy(), want)
+    fused = hg.resize_bicubic([torch.from_numpy(im).cuda() for im in imgs], normalize=((0.5,) * 3, (0.5,) * 3))
+    ref = torch.from_numpy(want).permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255).sub_(0.5).div_(0.5)
+    assert torch.equal(fused.cpu(), ref)
+    small = hg.resize_bicubic([torch.from_numpy(imgs[0]).cuda()], size=(64, 128))
+    assert np.array_equal(small[0].cpu().numpy(), np.array(Image.fromarray(imgs[0]).resize([64, 128])))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hg.resize_bicubic([torch.from_numpy(imgs[0])])

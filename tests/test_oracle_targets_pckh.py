@@ -89,6 +89,25 @@ def test_mpii_label_maps_match_pillow():
         assert np.array_equal(got_s, np.array(smap).astype(np.int64)), trial
 
 
+def test_bicubic_tables_reproduce_pillow_resize():
+    """`image.resize([256, 256])` of the reference datasets (try_with_torch.py:99): the product's coefficient tables
+    (precompute_coeffs + normalize_coeffs_8bpc restated on the host) + the integer passes == Pillow, bit for bit, for
+    down-scaling, up-scaling, odd and degenerate sizes."""
+    from PIL import Image
+
+    from oracle.resize_np import resize_reference_numpy
+    r = np.random.RandomState(0)
+    for (h, w) in [(480, 640), (427, 640), (256, 256), (100, 37), (500, 333), (64, 300), (257, 255), (3, 5), (1, 1)]:
+        img = r.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        if h > 300:
+            img[: h // 2] = np.linspace(0, 255, w)[None, :, None].astype(np.uint8)
+        want = np.array(Image.fromarray(img).convert("RGB").resize([256, 256]))
+        assert np.array_equal(resize_reference_numpy(img), want), (h, w)
+    img = r.randint(0, 256, (120, 90, 3)).astype(np.uint8)
+    want = np.array(Image.fromarray(img).resize([64, 128]))     # (width, height) like PIL
+    assert np.array_equal(resize_reference_numpy(img, 64, 128), want)
+
+
 def test_gauss_variants_against_reference_expressions():
     """Float-centre / x100 / accumulate variants evaluated with the reference's own numpy expressions."""
     import numpy.matlib  # noqa: F401

@@ -388,7 +388,7 @@ def run_ours(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
                 if traffic is not None and B != 32:
                     traffic = None  # captured at B=32 only
-            roofline = {"kernel": "conv_gemm_kernel<128,3,2,kPlain,alias> (fprop 3x3 128->128 @64x64, tcgen05 + TMA)",
+            roofline = {"kernel": "conv_gemm_kernel<128,2,3,kPlain,alias> (fprop 3x3 128->128 @64x64, tcgen05 + TMA)",
                         "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
                         "frac": round(ach / peak, 4), "traffic": traffic,
                         "algorithmic_flops_per_launch": flops, "peak_source": f"{src} bf16_tflops_sustained",
@@ -426,7 +426,7 @@ def run_ours(args):
             n, t = agg[k]
             tf = 2.0 * M64 * 128 * 128 * 9 / (t / n * 1e-3) / 1e12
             pk = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-            more.append({"kernel": "conv_gemm_kernel<128,3,2,kMask> dgrad 3x3 128->128 @64x64 (+ReLU mask, BN sums)",
+            more.append({"kernel": "conv_gemm_kernel<128,2,3,kMask,alias> dgrad 3x3 128->128 @64x64 (+ReLU mask, BN sums)",
                          "bound": "tensor", "achieved": round(tf, 1), "peak": pk, "unit": "TFLOP/s",
                          "frac": round(tf / pk, 4), "avg_us": round(t / n * 1e3, 2), "launches_per_step": n})
         if roofline is not None:

@@ -30,6 +30,7 @@
 
 namespace hg {
 
+int g_long_k_3cta = 1;         // 1: multi-wave 3x3 kernels with 2 stages and 3 CTAs/SM instead of 3 stages and 2 CTAs/SM
 int g_short_alias = 1;         // 1: multi-wave 1x1 kernels with a residual / raw BN input load it AFTER the (short) main loop
                                // into the aliased staging tile: 64 KB per CTA, 3 CTAs/SM instead of 2
 int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
@@ -594,8 +595,9 @@ static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   return HG_OK;
 }
 
-// Tile configuration: long K (3x3) = 3 stages, short K (1x1) = 2 stages; C aliases the stages unless a residual
-// has to be in C up front (then a dedicated buffer, still two CTAs per SM for the 1x1 kernels).  Grids of at most one
+// Tile configuration: multi-wave grids run 2 pipeline stages with the staging tile aliased onto them = 64 KB per CTA =
+// 3 CTAs/SM, for 1x1 AND 3x3 kernels (3 stages x 2 CTAs/SM for the 3x3: 53.7 us, 2 x 3: 49.8 us @64x64 -- more CTAs in
+// different phases hide the long epilogue better than a deeper pipeline).  Grids of at most one
 // wave (the 4x4 .. 16x16 levels of the hourglass) are pure latency: one CTA per SM with every K block's TMA load in
 // flight at once (6 / 4 stages).
 template <int BN, int MODE>
@@ -608,7 +610,8 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
     // multi-wave 3x3 kernel (two CTAs per SM) loads it after its (long) main loop
     if (single_wave) return long_k ? launch_conv_gemm<BN, 5, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st)
                                    : launch_conv_gemm<BN, 4, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st);
-    if (!long_k && g_short_alias) return launch_conv_gemm<BN, 2, 3, kMask, true>(tmA, tmB, tmC, tmR, p, st);
+    if ((!long_k && g_short_alias) || (long_k && g_long_k_3cta))
+      return launch_conv_gemm<BN, 2, 3, kMask, true>(tmA, tmB, tmC, tmR, p, st);
     return long_k ? launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st)
                   : launch_conv_gemm<BN, 2, 2, kMask, false>(tmA, tmB, tmC, tmR, p, st);
   } else {
@@ -619,6 +622,8 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
       return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st)
                          : launch_conv_gemm<BN, 2, 2, MODE, false>(tmA, tmB, tmC, tmR, p, st);
     }
+    if (long_k && !single_wave && g_long_k_3cta)
+      return launch_conv_gemm<BN, 2, kShortMinB, MODE, true>(tmA, tmB, tmC, tmR, p, st);
     if (long_k) return single_wave ? launch_conv_gemm<BN, 6, 1, MODE, true>(tmA, tmB, tmC, tmR, p, st)
                                    : launch_conv_gemm<BN, 3, 2, MODE, true>(tmA, tmB, tmC, tmR, p, st);
     return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, true>(tmA, tmB, tmC, tmR, p, st)

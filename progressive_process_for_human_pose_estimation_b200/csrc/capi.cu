@@ -10,7 +10,7 @@ static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 int g_use_pdl = 1;
-extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta;
+extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta, g_short_1stage;
 extern int g_bn_blocks_per_sm, g_bn_bwd_blocks_per_sm;
 extern long long* g_dbg_ts;
 
@@ -172,6 +172,10 @@ int hg_set_option(const char* name, int value) {
   }
   if (strcmp(name, "bn_bwd_blocks_per_sm") == 0 && value >= 0) {
     g_bn_bwd_blocks_per_sm = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "short_1stage") == 0) {
+    g_short_1stage = value;
     return HG_OK;
   }
   if (strcmp(name, "long_k_3cta") == 0) {

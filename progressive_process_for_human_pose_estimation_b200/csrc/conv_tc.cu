@@ -30,6 +30,7 @@
 
 namespace hg {
 
+int g_short_1stage = 0;        // 1: multi-wave 1x1 kernels without residual: ONE stage (32 KB), 4 CTAs/SM
 int g_long_k_3cta = 1;         // 1: multi-wave 3x3 kernels with 2 stages and 3 CTAs/SM instead of 3 stages and 2 CTAs/SM
 int g_short_alias = 1;         // 1: multi-wave 1x1 kernels with a residual / raw BN input load it AFTER the (short) main loop
                                // into the aliased staging tile: 64 KB per CTA, 3 CTAs/SM instead of 2
@@ -605,12 +606,15 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
                               const CUtensorMap& tmC, const CUtensorMap& tmR, const ConvGemmParams& p,
                               cudaStream_t st) {
   const bool single_wave = g_single_wave_deep && ceil_div(p.M_total, 128) * p.n_tiles <= kNumSMs;
+  // the 2-stage / 3-CTAs-per-SM configuration of the 3x3 kernels only pays when a third CTA per SM exists: at
+  // 32x32 (256 CTAs) every CTA is resident with two per SM and the deeper pipeline wins (12.0 vs 15.4 us)
+  const bool three_cta = g_long_k_3cta && ceil_div(p.M_total, 128) * p.n_tiles > 2 * kNumSMs;
   if constexpr (MODE == kMask) {
     // the raw BatchNorm input tile is prefetched into a dedicated C buffer wherever shared memory allows; only the
     // multi-wave 3x3 kernel (two CTAs per SM) loads it after its (long) main loop
     if (single_wave) return long_k ? launch_conv_gemm<BN, 5, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st)
                                    : launch_conv_gemm<BN, 4, 1, kMask, false>(tmA, tmB, tmC, tmR, p, st);
-    if ((!long_k && g_short_alias) || (long_k && g_long_k_3cta))
+    if ((!long_k && g_short_alias) || (long_k && three_cta))
       return launch_conv_gemm<BN, 2, 3, kMask, true>(tmA, tmB, tmC, tmR, p, st);
     return long_k ? launch_conv_gemm<BN, 3, 2, kMask, true>(tmA, tmB, tmC, tmR, p, st)
                   : launch_conv_gemm<BN, 2, 2, kMask, false>(tmA, tmB, tmC, tmR, p, st);
@@ -622,10 +626,13 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
       return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, false>(tmA, tmB, tmC, tmR, p, st)
                          : launch_conv_gemm<BN, 2, 2, MODE, false>(tmA, tmB, tmC, tmR, p, st);
     }
-    if (long_k && !single_wave && g_long_k_3cta)
+    if (long_k && !single_wave && three_cta)
       return launch_conv_gemm<BN, 2, kShortMinB, MODE, true>(tmA, tmB, tmC, tmR, p, st);
     if (long_k) return single_wave ? launch_conv_gemm<BN, 6, 1, MODE, true>(tmA, tmB, tmC, tmR, p, st)
                                    : launch_conv_gemm<BN, 3, 2, MODE, true>(tmA, tmB, tmC, tmR, p, st);
+    if constexpr (MODE == kPlain) {
+      if (!single_wave && g_short_1stage) return launch_conv_gemm<BN, 1, 4, MODE, true>(tmA, tmB, tmC, tmR, p, st);
+    }
     return single_wave ? launch_conv_gemm<BN, 4, 1, MODE, true>(tmA, tmB, tmC, tmR, p, st)
                        : launch_conv_gemm<BN, 2, kShortMinB, MODE, true>(tmA, tmB, tmC, tmR, p, st);
   }

@@ -39,6 +39,7 @@ class HGModule(nn.Module):
     """Base class: plan cache + dispatch.  Subclasses implement `_emit(b, x) -> Val` (or a list for models)."""
 
     _is_model = False  # models take the fp32 NCHW image batch and return a list of heatmaps
+    _single_output = False  # a model whose reference forward returns the head's tensor itself (train.generateMask)
 
     def _config_key(self):
         return ()
@@ -87,7 +88,7 @@ class HGModule(nn.Module):
             outs = run_plan(plan, x)
         if x.dtype != torch.float32:
             outs = [o.to(x.dtype) for o in outs]
-        return outs if self._is_model else outs[0]
+        return outs if (self._is_model and not self._single_output) else outs[0]
 
     def __getstate__(self):
         st = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
@@ -371,10 +372,32 @@ def make_train_family(g):
                     inter = b.cat([b.conv(ret, tmpOut), b.conv(ret2, ll), b.conv(down, inter)])
             return out
 
-    for cls in (hourglass, creatModel):
+    class generateMask(HGModule):
+        """train.py:604-622: the first stage alone (stem, three blocks, one hourglass, the 2-channel head); returns the
+        head's tensor itself, not a list."""
+
+        _is_model = True
+        _single_output = True
+
+        def __init__(self):
+            super(generateMask, self).__init__()
+            nFeats = g["nFeats"]
+            self.preprocess1 = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3), nn.ReLU(), ResidualBlock(64, 128, stride=2),
+                                             ResidualBlock(128, 128), ResidualBlock(128, nFeats))
+            self.stage1 = hourglass(nFeats)
+            self.stage1_out = nn.Conv2d(nFeats, g["nOutChannels_0"], 1, 1, 0, bias=False)
+
+        def _emit(self, b, x):
+            pre = self.preprocess1
+            inter = b.stem(pre[0], x)
+            for blk in (pre[2], pre[3], pre[4]):
+                inter = blk._emit(b, inter)
+            return [b.conv(self.stage1_out, self.stage1._emit(b, inter), head=True)]
+
+    for cls in (hourglass, creatModel, generateMask):
         cls.__module__ = g.get("__name__", cls.__module__)
         cls.__qualname__ = cls.__name__
-    return ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel
+    return ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel, generateMask
 
 
 def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4):

@@ -33,7 +33,7 @@ skeleton = 20
 inputsize = 256
 threshold = 1
 
-ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel = make_train_family(globals())
+ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel, generateMask = make_train_family(globals())
 
 
 class PCKh(_PCKhB):

@@ -296,3 +296,39 @@ def test_aspp_block_matches_reference_golden(dtype, tol):
         assert rel(om.detach().cpu(), torch.from_numpy(g["out_module"].astype(np.float32))) <= tol + 1e-3
     finally:
         hg.set_compute_dtype(torch.bfloat16)
+
+
+def test_generate_mask_state_dict_matches_reference():
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference tree not present (GPU box)")
+    import progressive_process_for_human_pose_estimation_b200.train as tr
+    ref = refload.load("train")
+    torch.manual_seed(0)
+    a = tr.generateMask().state_dict()
+    torch.manual_seed(0)
+    b = ref.generateMask().state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.gpu
+def test_generate_mask_is_the_first_stage_of_the_progressive_model():
+    """train.generateMask (train.py:604-622) shares its structure with creatModel's first stage: with the same weights
+    it must reproduce result[0] of the (golden-checked) three-stage model, as a tensor rather than a list."""
+    import progressive_process_for_human_pose_estimation_b200 as hg
+    import progressive_process_for_human_pose_estimation_b200.train as tr
+    hg.set_compute_dtype(torch.float32)
+    try:
+        torch.manual_seed(0)
+        full = tr.creatModel().cuda().eval()
+        gm = tr.generateMask().cuda().eval()
+        sd = full.state_dict()
+        gm.load_state_dict({k: sd[k] for k in gm.state_dict()})
+        x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(4)).cuda()
+        with torch.no_grad():
+            want = full(x)[0]
+            got = gm(x)
+        assert torch.is_tensor(got) and got.shape == want.shape == (2, 2, 32, 32)
+        assert rel(got.cpu(), want.cpu()) <= 1e-6
+    finally:
+        hg.set_compute_dtype(torch.bfloat16)

@@ -9,6 +9,10 @@
 // (reference try_with_torch.py:184-192,196-204,249-250,254-255).
 #include "hg_common.cuh"
 
+#ifndef HG_BN_BWD_MINB
+#define HG_BN_BWD_MINB 2   // resident blocks per SM the register allocation of bn_bwd_apply is held to
+#endif
+
 namespace hg {
 
 struct BnArgs {
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
 //   i.e. the bias gradient of the convolution that produced x.
 // ------------------------------------------------------------------------------------------------------
 template <typename T, bool ADD, bool CS>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ x,
+__global__ void __launch_bounds__(256, HG_BN_BWD_MINB) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ x,
                                                            const T* __restrict__ addend, T* __restrict__ dx,
                                                            long long M, BnArgs a, const float* __restrict__ redin,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,

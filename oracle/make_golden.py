@@ -246,6 +246,7 @@ FAMILIES = [
     ("try_with_aspp_remove_max_pool", "creatModel"),
     ("try_skeleton_and_keypoints", "creatModel"),
     ("hourglass_compare", "creatModel"),  # = performance_compare.creatModel_hourglass (same network, same fixture)
+    ("try_more_layer", "creatModel"),     # executed inline ASPP at the bottom level, 4 stacks, last head reused
     ("train", "creatModel"),              # progressive model: Q4 blocks, stride-2 down-sampling, ASPP bottom, cat skips
 ]
 

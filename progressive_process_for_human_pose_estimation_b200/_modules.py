@@ -400,7 +400,7 @@ def make_train_family(g):
     return ResidualBlock, _ASPPModule, ASPP_Block, hourglass, creatModel, generateMask
 
 
-def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4):
+def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4, repeat_last_head=False):
     """Shared body of the multi-head creatModel variants: per-stack heads conv2_k and re-injection conv4_k over a
     concatenation (try_different_stack.py:300-329; try_with_aspp_remove_max_pool.py:277-304)."""
     nStack = g["nStack"]
@@ -421,7 +421,11 @@ def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4):
             ll = self.residual4._emit(b, ll)
         ll = self.lin._emit(b, ll)
         if i >= len(heads):
-            continue  # the reference has no branch for further stacks: nothing is appended
+            if not repeat_last_head:
+                continue  # the reference has no branch for further stacks: nothing is appended
+            # try_more_layer.py:339-341 (`elif i >= 2`): every further stack goes through the last head, no re-injection
+            out.insert(i, b.conv(heads[-1], ll, head=True))
+            continue
         tmpOut = b.conv(heads[i], ll, head=True)
         out.insert(i, tmpOut)
         if i < len(reinj):
@@ -430,10 +434,12 @@ def _multihead_forward(self, b, x, g, cat_inter, with_pool, n_res4):
     return out
 
 
-def make_multihead_family(g, aspp_members=False, num_heads=3):
+def make_multihead_family(g, aspp_members=False, num_heads=3, aspp_executed=False):
     """try_different_stack.py / try_different_stack_without_skeleton.py (aspp_members=False) and try_with_aspp.py
     (aspp_members=True: ASPP modules are constructed -- they are in the state_dict -- but never executed, and the
-    bottom level has no extra residual blocks, try_with_aspp.py:250-279)."""
+    bottom level has no extra residual blocks, try_with_aspp.py:250-279).  aspp_executed=True is try_more_layer.py
+    (:249-296,339-341): the bottom level RUNS the inline ASPP (four dilated branches + image-level branch -> cat ->
+    1x1 conv without BN), and every stack beyond the third reuses the last head."""
     ResidualBlock, hourglass_s, lin, _ = make_s_family(g)
 
     # never called by this family's forward (quirk Q6) but executable on its own, like the reference class
@@ -472,7 +478,16 @@ def make_multihead_family(g, aspp_members=False, num_heads=3):
                 low1 = b.maxpool2(x)
                 for _ in range(nModules):
                     low1 = self.residual_block._emit(b, low1)
-                low2 = self.hourglass1._emit(b, low1) if self.n > 1 else low1
+                if self.n > 1:
+                    low2 = self.hourglass1._emit(b, low1)
+                elif aspp_executed:   # try_more_layer.py:281-290
+                    xs = [m._emit(b, low1) for m in (self.aspp1, self.aspp2, self.aspp3, self.aspp4)]
+                    x5 = b.global_avg_pool(low1)
+                    x5 = b.bn_relu(self.global_avg_pool[2], b.conv(self.global_avg_pool[1], x5))
+                    xs.append(b.broadcast_to(x5, low1.H, low1.W))
+                    low2 = b.conv_cat(self.conv1, xs)
+                else:
+                    low2 = low1
                 low3 = low2
                 for _ in range(nModules):
                     low3 = self.residual_block._emit(b, low3)
@@ -509,7 +524,8 @@ def make_multihead_family(g, aspp_members=False, num_heads=3):
             return (g["nStack"], g["nModules"])
 
         def _emit(self, b, x):
-            return _multihead_forward(self, b, x, g, cat_inter=False, with_pool=True, n_res4=g["nModules"])
+            return _multihead_forward(self, b, x, g, cat_inter=False, with_pool=True, n_res4=g["nModules"],
+                                      repeat_last_head=aspp_executed)
 
     for cls in (hourglass, creatModel, _ASPPModule):
         cls.__module__ = g.get("__name__", cls.__module__)

@@ -2,8 +2,9 @@
 Xinjie-Qiu/progressive_process_for_human_pose_estimation.
 
 Mirror modules keep the reference's script-level API (module-global configuration, class names, state_dict
-keys): try_with_torch, try_with_torch_100, only_one_hourgless.  Kernels live in libhg_sm100a.so
-(include/hg_sm100a.h); see DESIGN.md.
+keys): try_with_torch, try_with_torch_100, only_one_hourgless, try_different_stack(_without_skeleton), try_with_aspp,
+try_with_aspp_remove_max_pool, try_more_layer, try_skeleton_and_keypoints, hourglass_compare, performance_compare,
+train.  Kernels live in libhg_sm100a.so (include/hg_sm100a.h); see DESIGN.md.
 """
 from ._modules import get_compute_dtype, set_compute_dtype  # noqa: F401
 from .evaluate import (PCKh_from_logits, PCKh_half_standard, PCKh_hourglass, PCKh_softmax, decode_argmax,  # noqa: F401

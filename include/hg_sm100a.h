@@ -71,7 +71,9 @@ HG_API int hg_pack_conv_weight(const HgConvDesc* d, const float* w_oihw, void* w
 HG_API int hg_conv_fprop(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias,
                   const void* residual, void* y, float* stats, void* stream);
 
-/* dx = conv_transpose(dy, w) [+ addend]  (stride 1).  addend has the shape of dx, may be NULL. */
+/* dx = conv_transpose(dy, w) [+ addend].  addend has the shape of dx, may be NULL.  Stride 2 (the strided blocks of
+ * try_with_aspp_remove_max_pool.py:176,210,231 and train.py:411-447) runs as one tensor-core launch per input-pixel
+ * parity class, stored through a strided view of dx. */
 HG_API int hg_conv_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
                   void* stream);
 
@@ -109,9 +111,12 @@ typedef struct HgBnFold {
   int32_t pad_;
 } HgBnFold;
 
-/* 1 when the tensor-core kernels take this geometry (stride 1, "same" padding, power-of-two maps, <= 256 padded
- * channels, bf16); only then may the *_bn entry points be used. */
+/* 1 when the tensor-core kernels take this geometry: bf16, stride 1 with "same" padding (any dilation) or stride 2
+ * halving the map (3x3 pad 1 / 1x1 pad 0), power-of-two OUTPUT map at most 128 wide, <= 256 padded channels.  Every
+ * other bf16 geometry is HG_ERR_UNSUPPORTED unless hg_set_option("allow_ref_conv", 1) opted into the CUDA-core kernel. */
 HG_API int hg_conv_tc_eligible(const HgConvDesc* d);
+/* 1 when, additionally, the *_bn entry points below take it (stride 1). */
+HG_API int hg_conv_fold_eligible(const HgConvDesc* d);
 /* y = conv([relu](bn(x_raw))) + bias [+ residual]; stats / out_nchw as in hg_conv_fprop_ex. */
 HG_API int hg_conv_fprop_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* w_fprop,
                             const float* bias, const void* residual, void* y, float* stats, float* out_nchw,
@@ -147,7 +152,9 @@ HG_API int hg_unpack_conv_wgrad_slice(const HgConvDesc* d, const float* dw_packe
 HG_API int hg_mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
                        void* stream);
 
-/* Debug/validation switches: "force_ref_conv" = 1 routes bf16 convolutions to the CUDA-core kernels. */
+/* Switches: "allow_ref_conv" = 1 lets bf16 convolutions outside the tensor-core geometry run on the CUDA-core kernels
+ * (default 0: they fail with HG_ERR_UNSUPPORTED -- no silent slow path); "force_ref_conv" = 1 routes EVERY bf16
+ * convolution there (validation). */
 HG_API int hg_set_option(const char* name, int value);
 
 /* ---- BatchNorm2d + ReLU (try_with_torch.py:184-192,196-204,249-250,254-255) ------------------------- */

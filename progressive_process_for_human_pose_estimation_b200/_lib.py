@@ -99,6 +99,7 @@ SIGNATURES = {
     "hg_conv_dgrad": [C.POINTER(HgConvDesc), _P, _P, _P, _P, _P],
     "hg_conv_wgrad": [C.POINTER(HgConvDesc), _P, _P, _P, _P, _P],
     "hg_conv_tc_eligible": [C.POINTER(HgConvDesc)],
+    "hg_conv_fold_eligible": [C.POINTER(HgConvDesc)],
     "hg_conv_fprop_bn": [C.POINTER(HgConvDesc), C.POINTER(HgBnFold), _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_conv_fprop_bnout": [C.POINTER(HgConvDesc), C.POINTER(HgBnFold), _P, _P, _P, _P, _P, _P],
     "hg_conv_wgrad_bn": [C.POINTER(HgConvDesc), C.POINTER(HgBnFold), _P, _P, _P, _P, _P],

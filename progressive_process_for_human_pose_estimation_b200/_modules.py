@@ -54,8 +54,13 @@ class HGModule(nn.Module):
         params = list(self.named_parameters())
         train_params = torch.is_grad_enabled() and any(p.requires_grad for _, p in params)
         x_rg = torch.is_grad_enabled() and x.requires_grad
+        # lowering bakes in every parameter's requires_grad (gradient slots, frozen-parameter pruning) and every
+        # BatchNorm's own train / eval flag, so both are part of the key: unfreezing a parameter or calling .eval() on a
+        # sub-module after the first forward builds a new plan, as a stock nn.Module would simply honour the change
+        bn_flags = tuple(mod.training for mod in self.modules() if isinstance(mod, nn.BatchNorm2d))
         key = (tuple(x.shape), self.training, train_params, x_rg, _compute_dtype, self._config_key(),
-               tuple(p.data_ptr() for _, p in params))
+               tuple(p.data_ptr() for _, p in params),
+               tuple(p.requires_grad for _, p in params) if torch.is_grad_enabled() else (), bn_flags)
         cache = self.__dict__.setdefault("_plans", {})
         plan = cache.get(key)
         if plan is None:

@@ -9,6 +9,7 @@ namespace hg {
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
+static int g_allow_ref_conv = 0;
 int g_use_pdl = 1;
 extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta, g_short_1stage;
 extern int g_bn_blocks_per_sm, g_bn_bwd_blocks_per_sm;
@@ -76,9 +77,10 @@ struct BnFoldDev {
   int C, Cp;
 };
 BnFoldDev make_fold(const HgBnFold* f, int C, long long count);
-int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, int dil, int sign, const void* act,
-                   const void* wpk, const float* bias, const void* res, void* out, float* stats, float* out_nchw,
-                   int c_real, int mode, const BnFoldDev* fold, cudaStream_t st);
+int conv_tc_fprop(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias, const void* res, void* y,
+                  float* stats, float* out_nchw, int mode, const BnFoldDev* fold, cudaStream_t st);
+int conv_tc_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx, float* red,
+                  int mode, const BnFoldDev* fold, cudaStream_t st);
 int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
                     const BnFoldDev* fold, cudaStream_t st);
 template <typename T>
@@ -106,15 +108,36 @@ static int check_desc(const HgConvDesc* d) {
   return HG_OK;
 }
 
-// The tensor-core kernel takes stride-1 "same" convolutions on power-of-two maps.
+// The tensor-core kernels take stride-1 "same" convolutions and their stride-2 counterparts (output = input / 2:
+// 3x3 pad 1, 1x1 pad 0) whose OUTPUT map is a power of two no wider than 128, with at most 256 padded channels.
 static bool tc_eligible(const HgConvDesc* d) {
   if (g_force_ref_conv || d->dtype != HG_BF16) return false;
-  if (d->stride != 1 || d->R != d->S) return false;
-  if (2 * d->pad != d->dil * (d->R - 1)) return false;
-  if (!is_pow2(d->H) || !is_pow2(d->W) || d->W > 128) return false;
+  if ((d->stride != 1 && d->stride != 2) || d->R != d->S) return false;
+  int Ho = d->H, Wo = d->W;
+  if (d->stride == 1) {
+    if (2 * d->pad != d->dil * (d->R - 1)) return false;
+  } else {
+    if ((d->H & 1) || (d->W & 1) || d->dil != 1) return false;
+    if (!((d->R == 3 && d->pad == 1) || (d->R == 1 && d->pad == 0))) return false;
+    Ho = d->H / 2;
+    Wo = d->W / 2;
+  }
+  if (!is_pow2(Ho) || !is_pow2(Wo) || Wo > 128) return false;
+  if (d->R * d->S > 12 || d->dil * (d->R - 1) > 127) return false;
   const int ci = pad64(d->Cin), co = pad64(d->Cout);
   if (ci > 256 || co > 256 || co == 192 || ci == 192) return false;
   return true;
+}
+
+// bf16 convolutions the tensor-core kernels do not take: a hard error (north_star: no silent slow path) unless the
+// caller opted into the CUDA-core kernels with hg_set_option("allow_ref_conv", 1).
+static int ref_conv_allowed(const HgConvDesc* d, const char* who) {
+  if (d->dtype != HG_BF16 || g_allow_ref_conv || g_force_ref_conv) return HG_OK;
+  set_error("%s: bf16 convolution %dx%d k%d stride %d pad %d dil %d, %d -> %d channels is outside the tensor-core "
+            "kernels' geometry (stride 1 'same' or stride 2 halving, power-of-two output map <= 128 wide, <= 256 "
+            "padded channels); hg_set_option(\"allow_ref_conv\", 1) runs it on the 20-50x slower CUDA-core kernel",
+            who, d->H, d->W, d->R, d->stride, d->pad, d->dil, d->Cin, d->Cout);
+  return HG_ERR_UNSUPPORTED;
 }
 
 }  // namespace hg
@@ -137,6 +160,10 @@ int hg_device_ok(void) {
 int hg_set_option(const char* name, int value) {
   if (strcmp(name, "force_ref_conv") == 0) {
     g_force_ref_conv = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "allow_ref_conv") == 0) {
+    g_allow_ref_conv = value;
     return HG_OK;
   }
   if (strcmp(name, "dbg_ts") == 0) {   // 1: start stamping conv_gemm CTA 0 phases; 2: print the last kernel's stamps
@@ -250,10 +277,9 @@ int hg_conv_fprop_ex(const HgConvDesc* d, const void* x, const void* w_fprop, co
   if (rc) return rc;
   HG_REQUIRE(x && w_fprop && y, "hg_conv_fprop: x, w_fprop and y must be non-NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (tc_eligible(d)) {
-    return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cin), pad64(d->Cout), d->R, d->S, d->pad, d->dil, +1, x,
-                          w_fprop, bias, residual, y, stats, out_nchw, d->Cout, 0, nullptr, st);
-  }
+  if (tc_eligible(d)) return conv_tc_fprop(d, x, w_fprop, bias, residual, y, stats, out_nchw, 0, nullptr, st);
+  rc = ref_conv_allowed(d, "hg_conv_fprop");
+  if (rc) return rc;
   rc = d->dtype == HG_BF16 ? conv_ref_fprop<__nv_bfloat16>(d, x, w_fprop, bias, residual, y, out_nchw, st)
                            : conv_ref_fprop<float>(d, x, w_fprop, bias, residual, y, out_nchw, st);
   if (rc) return rc;
@@ -276,10 +302,9 @@ int hg_conv_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, cons
   if (rc) return rc;
   HG_REQUIRE(dy && w_dgrad && dx, "hg_conv_dgrad: dy, w_dgrad and dx must be non-NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (tc_eligible(d)) {
-    return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cout), pad64(d->Cin), d->R, d->S, d->pad, d->dil, -1, dy,
-                          w_dgrad, nullptr, addend, dx, nullptr, nullptr, 0, 0, nullptr, st);
-  }
+  if (tc_eligible(d)) return conv_tc_dgrad(d, dy, w_dgrad, addend, dx, nullptr, 0, nullptr, st);
+  rc = ref_conv_allowed(d, "hg_conv_dgrad");
+  if (rc) return rc;
   return d->dtype == HG_BF16 ? conv_ref_dgrad<__nv_bfloat16>(d, dy, w_dgrad, addend, dx, st)
                              : conv_ref_dgrad<float>(d, dy, w_dgrad, addend, dx, st);
 }
@@ -290,15 +315,18 @@ static int check_fold(const HgConvDesc* d, const HgBnFold* bn, const char* who) 
   HG_REQUIRE(bn != nullptr && bn->gamma && bn->beta, "%s: HgBnFold / gamma / beta is NULL", who);
   HG_REQUIRE(bn->use_running ? (bn->running_mean && bn->running_var) : (bn->stats != nullptr),
              "%s: statistics missing for the selected BatchNorm mode", who);
-  if (!tc_eligible(d)) {
-    set_error("%s: geometry not taken by the tensor-core kernels (hg_conv_tc_eligible() == 0); run hg_bn_apply and "
-              "the plain convolution instead", who);
+  if (!tc_eligible(d) || d->stride != 1) {
+    set_error("%s: geometry not taken by the BatchNorm-fused tensor-core kernels (hg_conv_fold_eligible() == 0); run "
+              "hg_bn_apply and the plain convolution instead", who);
     return HG_ERR_UNSUPPORTED;
   }
   return HG_OK;
 }
 
 int hg_conv_tc_eligible(const HgConvDesc* d) { return (d && check_desc(d) == HG_OK && tc_eligible(d)) ? 1 : 0; }
+int hg_conv_fold_eligible(const HgConvDesc* d) {
+  return (d && check_desc(d) == HG_OK && tc_eligible(d) && d->stride == 1) ? 1 : 0;
+}
 
 int hg_conv_fprop_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* w_fprop,
                      const float* bias, const void* residual, void* y, float* stats, float* out_nchw, void* stream) {
@@ -306,8 +334,7 @@ int hg_conv_fprop_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw,
   if (rc) return rc;
   HG_REQUIRE(x_raw && w_fprop && y, "hg_conv_fprop_bn: x_raw, w_fprop and y must be non-NULL");
   const BnFoldDev f = make_fold(bn, d->Cin, (long long)d->N * d->H * d->W);
-  return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cin), pad64(d->Cout), d->R, d->S, d->pad, d->dil, +1, x_raw,
-                        w_fprop, bias, residual, y, stats, out_nchw, d->Cout, 1, &f, (cudaStream_t)stream);
+  return conv_tc_fprop(d, x_raw, w_fprop, bias, residual, y, stats, out_nchw, 1, &f, (cudaStream_t)stream);
 }
 
 int hg_conv_fprop_bnout(const HgConvDesc* d, const HgBnFold* bn_out, const void* x, const void* w_fprop,
@@ -325,8 +352,7 @@ int hg_conv_fprop_bnout(const HgConvDesc* d, const HgBnFold* bn_out, const void*
     return HG_ERR_UNSUPPORTED;
   }
   const BnFoldDev f = make_fold(bn_out, d->Cout, (long long)d->N * d->H * d->W);
-  return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cin), pad64(d->Cout), d->R, d->S, d->pad, d->dil, +1, x, w_fprop,
-                        bias, nullptr, y, nullptr, out_nchw, d->Cout, 3, &f, (cudaStream_t)stream);
+  return conv_tc_fprop(d, x, w_fprop, bias, nullptr, y, nullptr, out_nchw, 3, &f, (cudaStream_t)stream);
 }
 
 int hg_conv_wgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* x_raw, const void* dy, float* dw_packed,
@@ -344,8 +370,7 @@ int hg_conv_dgrad_bn(const HgConvDesc* d, const HgBnFold* bn, const void* dy, co
   if (rc) return rc;
   HG_REQUIRE(dy && w_dgrad && x_raw && g && red, "hg_conv_dgrad_bn: NULL pointer");
   const BnFoldDev f = make_fold(bn, d->Cin, (long long)d->N * d->H * d->W);
-  return conv_gemm_bf16(d->N, d->H, d->W, pad64(d->Cout), pad64(d->Cin), d->R, d->S, d->pad, d->dil, -1, dy, w_dgrad,
-                        nullptr, x_raw, g, red, nullptr, 0, 2, &f, (cudaStream_t)stream);
+  return conv_tc_dgrad(d, dy, w_dgrad, x_raw, g, red, 2, &f, (cudaStream_t)stream);
 }
 
 int hg_unpack_conv_wgrad_slice(const HgConvDesc* d, const float* dw_packed, float* dw_oihw, int cin_total,
@@ -367,6 +392,8 @@ int hg_conv_wgrad(const HgConvDesc* d, const void* x, const void* dy, float* dw_
   HG_REQUIRE(x && dy, "hg_conv_wgrad: x and dy must be non-NULL");
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_eligible(d)) return conv_wgrad_bf16(d, x, dy, dw_oihw, dbias, nullptr, st);
+  rc = ref_conv_allowed(d, "hg_conv_wgrad");
+  if (rc) return rc;
   return d->dtype == HG_BF16 ? conv_ref_wgrad<__nv_bfloat16>(d, x, dy, dw_oihw, dbias, st)
                              : conv_ref_wgrad<float>(d, x, dy, dw_oihw, dbias, st);
 }

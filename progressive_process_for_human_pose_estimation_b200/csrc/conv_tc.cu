@@ -115,11 +115,14 @@ __device__ __forceinline__ void load_coef8(const float* p, float (&v)[8]) {
 }
 
 struct ConvGemmParams {
-  int M_total;        // output pixels = N*H*W
-  int H, W;           // spatial size (stride-1 "same" convolutions: in == out)
-  int taps_r, taps_s; // filter size
-  int dil, pad;       // dilation, padding
-  int sign;           // +1 fprop (offset = r*dil - pad), -1 dgrad (offset = pad - r*dil)
+  int M_total;        // output pixels of this GEMM = N*H*W
+  int H, W;           // spatial size of the GEMM's output grid (stride-2 data gradient: the half-resolution grid of one
+                      // output parity class)
+  int stride;         // A-operand origin = (h0, w0) * stride + tap offset (2: fprop of a stride-2 convolution)
+  int Hin, Win;       // spatial size of the A-operand tensor (kFold: which tile rows are convolution padding)
+  int ntaps;          // filter taps walked by this launch
+  signed char tap_dh[12], tap_dw[12];  // A-operand offset of each tap (fprop: r*dil - pad; dgrad: pad - r*dil; ...)
+  signed char tap_w[12];               // index of the tap's weight matrix inside the packed weight
   int kchunks;        // padded Cin / 64
   int n_total;        // padded Cout (row pitch of bias / stats)
   int c_real;         // real Cout (for the NCHW fp32 side output)
@@ -128,6 +131,8 @@ struct ConvGemmParams {
   float* out_nchw;    // optional fp32 NCHW copy of the first c_real channels (heatmap heads)
   int has_res;        // kPlain/kFold: residual added;  kMask: tmR is the raw BatchNorm input
   int n_tiles;        // padded Cout / BN
+  int parity;         // 1: tmC / tmR are 5-D parity views {C, pw, W, ph, N*H} of a tensor of twice the resolution: the
+  int par_h, par_w;   //    tile is stored to (read from) the pixels (2h + par_h, 2w + par_w)  (stride-2 data gradient)
   BnFoldDev fold;     // kFold: BatchNorm of the INPUT channels;  kMask: BatchNorm of the OUTPUT channels
   long long* ts;      // debug timestamps or null
 };
@@ -200,7 +205,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // 1-D grid, N tile fastest: the CTAs that share an activation tile run back to back (second read hits L2)
   const int m0 = (blockIdx.x / p.n_tiles) * 128;
   const int n_off = (blockIdx.x % p.n_tiles) * BN;
-  const int num_kb = p.taps_r * p.taps_s * p.kchunks;
+  const int num_kb = p.ntaps * p.kchunks;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
 
   if (threadIdx.x == 0) {
@@ -235,35 +240,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rem = m0 - n0 * hw;
       const int h0 = rem / p.W;
       const int w0 = rem - h0 * p.W;
-      if (!ALIAS && p.has_res) {
+      auto load_res = [&]() {
         mbar_expect_tx(res_full, L::kCBytes);
-        for (int pnl = 0; pnl < L::kCPanels; ++pnl)
-          tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
-      }
+        for (int pnl = 0; pnl < L::kCPanels; ++pnl) {
+          if (p.parity) tma_load_5d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, p.par_w, w0, p.par_h, n0 * p.H + h0);
+          else tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
+        }
+      };
+      if (!ALIAS && p.has_res) load_res();
       if (HG_TS && blockIdx.x == 0) p.ts[15] = clock64();
       int kb = 0;
-      for (int r = 0; r < p.taps_r; ++r) {
-        for (int s = 0; s < p.taps_s; ++s) {
-          const int dh = p.sign * (r * p.dil - p.pad);
-          const int dw = p.sign * (s * p.dil - p.pad);
-          for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
-            const int st = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&empty_bar[st], ph ^ 1);
-            mbar_expect_tx(&full_bar[st], L::kABytes + L::kBBytes);
-            tma_load_4d(sA + st * L::kABytes, &tmA, &full_bar[st], kc * 64, w0 + dw, h0 + dh, n0);
-            tma_load_3d(sB + st * L::kBBytes, &tmB, &full_bar[st], kc * 64, n_off, r * p.taps_s + s);
-            if (HG_TS && blockIdx.x == 0 && kb == 0) p.ts[3] = clock64();
-            if (HG_TS && blockIdx.x == 0 && kb < 8) p.ts[16 + kb] = clock64();
-          }
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int dh = p.tap_dh[t], dw = p.tap_dw[t], wt = p.tap_w[t];
+        for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
+          const int st = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_expect_tx(&full_bar[st], L::kABytes + L::kBBytes);
+          tma_load_4d(sA + st * L::kABytes, &tmA, &full_bar[st], kc * 64, w0 * p.stride + dw, h0 * p.stride + dh, n0);
+          tma_load_3d(sB + st * L::kBBytes, &tmB, &full_bar[st], kc * 64, n_off, wt);
+          if (HG_TS && blockIdx.x == 0 && kb == 0) p.ts[3] = clock64();
+          if (HG_TS && blockIdx.x == 0 && kb < 8) p.ts[16 + kb] = clock64();
         }
       }
       if (ALIAS && p.has_res) {
         // C aliases the pipeline stages: the residual / raw BatchNorm input may only land once every MMA has read them
         mbar_wait(tmem_full, 0);
-        mbar_expect_tx(res_full, L::kCBytes);
-        for (int pnl = 0; pnl < L::kCPanels; ++pnl)
-          tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
+        load_res();
       }
     }
     __syncwarp();
@@ -350,38 +353,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < kR; ++i) {
         const int mm = m0 + rbase + kRB * i;
         const int rem = mm % hw;
-        hrow[i] = mm < p.M_total ? rem / p.W : -0x40000000;  // out-of-range rows never pass the bounds test
+        hrow[i] = mm < p.M_total ? rem / p.W : -0x100000;  // out-of-range rows never pass the bounds test
         wrow[i] = rem % p.W;
       }
       const bool relu = p.fold.relu != 0;
       int kb = 0;
-      for (int r = 0; r < p.taps_r; ++r) {
-        for (int s = 0; s < p.taps_s; ++s) {
-          const int dh = p.sign * (r * p.dil - p.pad);
-          const int dw = p.sign * (s * p.dil - p.pad);
-          uint32_t vmask = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int dh = p.tap_dh[t], dw = p.tap_dw[t];
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int i = 0; i < kR; ++i)
+          if ((unsigned)(hrow[i] * p.stride + dh) < (unsigned)p.Hin && (unsigned)(wrow[i] * p.stride + dw) < (unsigned)p.Win)
+            vmask |= 1u << i;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
+          const int st = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          float sc[8], sh[8];
+          load_coef8(coef_s + kc * 64 + jch * 8, sc);
+          load_coef8(coef_s + 256 + kc * 64 + jch * 8, sh);
+          uint8_t* base = sA + st * L::kABytes + rbase * 128 + swz;
+          mbar_wait(&full_bar[st], ph);
+          uint4 u[kR];
+#pragma unroll
+          for (int i = 0; i < kR; ++i) u[i] = *reinterpret_cast<const uint4*>(base + i * kRB * 128);
 #pragma unroll
           for (int i = 0; i < kR; ++i)
-            if ((unsigned)(hrow[i] + dh) < (unsigned)p.H && (unsigned)(wrow[i] + dw) < (unsigned)p.W) vmask |= 1u << i;
-          for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
-            const int st = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            float sc[8], sh[8];
-            load_coef8(coef_s + kc * 64 + jch * 8, sc);
-            load_coef8(coef_s + 256 + kc * 64 + jch * 8, sh);
-            uint8_t* base = sA + st * L::kABytes + rbase * 128 + swz;
-            mbar_wait(&full_bar[st], ph);
-            uint4 u[kR];
+            u[i] = (vmask >> i) & 1u ? bn_relu_chunk(u[i], sc, sh, relu) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int i = 0; i < kR; ++i) u[i] = *reinterpret_cast<const uint4*>(base + i * kRB * 128);
-#pragma unroll
-            for (int i = 0; i < kR; ++i)
-              u[i] = (vmask >> i) & 1u ? bn_relu_chunk(u[i], sc, sh, relu) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int i = 0; i < kR; ++i) *reinterpret_cast<uint4*>(base + i * kRB * 128) = u[i];
-            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            mbar_arrive(&ready_bar[st]);
-          }
+          for (int i = 0; i < kR; ++i) *reinterpret_cast<uint4*>(base + i * kRB * 128) = u[i];
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          mbar_arrive(&ready_bar[st]);
         }
       }
     }
@@ -477,7 +478,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     named_bar_sync(1, kEpiThreads);
     if (et == 0) {
       const uint8_t* src = MODE == kMask ? sQ : sC;
-      for (int pnl = 0; pnl < L::kCPanels; ++pnl) tma_store_2d(&tmC, src + pnl * 16384, n_off + pnl * 64, m0);
+      if (p.parity) {
+        const int hw = p.H * p.W;
+        const int n0 = m0 / hw;
+        const int rem = m0 - n0 * hw;
+        const int h0 = rem / p.W;
+        const int w0 = rem - h0 * p.W;
+        for (int pnl = 0; pnl < L::kCPanels; ++pnl)
+          tma_store_5d(&tmC, src + pnl * 16384, n_off + pnl * 64, p.par_w, w0, p.par_h, n0 * p.H + h0);
+      } else {
+        for (int pnl = 0; pnl < L::kCPanels; ++pnl) tma_store_2d(&tmC, src + pnl * 16384, n_off + pnl * 64, m0);
+      }
       tma_store_commit();
     }
     if (p.stats != nullptr) {
@@ -638,14 +649,27 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
   }
 }
 
-// act: [N,H,W,Kp] bf16 (A operand); wpk: [taps][Np][Kp] bf16; out/res: [N,H,W,Np] bf16.
+// Geometry of one GEMM launch: the output grid [N,H,W] (128-pixel tiles), the A-operand tensor it gathers from and
+// the list of filter taps (A offset + weight index) it walks.
+struct GemmGeom {
+  int N, H, W;      // output grid of this launch
+  int Ha, Wa;       // spatial size of the A-operand tensor
+  int stride;       // A origin = output (h, w) * stride + tap offset; also the element stride of the A box
+  int ntaps;
+  signed char dh[12], dw[12], wt[12];
+  int wtaps;        // filter taps in the packed weight (R*S)
+  int parity, par_h, par_w;   // out / res are parity views of a [N,2H,2W,Np] tensor
+};
+
+// act: [N,Ha,Wa,Kp] bf16 (A operand); wpk: [wtaps][Np][Kp] bf16; out/res: [N,H,W,Np] bf16 (or the parity view).
 // mode kFold: `fold` describes the BatchNorm of act's channels (act is the raw tensor).
 // mode kMask: `fold` describes the BatchNorm of out's channels, `res` is its raw input, `stats` receives the sums.
-int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, int dil, int sign,
-                   const void* act, const void* wpk, const float* bias, const void* res, void* out,
-                   float* stats, float* out_nchw, int c_real, int mode, const BnFoldDev* fold, cudaStream_t st) {
+static int conv_gemm_bf16(const GemmGeom& g, int Kp, int Np, const void* act, const void* wpk, const float* bias,
+                          const void* res, void* out, float* stats, float* out_nchw, int c_real, int mode,
+                          const BnFoldDev* fold, cudaStream_t st) {
+  const int N = g.N, H = g.H, W = g.W;
   if (!is_pow2(H) || !is_pow2(W) || W > 128) {
-    set_error("conv_gemm_bf16: H and W must be powers of two with W <= 128 (got %dx%d)", H, W);
+    set_error("conv_gemm_bf16: output H and W must be powers of two with W <= 128 (got %dx%d)", H, W);
     return HG_ERR_UNSUPPORTED;
   }
   if (Kp % 64 || Np % 64 || Np > 256 || Kp > 256) {
@@ -669,16 +693,18 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   }
   CUtensorMap tmA, tmB, tmC, tmR;
   {
-    uint64_t dims[4] = {(uint64_t)Kp, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t str[3] = {(uint64_t)Kp * 2, (uint64_t)W * Kp * 2, (uint64_t)H * W * Kp * 2};
-    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-    uint32_t es[4] = {1, 1, 1, 1};
+    // a box of bw x bh x bn OUTPUT pixels walks the A tensor with element stride `stride` (TMA traverses
+    // ceil(box / elementStride) elements per dimension; out-of-bounds elements are zero = convolution padding)
+    uint64_t dims[4] = {(uint64_t)Kp, (uint64_t)g.Wa, (uint64_t)g.Ha, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Kp * 2, (uint64_t)g.Wa * Kp * 2, (uint64_t)g.Ha * g.Wa * Kp * 2};
+    uint32_t box[4] = {64, (uint32_t)(bw * g.stride), (uint32_t)(bh * g.stride), (uint32_t)bn};
+    uint32_t es[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
     int rc = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, act, dims, str, box, es,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)Np, (uint64_t)(R * S)};
+    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)Np, (uint64_t)g.wtaps};
     uint64_t str[2] = {(uint64_t)Kp * 2, (uint64_t)Np * Kp * 2};
     uint32_t box[3] = {64, (uint32_t)BN, 1};
     uint32_t es[3] = {1, 1, 1};
@@ -686,7 +712,7 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  {
+  if (!g.parity) {
     uint64_t dims[2] = {(uint64_t)Np, (uint64_t)M};
     uint64_t str[1] = {(uint64_t)Np * 2};
     uint32_t box[2] = {64, 128};
@@ -697,17 +723,38 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
     rc = encode_tmap(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, res ? res : out, dims, str, box, es,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  } else {
+    // [N, 2H, 2W, Np] seen as {Np, pw (2), W, ph (2), N*H}: pixel (2h + ph, 2w + pw) of image n sits at
+    // (c, pw, w, ph, n*H + h); a tile of 128 grid pixels is the box {64, 1, bw, 1, bh*bn}
+    const uint64_t row = (uint64_t)2 * W * Np * 2;   // bytes of one full-resolution image row
+    uint64_t dims[5] = {(uint64_t)Np, 2, (uint64_t)W, 2, (uint64_t)N * H};
+    uint64_t str[4] = {(uint64_t)Np * 2, (uint64_t)Np * 4, row, row * 2};
+    uint32_t box[5] = {64, 1, (uint32_t)bw, 1, (uint32_t)(bh * bn)};
+    uint32_t es[5] = {1, 1, 1, 1, 1};
+    int rc = encode_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, out, dims, str, box, es,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tmap(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, res ? res : out, dims, str, box, es,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
   }
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   p.M_total = (int)M;
   p.H = H;
   p.W = W;
-  p.taps_r = R;
-  p.taps_s = S;
-  p.dil = dil;
-  p.pad = pad;
-  p.sign = sign;
+  p.stride = g.stride;
+  p.Hin = g.Ha;
+  p.Win = g.Wa;
+  p.ntaps = g.ntaps;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.tap_dh[t] = g.dh[t];
+    p.tap_dw[t] = g.dw[t];
+    p.tap_w[t] = g.wt[t];
+  }
+  p.parity = g.parity;
+  p.par_h = g.par_h;
+  p.par_w = g.par_w;
   p.kchunks = Kp / 64;
   p.n_total = Np;
   p.c_real = c_real;
@@ -724,7 +771,11 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
       return HG_ERR_BAD_ARG;
     }
   }
-  const bool long_k = R * S * (Kp / 64) > 4;
+  if (g.parity && (mode != kPlain || stats || out_nchw)) {
+    set_error("conv_gemm_bf16: a parity-view output takes the plain epilogue only");
+    return HG_ERR_BAD_ARG;
+  }
+  const bool long_k = g.ntaps * (Kp / 64) > 4;
   const bool has_res = res != nullptr;
   if (mode == kMask && (!res || !stats)) {
     set_error("conv_gemm_bf16: mask mode needs the raw BatchNorm input and the reduction buffer");
@@ -742,6 +793,103 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
   return dispatch_conv_gemm<128, kPlain>(long_k, has_res, tmA, tmB, tmC, tmR, p, st);
 }
 
+static inline int out_size(int in, int k, int stride, int pad, int dil) {
+  return (in + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+}
+
+// y[N,Ho,Wo,Cout_p] = conv(x[N,H,W,Cin_p]) (+ epilogue of `mode`): stride 1 or 2.
+int conv_tc_fprop(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias, const void* res, void* y,
+                  float* stats, float* out_nchw, int mode, const BnFoldDev* fold, cudaStream_t st) {
+  GemmGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = d->N;
+  g.H = out_size(d->H, d->R, d->stride, d->pad, d->dil);
+  g.W = out_size(d->W, d->S, d->stride, d->pad, d->dil);
+  g.Ha = d->H;
+  g.Wa = d->W;
+  g.stride = d->stride;
+  g.wtaps = d->R * d->S;
+  for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->S; ++s) {
+      g.dh[g.ntaps] = (signed char)(r * d->dil - d->pad);
+      g.dw[g.ntaps] = (signed char)(s * d->dil - d->pad);
+      g.wt[g.ntaps] = (signed char)(r * d->S + s);
+      ++g.ntaps;
+    }
+  return conv_gemm_bf16(g, pad64(d->Cin), pad64(d->Cout), x, w_fprop, bias, res, y, stats, out_nchw, d->Cout, mode,
+                        fold, st);
+}
+
+// dx[N,H,W,Cin_p] = conv_transpose(dy[N,Ho,Wo,Cout_p]) [+ addend] (+ epilogue of `mode`, stride 1 only).
+// Stride 2: hi = 2*ho - pad + r*dil, so the input pixels of one parity class (hi & 1, wi & 1) receive contributions
+// from a fixed subset of the taps, each a plain shifted read of dy: one launch per class over the half-resolution
+// grid, stored through a parity view of dx (no scatter, no zero-stuffed dy).
+int conv_tc_dgrad(const HgConvDesc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx, float* red,
+                  int mode, const BnFoldDev* fold, cudaStream_t st) {
+  const int Ho = out_size(d->H, d->R, d->stride, d->pad, d->dil);
+  const int Wo = out_size(d->W, d->S, d->stride, d->pad, d->dil);
+  const int Kp = pad64(d->Cout), Np = pad64(d->Cin);
+  GemmGeom g;
+  memset(&g, 0, sizeof(g));
+  g.N = d->N;
+  g.Ha = Ho;
+  g.Wa = Wo;
+  g.stride = 1;
+  g.wtaps = d->R * d->S;
+  if (d->stride == 1) {
+    g.H = d->H;
+    g.W = d->W;
+    for (int r = 0; r < d->R; ++r)
+      for (int s = 0; s < d->S; ++s) {
+        g.dh[g.ntaps] = (signed char)(d->pad - r * d->dil);
+        g.dw[g.ntaps] = (signed char)(d->pad - s * d->dil);
+        g.wt[g.ntaps] = (signed char)(r * d->S + s);
+        ++g.ntaps;
+      }
+    return conv_gemm_bf16(g, Kp, Np, dy, w_dgrad, nullptr, addend, dx, red, nullptr, 0, mode, fold, st);
+  }
+  if (mode != kPlain) {
+    set_error("conv_tc_dgrad: the BatchNorm-fused data gradient takes stride-1 convolutions only");
+    return HG_ERR_UNSUPPORTED;
+  }
+  g.H = d->H / 2;
+  g.W = d->W / 2;
+  g.parity = 1;
+  GemmGeom cls[4];
+  bool any_empty = false;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      GemmGeom& c = cls[ph * 2 + pw];
+      c = g;
+      c.par_h = ph;
+      c.par_w = pw;
+      for (int r = 0; r < d->R; ++r) {
+        const int th = ph + d->pad - r * d->dil;
+        if (th & 1) continue;
+        for (int s = 0; s < d->S; ++s) {
+          const int tw = pw + d->pad - s * d->dil;
+          if (tw & 1) continue;
+          c.dh[c.ntaps] = (signed char)(th / 2);
+          c.dw[c.ntaps] = (signed char)(tw / 2);
+          c.wt[c.ntaps] = (signed char)(r * d->S + s);
+          ++c.ntaps;
+        }
+      }
+      any_empty = any_empty || c.ntaps == 0;
+    }
+  if (any_empty) {
+    // no tap reaches some parity class (1x1 stride 2): those pixels are the addend alone / zero
+    const size_t bytes = (size_t)d->N * d->H * d->W * Np * 2;
+    if (addend) HG_CUDA_OK(cudaMemcpyAsync(dx, addend, bytes, cudaMemcpyDeviceToDevice, st));
+    else HG_CUDA_OK(cudaMemsetAsync(dx, 0, bytes, st));
+  }
+  for (int i = 0; i < 4; ++i) {
+    if (cls[i].ntaps == 0) continue;
+    int rc = conv_gemm_bf16(cls[i], Kp, Np, dy, w_dgrad, nullptr, addend, dx, nullptr, nullptr, 0, kPlain, nullptr, st);
+    if (rc) return rc;
+  }
+  return HG_OK;
+}
 
 // ======================================================================================================
 // wgrad:  dw[tap][co][ci] += sum_m dy[m, co] * x[m (+) tap, ci]
@@ -757,7 +905,9 @@ int conv_gemm_bf16(int N, int H, int W, int Kp, int Np, int R, int S, int pad, i
 // are rewritten in shared memory as [relu](scale*x + shift) (zero in the padding) before the MMA reads them.
 // ======================================================================================================
 struct WgradParams {
-  int H, W, N;
+  int H, W, N;       // grid of dy (the reduction dimension): H, W are the OUTPUT size of the convolution
+  int stride;        // x origin = (h, w) * stride + tap offset
+  int Hin, Win;      // spatial size of x
   int taps_s;        // filter width S
   int dil, pad;
   int tap_rows;      // taps handled per CTA (T)
@@ -845,8 +995,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             const int r = tap / p.taps_s, s = tap - r * p.taps_s;
             const int dh = r * p.dil - p.pad, dw = s * p.dil - p.pad;
             for (int pn = 0; pn < p.n_panels; ++pn)
-              tma_load_4d(sB + (t * p.n_panels + pn) * 8192, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 + dw, h0 + dh,
-                          n0);
+              tma_load_4d(sB + (t * p.n_panels + pn) * 8192, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 * p.stride + dw,
+                          h0 * p.stride + dh, n0);
           }
         }
       }
@@ -904,7 +1054,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           for (int k = 0; k < 4; ++k) {
             const int mm = (kb_beg + i) * 64 + rbase + 16 * k;
             const int rem = mm % hw;
-            hrow[k] = mm / hw < p.N ? rem / p.W : -0x40000000;
+            hrow[k] = mm / hw < p.N ? rem / p.W : -0x100000;
             wrow[k] = rem % p.W;
           }
           uint8_t* sB = smem + st * p.stage_bytes + a_bytes + rbase * 128 + swz;
@@ -916,7 +1066,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             uint32_t vmask = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if ((unsigned)(hrow[k] + dh) < (unsigned)p.H && (unsigned)(wrow[k] + dw) < (unsigned)p.W) vmask |= 1u << k;
+              if ((unsigned)(hrow[k] * p.stride + dh) < (unsigned)p.Hin &&
+                  (unsigned)(wrow[k] * p.stride + dw) < (unsigned)p.Win)
+                vmask |= 1u << k;
             for (int pn = 0; pn < p.n_panels; ++pn) {
               float sc[8], sh[8];
               load_coef8(coef_s + (pn0 + pn) * 64 + jch * 8, sc);
@@ -1022,7 +1174,8 @@ int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* 
 int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
                     const BnFoldDev* fold, cudaStream_t st) {
   const int Cin_p = pad64(d->Cin), Cout_p = pad64(d->Cout);
-  const int H = d->H, W = d->W;
+  // the reduction runs over the pixels of dy: H, W = OUTPUT size of the convolution; x is read at stride `stride`
+  const int H = out_size(d->H, d->R, d->stride, d->pad, d->dil), W = out_size(d->W, d->S, d->stride, d->pad, d->dil);
   const long long M = (long long)d->N * H * W;
   if (dw) {
     const int taps = d->R * d->S;
@@ -1046,10 +1199,10 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
       if (rc) return rc;
     }
     {
-      uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
-      uint64_t str[3] = {(uint64_t)Cin_p * 2, (uint64_t)W * Cin_p * 2, (uint64_t)H * W * Cin_p * 2};
-      uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-      uint32_t es[4] = {1, 1, 1, 1};
+      uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+      uint64_t str[3] = {(uint64_t)Cin_p * 2, (uint64_t)d->W * Cin_p * 2, (uint64_t)d->H * d->W * Cin_p * 2};
+      uint32_t box[4] = {64, (uint32_t)(bw * d->stride), (uint32_t)(bh * d->stride), (uint32_t)bn};
+      uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
       int rc = encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box, es,
                            CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
@@ -1059,6 +1212,9 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.H = H;
     p.W = W;
     p.N = d->N;
+    p.stride = d->stride;
+    p.Hin = d->H;
+    p.Win = d->W;
     p.taps_s = d->S;
     p.dil = d->dil;
     p.pad = d->pad;

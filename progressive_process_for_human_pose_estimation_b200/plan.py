@@ -150,7 +150,9 @@ class Builder:
 
     def bn_relu(self, bn, x, relu=True):
         assert bn.num_features == x.C
-        if self.training or not bn.track_running_stats:
+        # per module, like nn.BatchNorm2d itself: a sub-module put in eval() under a training root uses (and keeps) its
+        # running statistics
+        if bn.training or not bn.track_running_stats:
             x.needs_stats = True
         out = Val(x.N, x.H, x.W, x.C, self._rg(x), "bn")
         self.ops.append(Op("bn", [x], out, bn=bn, relu=relu))
@@ -473,7 +475,7 @@ class Plan:
                 cons = op.out.consumers[0]
                 if cons.kind != "conv" or cons.ins[0] is not op.out or cons.ins[1] is op.out:
                     continue
-                if not lib.hg_conv_tc_eligible(C.byref(self._conv_desc(cons.attrs["conv"], op.out))):
+                if not lib.hg_conv_fold_eligible(C.byref(self._conv_desc(cons.attrs["conv"], op.out))):
                     continue
                 op.attrs["folded"] = _FOLD_BN >= 2   # activation not materialised
                 op.attrs["masked"] = True            # consumer's dgrad epilogue does the reduce
@@ -483,7 +485,7 @@ class Plan:
         # ---- inference: conv -> eval-mode BN(+ReLU) in ONE kernel (hg_conv_fprop_bnout): the BatchNorm is a per-channel
         # affine with known coefficients, applied in the convolution's epilogue; the raw conv output never exists
         self.n_bn_out = 0
-        if _FUSE_EVAL_BN and self.dt == torch.bfloat16 and not self.need_bwd and not self.training:
+        if _FUSE_EVAL_BN and self.dt == torch.bfloat16 and not self.need_bwd:
             lib = L.load()
             for op in ops:
                 if op.kind != "conv" or op.ins[1] is not None or op.attrs["head"] or op.attrs["mix"] is not None:
@@ -493,6 +495,8 @@ class Plan:
                     continue
                 cons = out.consumers[0]
                 if cons.kind != "bn" or cons.attrs.get("folded") or not cons.attrs["bn"].track_running_stats:
+                    continue
+                if cons.attrs["bn"].training:
                     continue
                 if op.attrs.get("fold") is not None and op.attrs["fold"].attrs.get("folded"):
                     continue
@@ -550,7 +554,7 @@ class Plan:
         return f"{cv.in_channels}->{cv.out_channels} k{cv.kernel_size[0]} @{x.H}x{x.W}"
 
     def _bn_desc(self, bn, x, relu):
-        use_running = 0 if (self.training or not bn.track_running_stats) else 1
+        use_running = 0 if (bn.training or not bn.track_running_stats) else 1
         d = L.HgBnDesc(x.M, x.C, self.hdt, float(bn.eps), 1 if relu else 0, use_running)
         self._keep.append(d)
         return d
@@ -558,7 +562,7 @@ class Plan:
     def _bn_fold(self, bnop):
         """HgBnFold of a folded BatchNorm op + the tensors a call using it reads through the struct."""
         bn, x = bnop.attrs["bn"], bnop.ins[0]
-        use_running = 0 if (self.training or not bn.track_running_stats) else 1
+        use_running = 0 if (bn.training or not bn.track_running_stats) else 1
         f = L.HgBnFold(x.stats.data_ptr() if x.stats is not None else None, self._p32(bn.weight).data_ptr(),
                        self._p32(bn.bias).data_ptr(),
                        self._rstat(bn.running_mean).data_ptr() if bn.running_mean is not None else None,
@@ -634,7 +638,7 @@ class Plan:
                                L.ptr(self._p32(bn.weight)), L.ptr(self._p32(bn.bias)),
                                L.ptr(self._rstat(bn.running_mean)),
                                L.ptr(self._rstat(bn.running_var)), L.ptr(out.buf), st)
-                if self.training and bn.track_running_stats:
+                if bn.training and bn.track_running_stats:
                     running.setdefault(id(bn), (bn, []))[1].append((x.stats, float(x.M)))
                 if out.needs_stats:  # BN output feeding another BN directly (hourglass_compare.py:549-553)
                     self._stats_call(f, out)
@@ -1039,7 +1043,7 @@ class Plan:
         self._refresh_bias()
         self.stats_arena.zero_()
         self._run_calls(self.fwd_calls)
-        if self.training:
+        if self.running_tables is not None:
             for buf, shadow in self._shadow_buf.values():
                 buf.copy_(shadow)
 

@@ -15,6 +15,7 @@ CPU part: the drop-in builds the same state_dict (keys, shapes, seeded values) a
 """
 import importlib
 import os
+import warnings
 
 import numpy as np
 import pytest
@@ -186,13 +187,19 @@ def test_family_fp32_train_step_vs_yardstick(script, factory, fixture):
     try:
         net = build(script, factory).cuda()
         out, losses = run_step(net, g)
+        vacuous = []
         for i, o in enumerate(out):
             err = rel(o.detach().cpu().numpy(), g[f"out{i}"])
             # 15 x the reference's own fp32-vs-fp64 divergence (try_more_layer normalises the image-level ASPP branch
             # over 2 samples at this fixture size: 11.5 x observed)
             tol = max(1e-4, 15 * float(g["out_noise_fp64"][i]))
-            if tol < 0.5:
-                assert err <= tol, (i, err, tol)
+            if tol >= 0.5:
+                # the reference's own fp32-vs-fp64 divergence makes this output's band vacuous (chaotic stage at random
+                # init): say so instead of passing silently; only gross failure is still caught
+                warnings.warn(f"{script} out{i}: yardstick band {tol:.2f} >= 0.5 -- comparison is vacuous here "
+                              f"(measured rel-L2 {err:.3f}); tight parity for this family is the eval-mode test")
+                vacuous.append(i)
+            assert err <= min(tol, 1.0), (i, err, tol)
             assert abs(losses[i].item() - g["losses"][i]) <= max(1e-4, tol) * abs(g["losses"][i])
         _check_grads(net, g, 2e-2, 4)
         sd = net.state_dict()
@@ -203,6 +210,7 @@ def test_family_fp32_train_step_vs_yardstick(script, factory, fixture):
                 a, b = digest(sd[k].float())[2:], g["after_digest"][i][2:]
                 rtol = max(2e-3, 10 * float(g["out_noise_fp64"].max()))
                 assert np.abs(a - b).max() <= rtol * np.abs(b).max() + 1e-5, k
+        assert len(vacuous) < len(out), f"{script}: every output band is vacuous ({vacuous})"
     finally:
         hg.set_compute_dtype(torch.bfloat16)
 

@@ -125,6 +125,104 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     close(dbias, 2 * dyr.sum((0, 2, 3)), 1e-3, "dbias")
 
 
+STRIDE2_CASES = [
+    # N, H, W (input), Cin, Cout, k
+    (2, 64, 64, 128, 128, 3),     # try_with_aspp_remove_max_pool.py:176 (conv2 of a stride-2 block)
+    (2, 64, 64, 256, 256, 1),     # downsaple[0] of the same block (:186), bias-free in the reference
+    (3, 128, 128, 64, 64, 3),     # residual1 = ResidualBlock(64, 128, stride=2) (:263)
+    (2, 128, 128, 64, 128, 1),
+    (4, 8, 8, 128, 128, 3),       # deepest level: 8x8 -> 4x4
+    (2, 8, 8, 256, 256, 1),
+    (1, 256, 256, 64, 64, 3),     # widest input the stride-2 box takes (output 128 wide)
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", STRIDE2_CASES)
+def test_conv_stride2_fprop_dgrad_wgrad(case, dtype):
+    """Stride-2 convolutions of the Q4 blocks (try_with_aspp_remove_max_pool.py:165-201, train.py:411-447): on the bf16
+    path they run on the tensor-core kernels (element-strided TMA box for fprop / wgrad, one launch per input parity
+    class for dgrad); hg_conv_tc_eligible says so and allow_ref_conv stays off."""
+    N, H, W, Cin, Cout, k = case
+    torch.manual_seed(1)
+    dev = "cuda"
+    pad = k // 2
+    Ho, Wo = H // 2, W // 2
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    d = L.HgConvDesc(N, H, W, Cin, Cout, k, k, 2, pad, 1, L.hg_dtype(dtype))
+    if dtype == torch.bfloat16:
+        assert L.load().hg_conv_tc_eligible(C.byref(d)) == 1
+        assert L.load().hg_conv_fold_eligible(C.byref(d)) == 0
+    Cin_p, Cout_p = L.pad64(Cin), L.pad64(Cout)
+    xq = nhwc(x, dtype)
+    wf = torch.empty(k * k, Cout_p, Cin_p, device=dev, dtype=dtype)
+    wd = torch.empty(k * k, Cin_p, Cout_p, device=dev, dtype=dtype)
+    bias_p = torch.zeros(Cout_p, device=dev)
+    bias_p[:Cout] = b
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
+    y = torch.full((N, Ho, Wo, Cout_p), float("nan"), device=dev, dtype=dtype)
+    stats = torch.zeros(2 * Cout_p, device=dev)
+    L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), None, L.ptr(y), L.ptr(stats), None, st)
+    xr, wr = nchw(xq, Cin), w.to(dtype).float()
+    ref = F.conv2d(xr, wr, b, 2, pad, 1)
+    close(nchw(y, Cout), ref, tol(dtype), "fprop stride 2")
+    yv = y[..., :Cout].float()
+    close(stats[:Cout], yv.sum((0, 1, 2)), 1e-3, "stats sum")
+    close(stats[Cout_p:Cout_p + Cout], (yv * yv).sum((0, 1, 2)), 1e-3, "stats sumsq")
+
+    dy = torch.randn(N, Cout, Ho, Wo, device=dev)
+    dyq = nhwc(dy, dtype)
+    dyr = nchw(dyq, Cout)
+    ref_dx0 = torch.nn.grad.conv2d_input(xr.shape, wr, dyr, 2, pad, 1)
+    dx = torch.full((N, H, W, Cin_p), float("nan"), device=dev, dtype=dtype)
+    L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), None, L.ptr(dx), st)
+    close(nchw(dx, Cin), ref_dx0, tol(dtype), "dgrad stride 2")
+    add = torch.randn(N, Cin, H, W, device=dev)
+    addq = nhwc(add, dtype)
+    dx.fill_(float("nan"))
+    L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), L.ptr(addq), L.ptr(dx), st)
+    close(nchw(dx, Cin), ref_dx0 + nchw(addq, Cin), tol(dtype), "dgrad stride 2 (+addend)")
+    dx2 = addq.clone()
+    L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), L.ptr(dx2), L.ptr(dx2), st)
+    assert torch.equal(dx2, dx), "in-place strided dgrad accumulation differs"
+
+    dwp = torch.zeros(k * k, Cout_p, Cin_p, device=dev)
+    dbias = torch.zeros(Cout, device=dev)
+    for _ in range(2):
+        L.call("hg_conv_wgrad", C.byref(d), L.ptr(xq), L.ptr(dyq), L.ptr(dwp), L.ptr(dbias), st)
+    dw = torch.zeros_like(w)
+    L.call("hg_unpack_conv_wgrad", C.byref(d), L.ptr(dwp), L.ptr(dw), 0, st)
+    ref_dw = 2 * torch.nn.grad.conv2d_weight(xr, w.shape, dyr, 2, pad, 1)
+    close(dw, ref_dw, 1e-3 if dtype == torch.bfloat16 else 2e-5, "wgrad stride 2")
+    close(dbias, 2 * dyr.sum((0, 2, 3)), 1e-3, "dbias")
+
+
+def test_bf16_conv_outside_tensor_core_geometry_fails_loudly():
+    """No silent CUDA-core route on the bf16 path: an odd map is HG_ERR_UNSUPPORTED unless allow_ref_conv is set."""
+    dev, dtype = "cuda", torch.bfloat16
+    N, H, W, Cin, Cout, k = 1, 24, 24, 64, 64, 3
+    d = L.HgConvDesc(N, H, W, Cin, Cout, k, k, 1, 1, 1, L.hg_dtype(dtype))
+    assert L.load().hg_conv_tc_eligible(C.byref(d)) == 0
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+    xq = nhwc(x, dtype)
+    wf = torch.empty(k * k, 64, 64, device=dev, dtype=dtype)
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), None, st)
+    y = torch.zeros(N, H, W, 64, device=dev, dtype=dtype)
+    with pytest.raises(RuntimeError, match="allow_ref_conv"):
+        L.call("hg_conv_fprop", C.byref(d), L.ptr(xq), L.ptr(wf), None, None, L.ptr(y), None, st)
+    L.call("hg_set_option", b"allow_ref_conv", 1)
+    try:
+        L.call("hg_conv_fprop", C.byref(d), L.ptr(xq), L.ptr(wf), None, None, L.ptr(y), None, st)
+        close(nchw(y, Cout), F.conv2d(nchw(xq, Cin), w.to(dtype).float(), None, 1, 1, 1), 2e-2, "ref conv")
+    finally:
+        L.call("hg_set_option", b"allow_ref_conv", 0)
+
+
 FOLD_CASES = [
     # N, H, W, Cin, Cout, k, dil, residual, relu, eval_mode
     (2, 64, 64, 128, 128, 3, 1, False, True, False),

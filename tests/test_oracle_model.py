@@ -139,3 +139,28 @@ def test_custom_losses_restate_reference():
         la.backward()
         lb.backward()
         assert torch.equal(la, lb) and torch.equal(a.grad, b.grad), fn.__name__
+
+
+def test_oracle_reproduces_warm_8stack_golden():
+    """Headline configuration on WARM weights (tests/golden/warm_s_8stack.npz: 80 Adam steps of the real reference):
+    the oracle port's train-mode forward and per-stack losses equal what the reference computed from those weights."""
+    g = np.load(os.path.join(GOLDEN, "warm_s_8stack.npz"))
+
+    def unbits(a):
+        return torch.from_numpy(a.astype(np.int32)).to(torch.int32).bitwise_left_shift(16).view(torch.float32)
+
+    sd = {}
+    for k in (str(k) for k in g["keys"]):
+        a = g["w:" + k]
+        sd[k] = unbits(a) if a.dtype == np.uint16 else torch.from_numpy(a)
+    twt.nStack, twt.nOutChannels = 8, 16
+    assert list(twt.creatModel().state_dict().keys()) == list(sd.keys())
+    with torch.no_grad():
+        out = ho.creat_model_s(ho.clone_state(sd), unbits(g["x_bits"]), ho.Config(nStack=8, nOutChannels=16))
+    tgt = torch.from_numpy(g["target"])
+    for k in range(8):
+        d = digest(out[k])
+        # same torch ops on the same host: identical up to the thread count's reduction order
+        np.testing.assert_allclose(d[2:], g["out_digest"][k][2:], rtol=2e-4, atol=1e-6)
+        assert abs(torch.nn.functional.mse_loss(out[k], tgt).item() - g["losses"][k]) <= 1e-4 * g["losses"][k]
+    np.testing.assert_allclose(out[7].numpy(), g["out7"], rtol=0, atol=2e-4 * np.abs(g["out7"]).max())

@@ -151,6 +151,12 @@ HG_API int hg_unpack_conv_wgrad_slice(const HgConvDesc* d, const float* dw_packe
  * and un-folded from their gradients (dW = T^T dW_eff). */
 HG_API int hg_mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
                        void* stream);
+/* Rectangular form: out[rows_out, cols] (=|+=) T[rows_out, rows_in] * in[rows_in, cols]; with transpose = 1,
+ * out[rows_in, cols] (=|+=) T^T * in[rows_out, cols].  The gather-add limb maps of
+ * try_skeleton_from_keypoints_merge.py:296-298 (tmpOut = cat(k, k[:, a_l] + k[:, b_l]): 17 keypoint maps -> 36
+ * channels) are T = [I; G] applied to the 17-channel head: folded into the head's weights like the in-place mix. */
+HG_API int hg_mix_rows_rect(const float* T, const float* in, float* out, int rows_out, int rows_in, int cols,
+                            int transpose, int accumulate, void* stream);
 
 /* Switches: "allow_ref_conv" = 1 lets bf16 convolutions outside the tensor-core geometry run on the CUDA-core kernels
  * (default 0: they fail with HG_ERR_UNSUPPORTED -- no silent slow path); "force_ref_conv" = 1 routes EVERY bf16
@@ -372,7 +378,8 @@ typedef struct HgLabelDesc {
   int32_t draw_points; /* 1: draw.point value k+1 for visible joints; 2: MPII draw.ellipse on the float centre +-0.5
                           (train.py:681-686) */
   int32_t draw_lines;  /* draw.line for limbs whose both ends are visible */
-  int32_t line_value;  /* 0: limb index + 1, otherwise this constant (background map = 1) */
+  int32_t line_value;  /* 0: limb index + 1; > 0: this constant (background map = 1); < 0: the limb index itself
+                          (try_skeleton_from_keypoints_merge.py:130-133) */
 } HgLabelDesc;
 HG_API int hg_render_labels(const HgLabelDesc* d, const double* keypoints, const int32_t* num_persons, const double* img_wh,
                      const int32_t* limbs, int64_t* out, void* stream);

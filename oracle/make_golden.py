@@ -248,6 +248,7 @@ FAMILIES = [
     ("hourglass_compare", "creatModel"),  # = performance_compare.creatModel_hourglass (same network, same fixture)
     ("try_more_layer", "creatModel"),     # executed inline ASPP at the bottom level, 4 stacks, last head reused
     ("train", "creatModel"),              # progressive model: Q4 blocks, stride-2 down-sampling, ASPP bottom, cat skips
+    ("try_skeleton_from_keypoints_merge", "creatModel"),   # gather-add limb maps: 17-ch head -> 36-ch output (N3)
 ]
 
 

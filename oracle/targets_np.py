@@ -107,7 +107,8 @@ def draw_line(canvas, x0, y0, x1, y1, ink):
 def label_map(persons, img_wh, J, limbs, H=64, W=64, center_mode=0, draw_points=False, draw_lines=True,
               line_value=0):
     """One image -> int64 [H, W] label map (try_different_stack.py:114-155; try_skeleton_and_keypoints.py:93-114).
-    Points carry value k+1, limbs value i+1 (or `line_value` when non-zero: the background map uses 1)."""
+    Points carry value k+1, limbs value i+1 (or `line_value` when positive: the background map uses 1; negative: the
+    limb index i itself, try_skeleton_from_keypoints_merge.py:130-133)."""
     persons = np.asarray(persons, dtype=np.float64).reshape(-1, J, 3)
     canvas = np.zeros([H, W], dtype=np.uint8)
     for p in range(persons.shape[0]):
@@ -133,5 +134,5 @@ def label_map(persons, img_wh, J, limbs, H=64, W=64, center_mode=0, draw_points=
         if draw_lines:
             for i, (a, b) in enumerate(limbs):
                 if v[a] > 0 and v[b] > 0:
-                    draw_line(canvas, x[a], y[a], x[b], y[b], line_value if line_value > 0 else i + 1)
+                    draw_line(canvas, x[a], y[a], x[b], y[b], line_value if line_value > 0 else (i if line_value < 0 else i + 1))
     return canvas.astype(np.int64)

@@ -125,6 +125,7 @@ SIGNATURES = {
     "hg_pack_conv_weight_slice": [C.POINTER(HgConvDesc), _P, _I, _I, _P, _P, _P],
     "hg_unpack_conv_wgrad_slice": [C.POINTER(HgConvDesc), _P, _P, _I, _I, _I, _P],
     "hg_mix_rows": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "hg_mix_rows_rect": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
     "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
     "hg_image_u8_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P, _P, _P],

@@ -606,6 +606,74 @@ def make_skeleton_family(g):
     return ResidualBlock, hourglass, lin, creatModel
 
 
+def make_merge_family(g):
+    """try_skeleton_from_keypoints_merge.py:264-305: S-family network whose 17-channel keypoint head is
+    extended with 19 limb maps GATHERED from it, out_skeleton[l] = k[sks[l][0]] + k[sks[l][1]], tmpOut = cat(k, skeleton)
+    (36 channels, returned to the loss and re-injected through conv4: 36 -> nFeats).  The gather-add and the cat are
+    one linear map T = [I; G] of the head's output, so the head runs as ONE convolution with the folded weights
+    T W / T b (plan.py `mix`, rectangular), and dW = T^T dW_eff: no gather kernel, no 36-channel copy."""
+    ResidualBlock, hourglass, lin, _ = make_s_family(g)
+
+    def gather_matrix():
+        C = g["nOutChannels"]
+        sks = g["sks"]
+        T = torch.zeros(C + len(sks), C)
+        T[:C] = torch.eye(C)
+        for l, (a, c) in enumerate(sks):
+            T[C + l, a] += 1.0
+            T[C + l, c] += 1.0
+        return T
+
+    class creatModel(HGModule):
+        _is_model = True
+
+        def __init__(self):
+            super(creatModel, self).__init__()
+            nFeats, nOutChannels = g["nFeats"], g["nOutChannels"]
+            self.conv1 = nn.Conv2d(3, 64, 7, 2, 3)
+            self.relu = nn.ReLU()
+            self.residual1 = ResidualBlock(64, 128)
+            self.max_pool1 = nn.MaxPool2d(2)
+            self.residual2 = ResidualBlock(128, 128)
+            self.residual3 = ResidualBlock(128, nFeats)
+            self.hourglass1 = hourglass(4, nFeats)
+            self.residual4 = ResidualBlock(nFeats, nFeats)
+            self.lin = lin(nFeats, nFeats)
+            self.conv2 = nn.Conv2d(nFeats, nOutChannels, 1, 1, 0)
+            self.conv3 = nn.Conv2d(nFeats, nFeats, 1, 1, 0)
+            self.conv4 = nn.Conv2d(nOutChannels + 19, nFeats, 1, 1, 0)
+
+        def _config_key(self):
+            return (g["nStack"], g["nModules"], tuple(map(tuple, g["sks"])))
+
+        def _emit(self, b, x):
+            nStack, nModules = g["nStack"], g["nModules"]
+            T = gather_matrix()
+            x = b.stem(self.conv1, x)
+            x = self.residual1._emit(b, x)
+            x = b.maxpool2(x)
+            x = self.residual2._emit(b, x)
+            x = self.residual3._emit(b, x)
+            out = []
+            inter = x
+            for i in range(nStack):
+                hg = self.hourglass1._emit(b, inter)
+                ll = hg
+                for _ in range(nModules):
+                    ll = self.residual4._emit(b, ll)
+                ll = self.lin._emit(b, ll)
+                tmpOut = b.conv(self.conv2, ll, head=True, mix=T)   # cat(out_keypoints, out_skeleton)
+                out.insert(i, tmpOut)
+                if i < nStack:
+                    ll_ = b.conv(self.conv3, ll)
+                    inter = b.conv(self.conv4, tmpOut, residual=ll_)
+            return out
+
+    creatModel.__module__ = g.get("__name__", creatModel.__module__)
+    creatModel.__qualname__ = "creatModel"
+    return ResidualBlock, hourglass, lin, creatModel
+
+
 def make_q4_block(g):
     """ResidualBlock of the later scripts (try_with_aspp_remove_max_pool.py:165-201 = hourglass_compare.py:405-441 =
     train.py:411-447): stride on the 3x3, bn4 after conv3, and -- because `self.stride != 1 | self.numIn !=

@@ -94,7 +94,7 @@ template <typename T>
 int pack_weight(const HgConvDesc*, const float*, void*, void*, int, int, cudaStream_t);
 int unpack_wgrad(const HgConvDesc* d, const float* g, float* dw, int accumulate, int cin_total, int cin_off,
                  cudaStream_t st);
-int mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
+int mix_rows(const float* T, const float* in, float* out, int Ro, int Ri, int cols, int transpose, int accumulate,
              cudaStream_t st);
 int bn_stats_launch(int dtype, const void* x, long long M, int Cp, float* stats, cudaStream_t st);
 
@@ -268,7 +268,14 @@ int hg_mix_rows(const float* T, const float* in, float* out, int R, int cols, in
                 void* stream) {
   HG_REQUIRE(T && in && out && R > 0 && cols > 0, "hg_mix_rows: bad arguments");
   HG_REQUIRE(in != out, "hg_mix_rows: in-place recombination is not supported");
-  return mix_rows(T, in, out, R, cols, transpose, accumulate, (cudaStream_t)stream);
+  return mix_rows(T, in, out, R, R, cols, transpose, accumulate, (cudaStream_t)stream);
+}
+
+int hg_mix_rows_rect(const float* T, const float* in, float* out, int rows_out, int rows_in, int cols, int transpose,
+                     int accumulate, void* stream) {
+  HG_REQUIRE(T && in && out && rows_out > 0 && rows_in > 0 && cols > 0, "hg_mix_rows_rect: bad arguments");
+  HG_REQUIRE(in != out, "hg_mix_rows_rect: in-place recombination is not supported");
+  return mix_rows(T, in, out, rows_out, rows_in, cols, transpose, accumulate, (cudaStream_t)stream);
 }
 
 int hg_conv_fprop_ex(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias,

@@ -318,28 +318,30 @@ int pack_weight(const HgConvDesc* d, const float* w, void* wf, void* wd, int cin
 template int pack_weight<float>(const HgConvDesc*, const float*, void*, void*, int, int, cudaStream_t);
 template int pack_weight<__nv_bfloat16>(const HgConvDesc*, const float*, void*, void*, int, int, cudaStream_t);
 
-// out[R, cols] (=|+=) T[R, R] (or its transpose) * in[R, cols]: recombination of head channels
-// (limb mix of try_skeleton_and_keypoints.py:279-298 folded into the head's weights and gradients)
+// out[Ro, cols] (=|+=) T[Ro, Ri] * in[Ri, cols]   or, transposed,   out[Ri, cols] (=|+=) T^T * in[Ro, cols]:
+// recombination of head channels (limb mix of try_skeleton_and_keypoints.py:279-298, gather-add limb maps of
+// try_skeleton_from_keypoints_merge.py:296-298) folded into the head's weights and un-folded from their gradients
 __global__ void mix_rows_kernel(const float* __restrict__ T, const float* __restrict__ in, float* __restrict__ out,
-                                int R, int cols, int transpose, int accumulate) {
-  const long long total = (long long)R * cols;
+                                int Ro, int Ri, int cols, int transpose, int accumulate) {
+  const int rows_out = transpose ? Ri : Ro, rows_in = transpose ? Ro : Ri;
+  const long long total = (long long)rows_out * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cols), r = (int)(i / cols);
     float acc = 0.f;
-    for (int k = 0; k < R; ++k) {
-      const float t = transpose ? T[k * R + r] : T[r * R + k];
+    for (int k = 0; k < rows_in; ++k) {
+      const float t = transpose ? T[k * Ri + r] : T[r * Ri + k];
       if (t != 0.f) acc = fmaf(t, in[(long long)k * cols + c], acc);
     }
     out[i] = accumulate ? out[i] + acc : acc;
   }
 }
-int mix_rows(const float* T, const float* in, float* out, int R, int cols, int transpose, int accumulate,
+int mix_rows(const float* T, const float* in, float* out, int Ro, int Ri, int cols, int transpose, int accumulate,
              cudaStream_t st) {
-  const long long total = (long long)R * cols;
+  const long long total = (long long)(transpose ? Ri : Ro) * cols;
   int blocks = ceil_div(total, 256);
   if (blocks > 1184) blocks = 1184;
-  mix_rows_kernel<<<blocks, 256, 0, st>>>(T, in, out, R, cols, transpose, accumulate);
+  mix_rows_kernel<<<blocks, 256, 0, st>>>(T, in, out, Ro, Ri, cols, transpose, accumulate);
   HG_LAUNCH_OK("mix_rows_kernel");
   count_launch();
   return HG_OK;

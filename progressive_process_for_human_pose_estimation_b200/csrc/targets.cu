@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) render_labels_kernel(HgLabelDesc d, const
           const int y0 = (int)centre_of(k[3 * a + 1], ih, (double)d.H, d.center_mode, 1);
           const int x1 = (int)centre_of(k[3 * c], iw, (double)d.W, d.center_mode, 1);
           const int y1 = (int)centre_of(k[3 * c + 1], ih, (double)d.H, d.center_mode, 1);
-          line8(canvas, d.W, d.H, x0, y0, x1, y1, d.line_value > 0 ? d.line_value : l + 1);
+          line8(canvas, d.W, d.H, x0, y0, x1, y1, d.line_value > 0 ? d.line_value : (d.line_value < 0 ? l : l + 1));
         }
       }
     }

@@ -23,6 +23,9 @@ _USE_LANES = os.environ.get("HG_STREAM_LANES", "1") != "0"
 _WGRAD_LANES = int(os.environ.get("HG_WGRAD_LANES", "4"))
 # 0: BatchNorm kernels stay separate; 1: only the data-gradient epilogue is fused (ReLU mask + BN-backward sums);
 # 2: additionally the forward / weight-gradient convolutions apply BN+ReLU to their operand tiles (no activation in HBM)
+# 3: like 2, but only where the consumer is a 1x1 convolution (bn1 -> conv1, bn3 -> conv3 of a residual block)
+# 4: 3 + every consumer whose grid is a single wave (the 4x4 .. 16x16 levels are latency chains: a separate BatchNorm
+#    kernel costs a launch there, the shared-memory rewrite nothing);  5: only the single-wave consumers
 _FOLD_BN = int(os.environ.get("HG_FOLD_BN", "1"))
 # inference (eval mode, no gradients): a BatchNorm(+ReLU) whose producer is a tensor-core convolution runs in that
 # convolution's epilogue (hg_conv_fprop_bnout)
@@ -125,17 +128,20 @@ class Builder:
     def conv(self, conv, x, residual=None, head=False, cin_off=0, use_bias=True, mix=None):
         """nn.Conv2d (+ fused residual add).  head=True also produces the fp32 NCHW tensor the module returns.
         cin_off: x feeds the input-channel slice [cin_off, cin_off + x.C) of the weight (see conv_cat).
-        mix: [Cout, Cout] matrix T applied to the output channels (folded into the weights: T W, T b)."""
+        mix: [Cout', Cout] matrix T applied to the output channels (folded into the weights: T W, T b); the op then
+        produces Cout' channels (square for the in-place limb mix, [36, 17] for the gather-add limb maps)."""
         k, s, p, d = conv.kernel_size, conv.stride, conv.padding, conv.dilation
         assert k[0] == k[1] and s[0] == s[1] and p[0] == p[1] and d[0] == d[1]
         assert cin_off + x.C <= conv.in_channels and (cin_off > 0 or x.C <= conv.in_channels), (conv.in_channels, x.C)
         Ho = (x.H + 2 * p[0] - d[0] * (k[0] - 1) - 1) // s[0] + 1
         Wo = (x.W + 2 * p[0] - d[0] * (k[0] - 1) - 1) // s[0] + 1
-        out = Val(x.N, Ho, Wo, conv.out_channels, self._rg(x, residual), "conv")
+        cout = conv.out_channels if mix is None else int(mix.shape[0])
+        assert mix is None or int(mix.shape[1]) == conv.out_channels
+        out = Val(x.N, Ho, Wo, cout, self._rg(x, residual), "conv")
         self.ops.append(Op("conv", [x, residual], out, conv=conv, head=head, cin_off=cin_off,
-                           use_bias=use_bias and conv.bias is not None, mix=mix))
+                           use_bias=use_bias and conv.bias is not None, mix=mix, cout=cout))
         if head:
-            self.outputs.append((out, conv.out_channels))
+            self.outputs.append((out, cout))
         return out
 
     def conv_cat(self, conv, xs, head=False):
@@ -431,11 +437,12 @@ class Plan:
                 assert self.conv_info[key]["cin_seg"] == x.C
                 continue
             k = cv.kernel_size[0]
-            cin_p, cout_p = L.pad64(x.C), L.pad64(cv.out_channels)
             mix = op.attrs["mix"]
+            cout = op.attrs["cout"]   # != cv.out_channels under a rectangular channel mix
+            cin_p, cout_p = L.pad64(x.C), L.pad64(cout)
             whole = (op.attrs["cin_off"] == 0 and x.C == cv.in_channels)
             direct = (k == 1 and whole and mix is None and cin_p == x.C and cout_p == cv.out_channels)
-            info = dict(conv=cv, cin_off=op.attrs["cin_off"], cin_seg=x.C, mix=None,
+            info = dict(conv=cv, cin_off=op.attrs["cin_off"], cin_seg=x.C, mix=None, cout=cout,
                         wf=torch.zeros(k * k, cout_p, cin_p, device=dev, dtype=self.dt),
                         wd=torch.zeros(k * k, cin_p, cout_p, device=dev, dtype=self.dt),
                         bias=torch.zeros(cout_p, device=dev, dtype=torch.float32), direct=direct,
@@ -445,9 +452,9 @@ class Plan:
             if mix is not None:
                 assert whole, "channel mixing is only supported on un-sliced convolutions"
                 info["mix"] = mix.to(device=dev, dtype=torch.float32).contiguous()
-                info["w_eff"] = torch.zeros(cv.out_channels, cv.in_channels * k * k, device=dev)
+                info["w_eff"] = torch.zeros(cout, cv.in_channels * k * k, device=dev)
                 info["dweff_off"] = packed_total
-                packed_total += cv.out_channels * cv.in_channels * k * k
+                packed_total += cout * cv.in_channels * k * k
                 info["dbeff_off"] = packed_total
                 packed_total += cout_p
                 info["bias_copy"] = False
@@ -477,7 +484,12 @@ class Plan:
                     continue
                 if not lib.hg_conv_fold_eligible(C.byref(self._conv_desc(cons.attrs["conv"], op.out))):
                     continue
-                op.attrs["folded"] = _FOLD_BN >= 2   # activation not materialised
+                # activation not materialised: every consumer (2), or only 1x1 consumers (3: one shared-memory rewrite per
+                # operand element instead of nine for a 3x3)
+                k1 = cons.attrs["conv"].kernel_size[0] == 1
+                one_wave = (op.out.M + 127) // 128 * max(1, L.pad64(cons.attrs["conv"].out_channels) // 128) <= 148
+                op.attrs["folded"] = (_FOLD_BN == 2 or (_FOLD_BN == 3 and k1) or (_FOLD_BN == 4 and (k1 or one_wave))
+                                      or (_FOLD_BN == 5 and one_wave))
                 op.attrs["masked"] = True            # consumer's dgrad epilogue does the reduce
                 cons.attrs["fold"] = op
                 self.n_masked += 1
@@ -543,8 +555,8 @@ class Plan:
                 c.tag = f"C{d.C} M{d.M}" + (" +addend" if c.name == "hg_bn_bwd_apply" and c.args[9] is not None else "")
 
     # ------------------------------------------------------------------------------------------------
-    def _conv_desc(self, cv, x):
-        d = L.HgConvDesc(x.N, x.H, x.W, x.C, cv.out_channels, cv.kernel_size[0], cv.kernel_size[1],
+    def _conv_desc(self, cv, x, cout=None):
+        d = L.HgConvDesc(x.N, x.H, x.W, x.C, cv.out_channels if cout is None else cout, cv.kernel_size[0], cv.kernel_size[1],
                          cv.stride[0], cv.padding[0], cv.dilation[0], self.hdt)
         self._keep.append(d)
         return d
@@ -578,16 +590,16 @@ class Plan:
             info = self.conv_info[key]
             cv = info["conv"]
             k = cv.kernel_size[0]
-            d = L.HgConvDesc(1, 1, 1, info["cin_seg"], cv.out_channels, k, k, 1, 0, 1, self.hdt)
+            d = L.HgConvDesc(1, 1, 1, info["cin_seg"], info["cout"], k, k, 1, 0, 1, self.hdt)
             self._keep.append(d)
             src = self._p32(cv.weight)
             if info["mix"] is not None:  # W_eff = T W, b_eff = T b
-                self._emit(f, "hg_mix_rows", L.ptr(info["mix"]), L.ptr(src), L.ptr(info["w_eff"]), cv.out_channels,
-                           cv.in_channels * k * k, 0, 0, st)
+                self._emit(f, "hg_mix_rows_rect", L.ptr(info["mix"]), L.ptr(src), L.ptr(info["w_eff"]), info["cout"],
+                           cv.out_channels, cv.in_channels * k * k, 0, 0, st)
                 src = info["w_eff"]
                 if cv.bias is not None:
-                    self._emit(f, "hg_mix_rows", L.ptr(info["mix"]), L.ptr(self._p32(cv.bias)), L.ptr(info["bias"]),
-                               cv.out_channels, 1, 0, 0, st)
+                    self._emit(f, "hg_mix_rows_rect", L.ptr(info["mix"]), L.ptr(self._p32(cv.bias)), L.ptr(info["bias"]),
+                               info["cout"], cv.out_channels, 1, 0, 0, st)
             self._emit(f, "hg_pack_conv_weight_slice", C.byref(d), L.ptr(src), cv.in_channels, info["cin_off"],
                        L.ptr(info["wf"]), L.ptr(info["wd"]) if self.need_bwd else None, st)
         for v, kind in self.b.inputs:
@@ -610,7 +622,7 @@ class Plan:
             elif k == "conv":
                 cv, x, res, out = op.attrs["conv"], op.ins[0], op.ins[1], op.out
                 info = self.conv_info[op.attrs["key"]]
-                d = self._conv_desc(cv, x)
+                d = self._conv_desc(cv, x, info["cout"])
                 nchw = self.out_static[self.out_index[id(out)]] if op.attrs["head"] else None
                 bias = self._bias_ptr(cv, info) if op.attrs["use_bias"] else None
                 if op.attrs.get("bn_out") is not None:
@@ -745,7 +757,7 @@ class Plan:
             if k == "conv":
                 cv, x, res = op.attrs["conv"], op.ins[0], op.ins[1]
                 info = self.conv_info[op.attrs["key"]]
-                d = self._conv_desc(cv, x)
+                d = self._conv_desc(cv, x, info["cout"])
                 foldop = op.attrs.get("fold")
                 if res is not None:
                     self._grad_passthrough(res, G)
@@ -757,7 +769,7 @@ class Plan:
                 if bn_only:
                     bslot = None
                 if info["mix"] is not None and bslot is not None:  # db_eff first, un-mixed at the end
-                    bslot = self.packed_arena[info["dbeff_off"]:info["dbeff_off"] + cv.out_channels]
+                    bslot = self.packed_arena[info["dbeff_off"]:info["dbeff_off"] + info["cout"]]
                 if wslot is not None or bslot is not None:
                     if wslot is None:
                         dwp = None
@@ -880,7 +892,7 @@ class Plan:
                 continue
             cv = info["conv"]
             k = cv.kernel_size[0]
-            d = L.HgConvDesc(1, 1, 1, info["cin_seg"], cv.out_channels, k, k, 1, 0, 1, self.hdt)
+            d = L.HgConvDesc(1, 1, 1, info["cin_seg"], info["cout"], k, k, 1, 0, 1, self.hdt)
             self._keep.append(d)
             dwp = self.packed_arena[info["goff"]:info["goff"] + info["gsize"]]
             self._pending_writes = []
@@ -891,16 +903,17 @@ class Plan:
                 tail.append(_Call("hg_unpack_conv_wgrad_slice", (C.byref(d), L.ptr(dwp), L.ptr(slot), cv.in_channels,
                                                                  info["cin_off"], 1, st)))
             else:  # dW = T^T dW_eff, db = T^T db_eff
-                n = cv.out_channels * cv.in_channels * k * k
+                n = info["cout"] * cv.in_channels * k * k
                 dweff = self.packed_arena[info["dweff_off"]:info["dweff_off"] + n]
                 tail.append(_Call("hg_unpack_conv_wgrad_slice", (C.byref(d), L.ptr(dwp), L.ptr(dweff), cv.in_channels,
                                                                  0, 0, st)))
-                tail.append(_Call("hg_mix_rows", (L.ptr(info["mix"]), L.ptr(dweff), L.ptr(slot), cv.out_channels,
-                                                  cv.in_channels * k * k, 1, 1, st)))
+                tail.append(_Call("hg_mix_rows_rect", (L.ptr(info["mix"]), L.ptr(dweff), L.ptr(slot), info["cout"],
+                                                       cv.out_channels, cv.in_channels * k * k, 1, 1, st)))
                 if cv.bias is not None and self._gslot(cv.bias) is not None:
-                    dbeff = self.packed_arena[info["dbeff_off"]:info["dbeff_off"] + cv.out_channels]
-                    tail.append(_Call("hg_mix_rows", (L.ptr(info["mix"]), L.ptr(dbeff), L.ptr(self._gslot(cv.bias)),
-                                                      cv.out_channels, 1, 1, 1, st)))
+                    dbeff = self.packed_arena[info["dbeff_off"]:info["dbeff_off"] + info["cout"]]
+                    tail.append(_Call("hg_mix_rows_rect", (L.ptr(info["mix"]), L.ptr(dbeff),
+                                                           L.ptr(self._gslot(cv.bias)), info["cout"], cv.out_channels,
+                                                           1, 1, 1, st)))
             tail[-1].writes = tuple(self._pending_writes)
             self._pending_writes = []
             # the wgrad calls themselves only touch the packed accumulator, not the OIHW slot

@@ -36,6 +36,7 @@ FAMILIES = [
     ("performance_compare", "creatModel_hourglass", "hourglass_compare"),  # same network as hourglass_compare
     ("train", "creatModel", "train"),
     ("try_more_layer", "creatModel", "try_more_layer"),
+    ("try_skeleton_from_keypoints_merge", "creatModel", "try_skeleton_from_keypoints_merge"),
 ]
 IDS = [f[0] for f in FAMILIES]
 # try_more_layer runs its image-level ASPP BatchNorm (train.py-style global average pool -> 1x1 -> BN) over only TWO

@@ -434,7 +434,7 @@ def test_warm_weight_8stack_train_step_vs_reference_golden(dtype):
         worst = max(worst, e)
         assert e <= gtol, (n, e)
         checked += 1
-    assert checked > 100, checked
+    assert checked > 60, checked   # 199 tensors - 28 grad-less - the analytically-zero bias gradients
     if fp32:
         for n in (str(s) for s in g["small_grad_names"]):
             i = names.index(n)

@@ -330,8 +330,8 @@ def test_conv_with_folded_batchnorm(case):
 
 
 def test_folded_entry_points_reject_unsupported_geometry():
-    d = L.HgConvDesc(2, 32, 32, 128, 128, 3, 3, 2, 1, 1, L.HG_BF16)  # stride 2: CUDA-core path only
-    assert L.load().hg_conv_tc_eligible(C.byref(d)) == 0
+    d = L.HgConvDesc(2, 32, 32, 128, 128, 3, 3, 2, 1, 1, L.HG_BF16)  # stride 2: tensor cores yes, BatchNorm folding no
+    assert L.load().hg_conv_tc_eligible(C.byref(d)) == 1 and L.load().hg_conv_fold_eligible(C.byref(d)) == 0
     t = torch.zeros(4096, device="cuda")
     fold = L.HgBnFold(t.data_ptr(), t.data_ptr(), t.data_ptr(), None, None, 1e-5, 1, 0, 0)
     rc = L.load().hg_conv_fprop_bn(C.byref(d), C.byref(fold), L.ptr(t), L.ptr(t), None, None, L.ptr(t), None, None,

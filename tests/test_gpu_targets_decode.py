@@ -93,6 +93,20 @@ def test_label_maps_bit_exact(mode):
     assert int(got[0].abs().sum()) == 0
 
 
+def test_merge_script_targets_bit_exact():
+    """try_skeleton_from_keypoints_merge.render_targets: Gaussians (last person) + skeleton map with value = limb index
+    (reference :91-135; oracle pinned to the reference dataset class by tests/test_oracle_targets_pckh.py)."""
+    import progressive_process_for_human_pose_estimation_b200.try_skeleton_from_keypoints_merge as mg
+    kp, wh, npers = synth_people(21, 8, 3, 17)
+    gauss, smap = mg.render_targets(kp, wh, num_persons=npers)
+    assert gauss.shape == (8, 17, 64, 64) and smap.shape == (8, 64, 64) and smap.dtype == torch.int64
+    for b in range(8):
+        ref = targets_np.label_map(kp[b, :npers[b]], wh[b], 17, mg.sks, line_value=-1)
+        assert np.array_equal(smap[b].cpu().numpy(), ref), b
+        gref = targets_np.gauss_map(kp[b, :npers[b]], wh[b], 17, truncate=True)
+        assert np.abs(gauss[b].cpu().numpy() - gref).max() <= 1.2e-7
+
+
 def test_mpii_label_maps_bit_exact():
     """MPII keypoint (ImageDraw.ellipse on the float centre) and skeleton maps of train.py:668-690 against the numpy
     oracle (pinned to Pillow by tests/test_oracle_targets_pckh.py::test_mpii_label_maps_match_pillow)."""

@@ -207,3 +207,33 @@ def test_pckh_oracle_vs_reference_classes_many_seeds():
         a = oo.PCKh().forward(torch.from_numpy(d["x14"]), torch.from_numpy(d["t14"]))
         c, t = pckh_np.pckh_a(d["x14"], d["t14"], d["x14"].shape[0])
         assert a == c / t
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_merge_dataset_targets_vs_reference_class():
+    """try_skeleton_from_keypoints_merge.myImageDataset_COCO.__getitem__ (reference :91-135) through the fake-COCO
+    shim: Gaussians of the last person, skeleton label map drawn with value = limb index over all persons."""
+    import tempfile
+
+    from PIL import Image
+
+    from oracle.make_golden import FakeCOCO
+    mg = refload.load("try_skeleton_from_keypoints_merge")
+    r = np.random.RandomState(2)
+    W, H, n_img, P, J = 640, 480, 5, 3, 17
+    kp = np.zeros([n_img, P, J, 3])
+    kp[..., 0], kp[..., 1] = r.randint(0, W, [n_img, P, J]), r.randint(0, H, [n_img, P, J])
+    kp[..., 2] = r.randint(0, 3, [n_img, P, J])
+    npers = r.randint(1, P + 1, n_img)
+    FakeCOCO.skeleton = (np.array(mg.sks) + 1).tolist()
+    FakeCOCO.persons = {i: [kp[i, p].reshape(-1).astype(np.int64).tolist() for p in range(npers[i])] for i in range(n_img)}
+    tmp = tempfile.mkdtemp()
+    Image.fromarray(np.zeros([H, W, 3], dtype=np.uint8)).save(os.path.join(tmp, "img.jpg"))
+    mg.COCO = FakeCOCO
+    ds = mg.myImageDataset_COCO("x", tmp, lambda im: torch.zeros(1))
+    for i in range(n_img):
+        _, g, s = ds[i]
+        persons = kp[i, :npers[i]]
+        np.testing.assert_array_equal(targets_np.gauss_map(persons, (W, H), J, truncate=True), g.numpy())
+        want = targets_np.label_map(persons, (W, H), J, mg.sks, line_value=-1)
+        assert np.array_equal(want, s.numpy()), i

@@ -384,6 +384,22 @@ typedef struct HgLabelDesc {
 HG_API int hg_render_labels(const HgLabelDesc* d, const double* keypoints, const int32_t* num_persons, const double* img_wh,
                      const int32_t* limbs, int64_t* out, void* stream);
 
+/* Annotation -> keypoint tensor on the device (next row N1: the `anno.loadAnns(...)` / `annopoints.point` loops of
+ * try_with_torch.py:103-113 and hourglass_compare.py:691-703).  The dataset's annotations are uploaded ONCE:
+ *   mode 0 (COCO): table[row] = one person's J*3 doubles (x, y, v) as in the JSON, offset[i .. i+1) = rows of image i;
+ *                  an image with more than P persons keeps its LAST P (the last person wins in the reference, quirk Q7);
+ *   mode 1 (MPII): table[row] = one annotated point (id, x, y, is_visible), offset[i .. i+1) = points of sample i,
+ *                  scattered into one person: kp[id] = (x, y, is_visible != 0), later records overwrite earlier ones.
+ * wh_all[i] = (width, height) of image i.  For the B samples `sample_index` the kernel writes keypoints [B,P,J,3],
+ * num_persons [B] and img_wh [B,2] -- the inputs of hg_render_gauss / hg_render_labels. */
+typedef struct HgAnnotDesc {
+  int32_t B, P, J;
+  int32_t mode;
+} HgAnnotDesc;
+HG_API int hg_gather_annotations(const HgAnnotDesc* d, const double* table, const int32_t* offset, const double* wh_all,
+                                 const int64_t* sample_index, double* keypoints, int32_t* num_persons, double* img_wh,
+                                 void* stream);
+
 /* ---- decode + PCKh -------------------------------------------------------------------------------- */
 /* first row-major (y, x) of the maximum of each of num_maps [H,W] maps
  * (hourglass_compare.py:831,1092; only_one_hourgless.py:294-295). */

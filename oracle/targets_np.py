@@ -136,3 +136,18 @@ def label_map(persons, img_wh, J, limbs, H=64, W=64, center_mode=0, draw_points=
                 if v[a] > 0 and v[b] > 0:
                     draw_line(canvas, x[a], y[a], x[b], y[b], line_value if line_value > 0 else (i if line_value < 0 else i + 1))
     return canvas.astype(np.int64)
+
+
+def mpii_points_to_dense(points, J=16):
+    """hourglass_compare.py:691-703 (= train.py:655-667): the sparse `annopoints.point` records of one MPII person ->
+    points_rect[J, 3]; is_visible == 0 -> 0, anything else (1, or a missing / empty field) -> 1; later records of the same
+    id overwrite earlier ones.  points: iterable of (id, x, y, is_visible)."""
+    out = np.zeros([J, 3])
+    for pid, x, y, vis in points:
+        out[int(pid)] = [x, y, 0 if vis == 0 else 1]
+    return out
+
+
+def coco_persons_to_dense(persons, J=17):
+    """try_with_torch.py:103-113: every `label['keypoints']` list of one image as [P, J, 3] (x, y, v)."""
+    return np.asarray(persons, dtype=np.float64).reshape(-1, J, 3)

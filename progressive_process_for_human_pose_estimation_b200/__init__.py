@@ -12,7 +12,7 @@ from .evaluate import (PCKh_from_logits, PCKh_half_standard, PCKh_hourglass, PCK
 from .losses import cross_entropy_losses, mse_losses  # noqa: F401
 from .optim import Adam  # noqa: F401
 from .preprocess import resize_bicubic  # noqa: F401
-from .targets import gaussian_heatmaps, label_maps, to_tensor_normalize  # noqa: F401
+from .targets import AnnotationTable, gaussian_heatmaps, label_maps, to_tensor_normalize  # noqa: F401
 
 __all__ = ["set_compute_dtype", "get_compute_dtype", "gaussian_heatmaps", "label_maps", "decode_argmax",
-           "pckh_sweep_counts", "PCKh_hourglass", "PCKh_softmax", "PCKh_half_standard", "PCKh_from_logits", "mse_losses", "cross_entropy_losses", "Adam", "to_tensor_normalize", "resize_bicubic"]
+           "pckh_sweep_counts", "PCKh_hourglass", "PCKh_softmax", "PCKh_half_standard", "PCKh_from_logits", "mse_losses", "cross_entropy_losses", "Adam", "to_tensor_normalize", "resize_bicubic", "AnnotationTable"]

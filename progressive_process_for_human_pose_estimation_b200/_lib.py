@@ -80,6 +80,10 @@ class HgResizeImage(C.Structure):
                 ("tmp_off", C.c_int64)]
 
 
+class HgAnnotDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "P", "J", "mode")]
+
+
 class HgLabelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "P", "J", "L", "H", "W", "center_mode", "draw_points", "draw_lines",
                                          "line_value")]
@@ -126,6 +130,7 @@ SIGNATURES = {
     "hg_unpack_conv_wgrad_slice": [C.POINTER(HgConvDesc), _P, _P, _I, _I, _I, _P],
     "hg_mix_rows": [_P, _P, _P, _I, _I, _I, _I, _P],
     "hg_mix_rows_rect": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "hg_gather_annotations": [C.POINTER(HgAnnotDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
     "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
     "hg_image_u8_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P, _P, _P],

@@ -146,6 +146,7 @@ int g_bn_blocks_per_sm = 6;       // grid cap of bn_apply (no per-block atomics)
 // (B200, batch 32, bn_bwd_apply C128): 6 blocks/SM 24.4 us @64x64, 12.4 us @32x32;  2 blocks/SM 18.5 / 7.0 us;
 // C256+addend @16x16: 9.7 us (6/SM) -> 6.0 us (1/SM).  0 = policy below, > 0 = fixed blocks per SM.
 int g_bn_bwd_blocks_per_sm = 0;
+int g_bn_apply_u4 = 1;            // bn_apply on large bf16 tensors: 4 rows in flight per thread (hg_set_option "bn_apply_u4")
 
 static inline int atomic_grid_per_sm(long long M) {
   if (g_bn_bwd_blocks_per_sm > 0) return g_bn_bwd_blocks_per_sm;
@@ -236,13 +237,14 @@ int colsum_launch(int dtype, const void* dy, long long M, int Cp, int C, float* 
 // ------------------------------------------------------------------------------------------------------
 // apply: y = [relu](gamma * (x - mean) * invstd + beta)
 // ------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long M,
                                                        BnArgs a) {
   pdl_wait();     // PDL: nothing below may touch global memory before the previous kernel has drained
   pdl_trigger();  // elementwise / streaming kernel: let the next kernel's CTAs queue up behind ours
 
-  constexpr int U = 2;  // rows in flight per thread
+  // U rows in flight per thread, kept unconverted (a bf16 row = 4 registers): at full occupancy (8 blocks/SM) U = 2 is
+  // 64 KB of loads in flight per SM -- short of what HBM3e needs at ~1 us latency (4.7 TB/s measured); U = 4 doubles it
   const int vecs = a.Cp >> 3;
   const int vc = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
@@ -251,10 +253,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
   long long m = (long long)blockIdx.x * rlanes + rl;
   // the first batch of rows is requested BEFORE the per-channel coefficients: one memory round trip instead of two
   // (small tensors are pure latency)
-  float v[U][8];
+  Raw8<T> r[U];
 #pragma unroll
   for (int u = 0; u < U; ++u)
-    if (m + u * stride < M) load8(x + (m + u * stride) * a.Cp + vc * 8, v[u]);
+    if (m + u * stride < M) load_raw(x + (m + u * stride) * a.Cp + vc * 8, r[u]);
   __shared__ float coef[4][256];
   float mean[8], invstd[8], scale[8], shift[8];
   bn_coeffs_block(a, coef, vc, mean, invstd, scale, shift);
@@ -262,19 +264,21 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (m + u * stride < M) {
+        float v[8];
+        unpack(r[u], v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float o = fmaf(v[u][e], scale[e], shift[e]);
+          float o = fmaf(v[e], scale[e], shift[e]);
           if (a.relu) o = fmaxf(o, 0.f);
-          v[u][e] = o;
+          v[e] = o;
         }
-        store8(y + (m + u * stride) * a.Cp + vc * 8, v[u]);
+        store8(y + (m + u * stride) * a.Cp + vc * 8, v);
       }
     }
     m += U * stride;
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (m + u * stride < M) load8(x + (m + u * stride) * a.Cp + vc * 8, v[u]);
+      if (m + u * stride < M) load_raw(x + (m + u * stride) * a.Cp + vc * 8, r[u]);
   }
 }
 
@@ -537,12 +541,15 @@ int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const floa
   BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
   const int rlanes = 256 / (a.Cp >> 3);
   int blocks = ceil_div(d->M, rlanes * 2);  // two rows in flight per thread; large tensors: 8 blocks per SM
+  const bool deep = g_bn_apply_u4 && blocks > kNumSMs * 8 * 2;   // >= 4 rows per thread at the grid cap
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->dtype == HG_BF16)
-    launch_k(bn_apply_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, d->M, a);
-  else
-    launch_k(bn_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)x, (float*)y, d->M, a);
+  if (d->dtype == HG_BF16) {
+    if (deep) launch_k(bn_apply_kernel<__nv_bfloat16, 4>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, d->M, a);
+    else launch_k(bn_apply_kernel<__nv_bfloat16, 2>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, d->M, a);
+  } else {
+    launch_k(bn_apply_kernel<float, 2>, dim3(blocks), dim3(256), 0, st, (const float*)x, (float*)y, d->M, a);
+  }
   HG_LAUNCH_OK("bn_apply_kernel");
   count_launch();
   return HG_OK;

@@ -44,6 +44,7 @@ int g_wgrad_dbg = 0;            // HG_DBG_TS builds only: 1 = wgrad epilogue wit
 long long* g_dbg_ts = nullptr;  // debug: per-phase clock64 stamps of CTA 0 (hg_set_option dbg_ts)
 int g_single_wave_deep = 1;   // 1: one-wave grids use the deep (6/4-stage, ~190 KB) pipelines
 int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
+int g_wgrad_fused_bias = 1;   // 1: the bias gradient is an extra all-ones N slab of the wgrad GEMM (no column-sum kernel)
 
 // Epilogue / prologue fusion modes of the GEMM kernel.
 //   kPlain : y = conv(x) [+bias][+residual][+stats]                                   (fprop, dgrad)
@@ -921,6 +922,8 @@ struct WgradParams {
   int bulk_reduce;   // epilogue: partial tile -> shared memory -> cp.reduce.async.bulk (else per-thread red.v4)
   int stage_bytes;
   float* dw;         // [taps][Cout_p][Cin_p] fp32, accumulated
+  float* dbias;      // optional [Cout]: += sum over pixels of dy (bias gradient), from an extra all-ones N slab
+  int Cout;          // real output channels (rows of dbias)
   BnFoldDev fold;
 };
 
@@ -938,6 +941,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   uint64_t* ready_bar = bars + 18;                             // [8]
   float* coef_s = reinterpret_cast<float*>(bars + 32);         // scale[256], shift[256]
+  // Bias gradient on the tensor core: dbias[co] = sum_m dy[m, co] * 1 -- one more N slab (16 columns) whose B operand is
+  // a constant all-ones tile, so the dy tiles already in shared memory are reused and no separate column-sum pass over
+  // dy exists (it was a second kernel: 67 MB re-read per 128->256 convolution at 64x64).
+  uint8_t* ones_s = reinterpret_cast<uint8_t*>(bars) + 4096;   // [64 K rows][128 B], 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -950,8 +957,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   int kb_end = kb_beg + p.kb_per_cta;
   if (kb_end > p.total_kb) kb_end = p.total_kb;
   const int nkb = kb_end - kb_beg;
+  const bool with_bias = p.dbias != nullptr && blockIdx.y == 0;   // tap group 0, input-channel group 0 only
   uint32_t cols = 32;
-  while ((int)cols < T * N) cols <<= 1;
+  while ((int)cols < T * N + (p.dbias != nullptr ? 16 : 0)) cols <<= 1;
+  if (p.dbias != nullptr) {
+    for (int i = threadIdx.x; i < 8192 / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(ones_s)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmDy);
@@ -1019,6 +1032,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
               const uint64_t adesc = make_smem_desc(sA + k * 2048, 8192, 1024);
               const uint64_t bdesc = make_smem_desc(sB + t * p.n_panels * 8192 + k * 2048, 8192, 1024);
               umma_bf16(tmem_base + t * N, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          if (with_bias) {
+            const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = make_smem_desc(sA + k * 2048, 8192, 1024);
+              const uint64_t bdesc = make_smem_desc(smem_u32(ones_s) + k * 2048, 8192, 1024);
+              umma_bf16(tmem_base + T * N, adesc, bdesc, idesc1, (i > 0 || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[st]);
@@ -1094,6 +1116,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       tc_fence_after();
       pdl_trigger();
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+      if (with_bias) {
+        float v[16];
+        tmem_ld16(taddr + T * N, v);
+        tmem_ld_wait();
+        if (co < p.Cout) atomicAdd(p.dbias + co, v[0]);
+      }
       if (p.bulk_reduce) {
         // The partial tile goes through shared memory (the pipeline stages are idle: every MMA has completed) as a
         // linear [128 co][N ci] fp32 image per tap and is added to the gradient by ONE bulk reduce per tap: the
@@ -1261,7 +1289,11 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
       if (need <= 8 && need * p.stage_bytes <= 220 * 1024) p.stages = need;
       else p.bulk_reduce = 0;
     }
-    const int smem_bytes = p.stages * p.stage_bytes + 4096 + 1024;
+    // dbias rides on the weight-gradient GEMM (all-ones N slab) whenever both are wanted
+    p.dbias = (dbias && g_wgrad_fused_bias) ? dbias : nullptr;
+    p.Cout = d->Cout;
+    if (p.dbias) dbias = nullptr;
+    const int smem_bytes = p.stages * p.stage_bytes + 4096 + 8192 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
       HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

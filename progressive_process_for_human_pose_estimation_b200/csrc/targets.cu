@@ -142,6 +142,54 @@ __global__ void __launch_bounds__(128) render_labels_kernel(HgLabelDesc d, const
   for (int i = threadIdx.x; i < npx; i += blockDim.x) out[(long long)b * npx + i] = (long long)canvas[i];
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Annotation -> keypoint tensor: the dataset's annotations live in HBM once; a batch of sample indices
+// becomes the dense [B, P, J, 3] (x, y, v) tensor + num_persons[B] + img_wh[B, 2] the render kernels consume.
+//   mode 0 (COCO, try_with_torch.py:103-113): table row = one person, J*3 doubles exactly as the JSON `keypoints` list;
+//           CSR offsets per image; the LAST P persons are kept when an image has more (quirk Q7: last person wins).
+//   mode 1 (MPII, hourglass_compare.py:691-703): table row = one annotated point (id, x, y, is_visible): scattered into
+//           ONE person row, points_rect[id] = [x, y, is_visible != 0], later records of the same id overwrite earlier ones.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gather_annotations_kernel(HgAnnotDesc d, const double* __restrict__ table,
+                                                                 const int* __restrict__ offset,
+                                                                 const double* __restrict__ wh_all,
+                                                                 const long long* __restrict__ index,
+                                                                 double* __restrict__ kp, int* __restrict__ num_persons,
+                                                                 double* __restrict__ img_wh) {
+  const int b = blockIdx.x;
+  const long long idx = index[b];
+  const int beg = offset[idx], end = offset[idx + 1];
+  double* dst = kp + (long long)b * d.P * d.J * 3;
+  const int row = d.J * 3;
+  if (threadIdx.x == 0) {
+    img_wh[2 * b] = wh_all[2 * idx];
+    img_wh[2 * b + 1] = wh_all[2 * idx + 1];
+  }
+  if (d.mode == 0) {
+    const int n = end - beg;
+    const int np = n < d.P ? n : d.P;
+    const int first = end - np;
+    for (int i = threadIdx.x; i < d.P * row; i += blockDim.x)
+      dst[i] = i < np * row ? table[(long long)first * row + i] : 0.0;
+    if (threadIdx.x == 0) num_persons[b] = np;
+  } else {
+    for (int i = threadIdx.x; i < d.P * row; i += blockDim.x) dst[i] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int r = beg; r < end; ++r) {
+        const double* rec = table + (long long)r * 4;
+        const int id = (int)rec[0];
+        if (id >= 0 && id < d.J) {
+          dst[id * 3] = rec[1];
+          dst[id * 3 + 1] = rec[2];
+          dst[id * 3 + 2] = rec[3] != 0.0 ? 1.0 : 0.0;
+        }
+      }
+      num_persons[b] = 1;
+    }
+  }
+}
+
 }  // namespace hg
 
 using namespace hg;
@@ -174,6 +222,20 @@ int hg_render_labels(const HgLabelDesc* d, const double* keypoints, const int32_
   render_labels_kernel<<<d->B, 128, d->H * d->W, (cudaStream_t)stream>>>(*d, keypoints, num_persons, img_wh, limbs,
                                                                           (long long*)out);
   HG_LAUNCH_OK("render_labels_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_gather_annotations(const HgAnnotDesc* d, const double* table, const int32_t* offset, const double* wh_all,
+                          const int64_t* sample_index, double* keypoints, int32_t* num_persons, double* img_wh,
+                          void* stream) {
+  HG_REQUIRE(d && d->B > 0 && d->P > 0 && d->J > 0 && (d->mode == 0 || d->mode == 1), "hg_gather_annotations: bad desc");
+  HG_REQUIRE(table && offset && wh_all && sample_index && keypoints && num_persons && img_wh,
+             "hg_gather_annotations: NULL pointer");
+  gather_annotations_kernel<<<d->B, 128, 0, (cudaStream_t)stream>>>(*d, table, offset, wh_all,
+                                                                    (const long long*)sample_index, keypoints,
+                                                                    num_persons, img_wh);
+  HG_LAUNCH_OK("gather_annotations_kernel");
   count_launch();
   return HG_OK;
 }

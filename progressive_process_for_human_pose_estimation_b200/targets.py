@@ -95,3 +95,75 @@ def to_tensor_normalize(images_u8, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
     with torch.cuda.device(x.device):
         L.call("hg_image_u8_to_nchw_f32", L.ptr(x), B, H, W, Ch, m, s, L.ptr(out), L.stream_ptr())
     return out
+
+
+class AnnotationTable:
+    """The dataset's annotations, uploaded to HBM once; `batch(indices)` turns a batch of sample indices into the
+    [B,P,J,3] keypoint tensor + num_persons + img_wh on the device (one kernel, no host loop) -- the step the reference
+    runs per image inside `__getitem__` (`anno.loadAnns(...)`, try_with_torch.py:103-113; `annopoints.point`,
+    hourglass_compare.py:691-703).  JSON / .mat parsing and JPEG decoding stay on the host (done once at start-up).
+
+    from_coco(persons_per_image, sizes): persons_per_image[i] = list of flat 3*J `keypoints` lists (ints, as in the
+        COCO JSON) of image i, sizes[i] = (width, height).
+    from_mpii(points_per_sample, sizes, J=16): points_per_sample[i] = list of (id, x, y, is_visible) records."""
+
+    def __init__(self, table, offsets, sizes, J, mode, device="cuda"):
+        self.J, self.mode = int(J), int(mode)
+        self.offsets_host = np.asarray(offsets, dtype=np.int32)
+        self.table = torch.as_tensor(np.ascontiguousarray(table, dtype=np.float64)).to(device)
+        self.offsets = torch.as_tensor(self.offsets_host).to(device)
+        self.sizes = torch.as_tensor(np.ascontiguousarray(sizes, dtype=np.float64).reshape(-1, 2)).to(device)
+        self.device = self.table.device
+        if self.offsets_host[0] != 0 or self.offsets_host[-1] != (self.table.shape[0] if self.table.numel() else 0):
+            raise ValueError("AnnotationTable: offsets do not cover the table")
+        if len(self.offsets_host) != self.sizes.shape[0] + 1:
+            raise ValueError("AnnotationTable: one (width, height) per sample expected")
+
+    @classmethod
+    def from_coco(cls, persons_per_image, sizes, J=17, device="cuda"):
+        rows, off = [], [0]
+        for persons in persons_per_image:
+            for kp in persons:
+                kp = np.asarray(kp, dtype=np.float64).reshape(-1)
+                if kp.size != 3 * J:
+                    raise ValueError(f"a COCO person has {3 * J} keypoint numbers, got {kp.size}")
+                rows.append(kp)
+            off.append(len(rows))
+        table = np.stack(rows) if rows else np.zeros([0, 3 * J])
+        return cls(table, off, sizes, J, 0, device)
+
+    @classmethod
+    def from_mpii(cls, points_per_sample, sizes, J=16, device="cuda"):
+        rows, off = [], [0]
+        for pts in points_per_sample:
+            for rec in pts:
+                rows.append(np.asarray(rec, dtype=np.float64).reshape(4))
+            off.append(len(rows))
+        table = np.stack(rows) if rows else np.zeros([0, 4])
+        return cls(table, off, sizes, J, 1, device)
+
+    def __len__(self):
+        return len(self.offsets_host) - 1
+
+    def batch(self, indices, max_persons=None):
+        """-> (keypoints float64 [B,P,J,3], num_persons int32 [B], img_wh float64 [B,2]), all on the device.
+        P = the largest person count of the batch (host arithmetic on the CSR offsets only) unless max_persons is
+        given; images with more persons keep their last `max_persons` (the last person wins, quirk Q7)."""
+        idx_host = np.asarray(indices, dtype=np.int64).reshape(-1)
+        if idx_host.size == 0 or idx_host.min() < 0 or idx_host.max() >= len(self):
+            raise IndexError("AnnotationTable.batch: sample index out of range")
+        if self.mode == 1:
+            P = 1
+        else:
+            counts = self.offsets_host[idx_host + 1] - self.offsets_host[idx_host]
+            P = int(max(1, counts.max())) if max_persons is None else int(max_persons)
+        B = idx_host.size
+        idx = torch.as_tensor(idx_host).to(self.device)
+        kp = torch.empty(B, P, self.J, 3, device=self.device, dtype=torch.float64)
+        npers = torch.empty(B, device=self.device, dtype=torch.int32)
+        wh = torch.empty(B, 2, device=self.device, dtype=torch.float64)
+        d = L.HgAnnotDesc(B, P, self.J, self.mode)
+        with torch.cuda.device(self.device):
+            L.call("hg_gather_annotations", C.byref(d), L.ptr(self.table), L.ptr(self.offsets), L.ptr(self.sizes),
+                   L.ptr(idx), L.ptr(kp), L.ptr(npers), L.ptr(wh), L.stream_ptr())
+        return kp, npers, wh

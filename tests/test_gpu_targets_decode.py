@@ -107,6 +107,62 @@ def test_merge_script_targets_bit_exact():
         assert np.abs(gauss[b].cpu().numpy() - gref).max() <= 1.2e-7
 
 
+def test_annotation_table_coco_matches_reference_dataset_golden():
+    """Annotation -> keypoint tensor -> targets entirely on the device (N1): the COCO annotations of the reference-dataset
+    golden (tests/golden/targets_coco.npz, produced by try_different_stack.myImageDataset_COCO through the fake-COCO
+    shim) uploaded once as an AnnotationTable; batches of image indices reproduce the reference's Gaussian, skeleton and
+    background maps."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "targets_coco.npz"))
+    kp, npers, wh = g["keypoints"], g["num_persons"], g["img_wh"]
+    persons = [[kp[i, p].reshape(-1).astype(np.int64).tolist() for p in range(npers[i])] for i in range(len(kp))]
+    table = hg.AnnotationTable.from_coco(persons, wh)
+    assert len(table) == len(kp)
+    order = [5, 0, 3, 3, 1, 2, 4]
+    k, n, w = table.batch(order)
+    assert k.is_cuda and k.dtype == torch.float64 and k.shape[0] == len(order) and k.shape[2:] == (17, 3)
+    assert np.array_equal(n.cpu().numpy(), npers[order]) and np.array_equal(w.cpu().numpy(), wh[order])
+    for j, i in enumerate(order):
+        assert np.array_equal(k[j, :npers[i]].cpu().numpy(), targets_np.coco_persons_to_dense(persons[i]))
+    gauss = hg.gaussian_heatmaps(k, w, num_persons=n, truncate=True)
+    skel = hg.label_maps(k, w, g["limbs"], num_persons=n)
+    bg = hg.label_maps(k, w, g["limbs"], num_persons=n, line_value=1)
+    assert ulp_diff(gauss.cpu().numpy(), g["gauss"][order]) <= 1
+    assert np.array_equal(skel.cpu().numpy(), g["skeleton"][order])
+    assert np.array_equal(bg.cpu().numpy(), g["background"][order])
+    # an image with more persons than the tensor holds keeps its LAST ones (quirk Q7: the last person wins)
+    k1, n1, _ = table.batch(order, max_persons=1)
+    assert int(n1.max()) == 1
+    g1 = hg.gaussian_heatmaps(k1, w, num_persons=n1, truncate=True)
+    assert torch.equal(g1, gauss)
+
+
+def test_annotation_table_mpii_scatter():
+    """MPII: sparse (id, x, y, is_visible) point records -> dense [16, 3] rows (hourglass_compare.py:691-703): missing
+    joints stay (0, 0, 0), is_visible == 0 -> invisible, duplicates: the last record wins."""
+    r = np.random.RandomState(9)
+    samples, sizes = [], []
+    for i in range(12):
+        ids = r.choice(16, r.randint(0, 17), replace=False).tolist()
+        pts = [(j, float(r.uniform(0, 900)), float(r.uniform(0, 700)), int(r.randint(0, 2))) for j in ids]
+        if i % 3 == 0 and ids:
+            pts.append((ids[0], 11.0, 12.0, 1))   # duplicate id
+        samples.append(pts)
+        sizes.append((float(r.randint(200, 1000)), float(r.randint(200, 1000))))
+    table = hg.AnnotationTable.from_mpii(samples, sizes)
+    idx = [3, 0, 11, 7, 0]
+    k, n, w = table.batch(idx)
+    assert k.shape == (5, 1, 16, 3) and int(n.min()) == 1 and int(n.max()) == 1
+    for j, i in enumerate(idx):
+        assert np.array_equal(k[j, 0].cpu().numpy(), targets_np.mpii_points_to_dense(samples[i]))
+        assert tuple(w[j].cpu().numpy()) == sizes[i]
+    gm = hg.gaussian_heatmaps(k, w, truncate=False, accumulate=True, center_mode=1)
+    for j, i in enumerate(idx):
+        ref = targets_np.gauss_map(targets_np.mpii_points_to_dense(samples[i])[None], sizes[i], 16, center_mode=1,
+                                   truncate=False, accumulate=True)
+        assert ulp_diff(gm[j].cpu().numpy(), ref) <= 1
+
+
 def test_mpii_label_maps_bit_exact():
     """MPII keypoint (ImageDraw.ellipse on the float centre) and skeleton maps of train.py:668-690 against the numpy
     oracle (pinned to Pillow by tests/test_oracle_targets_pckh.py::test_mpii_label_maps_match_pillow)."""

@@ -271,6 +271,35 @@ def run_ours(args):
         phases = {"forward_ms": round(med([e[0].elapsed_time(e[1]) for e in ev]), 3),
                   "loss_backward_ms": round(med([e[1].elapsed_time(e[2]) for e in ev]), 3),
                   "optimizer_ms": round(med([e[2].elapsed_time(e[3]) for e in ev]), 3)}
+        if world > 1:
+            # the same backward pass WITHOUT the gradient all-reduce (one graph, gradients stay local: timing only):
+            # the difference is what the bucketed, overlapped all-reduce still costs the step
+            plan_ = list(net.__dict__["_plans"].values())[-1]
+            saved_red, plan_.reducer = plan_.reducer, None
+            ev2 = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(4)]
+            for e in ev2:
+                out = model(x)
+                loss = total_loss(out, y)
+                opt.zero_grad()
+                e[0].record()
+                loss.backward()
+                e[1].record()
+            torch.cuda.synchronize()
+            plan_.reducer = saved_red
+            nocomm = med([e[0].elapsed_time(e[1]) for e in ev2[1:]])
+            ev3 = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(3)]
+            for e in ev3:
+                out = model(x)
+                loss = total_loss(out, y)
+                opt.zero_grad()
+                e[0].record()
+                loss.backward()
+                e[1].record()
+            torch.cuda.synchronize()
+            withcomm = med([e[0].elapsed_time(e[1]) for e in ev3])
+            phases["backward_ms"] = round(withcomm, 3)
+            phases["backward_ms_no_allreduce"] = round(nocomm, 3)
+            phases["allreduce_exposed_ms"] = round(withcomm - nocomm, 3)
 
     # ---- end to end: pinned host batch -> device every step, loss read back every step ---------------
     xh = x_cpu.pin_memory()

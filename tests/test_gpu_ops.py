@@ -125,6 +125,29 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     close(dbias, 2 * dyr.sum((0, 2, 3)), 1e-3, "dbias")
 
 
+P1_CASES = [c for c in CONV_CASES if c[5] == 1 and not c[8]] + [
+    (12, 64, 64, 256, 128, 1, 1, False, False),   # 384 tiles: the size class the dispatcher picks by itself
+    (10, 64, 64, 128, 256, 1, 1, True, False),
+    (3, 32, 32, 256, 256, 1, 1, True, False),     # 24 tiles < 148 CTAs
+    (1, 8, 8, 64, 64, 1, 1, False, False),        # half a tile
+    (5, 16, 16, 128, 64, 1, 1, True, False),      # 10 tiles, Np = 64 (one 64-column panel)
+]
+
+
+@pytest.mark.parametrize("case", P1_CASES)
+def test_persistent_pointwise_kernel(case):
+    """conv1x1_persist_kernel (weights resident in shared memory, two TMEM accumulators, 148 resident CTAs) forced for
+    every size (persist_min_tiles = 1): same checks as the tile-per-CTA kernel -- fprop (+bias, +residual, statistics),
+    dgrad (+addend, in place), against PyTorch fp32 on bf16-rounded operands."""
+    L.call("hg_set_option", b"persist_1x1", 1)
+    L.call("hg_set_option", b"persist_min_tiles", 1)
+    try:
+        test_conv_fprop_dgrad_wgrad(case, torch.bfloat16)
+    finally:
+        L.call("hg_set_option", b"persist_min_tiles", 296)
+        L.call("hg_set_option", b"persist_1x1", 0)
+
+
 STRIDE2_CASES = [
     # N, H, W (input), Cin, Cout, k
     (2, 64, 64, 128, 128, 3),     # try_with_aspp_remove_max_pool.py:176 (conv2 of a stride-2 block)
@@ -327,6 +350,20 @@ def test_conv_with_folded_batchnorm(case):
         L.call("hg_bn_bwd_apply", C.byref(bnd), L.ptr(dsrc), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta),
                L.ptr(rmean), L.ptr(rvar), L.ptr(redsrc), None, L.ptr(dx1 if dst is dx1 else dx0), None, None, None, st)
     close(dx1.float(), dx0.float(), 1e-2, "bn backward from the fused sums")
+
+
+@pytest.mark.parametrize("case", [c for c in FOLD_CASES if c[5] == 1] + [(10, 64, 64, 256, 128, 1, 1, False, True, False),
+                                                                       (10, 64, 64, 128, 256, 1, 1, False, True, False)])
+def test_persistent_pointwise_kernel_masked_dgrad(case):
+    """The ReLU-mask / BatchNorm-backward-sums epilogue (hg_conv_dgrad_bn) of the persistent pointwise kernel, forced
+    for every size: bit-identical masked gradient, same sums as hg_bn_bwd_reduce."""
+    L.call("hg_set_option", b"persist_1x1", 1)
+    L.call("hg_set_option", b"persist_min_tiles", 1)
+    try:
+        test_conv_with_folded_batchnorm(case)
+    finally:
+        L.call("hg_set_option", b"persist_min_tiles", 296)
+        L.call("hg_set_option", b"persist_1x1", 0)
 
 
 def test_folded_entry_points_reject_unsupported_geometry():

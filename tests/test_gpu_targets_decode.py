@@ -127,7 +127,7 @@ def test_annotation_table_coco_matches_reference_dataset_golden():
     gauss = hg.gaussian_heatmaps(k, w, num_persons=n, truncate=True)
     skel = hg.label_maps(k, w, g["limbs"], num_persons=n)
     bg = hg.label_maps(k, w, g["limbs"], num_persons=n, line_value=1)
-    assert ulp_diff(gauss.cpu().numpy(), g["gauss"][order]) <= 1
+    assert ulp_diff(gauss.cpu().numpy(), g["gauss"][order]).max() <= 1
     assert np.array_equal(skel.cpu().numpy(), g["skeleton"][order])
     assert np.array_equal(bg.cpu().numpy(), g["background"][order])
     # an image with more persons than the tensor holds keeps its LAST ones (quirk Q7: the last person wins)
@@ -160,7 +160,7 @@ def test_annotation_table_mpii_scatter():
     for j, i in enumerate(idx):
         ref = targets_np.gauss_map(targets_np.mpii_points_to_dense(samples[i])[None], sizes[i], 16, center_mode=1,
                                    truncate=False, accumulate=True)
-        assert ulp_diff(gm[j].cpu().numpy(), ref) <= 1
+        assert ulp_diff(gm[j].cpu().numpy(), ref).max() <= 1
 
 
 def test_mpii_label_maps_bit_exact():

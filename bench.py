@@ -421,6 +421,50 @@ def run_ours(args):
                      "pckh_total_joints": int(res["total"][:, 0].sum().item())}
         m.nStack, m.nOutChannels = NSTACK, NJOINT
 
+    # ---- other configurations of BASELINE.json (1 GPU only): training steps of the no-max-pool / strided-block family
+    # (configs[3], try_with_aspp_remove_max_pool.creatModel: 3 stacks, heads 2/20/17, Q4 blocks with stride-2 3x3 and
+    # 1x1 convolutions -- all on the tensor-core kernels) and of the skeleton+keypoint family (configs[2]) ----------
+    extras = None
+    if world == 1 and not args.no_extras:
+        import importlib
+
+        extras = {}
+        for key, modname, note in (("c4_no_max_pool_train", "try_with_aspp_remove_max_pool",
+                                    "BASELINE configs[3]: 3-stack, stride-2 Q4 blocks instead of max-pool"),
+                                   ("c3_skeleton_keypoints_train", "try_skeleton_and_keypoints",
+                                    "BASELINE configs[2]: 4-stack, 38-channel head with the folded limb mix")):
+            try:
+                fm = importlib.import_module("progressive_process_for_human_pose_estimation_b200." + modname)
+                torch.manual_seed(0)
+                fnet = fm.creatModel().to(dev)
+                fopt = hg.Adam(fnet.parameters(), lr=1e-4)
+                with torch.no_grad():
+                    shapes = [tuple(o.shape) for o in fnet(x)]
+                tg = [torch.rand(sh, device=dev) for sh in shapes]
+
+                def fstep():
+                    out = fnet(x)
+                    loss = hg.mse_losses(out, tg[0]).sum() if all(sh == shapes[0] for sh in shapes) else \
+                        sum(torch.nn.functional.mse_loss(o, t) for o, t in zip(out, tg))
+                    fopt.zero_grad()
+                    loss.backward()
+                    fopt.step()
+
+                for _ in range(3):
+                    fstep()
+                ms_f = timed(fstep, args.steps)
+                fplan = list(fnet.__dict__["_plans"].values())[-1]
+                names = [c.name for c in fplan.fwd_calls + fplan.bwd_calls]
+                extras[key] = {"value": round(B * args.steps / (ms_f / 1e3), 2), "unit": UNIT,
+                               "ms_per_step": round(ms_f / args.steps, 3), "batch_per_gpu": B, "note": note,
+                               "loss": "MSE against uniform random targets on every output (throughput only)",
+                               "conv_calls": sum(1 for n_ in names if n_.startswith("hg_conv_")),
+                               "launches_per_step": len(names)}
+                del fnet, fopt, tg
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                extras[key] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     # ---- per-kernel profile of one step (eager, CUDA events around every C-ABI call) ------------------
     roofline, table = None, None
     if rank == 0:
@@ -504,6 +548,7 @@ def run_ours(args):
             "loss_and_optimizer": "torch (nn.MSELoss x8, torch.optim.Adam)" if stock else "hg.mse_losses + hg.Adam",
             "e2e_u8_input": e2e_u8,
             "inference": inference,
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -653,6 +698,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] / configs[3] training-step extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -65,8 +65,12 @@ HG_API int hg_device_ok(void);
  * Either destination may be NULL. */
 HG_API int hg_pack_conv_weight(const HgConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream);
 
-/* y = conv(x, w) + bias [+ residual]; optional per-channel statistics of y for the BatchNorm that
- * follows: stats[0..Cout) += sum(y), stats[Cout..2Cout) += sum(y*y) (the caller zeroes stats).
+/* y = conv(x, w) + bias [+ residual]; optional per-channel statistics of y for the BatchNorm that follows.
+ * Statistics slots are [3*Cp] floats (Cp = channels padded to 64): {S1, S2, pivot} with
+ *   S1[c] += sum(y_c - pivot_c),  S2[c] += sum((y_c - pivot_c)^2),  pivot READ, never written by a producer;
+ * the consumers use mean = pivot + S1/n, var = S2/n - (S1/n)^2, so the variance cancels against (mean - pivot)^2
+ * instead of mean^2.  The caller initialises a slot (S1 = S2 = 0, pivot = anything close to the expected mean: 0 gives
+ * plain sums; hg_bn_prepare_stats does it for a whole forward pass with the consuming BatchNorm's running mean).
  * bias, residual, stats may be NULL.  residual has the shape of y. */
 HG_API int hg_conv_fprop(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias,
                   const void* residual, void* y, float* stats, void* stream);
@@ -97,7 +101,7 @@ HG_API int hg_unpack_conv_wgrad(const HgConvDesc* d, const float* dw_packed, flo
  * normalised activation a = [relu](gamma*(x-mean)*invstd + beta) is never written to HBM: the convolution reads the
  * RAW tensor x and applies the transform to its operand tiles in shared memory (fprop, wgrad), and the data-gradient
  * kernel applies the ReLU mask and accumulates the two BatchNorm-backward sums in its epilogue.
- * HgBnFold describes that BatchNorm call site; `stats` = {sum, sum of squares} of x as accumulated by the kernel
+ * HgBnFold describes that BatchNorm call site; `stats` = the [3*Cp] statistics slot of x as accumulated by the kernel
  * that produced x (training mode), or running statistics (eval mode, use_running = 1). */
 typedef struct HgBnFold {
   const float* stats;
@@ -165,7 +169,7 @@ HG_API int hg_set_option(const char* name, int value);
 
 /* ---- BatchNorm2d + ReLU (try_with_torch.py:184-192,196-204,249-250,254-255) ------------------------- */
 /* x is [M, C] NHWC-flattened (M = N*H*W, channels padded to 64 in memory).  Training mode
- * (use_running = 0) normalises with the batch statistics `stats` = {sum[Cp], sum of squares[Cp]} that the
+ * (use_running = 0) normalises with the batch statistics slot `stats` = {S1[Cp], S2[Cp], pivot[Cp]} that the
  * producing kernel accumulated (hg_conv_fprop's `stats`, or hg_bn_stats); eval mode uses running_mean/var. */
 typedef struct HgBnDesc {
   int64_t M;
@@ -176,7 +180,15 @@ typedef struct HgBnDesc {
   int32_t use_running; /* 0 = batch statistics (train), 1 = running statistics (eval) */
 } HgBnDesc;
 
-HG_API int hg_bn_stats(const HgBnDesc* d, const void* x, float* stats, void* stream); /* stats += ; caller zeroes */
+HG_API int hg_bn_stats(const HgBnDesc* d, const void* x, float* stats, void* stream); /* slot [3*Cp], see hg_conv_fprop */
+/* Initialise the statistics slots of a forward pass in one launch: S1 = S2 = 0, pivot = pivot_src[c] (the running mean
+ * of the BatchNorm that consumes the tensor; NULL = 0).  slots_dev is a DEVICE array. */
+typedef struct HgBnStatsSlot {
+  float* stats;           /* [3*Cp] */
+  const float* pivot_src; /* [C] or NULL */
+  int32_t C, Cp;
+} HgBnStatsSlot;
+HG_API int hg_bn_prepare_stats(const HgBnStatsSlot* slots_dev, int num_slots, void* stream);
 HG_API int hg_bn_apply(const HgBnDesc* d, const void* x, const float* stats, const float* gamma, const float* beta,
                 const float* running_mean, const float* running_var, void* y, void* stream);
 /* red[0..Cp) += sum g, red[Cp..2Cp) += sum g*xhat, g = da * [bn(x) > 0]  (caller zeroes red).  In eval mode xhat is
@@ -212,8 +224,8 @@ HG_API int hg_bn_update_running(const void* modules_dev, const void* sites_dev, 
 
 /* ---- spatial ops -------------------------------------------------------------------------------- */
 /* nn.MaxPool2d(2) (try_with_torch.py:220,226,265); backward routes to the first row-major maximum.
- * stats (optional, here and in hg_upsample2x_add_fwd): {sum, sum of squares}[2*Cp] of the tensor just written,
- * accumulated for the BatchNorm that reads it (caller zeroes), like hg_conv_fprop's `stats`. */
+ * stats (optional, here and in hg_upsample2x_add_fwd): the [3*Cp] statistics slot of the tensor just written,
+ * accumulated for the BatchNorm that reads it, like hg_conv_fprop's `stats`. */
 HG_API int hg_maxpool2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, float* stats, void* stream);
 HG_API int hg_maxpool2_bwd(int dtype, const void* x, const void* dy, const void* addend, int N, int H, int W, int C,
                     void* dx, void* stream);

@@ -33,6 +33,10 @@ class HgBnFold(C.Structure):
                 ("pad_", C.c_int32)]
 
 
+class HgBnStatsSlot(C.Structure):
+    _fields_ = [("stats", C.c_void_p), ("pivot_src", C.c_void_p), ("C", C.c_int32), ("Cp", C.c_int32)]
+
+
 class HgBnRunningSite(C.Structure):
     _fields_ = [("stats", C.c_void_p), ("count", C.c_float), ("pad_", C.c_int32)]
 
@@ -114,6 +118,7 @@ SIGNATURES = {
     "hg_bn_bwd_reduce": [C.POINTER(HgBnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_bn_bwd_apply": [C.POINTER(HgBnDesc)] + [_P] * 14,
     "hg_bn_update_running": [_P, _P, _I, _P],
+    "hg_bn_prepare_stats": [_P, _I, _P],
     "hg_maxpool2_fwd": [_I, _P, _I, _I, _I, _I, _P, _P, _P],
     "hg_maxpool2_bwd": [_I, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "hg_upsample2x_add_fwd": [_I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P],

@@ -15,8 +15,12 @@
 
 namespace hg {
 
+// Batch statistics are SHIFTED sums: stats = {S1[Cp], S2[Cp], pivot[Cp]} with S1 = sum(x - pivot), S2 = sum((x - pivot)^2);
+// mean = pivot + S1/n, var = S2/n - (S1/n)^2.  The cancellation in the variance is governed by (mean - pivot)^2 / var
+// instead of mean^2 / var; the plan sets pivot = running_mean of the consuming BatchNorm (0 for a fresh module = plain
+// sums), so a channel whose mean is large against its spread keeps its variance once the running mean has found it.
 struct BnArgs {
-  const float* stats;   // [2*Cp]: sum, sum of squares  (training mode)
+  const float* stats;   // [3*Cp]: shifted sum, shifted sum of squares, pivot  (training mode)
   const float* gamma;   // [C]
   const float* beta;    // [C]
   const float* rmean;   // [C] running mean (eval mode)
@@ -40,8 +44,9 @@ __device__ __forceinline__ void bn_coeffs(const BnArgs& a, int c0, float (&mean)
         mu = a.rmean[c];
         var = a.rvar[c];
       } else {
-        mu = a.stats[c] / a.count;
-        var = fmaxf(a.stats[a.Cp + c] / a.count - mu * mu, 0.f);
+        const float m1 = a.stats[c] / a.count;
+        mu = a.stats[2 * a.Cp + c] + m1;
+        var = fmaxf(a.stats[a.Cp + c] / a.count - m1 * m1, 0.f);
       }
       const float is = rsqrtf(var + a.eps);
       mean[e] = mu;
@@ -70,8 +75,9 @@ __device__ __forceinline__ void bn_coeffs_block(const BnArgs& a, float (*coef)[2
         mu = a.rmean[c];
         var = a.rvar[c];
       } else {
-        mu = a.stats[c] / a.count;
-        var = fmaxf(a.stats[a.Cp + c] / a.count - mu * mu, 0.f);
+        const float m1 = a.stats[c] / a.count;
+        mu = a.stats[2 * a.Cp + c] + m1;
+        var = fmaxf(a.stats[a.Cp + c] / a.count - m1 * m1, 0.f);
       }
       is = rsqrtf(var + a.eps);
       sc = a.gamma[c] * is;
@@ -93,7 +99,7 @@ __device__ __forceinline__ void bn_coeffs_block(const BnArgs& a, float (*coef)[2
 }
 
 // ------------------------------------------------------------------------------------------------------
-// statistics: stats[c] += sum_m x[m,c]; stats[Cp+c] += sum_m x[m,c]^2
+// statistics: stats[c] += sum_m (x[m,c] - pivot[c]); stats[Cp+c] += sum_m (x[m,c] - pivot[c])^2; pivot = stats[2Cp+c]
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long long M, int Cp,
@@ -109,15 +115,18 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   const long long m0 = (long long)blockIdx.x * rows_per_block;
   long long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
-  float s[8] = {}, ss[8] = {};
+  float s[8] = {}, ss[8] = {}, pv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) pv[e] = stats[2 * Cp + vc * 8 + e];
 #pragma unroll 4
   for (long long m = m0 + rl; m < m1; m += rlanes) {
     float v[8];
     load8(x + m * Cp + vc * 8, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      s[e] += v[e];
-      ss[e] = fmaf(v[e], v[e], ss[e]);
+      const float d = v[e] - pv[e];
+      s[e] += d;
+      ss[e] = fmaf(d, d, ss[e]);
     }
   }
 #pragma unroll
@@ -477,8 +486,9 @@ __global__ void bn_running_kernel(const BnRunningModule* __restrict__ mods, cons
     float rm = md.rmean[c], rv = md.rvar[c];
     for (int i = 0; i < md.num_sites; ++i) {
       const BnRunningSite s = sites[md.first_site + i];
-      const float mu = s.stats[c] / s.count;
-      const float var = fmaxf(s.stats[md.Cp + c] / s.count - mu * mu, 0.f);
+      const float m1 = s.stats[c] / s.count;
+      const float mu = s.stats[2 * md.Cp + c] + m1;
+      const float var = fmaxf(s.stats[md.Cp + c] / s.count - m1 * m1, 0.f);
       const float unb = s.count > 1.f ? var * s.count / (s.count - 1.f) : var;
       rm = (1.f - md.momentum) * rm + md.momentum * mu;
       rv = (1.f - md.momentum) * rv + md.momentum * unb;
@@ -487,6 +497,18 @@ __global__ void bn_running_kernel(const BnRunningModule* __restrict__ mods, cons
     md.rvar[c] = rv;
   }
   if (threadIdx.x == 0 && md.nbt) *md.nbt += md.num_sites;
+}
+
+// One block per statistics slot: S1 = S2 = 0, pivot = pivot_src (running mean of the consuming BatchNorm) or 0.
+__global__ void bn_prepare_stats_kernel(const HgBnStatsSlot* __restrict__ slots) {
+  pdl_wait();
+  pdl_trigger();
+  const HgBnStatsSlot sl = slots[blockIdx.x];
+  for (int c = threadIdx.x; c < sl.Cp; c += blockDim.x) {
+    sl.stats[c] = 0.f;
+    sl.stats[sl.Cp + c] = 0.f;
+    sl.stats[2 * sl.Cp + c] = (sl.pivot_src != nullptr && c < sl.C) ? sl.pivot_src[c] : 0.f;
+  }
 }
 
 static int check_bn(const HgBnDesc* d) {
@@ -603,6 +625,14 @@ int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const floa
 #undef HG_BWD_APPLY_T
 #undef HG_BWD_APPLY
   HG_LAUNCH_OK("bn_bwd_apply_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int hg_bn_prepare_stats(const HgBnStatsSlot* slots_dev, int num_slots, void* stream) {
+  HG_REQUIRE(slots_dev && num_slots > 0, "hg_bn_prepare_stats: bad arguments");
+  launch_k(bn_prepare_stats_kernel, dim3(num_slots), dim3(64), 0, (cudaStream_t)stream, slots_dev);
+  HG_LAUNCH_OK("bn_prepare_stats_kernel");
   count_launch();
   return HG_OK;
 }

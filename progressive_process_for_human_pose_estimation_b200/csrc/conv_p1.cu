@@ -74,8 +74,9 @@ __device__ __forceinline__ void p1_coeffs(const BnFoldDev& f, int c, float& mean
       mu = f.rmean[c];
       var = f.rvar[c];
     } else {
-      mu = f.stats[c] / f.count;
-      var = fmaxf(f.stats[f.Cp + c] / f.count - mu * mu, 0.f);
+      const float m1 = f.stats[c] / f.count;     // shifted sums: {S1, S2, pivot} (bn.cu)
+      mu = f.stats[2 * f.Cp + c] + m1;
+      var = fmaxf(f.stats[f.Cp + c] / f.count - m1 * m1, 0.f);
     }
     invstd = rsqrtf(var + f.eps);
     mean = mu;
@@ -314,12 +315,17 @@ conv1x1_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint8_t* vcol = gbuf + coff;
           const uint8_t* ycol = (MODE == kMask ? sY : gbuf) + coff;
           float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+          float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);   // statistics are sums of (y - pivot) (bn.cu)
+          if constexpr (MODE != kMask) pv = *reinterpret_cast<const float4*>(p.stats + 2 * Np + grp * 128 + c);
           for (int k = 0; k < kRows; ++k) {
             const int r = rg * kRows + k;
             const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
             const uint2 u = *reinterpret_cast<const uint2*>(vcol + off);
-            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            if constexpr (MODE != kMask) {
+              f0.x -= pv.x; f0.y -= pv.y; f1.x -= pv.z; f1.y -= pv.w;
+            }
             float2 y0 = f0, y1 = f1;
             if constexpr (MODE == kMask) {
               const uint2 uy = *reinterpret_cast<const uint2*>(ycol + off);

@@ -79,8 +79,9 @@ __device__ __forceinline__ void bn_fold_coeffs(const BnFoldDev& f, int c, float&
       mu = f.rmean[c];
       var = f.rvar[c];
     } else {
-      mu = f.stats[c] / f.count;
-      var = fmaxf(f.stats[f.Cp + c] / f.count - mu * mu, 0.f);
+      const float m1 = f.stats[c] / f.count;     // shifted sums: {S1, S2, pivot} (bn.cu)
+      mu = f.stats[2 * f.Cp + c] + m1;
+      var = fmaxf(f.stats[f.Cp + c] / f.count - m1 * m1, 0.f);
     }
     invstd = rsqrtf(var + f.eps);
     mean = mu;
@@ -514,6 +515,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint8_t* vcol = (MODE == kMask ? sQ : sC) + coff;   // the values whose sum is taken
         const uint8_t* ycol = sC + coff;                          // kMask: raw BatchNorm input
         float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+        // BatchNorm statistics are sums of (y - pivot): the pivot of these four channels (0 for the backward sums)
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (MODE != kMask) pv = *reinterpret_cast<const float4*>(p.stats + 2 * p.n_total + n_off + c);
 #pragma unroll 8
         for (int i = 0; i < kRows; ++i) {
           const int r = grp * kRows + i;
@@ -521,6 +525,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint2 u = *reinterpret_cast<const uint2*>(vcol + off);
           float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
           float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+          if constexpr (MODE != kMask) {
+            f0.x -= pv.x; f0.y -= pv.y; f1.x -= pv.z; f1.y -= pv.w;
+          }
           float2 y0 = f0, y1 = f1;
           if constexpr (MODE == kMask) {
             const uint2 uy = *reinterpret_cast<const uint2*>(ycol + off);

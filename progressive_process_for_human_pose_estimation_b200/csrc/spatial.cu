@@ -20,7 +20,11 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
 
   const int vecs = Cp >> 3, Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * Ho * Wo * vecs;
-  float st_s[8] = {}, st_q[8] = {};
+  float st_s[8] = {}, st_q[8] = {}, pv[8] = {};
+  if (stats != nullptr) {   // shifted sums (bn.cu): the pivots of this thread's channels
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pv[e] = stats[2 * Cp + (threadIdx.x % vecs) * 8 + e];
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int vc = (int)(i % vecs);
@@ -38,7 +42,7 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       o[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
-      const float r = to_f(from_f<T>(o[e]));  // statistics of the values as stored
+      const float r = to_f(from_f<T>(o[e])) - pv[e];  // statistics of the values as stored
       st_s[e] += r;
       st_q[e] = fmaf(r, r, st_q[e]);
     }
@@ -128,7 +132,11 @@ __global__ void __launch_bounds__(256) upsample2_add_fwd_kernel(const T* __restr
   const int row_vecs = W * vecs;
   // 256 % vecs == 0 (vecs = 8, 16 or 32): a thread keeps its channel vector across iterations (per-thread statistics)
   const int vc = threadIdx.x % vecs;
-  float st_s[8] = {}, st_q[8] = {};
+  float st_s[8] = {}, st_q[8] = {}, pv[8] = {};
+  if (stats != nullptr) {   // shifted sums (bn.cu): the pivots of this thread's channels
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pv[e] = stats[2 * Cp + vc * 8 + e];
+  }
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     const int n = r / H, y = r - n * H;
     int y0, y1;
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(256) upsample2_add_fwd_kernel(const T* __restr
       if (stats != nullptr) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float rr = to_f(from_f<T>(o[e]));
+          const float rr = to_f(from_f<T>(o[e])) - pv[e];
           st_s[e] += rr;
           st_q[e] = fmaf(rr, rr, st_q[e]);
         }

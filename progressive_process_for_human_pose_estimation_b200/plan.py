@@ -524,13 +524,27 @@ class Plan:
         for v in all_vals:
             if v.needs_stats:
                 stat_vals.append(v)
-        n_stats = sum(2 * v.Cp for v in stat_vals)
+        # statistics slots: {S1, S2, pivot}[3*Cp] per tensor (shifted sums, include/hg_sm100a.h); the pivot is the running
+        # mean of the BatchNorm that consumes the tensor, written into the slot at the start of every forward by
+        # hg_bn_prepare_stats (which also zeroes S1 / S2: no separate memset of the arena)
+        n_stats = sum(3 * v.Cp for v in stat_vals)
         self.stats_arena = torch.zeros(max(1, n_stats), device=dev, dtype=torch.float32)
         off = 0
+        slots = []
         for v in stat_vals:
-            v.stats = self.stats_arena[off:off + 2 * v.Cp]
+            v.stats = self.stats_arena[off:off + 3 * v.Cp]
             self._tracked.add(v.stats.data_ptr())
-            off += 2 * v.Cp
+            off += 3 * v.Cp
+            pivot = None
+            for cons in v.consumers:
+                if cons.kind == "bn" and cons.attrs["bn"].running_mean is not None:
+                    pivot = self._rstat(cons.attrs["bn"].running_mean)
+                    break
+            slots.append(L.HgBnStatsSlot(v.stats.data_ptr(), pivot.data_ptr() if pivot is not None else None, v.C, v.Cp))
+        self.stats_slots = None
+        if slots:
+            arr = (L.HgBnStatsSlot * len(slots))(*slots)
+            self.stats_slots = (torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev), len(slots))
         bn_ops = [op for op in ops if op.kind == "bn"]
         self.red_arena = torch.zeros(max(1, sum(2 * op.ins[0].Cp for op in bn_ops)), device=dev, dtype=torch.float32)
         off = 0
@@ -540,8 +554,21 @@ class Plan:
             off += 2 * op.ins[0].Cp
 
         # ---- outputs -------------------------------------------------------------------------------
-        self.out_static = [torch.zeros(v.N, c, v.H, v.W, device=dev, dtype=torch.float32) for v, c in b.outputs]
-        self.gout_static = [torch.zeros_like(t) for t in self.out_static] if self.need_bwd else []
+        # the tensors the module returns: views of ONE arena, so that handing the caller its own copies is a single
+        # device-to-device copy per forward (not one per stack), and the incoming gradients land in a second arena
+        shapes = [(v.N, c, v.H, v.W) for v, c in b.outputs]
+        numels = [(n * c * h * w + 3) // 4 * 4 for n, c, h, w in shapes]   # 16-byte aligned slots
+        self.out_arena = torch.zeros(max(4, sum(numels)), device=dev, dtype=torch.float32)
+        self.out_static, off = [], 0
+        for shp, n in zip(shapes, numels):
+            self.out_static.append(self.out_arena[off:off + shp[0] * shp[1] * shp[2] * shp[3]].view(shp))
+            off += n
+        self._out_slices = [(o, shp) for o, shp in zip([sum(numels[:i]) for i in range(len(numels))], shapes)]
+        self.gout_static = []
+        if self.need_bwd:
+            self.gout_arena = torch.zeros_like(self.out_arena)
+            for o, shp in self._out_slices:
+                self.gout_static.append(self.gout_arena[o:o + shp[0] * shp[1] * shp[2] * shp[3]].view(shp))
         self.out_index = {id(v): i for i, (v, _) in enumerate(b.outputs)}
         for t in self.out_static + self.gout_static:
             self._tracked.add(t.data_ptr())
@@ -585,6 +612,8 @@ class Plan:
 
     def _lower_forward(self, convs):
         f, st = self.fwd_calls, self.stream
+        if self.stats_slots is not None:
+            self._emit(f, "hg_bn_prepare_stats", L.ptr(self.stats_slots[0]), self.stats_slots[1], st)
         # weights -> GEMM operand layouts (the optimizer changed them since the last step)
         for key in convs:
             info = self.conv_info[key]
@@ -1054,7 +1083,6 @@ class Plan:
         for buf, shadow in self._shadow_buf.values():
             shadow.copy_(buf)
         self._refresh_bias()
-        self.stats_arena.zero_()
         self._run_calls(self.fwd_calls)
         if self.running_tables is not None:
             for buf, shadow in self._shadow_buf.values():
@@ -1089,15 +1117,17 @@ class Plan:
         else:
             self._fwd_body()
         self.n_fwd_runs += 1
-        return [t.clone() for t in self.out_static]
+        # the caller owns what it gets (a stock module returns new tensors every call): one multi-tensor copy
+        outs = [torch.empty_like(t) for t in self.out_static]
+        torch._foreach_copy_(outs, self.out_static)
+        return outs
 
     def run_backward(self, gouts):
-        for i, gbuf in enumerate(self.gout_static):
-            go = gouts[i] if i < len(gouts) else None
-            if go is None:
-                gbuf.zero_()
-            else:
-                gbuf.copy_(go)
+        present = [(gbuf, gouts[i]) for i, gbuf in enumerate(self.gout_static) if i < len(gouts) and gouts[i] is not None]
+        if len(present) < len(self.gout_static):
+            self.gout_arena.zero_()
+        if present:   # one multi-tensor copy for the incoming heatmap gradients
+            torch._foreach_copy_([p[0] for p in present], [p[1].to(torch.float32) for p in present])
         segments = self.bwd_segments if (self.reducer is not None and self.bwd_segments) else [(0, None, None)]
         for a, b, ranges in segments:
             if _USE_GRAPHS and self.n_fwd_runs >= 2 and self.profile_records is None:

@@ -83,7 +83,7 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     st = L.stream_ptr()
     L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
     y = torch.full((N, H, W, Cout_p), float("nan"), device=dev, dtype=dtype)
-    stats = torch.zeros(2 * Cout_p, device=dev)
+    stats = torch.zeros(3 * Cout_p, device=dev)   # {S1, S2, pivot}: pivot 0 = plain sums
     out_nchw = torch.full((N, Cout, H, W), float("nan"), device=dev) if head else None
     L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), L.ptr(rq), L.ptr(y), L.ptr(stats),
            L.ptr(out_nchw), st)
@@ -148,6 +148,36 @@ def test_persistent_pointwise_kernel(case):
         L.call("hg_set_option", b"persist_1x1", 0)
 
 
+def test_batchnorm_shifted_statistics_survive_large_means():
+    """Statistics slots hold sums of (x - pivot) (include/hg_sm100a.h): with the pivot near the channel mean -- the plan
+    uses the consuming BatchNorm's running mean -- the variance of a channel whose mean is 1000x its spread is exact to
+    fp32 rounding, where the plain one-pass E[x^2] - E[x]^2 (pivot 0) has lost it entirely.  fp32 path, 32768 rows."""
+    torch.manual_seed(5)
+    dev, Cc, M = "cuda", 64, 32768
+    mean = torch.linspace(50.0, 400.0, Cc, device=dev)
+    std = torch.linspace(0.05, 0.4, Cc, device=dev)
+    x = (torch.randn(M, Cc, device=dev) * std + mean).contiguous()
+    gamma, beta = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
+    d = L.HgBnDesc(M, Cc, L.HG_F32, 1e-5, 0, 0)
+    st = L.stream_ptr()
+    ref = F.batch_norm(x.double().t()[None], None, None, None, None, True, 0.1, 1e-5)[0].t()
+    errs = {}
+    for name, pivot in (("plain", torch.zeros(Cc, device=dev)), ("shifted", mean + 0.3 * std)):
+        slot = torch.zeros(3 * Cc, device=dev)
+        slots = (L.HgBnStatsSlot * 1)(L.HgBnStatsSlot(slot.data_ptr(), pivot.data_ptr(), Cc, Cc))
+        sdev = torch.frombuffer(bytearray(bytes(slots)), dtype=torch.uint8).cuda()
+        slot.fill_(float("nan"))
+        L.call("hg_bn_prepare_stats", L.ptr(sdev), 1, st)
+        assert torch.equal(slot[2 * Cc:], pivot) and float(slot[:2 * Cc].abs().max()) == 0.0
+        L.call("hg_bn_stats", C.byref(d), L.ptr(x), L.ptr(slot), st)
+        y = torch.empty_like(x)
+        L.call("hg_bn_apply", C.byref(d), L.ptr(x), L.ptr(slot), L.ptr(gamma), L.ptr(beta), None, None, L.ptr(y), st)
+        errs[name] = ((y.double() - ref).abs().max() / ref.abs().max()).item()
+    # the input itself only carries ~1e-7 * mean / std ~ 1e-4 of relative precision per element in fp32
+    assert errs["shifted"] <= 2e-3, errs
+    assert errs["plain"] > 10 * errs["shifted"], errs   # what the old formula did to these channels
+
+
 STRIDE2_CASES = [
     # N, H, W (input), Cin, Cout, k
     (2, 64, 64, 128, 128, 3),     # try_with_aspp_remove_max_pool.py:176 (conv2 of a stride-2 block)
@@ -187,7 +217,7 @@ def test_conv_stride2_fprop_dgrad_wgrad(case, dtype):
     st = L.stream_ptr()
     L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
     y = torch.full((N, Ho, Wo, Cout_p), float("nan"), device=dev, dtype=dtype)
-    stats = torch.zeros(2 * Cout_p, device=dev)
+    stats = torch.zeros(3 * Cout_p, device=dev)
     L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), None, L.ptr(y), L.ptr(stats), None, st)
     xr, wr = nchw(xq, Cin), w.to(dtype).float()
     ref = F.conv2d(xr, wr, b, 2, pad, 1)
@@ -289,7 +319,7 @@ def test_conv_with_folded_batchnorm(case):
     st = L.stream_ptr()
     L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
     bnd = L.HgBnDesc(M, Cin, L.HG_BF16, 1e-5, 1 if relu else 0, 1 if eval_mode else 0)
-    xstats = torch.zeros(2 * Cin_p, device=dev)
+    xstats = torch.zeros(3 * Cin_p, device=dev)
     L.call("hg_bn_stats", C.byref(bnd), L.ptr(xq), L.ptr(xstats), st)
     fold = L.HgBnFold(xstats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr(), 1e-5,
                       1 if relu else 0, 1 if eval_mode else 0, 0)
@@ -420,7 +450,7 @@ def test_batchnorm_train_fwd_bwd(shape, dtype, relu):
     M = N * H * W
     d = L.HgBnDesc(M, Cc, L.hg_dtype(dtype), 1e-5, 1 if relu else 0, 0)
     st = L.stream_ptr()
-    stats = torch.zeros(2 * Cp, device=dev)
+    stats = torch.zeros(3 * Cp, device=dev)
     L.call("hg_bn_stats", C.byref(d), L.ptr(xq), L.ptr(stats), st)
     y = torch.empty_like(xq)
     L.call("hg_bn_apply", C.byref(d), L.ptr(xq), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, L.ptr(y), st)
@@ -501,7 +531,7 @@ def test_batchnorm_eval_and_running_update():
     dtr = L.HgBnDesc(N * H * W, Cc, L.HG_F32, 1e-5, 1, 0)
     for x in xs:
         ref_bn(x)
-        s = torch.zeros(2 * Cc, device=dev)
+        s = torch.zeros(3 * Cc, device=dev)
         L.call("hg_bn_stats", C.byref(dtr), L.ptr(nhwc(x, torch.float32)), L.ptr(s), st)
         stats.append(s)
     sites = (L.HgBnRunningSite * 3)(*[L.HgBnRunningSite(s.data_ptr(), float(N * H * W), 0) for s in stats])
@@ -524,7 +554,7 @@ def test_maxpool_fwd_bwd_first_max_tiebreak(dtype):
     xq = nhwc(x, dtype)
     y = torch.empty(N, H // 2, W // 2, 64, device=dev, dtype=dtype)
     st = L.stream_ptr()
-    pstats = torch.zeros(2 * 64, device=dev)
+    pstats = torch.zeros(3 * 64, device=dev)
     L.call("hg_maxpool2_fwd", L.hg_dtype(dtype), L.ptr(xq), N, H, W, Cc, L.ptr(y), L.ptr(pstats), st)
     xr = x.clone().requires_grad_(True)
     ref = F.max_pool2d(xr, 2)
@@ -556,7 +586,7 @@ def test_upsample_add_fwd_bwd(dtype, mode, hw):
     lq, sq = nhwc(low, dtype), nhwc(skip, dtype)
     out = torch.empty_like(sq)
     st = L.stream_ptr()
-    ustats = torch.zeros(2 * 64, device=dev)
+    ustats = torch.zeros(3 * 64, device=dev)
     L.call("hg_upsample2x_add_fwd", L.hg_dtype(dtype), mode, L.ptr(lq), L.ptr(sq), N, hw, hw, Cc, L.ptr(out),
            L.ptr(ustats), st)
     ov = nchw(out, Cc)

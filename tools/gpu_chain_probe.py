@@ -43,7 +43,7 @@ def conv_chain(B, hw, cin, cout, k, n=100, with_stats=True):
     y = torch.zeros(B, hw, hw, cout, device=dev, dtype=DT)
     w = torch.randn(k * k, cout, cin, device=dev).to(DT) * 0.05
     bias = torch.zeros(cout, device=dev)
-    stats = torch.zeros(2 * cout, device=dev)
+    stats = torch.zeros(3 * cout, device=dev)
     # ping-pong so that every call depends on the previous one when cin == cout
     bufs = [x, y] if cin == cout else None
 
@@ -64,7 +64,7 @@ def bn_chain(B, hw, c, n=100):
     d = L.HgBnDesc(B * hw * hw, c, L.HG_BF16, 1e-5, 1, 0)
     x = torch.randn(B, hw, hw, c, device=dev).to(DT)
     y = torch.zeros_like(x)
-    stats = torch.zeros(2 * c, device=dev)
+    stats = torch.zeros(3 * c, device=dev)
     stats[:c] = 0.0
     stats[c:] = float(B * hw * hw)
     gam, bet = torch.ones(c, device=dev), torch.zeros(c, device=dev)
@@ -84,7 +84,7 @@ def bn_bwd_chain(B, hw, c, n=100, with_addend=False):
     g = torch.randn(B, hw, hw, c, device=dev).to(DT)
     dx = torch.zeros_like(x)
     add = torch.randn(B, hw, hw, c, device=dev).to(DT) if with_addend else None
-    stats = torch.zeros(2 * c, device=dev)
+    stats = torch.zeros(3 * c, device=dev)
     stats[c:] = float(B * hw * hw)
     red = torch.zeros(2 * c, device=dev)
     gam, bet = torch.ones(c, device=dev), torch.zeros(c, device=dev)
@@ -139,7 +139,7 @@ if __name__ == "__main__":
             y = torch.zeros(B, hw, hw, cout, device=dev, dtype=DT)
             w = (torch.randn(k * k, cout, cin, device=dev) * 0.05).to(DT)
             bias = torch.zeros(cout, device=dev)
-            stats = torch.zeros(2 * cout, device=dev)
+            stats = torch.zeros(3 * cout, device=dev)
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(x), L.ptr(w), L.ptr(bias), None, L.ptr(y), L.ptr(stats), None, st)
             torch.cuda.synchronize()

@@ -53,7 +53,7 @@ def run_case(N, H, W, Cin, Cout, k, dil=1, res=False, head=False, dtype=torch.bf
     st = L.stream_ptr()
     L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
     y = torch.full((N, H, W, Cout_p), float("nan"), device=dev, dtype=dtype)
-    stats = torch.zeros(2 * Cout_p, device=dev)
+    stats = torch.zeros(3 * Cout_p, device=dev)
     nchw = torch.full((N, Cout, H, W), float("nan"), device=dev) if head else None
     L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), L.ptr(rq), L.ptr(y), L.ptr(stats),
            L.ptr(nchw), st)

@@ -39,8 +39,8 @@ def run(B, hw, cin, cout, k):
     wf = (torch.randn(k * k, cout, cin, device=dev) * 0.05).to(DT)
     wd = (torch.randn(k * k, cin, cout, device=dev) * 0.05).to(DT)
     bias = torch.zeros(cout, device=dev)
-    stats = torch.zeros(2 * cout, device=dev)
-    xstats = torch.zeros(2 * cin, device=dev)
+    stats = torch.zeros(3 * cout, device=dev)
+    xstats = torch.zeros(3 * cin, device=dev)
     bnd = L.HgBnDesc(M, cin, L.HG_BF16, 1e-5, 1, 0)
     L.call("hg_bn_stats", C.byref(bnd), L.ptr(xs[0]), L.ptr(xstats), st)
     gam, bet = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)

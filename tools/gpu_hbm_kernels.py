@@ -58,7 +58,7 @@ def bn_cases(H, Cc):
     gs = [torch.randn(M, cp, device=DEV, dtype=BF) for _ in range(nrot)]
     ad = [torch.randn(M, cp, device=DEV, dtype=BF) for _ in range(nrot)]
     gamma, beta = torch.ones(Cc, device=DEV), torch.zeros(Cc, device=DEV)
-    stats, red = torch.zeros(2 * cp, device=DEV), torch.zeros(2 * cp, device=DEV)
+    stats, red = torch.zeros(3 * cp, device=DEV), torch.zeros(2 * cp, device=DEV)
     dg, db = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
     d = L.HgBnDesc(M, Cc, L.HG_BF16, 1e-5, 1, 0)
     st = L.stream_ptr()
@@ -85,7 +85,7 @@ def spatial_cases(H, Cc):
     ps = [torch.empty(B, H // 2, H // 2, cp, device=DEV, dtype=BF) for _ in range(nrot)]
     gp = [torch.randn(B, H // 2, H // 2, cp, device=DEV, dtype=BF) for _ in range(nrot)]
     os_ = [torch.empty(B, H, H, cp, device=DEV, dtype=BF) for _ in range(nrot)]
-    stats = torch.zeros(2 * cp, device=DEV)
+    stats = torch.zeros(3 * cp, device=DEV)
     st = L.stream_ptr()
     run(f"maxpool2_fwd (+stats) C{Cc} @{H}x{H}", "maxpool2_fwd", big + small,
         lambda i: L.call("hg_maxpool2_fwd", L.HG_BF16, L.ptr(xs[i]), B, H, H, Cc, L.ptr(ps[i]), L.ptr(stats), st), nrot)

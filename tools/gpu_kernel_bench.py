@@ -40,7 +40,7 @@ def conv_case(H, Cin, Cout, k, res):
     wf = torch.empty(k * k, cout_p, cin_p, device=dev, dtype=torch.bfloat16)
     wd = torch.empty(k * k, cin_p, cout_p, device=dev, dtype=torch.bfloat16)
     bias = torch.zeros(cout_p, device=dev)
-    stats = torch.zeros(2 * cout_p, device=dev)
+    stats = torch.zeros(3 * cout_p, device=dev)
     dwp = torch.zeros(k * k, cout_p, cin_p, device=dev)
     dbias = torch.zeros(cout_p, device=dev)
     st = L.stream_ptr()
@@ -69,8 +69,8 @@ def bn_case(H, Cc):
     ys = [torch.empty(M, cp, device=dev, dtype=torch.bfloat16) for _ in range(nrot)]
     gs = [torch.randn(M, cp, device=dev, dtype=torch.bfloat16) for _ in range(nrot)]
     gamma, beta = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
-    stats = torch.zeros(2 * cp, device=dev)
-    red = torch.zeros(2 * cp, device=dev)
+    stats = torch.zeros(3 * cp, device=dev)
+    red = torch.zeros(3 * cp, device=dev)
     dg, db = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev)
     d = L.HgBnDesc(M, Cc, L.HG_BF16, 1e-5, 1, 0)
     st = L.stream_ptr()

@@ -27,8 +27,8 @@ def run(H, Cin, Cout, k, res):
     wf = (torch.randn(k * k, Cout, Cin, device=DEV) * 0.05).to(BF)
     wd = (torch.randn(k * k, Cin, Cout, device=DEV) * 0.05).to(BF)
     bias = torch.zeros(Cout, device=DEV)
-    stats = torch.zeros(2 * Cout, device=DEV)
-    xstats = torch.zeros(2 * Cin, device=DEV)
+    stats = torch.zeros(3 * Cout, device=DEV)
+    xstats = torch.zeros(3 * Cin, device=DEV)
     bnd = L.HgBnDesc(M, Cin, L.HG_BF16, 1e-5, 1, 0)
     st = L.stream_ptr()
     L.call("hg_bn_stats", C.byref(bnd), L.ptr(xs[0]), L.ptr(xstats), st)

@@ -2,7 +2,7 @@
 tools/gpu_hbm_kernels.py with that tool's manifest (gpurun_out/hbm_kernels_events.json): per kernel and launch shape the
 median device duration, the DRAM bytes actually moved and the algorithmic bytes, both as GB/s against the measured peak.
 
-    python tools/ncu_hbm_summary.py gpurun_out/hbm_ncu.csv gpurun_out/hbm_kernels_events.json > profiles/r02_hbm_kernels_ncu.summary.txt
+    python tools/ncu_hbm_summary.py <ncu csv> <manifest of the ncu run> [<manifest of a plain run>] > profiles/r02_hbm_kernels_ncu.summary.txt
 """
 import collections
 import csv
@@ -34,9 +34,11 @@ def load_csv(path):
     return list(launches.values())
 
 
-def main(csv_path, manifest_path):
+def main(csv_path, manifest_path, plain_manifest_path=None):
     launches = load_csv(csv_path)
     man = json.load(open(manifest_path))
+    # event timings are only meaningful from a run WITHOUT ncu: take them from the plain run's manifest when given
+    plain = {k["label"]: k for k in json.load(open(plain_manifest_path))["kernels"]} if plain_manifest_path else {}
     peak = float(man["hbm_gbs_peak"])
     print(f"# HBM-bound kernels of the hot path, B={man['B']} (tools/gpu_hbm_kernels.py under ncu --metrics "
           f"gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none); peak = {peak:.1f} GB/s "
@@ -62,10 +64,10 @@ def main(csv_path, manifest_path):
         rd = statistics.median(g.get("rd", 0.0) for g in got) * per_call
         wr = statistics.median(g.get("wr", 0.0) for g in got) * per_call
         alg = k["algorithmic_bytes"]
-        ev = k.get("event_us", k.get("event_us_median"))
+        ev = plain.get(k["label"], k).get("event_us", k.get("event_us_median"))
         print(f"  {k['label']:58s} {alg / 1e6:8.1f} {ev:8.2f} {alg / ev / 1e3:9.0f} {alg / ev / 1e3 / peak:6.3f} | {us:8.2f} "
               f"{rd / 1e6:10.1f} {wr / 1e6:10.1f} {(rd + wr) / us / 1e3:9.0f} {alg / us / 1e3:9.0f} {alg / us / 1e3 / peak:6.3f}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

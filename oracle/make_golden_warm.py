@@ -78,8 +78,11 @@ def main():
         oa = [o.float() for o in net(x)]
     # fp64 yardstick: the reference's own fp32-vs-fp64 divergence on these weights
     net.double()
-    with torch.no_grad():
-        o64 = net(x.double())
+    net.zero_grad(set_to_none=True)
+    o64 = net(x.double())
+    sum(torch.nn.functional.mse_loss(o, y.double()) for o in o64).backward()
+    g64 = {n: (p.grad.clone() if p.grad is not None else None) for n, p in net.named_parameters()}
+    o64 = [o.detach() for o in o64]
     net.float()
     net.load_state_dict(sd)
     net.zero_grad(set_to_none=True)
@@ -110,6 +113,9 @@ def main():
         grad_digest=np.stack([digest(p.grad) if p.grad is not None else np.zeros(26) for _, p in net.named_parameters()]),
         grad_norm=np.array([p.grad.double().norm().item() if p.grad is not None else 0.0
                             for _, p in net.named_parameters()]),
+        # the reference's own fp32-vs-fp64 divergence per gradient tensor (yardstick for the fp32 path)
+        grad_noise_fp64=np.array([rel(p.grad, g64[n]) if p.grad is not None and g64[n] is not None and
+                                  g64[n].norm() > 0 else 0.0 for n, p in net.named_parameters()]),
         small_grad_names=np.array(small),
         **{"g:" + n: dict(net.named_parameters())[n].grad.numpy() for n in small},
         after_digest=np.stack([digest(after[k].float()) for k in keys]),

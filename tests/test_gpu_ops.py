@@ -328,11 +328,11 @@ def test_conv_with_folded_batchnorm(case):
     L.call("hg_bn_apply", C.byref(bnd), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta), L.ptr(rmean),
            L.ptr(rvar), L.ptr(a), st)
     y0 = torch.empty(N, H, W, Cout_p, device=dev, dtype=dtype)
-    s0 = torch.zeros(2 * Cout_p, device=dev)
+    s0 = torch.zeros(3 * Cout_p, device=dev)
     L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(a), L.ptr(wf), L.ptr(bias_p), L.ptr(rq), L.ptr(y0), L.ptr(s0), None, st)
     # ---- fused forward
     y1 = torch.full((N, H, W, Cout_p), float("nan"), device=dev, dtype=dtype)
-    s1 = torch.zeros(2 * Cout_p, device=dev)
+    s1 = torch.zeros(3 * Cout_p, device=dev)
     L.call("hg_conv_fprop_bn", C.byref(d), C.byref(fold), L.ptr(xq), L.ptr(wf), L.ptr(bias_p), L.ptr(rq), L.ptr(y1),
            L.ptr(s1), None, st)
     assert torch.equal(y1, y0), f"fused fprop differs from bn_apply -> conv: {(y1.float() - y0.float()).abs().max()}"

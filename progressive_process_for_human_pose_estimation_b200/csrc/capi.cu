@@ -11,7 +11,7 @@ unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 static int g_allow_ref_conv = 0;
 int g_use_pdl = 1;
-extern int g_wgrad_fused_bias, g_persist_1x1, g_persist_min_tiles;
+extern int g_wgrad_fused_bias, g_persist_1x1, g_persist_min_tiles, g_mid_n_tiles, g_wgrad_kpx;
 extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta, g_short_1stage;
 extern int g_bn_blocks_per_sm, g_bn_bwd_blocks_per_sm, g_bn_apply_u4;
 extern long long* g_dbg_ts;
@@ -244,6 +244,14 @@ int hg_set_option(const char* name, int value) {
   }
   if (strcmp(name, "wgrad_dbg") == 0) {
     g_wgrad_dbg = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "wgrad_kpx") == 0 && (value == 64 || value == 128)) {
+    g_wgrad_kpx = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "mid_n_tiles") == 0) {
+    g_mid_n_tiles = value;
     return HG_OK;
   }
   if (strcmp(name, "small_n_tiles") == 0) {

@@ -35,6 +35,7 @@ int g_long_k_3cta = 1;         // 1: multi-wave 3x3 kernels with 2 stages and 3 
 int g_short_alias = 1;         // 1: multi-wave 1x1 kernels with a residual / raw BN input load it AFTER the (short) main loop
                                // into the aliased staging tile: 64 KB per CTA, 3 CTAs/SM instead of 2
 int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
+int g_mid_n_tiles = 0;         // 1: grids of 1..2 waves of 128-wide tiles use 64-channel N tiles
 int g_wgrad_big_n_panels = 0;   // larger maps: input-channel panels per CTA (0 = all): fewer K splits, fewer atomics
 int g_wgrad_small_n_panels = 0; // small maps (see g_wgrad_t1_max_kb): input-channel panels (of 64) per CTA; 0 = policy
                                 // (1x1 or <= 32 K blocks: 1 panel, else 2), -1 = never split the input channels
@@ -44,6 +45,7 @@ int g_wgrad_dbg = 0;            // HG_DBG_TS builds only: 1 = wgrad epilogue wit
 long long* g_dbg_ts = nullptr;  // debug: per-phase clock64 stamps of CTA 0 (hg_set_option dbg_ts)
 int g_single_wave_deep = 1;   // 1: one-wave grids use the deep (6/4-stage, ~190 KB) pipelines
 int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
+int g_wgrad_kpx = 128;        // pixels per K block on the large maps (64 or 128; 128: 3x3 @32x32 29.1 -> 20.7 us, @64x64 71 -> 60 us)
 int g_wgrad_fused_bias = 1;   // 1: the bias gradient is an extra all-ones N slab of the wgrad GEMM (no column-sum kernel)
 
 // Epilogue / prologue fusion modes of the GEMM kernel.
@@ -738,6 +740,12 @@ static int conv_gemm_bf16(const GemmGeom& g, int Kp, int Np, const void* act, co
   // the per-CTA epilogue and weight-load time (the activation tile is then read by two SMs in parallel).
   int BN = Np > 128 ? 128 : Np;
   if (g_small_n_tiles && BN == 128 && ceil_div(M, 128) * (Np / 64) <= kNumSMs) BN = 64;
+  // grids between one and two waves of 128-wide tiles (the 32x32 level: 256 CTAs on 148 SMs leave 40 SMs with one CTA
+  // and 108 with two): 64-wide tiles double the CTAs (option, measured in DESIGN 8)
+  if (g_mid_n_tiles && BN == 128) {
+    const long long ctas = (long long)ceil_div(M, 128) * (Np / 128);
+    if (ctas > kNumSMs && ctas <= 2 * kNumSMs) BN = 64;
+  }
   if (BN != 64 && BN != 128) {
     set_error("conv_gemm_bf16: unsupported padded Cout %d", Np);
     return HG_ERR_UNSUPPORTED;
@@ -961,6 +969,7 @@ struct WgradParams {
   int Hin, Win;      // spatial size of x
   int taps_s;        // filter width S
   int dil, pad;
+  int kpx;           // pixels per K block (64, or 128: half as many TMA operations per byte)
   int tap_rows;      // taps handled per CTA (T)
   int n_panels;      // 64-channel input panels per CTA (Cin_p / 64 / n_groups)
   int n_groups;      // CTAs that split the input channels
@@ -994,7 +1003,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   // Bias gradient on the tensor core: dbias[co] = sum_m dy[m, co] * 1 -- one more N slab (16 columns) whose B operand is
   // a constant all-ones tile, so the dy tiles already in shared memory are reused and no separate column-sum pass over
   // dy exists (it was a second kernel: 67 MB re-read per 128->256 convolution at 64x64).
-  uint8_t* ones_s = reinterpret_cast<uint8_t*>(bars) + 4096;   // [64 K rows][128 B], 1024-byte aligned
+  uint8_t* ones_s = reinterpret_cast<uint8_t*>(bars) + 4096;   // [kpx K rows][128 B], 1024-byte aligned
+  const int pb = p.kpx * 128;                                  // bytes of one 64-channel operand panel
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1011,7 +1021,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   uint32_t cols = 32;
   while ((int)cols < T * N + (p.dbias != nullptr ? 16 : 0)) cols <<= 1;
   if (p.dbias != nullptr) {
-    for (int i = threadIdx.x; i < 8192 / 16; i += blockDim.x)
+    for (int i = threadIdx.x; i < pb / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(ones_s)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
@@ -1033,7 +1043,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
-  const int a_bytes = 2 * 8192;
+  const int a_bytes = 2 * pb;
+  const int ksteps = p.kpx / 16;
 
   if (nkb > 0) {
     if (warp == 0) {
@@ -1044,7 +1055,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           const uint32_t ph = (i / p.stages) & 1;
           uint8_t* sA = smem + st * p.stage_bytes;
           uint8_t* sB = sA + a_bytes;
-          const int m0 = (kb_beg + i) * 64;
+          const int m0 = (kb_beg + i) * p.kpx;
           const int n0 = m0 / hw;
           const int rem = m0 - n0 * hw;
           const int h0 = rem / p.W;
@@ -1052,13 +1063,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           mbar_wait(&empty_bar[st], ph ^ 1);
           mbar_expect_tx(&full_bar[st], p.stage_bytes);
           tma_load_2d(sA, &tmDy, &full_bar[st], co_off, m0);
-          tma_load_2d(sA + 8192, &tmDy, &full_bar[st], co_off + 64, m0);
+          tma_load_2d(sA + pb, &tmDy, &full_bar[st], co_off + 64, m0);
           for (int t = 0; t < T; ++t) {
             const int tap = tap0 + t;
             const int r = tap / p.taps_s, s = tap - r * p.taps_s;
             const int dh = r * p.dil - p.pad, dw = s * p.dil - p.pad;
             for (int pn = 0; pn < p.n_panels; ++pn)
-              tma_load_4d(sB + (t * p.n_panels + pn) * 8192, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 * p.stride + dw,
+              tma_load_4d(sB + (t * p.n_panels + pn) * pb, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 * p.stride + dw,
                           h0 * p.stride + dh, n0);
           }
         }
@@ -1077,19 +1088,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           const uint32_t sA = smem_u32(smem + st * p.stage_bytes);
           const uint32_t sB = sA + a_bytes;
           for (int t = 0; t < T; ++t) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = make_smem_desc(sA + k * 2048, 8192, 1024);
-              const uint64_t bdesc = make_smem_desc(sB + t * p.n_panels * 8192 + k * 2048, 8192, 1024);
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_smem_desc(sA + k * 2048, pb, 1024);
+              const uint64_t bdesc = make_smem_desc(sB + t * p.n_panels * pb + k * 2048, pb, 1024);
               umma_bf16(tmem_base + t * N, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
             }
           }
           if (with_bias) {
             const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = make_smem_desc(sA + k * 2048, 8192, 1024);
-              const uint64_t bdesc = make_smem_desc(smem_u32(ones_s) + k * 2048, 8192, 1024);
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_smem_desc(sA + k * 2048, pb, 1024);
+              const uint64_t bdesc = make_smem_desc(smem_u32(ones_s) + k * 2048, pb, 1024);
               umma_bf16(tmem_base + T * N, adesc, bdesc, idesc1, (i > 0 || k > 0) ? 1u : 0u);
             }
           }
@@ -1262,15 +1273,28 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     // K slices anyway: there one tap per CTA triples the CTAs that share the atomics.
     int T = 1;
     if (taps == 9 && Cin_p <= 128 && (M + 63) / 64 > g_wgrad_t1_max_kb) T = 3;
-    const int bw = W < 64 ? W : 64;
-    int bh = 64 / bw;
+    // K block = 64 pixels, or 128 on the large maps (option wgrad_kpx): the TMA unit of an SM retires about one bulk
+    // tensor operation per ~320 cycles whatever its size (16 KB boxes: ~50 B/clk, the forward kernels; 8 KB boxes:
+    // ~26 B/clk, this kernel), so twice the pixels per box is half the operations per byte
+    int kpx = 64;
+    if (g_wgrad_kpx == 128 && !fold && (M + 63) / 64 > g_wgrad_t1_max_kb && M % 128 == 0 && W <= 128 &&
+        (long long)H * W >= 128) {
+      const int sb = 2 * 16384 + T * (Cin_p / 64) * 16384;
+      if (2 * sb <= g_wgrad_smem_kb * 1024) kpx = 128;
+      else if (T == 3 && 2 * (2 * 16384 + (Cin_p / 64) * 16384) <= g_wgrad_smem_kb * 1024) {
+        kpx = 128;   // one tap per CTA so that two 128-pixel stages fit
+        T = 1;
+      }
+    }
+    const int bw = W < kpx ? W : kpx;
+    int bh = kpx / bw;
     if (bh > H) bh = H;
-    const int bn = 64 / (bw * bh);
+    const int bn = kpx / (bw * bh);
     CUtensorMap tmDy, tmX;
     {
       uint64_t dims[2] = {(uint64_t)Cout_p, (uint64_t)M};
       uint64_t str[1] = {(uint64_t)Cout_p * 2};
-      uint32_t box[2] = {64, 64};
+      uint32_t box[2] = {64, (uint32_t)kpx};
       uint32_t es[2] = {1, 1};
       int rc = encode_tmap(&tmDy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy, dims, str, box, es,
                            CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1297,6 +1321,7 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.dil = d->dil;
     p.pad = d->pad;
     p.tap_rows = T;
+    p.kpx = kpx;
     // small maps: split the input channels over CTAs as well (same reason as one tap per CTA: the fp32 adds a CTA
     // pushes through its SM's L2 port are what a small wgrad launch costs)
     // (B200, batch 32, us per launch: 3x3 128->128 @4x4 11.5 -> 4.5, 1x1 256->128 8.1 -> 4.5, 3x3 @16x16 15.8 -> 10.7)
@@ -1312,8 +1337,8 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.n_panels = Cin_p / 64 / p.n_groups;
     p.Cin_p = Cin_p;
     p.Cout_p = Cout_p;
-    p.total_kb = (int)((M + 63) / 64);
-    p.stage_bytes = 2 * 8192 + T * p.n_panels * 8192;
+    p.total_kb = (int)((M + kpx - 1) / kpx);
+    p.stage_bytes = (2 + T * p.n_panels) * kpx * 128;
     p.stages = (g_wgrad_smem_kb * 1024) / p.stage_bytes;
     if (p.stages < 2) p.stages = 2;
     if (p.stages > 6) p.stages = 6;
@@ -1322,7 +1347,8 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     // one wave of CTAs, and at least 8 K-blocks (512 pixels) of work per CTA: the split-K partial sums are
     // reduced with atomics, so small problems must not be cut into many slices
     // (small maps are latency-bound: there, two K blocks per CTA and more atomics beat a long serial loop)
-    const int min_kb = p.total_kb <= 256 ? 2 : 8;
+    int min_kb = (M + 63) / 64 <= 256 ? 2 : 8;   // in 64-pixel blocks
+    min_kb = min_kb / (kpx / 64) > 0 ? min_kb / (kpx / 64) : 1;
     int nsplit = kNumSMs / (tap_groups * mgroups * p.n_groups);
     if (nsplit > p.total_kb / min_kb) nsplit = p.total_kb / min_kb;
     if (nsplit < 1) nsplit = 1;
@@ -1343,7 +1369,7 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.dbias = (dbias && g_wgrad_fused_bias) ? dbias : nullptr;
     p.Cout = d->Cout;
     if (p.dbias) dbias = nullptr;
-    const int smem_bytes = p.stages * p.stage_bytes + 4096 + 8192 + 1024;
+    const int smem_bytes = p.stages * p.stage_bytes + 4096 + kpx * 128 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
       HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

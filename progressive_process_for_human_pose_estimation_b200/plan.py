@@ -38,6 +38,10 @@ _FWD_MAIN_PRIORITY = int(os.environ.get("HG_FWD_MAIN_PRIORITY", "-3"))
 # skip-branch and wgrad lanes, which fill the SMs it leaves idle; several wgrad lanes keep enough of that deferred work
 # in flight (4 lanes: backward 27.45 -> 26.9 ms; skip lanes at normal priority too: 850.5 -> 856.8 images/s).
 _BWD_PRIO = [int(v) for v in os.environ.get("HG_BWD_PRIORITY", "-3,0,0").split(",")]  # main, skip lanes, wgrad lanes
+# 1: (round 1) the packed-gradient unpack of every shared weight runs on the main lane behind a barrier over all lanes
+_UNPACK_BARRIER = os.environ.get("HG_UNPACK_BARRIER", "0") == "1"
+# 1: the per-step weight repacking runs on a side lane under the stem convolution (which needs no packed weight)
+_PACK_SIDE_LANE = os.environ.get("HG_PACK_SIDE_LANE", "1") == "1"
 
 
 class Val:
@@ -372,6 +376,12 @@ class Plan:
             lw = self._last_writer.get(t.data_ptr()) if t is not None else None
             if lw is not None and lw.lane != c.lane and lw not in deps:
                 deps.append(lw)
+        pd = getattr(self, "_pack_done", None)
+        if (lst is self.fwd_calls and pd is not None and name.startswith("hg_conv_") and c.lane != pd.lane
+                and c.lane not in self._pack_synced):
+            self._pack_synced.add(c.lane)   # later calls of the lane follow in stream order
+            if pd not in deps:
+                deps.append(pd)
         c.deps = tuple(deps)
         lst.append(c)
         return c
@@ -614,7 +624,12 @@ class Plan:
         f, st = self.fwd_calls, self.stream
         if self.stats_slots is not None:
             self._emit(f, "hg_bn_prepare_stats", L.ptr(self.stats_slots[0]), self.stats_slots[1], st)
-        # weights -> GEMM operand layouts (the optimizer changed them since the last step)
+        # weights -> GEMM operand layouts (the optimizer changed them since the last step).  ~30 small launches: on a
+        # side lane they run under the stem convolution, which reads the fp32 OIHW weight itself; the first convolution
+        # of every lane waits for the last of them (`_pack_done`)
+        self._pack_done, self._pack_synced = None, set()
+        if _PACK_SIDE_LANE and self.wgrad_lanes and self.num_lanes > 1:
+            self._cur_lane = self.wgrad_lanes[0]
         for key in convs:
             info = self.conv_info[key]
             cv = info["conv"]
@@ -629,8 +644,10 @@ class Plan:
                 if cv.bias is not None:
                     self._emit(f, "hg_mix_rows_rect", L.ptr(info["mix"]), L.ptr(self._p32(cv.bias)), L.ptr(info["bias"]),
                                info["cout"], cv.out_channels, 1, 0, 0, st)
-            self._emit(f, "hg_pack_conv_weight_slice", C.byref(d), L.ptr(src), cv.in_channels, info["cin_off"],
-                       L.ptr(info["wf"]), L.ptr(info["wd"]) if self.need_bwd else None, st)
+            self._pack_done = self._emit(f, "hg_pack_conv_weight_slice", C.byref(d), L.ptr(src), cv.in_channels,
+                                         info["cin_off"], L.ptr(info["wf"]), L.ptr(info["wd"]) if self.need_bwd else None,
+                                         st)
+        self._cur_lane = 0
         for v, kind in self.b.inputs:
             if kind == "nchw":
                 self._emit(f, "hg_nchw_f32_to_nhwc", self.hdt, L.ptr(self.in_nchw), None, v.N, v.C, v.H, v.W,
@@ -824,6 +841,7 @@ class Plan:
                     self._cur_lane = keep_lane
                     if wslot is not None and not info["direct"]:
                         info["last_wgrad"] = g[-1]
+                        info.setdefault("wgrads", []).append(g[-1])
                 if x.requires_grad:
                     addend, dst = self._grad_target(x)
                     if foldop is not None:
@@ -949,11 +967,22 @@ class Plan:
             for call in g:
                 if call.name == "hg_conv_wgrad" and widx in call.writes:
                     call.writes = tuple(w for w in call.writes if w != widx)
-            # other call sites of this weight may still be running on other lanes: wait for all issued work
+            # The unpack runs on the lane of the weight's last wgrad call and waits (events) for the call sites that ran
+            # on the OTHER wgrad lanes -- not on the main lane behind a barrier over every lane, which made the critical
+            # dgrad / BatchNorm chain of the last stack wait ~30 times for all queued low-priority wgrad work to drain.
             pos = g.index(info["last_wgrad"]) + 1
+            lane = info["last_wgrad"].lane
+            last_per_lane = {}
+            for wc in info.get("wgrads", []):
+                last_per_lane[wc.lane] = wc
+            deps = tuple(wc for ln, wc in last_per_lane.items() if ln != lane)
             for i, c in enumerate(tail):
-                c.lane = 0
-                c.barrier = (i == 0)
+                c.lane = lane
+                c.barrier = _UNPACK_BARRIER and i == 0
+                if _UNPACK_BARRIER:
+                    c.lane = 0
+                elif i == 0:
+                    c.deps = deps
                 g.insert(pos + i, c)
 
     def plan_gradient_buckets(self, quantiles=(0.5, 0.97)):

@@ -420,7 +420,7 @@ def test_warm_weight_8stack_train_step_vs_reference_golden(dtype):
     assert list(params) == names
     gnorm = g["grad_norm"]
     small = 1e-4 * np.median(gnorm[gnorm > 0])
-    gtol = 2e-2 if fp32 else 0.5   # fp32: the stem weight's gradient is a heavily cancelling sum (0.7 % observed)
+    gtol = 2e-2 if fp32 else 0.5
     checked, worst = 0, 0.0
     for i, n in enumerate(names):
         p = params[n]
@@ -432,9 +432,10 @@ def test_warm_weight_8stack_train_step_vs_reference_golden(dtype):
             continue   # analytically-zero gradients (conv biases that feed a BatchNorm): rounding noise on both sides
         e = abs(p.grad.double().norm().item() - gnorm[i]) / gnorm[i]
         worst = max(worst, e)
-        # the stem's gradient is the sum of all eight stacks' contributions through every block: a heavily cancelling
-        # sum (0.7 - 2.7 % run to run on the fp32 path with its unordered fp32 statistics atomics)
-        assert e <= (max(gtol, 0.1) if n.startswith("conv1.") else gtol), (n, e)
+        # yardstick per tensor: the reference's own fp32-vs-fp64 gradient divergence on these weights (median 1.8 %:
+        # eight weight-shared stacks amplify rounding in the backward pass too; the stem's gradient, a cancelling sum
+        # over every block of every stack, is the noisiest)
+        assert e <= max(gtol, 4 * float(g["grad_noise_fp64"][i])), (n, e, float(g["grad_noise_fp64"][i]))
         checked += 1
     assert checked > 60, checked   # 199 tensors - 28 grad-less - the analytically-zero bias gradients
     if fp32:
@@ -442,8 +443,8 @@ def test_warm_weight_8stack_train_step_vs_reference_golden(dtype):
             i = names.index(n)
             if gnorm[i] < small:
                 continue
-            # (the stem's tensors: see above -- cancelling sums over all eight stacks)
-            assert rel(params[n].grad.cpu(), torch.from_numpy(g["g:" + n])) <= (0.1 if n.startswith("conv1.") else 2e-2), n
+            tol_n = max(2e-2, 4 * float(g["grad_noise_fp64"][i]))
+            assert rel(params[n].grad.cpu(), torch.from_numpy(g["g:" + n])) <= tol_n, (n, tol_n)
     sdn = net.state_dict()
     for i, k in enumerate(str(k) for k in g["keys"]):
         if "num_batches_tracked" in k:

@@ -178,6 +178,20 @@ def test_batchnorm_shifted_statistics_survive_large_means():
     assert errs["plain"] > 10 * errs["shifted"], errs   # what the old formula did to these channels
 
 
+@pytest.mark.parametrize("case", [(12, 64, 64, 256, 128, 1, 1, False, False), (10, 64, 64, 128, 256, 1, 1, True, False),
+                                  (4, 64, 64, 128, 128, 3, 1, False, False), (16, 32, 32, 128, 128, 3, 1, False, False),
+                                  (3, 128, 128, 64, 64, 3, 1, False, False)])
+def test_wgrad_128_pixel_k_blocks(case):
+    """conv_wgrad_kernel with 128-pixel K blocks (the default on the large maps: half as many TMA operations per byte)
+    and with 64-pixel K blocks (hg_set_option("wgrad_kpx", 64)): same weight / bias gradients."""
+    for kpx in (128, 64):
+        L.call("hg_set_option", b"wgrad_kpx", kpx)
+        try:
+            test_conv_fprop_dgrad_wgrad(case, torch.bfloat16)
+        finally:
+            L.call("hg_set_option", b"wgrad_kpx", 128)
+
+
 STRIDE2_CASES = [
     # N, H, W (input), Cin, Cout, k
     (2, 64, 64, 128, 128, 3),     # try_with_aspp_remove_max_pool.py:176 (conv2 of a stride-2 block)

@@ -59,6 +59,10 @@ def run(H, Cin, Cout, k, res):
 
 
 def main():
+    for opt in os.environ.get("HG_OPTIONS", "").split(","):   # e.g. HG_OPTIONS=wgrad_kpx=128
+        if "=" in opt:
+            k_, v_ = opt.split("=")
+            L.call("hg_set_option", k_.encode(), int(v_))
     shapes = os.environ.get("SHAPES", "64:128:128:3:0,64:128:256:1:1,64:256:128:1:0,64:256:256:1:0,32:128:128:3:0,32:128:256:1:1")
     print(torch.cuda.get_device_name(0), f"B={B}")
     for s in shapes.split(","):

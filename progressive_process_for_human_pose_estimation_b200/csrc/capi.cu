@@ -11,6 +11,7 @@ unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 static int g_allow_ref_conv = 0;
 int g_use_pdl = 1;
+extern int g_persist_3x3, g_persist3_min_units, g_p3_dbg;
 extern int g_wgrad_fused_bias, g_persist_1x1, g_persist_min_tiles, g_mid_n_tiles, g_wgrad_kpx;
 extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta, g_short_1stage;
 extern int g_bn_blocks_per_sm, g_bn_bwd_blocks_per_sm, g_bn_apply_u4;
@@ -65,18 +66,6 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
 }
 
 // implemented in conv_tc.cu / conv_ref.cu
-struct BnFoldDev {
-  const float* stats;
-  const float* gamma;
-  const float* beta;
-  const float* rmean;
-  const float* rvar;
-  float count;
-  float eps;
-  int relu;
-  int use_running;
-  int C, Cp;
-};
 BnFoldDev make_fold(const HgBnFold* f, int C, long long count);
 int conv_tc_fprop(const HgConvDesc* d, const void* x, const void* w_fprop, const float* bias, const void* res, void* y,
                   float* stats, float* out_nchw, int mode, const BnFoldDev* fold, cudaStream_t st);
@@ -185,6 +174,14 @@ int hg_set_option(const char* name, int value) {
       fprintf(stderr, "\n  MMA warp saw tile k at:");
       for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[24 + i] - h[0]);
       fprintf(stderr, "\n");
+    } else if (value == 3 && g_dbg_ts) {   // conv3x3_persist_kernel (DBG build): per-role wait / phase cycles of CTA 0
+      long long h[32];
+      cudaDeviceSynchronize();
+      cudaMemcpy(h, g_dbg_ts, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "  producer: total %lld, a_empty %lld, b_empty %lld\n", h[0], h[1], h[2]);
+      fprintf(stderr, "  mma     : total %lld, tmem_empty %lld, a_full %lld, b_full %lld\n", h[4], h[5], h[6], h[7]);
+      fprintf(stderr, "  epilogue: total %lld, tmem_full %lld, y+ld %lld, row %lld, col %lld, store wait %lld\n", h[8], h[9],
+              h[10], h[11], h[12], h[13]);
     } else if (value == 0) {
       g_dbg_ts = nullptr;
     }
@@ -204,6 +201,18 @@ int hg_set_option(const char* name, int value) {
   }
   if (strcmp(name, "persist_1x1") == 0) {
     g_persist_1x1 = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "p3_dbg") == 0) {
+    g_p3_dbg = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "persist_3x3") == 0) {
+    g_persist_3x3 = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "persist3_min_units") == 0 && value > 0) {
+    g_persist3_min_units = value;
     return HG_OK;
   }
   if (strcmp(name, "persist_min_tiles") == 0 && value > 0) {

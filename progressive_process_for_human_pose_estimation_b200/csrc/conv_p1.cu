@@ -30,21 +30,6 @@ namespace hg {
 int g_persist_1x1 = 0;
 int g_persist_min_tiles = 296;    // used for at least this many 128-pixel tiles (2 per SM)
 
-enum { kPlain = 0, kFold = 1, kMask = 2, kPlainBnOut = 3 };
-
-struct BnFoldDev {
-  const float* stats;
-  const float* gamma;
-  const float* beta;
-  const float* rmean;
-  const float* rvar;
-  float count;
-  float eps;
-  int relu;
-  int use_running;
-  int C, Cp;
-};
-
 struct P1Params {
   int M_total;
   int num_tiles;
@@ -65,27 +50,6 @@ struct P1Params {
 constexpr int kP1Threads = 320;   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 constexpr int kP1Epi = 256;
 constexpr int kCBufs = 2;
-
-__device__ __forceinline__ void p1_coeffs(const BnFoldDev& f, int c, float& mean, float& invstd, float& scale,
-                                          float& shift) {
-  if (c < f.C) {
-    float mu, var;
-    if (f.use_running) {
-      mu = f.rmean[c];
-      var = f.rvar[c];
-    } else {
-      const float m1 = f.stats[c] / f.count;     // shifted sums: {S1, S2, pivot} (bn.cu)
-      mu = f.stats[2 * f.Cp + c] + m1;
-      var = fmaxf(f.stats[f.Cp + c] / f.count - m1 * m1, 0.f);
-    }
-    invstd = rsqrtf(var + f.eps);
-    mean = mu;
-    scale = f.gamma[c] * invstd;
-    shift = f.beta[c] - mu * scale;
-  } else {
-    mean = invstd = scale = shift = 0.f;
-  }
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(kP1Threads, 1)
@@ -196,7 +160,7 @@ conv1x1_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if constexpr (MODE == kMask) {
       for (int c = et; c < Np; c += kP1Epi) {
         float mu, is, sc, sh;
-        p1_coeffs(p.fold, c, mu, is, sc, sh);
+        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
         coef_s[c] = sc;                 // ReLU mask: scale * y + shift > 0 (the forward's own expression)
         coef_s[256 + c] = sh;
         coef_s[512 + c] = is;           // xhat = y * A + B  ->  sum g*xhat = A * sum(g*y) + B * sum(g)

@@ -48,52 +48,6 @@ int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
 int g_wgrad_kpx = 128;        // pixels per K block on the large maps (64 or 128; 128: 3x3 @32x32 29.1 -> 20.7 us, @64x64 71 -> 60 us)
 int g_wgrad_fused_bias = 1;   // 1: the bias gradient is an extra all-ones N slab of the wgrad GEMM (no column-sum kernel)
 
-// Epilogue / prologue fusion modes of the GEMM kernel.
-//   kPlain : y = conv(x) [+bias][+residual][+stats]                                   (fprop, dgrad)
-//   kFold  : the A operand is a RAW tensor x that a BatchNorm(+ReLU) normalises: every A tile is rewritten in
-//            shared memory as a = [relu](scale_c * x + shift_c) before the tensor core reads it, so the normalised
-//            activation never exists in HBM (fprop of BN -> ReLU -> conv, reference try_with_torch.py:196-205)
-//   kMask  : dgrad whose result is the gradient of a BatchNorm(+ReLU) output: the epilogue applies the ReLU mask
-//            g = da * [bn(x) > 0], stores g and accumulates the two BatchNorm-backward sums (sum g, sum g*xhat)
-//   kPlainBnOut : kPlain whose epilogue also applies an inference-mode BatchNorm(+ReLU) to the OUTPUT channels,
-//            y = [relu](scale_c * (conv + bias_c) + shift_c) with running statistics (no residual, no statistics)
-enum { kPlain = 0, kFold = 1, kMask = 2, kPlainBnOut = 3 };
-
-// BatchNorm folded into a convolution (device view of HgBnFold)
-struct BnFoldDev {
-  const float* stats;   // {sum, sum of squares}[2*Cp] of the raw tensor (training mode)
-  const float* gamma;
-  const float* beta;
-  const float* rmean;
-  const float* rvar;
-  float count;
-  float eps;
-  int relu;
-  int use_running;
-  int C, Cp;
-};
-
-__device__ __forceinline__ void bn_fold_coeffs(const BnFoldDev& f, int c, float& mean, float& invstd, float& scale,
-                                               float& shift) {
-  if (c < f.C) {
-    float mu, var;
-    if (f.use_running) {
-      mu = f.rmean[c];
-      var = f.rvar[c];
-    } else {
-      const float m1 = f.stats[c] / f.count;     // shifted sums: {S1, S2, pivot} (bn.cu)
-      mu = f.stats[2 * f.Cp + c] + m1;
-      var = fmaxf(f.stats[f.Cp + c] / f.count - m1 * m1, 0.f);
-    }
-    invstd = rsqrtf(var + f.eps);
-    mean = mu;
-    scale = f.gamma[c] * invstd;
-    shift = f.beta[c] - mu * scale;
-  } else {
-    mean = invstd = scale = shift = 0.f;
-  }
-}
-
 // a = [relu](scale * x + shift) on 8 consecutive channels held in one 16-byte register quad
 __device__ __forceinline__ uint4 bn_relu_chunk(uint4 u, const float (&sc)[8], const float (&sh)[8], bool relu) {
   __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -109,13 +63,6 @@ __device__ __forceinline__ uint4 bn_relu_chunk(uint4 u, const float (&sc)[8], co
     h2[e] = __floats2bfloat162_rn(f.x, f.y);
   }
   return u;
-}
-
-__device__ __forceinline__ void load_coef8(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 struct ConvGemmParams {
@@ -665,6 +612,13 @@ int conv_p1_launch(long long M, int Kp, int Np, int mode, const CUtensorMap& tmA
                    const CUtensorMap& tmC, const CUtensorMap& tmR, const float* bias, float* stats, const void* res,
                    const BnFoldDev* fold, cudaStream_t st);
 
+// persistent 3x3 kernel (conv_p3.cu)
+bool conv_p3_eligible(int N, int H, int W, int Kp, int Np, int ntaps, const signed char* dh, const signed char* dw,
+                      int stride, int parity, int mode, const float* out_nchw, bool has_res);
+int conv_p3_launch(int N, int H, int W, int Kp, int Np, int mode, const signed char* dh, const signed char* dw,
+                   const signed char* wt, const void* act, const void* wpk, int wtaps, const float* bias,
+                   const void* res, void* out, float* stats, const BnFoldDev* fold, cudaStream_t st);
+
 // Geometry of one GEMM launch: the output grid [N,H,W] (128-pixel tiles), the A-operand tensor it gathers from and
 // the list of filter taps (A offset + weight index) it walks.
 struct GemmGeom {
@@ -697,6 +651,10 @@ static int conv_gemm_bf16(const GemmGeom& g, int Kp, int Np, const void* act, co
   if (bh > H) bh = H;
   const int bn = 128 / (bw * bh);
   const long long M = (long long)N * H * W;
+  if (g.Ha == H && g.Wa == W &&
+      conv_p3_eligible(N, H, W, Kp, Np, g.ntaps, g.dh, g.dw, g.stride, g.parity, mode, out_nchw, res != nullptr))
+    // large-map 3x3 convolution: persistent kernel, 256-pixel tiles, one activation box per three taps
+    return conv_p3_launch(N, H, W, Kp, Np, mode, g.dh, g.dw, g.wt, act, wpk, g.wtaps, bias, res, out, stats, fold, st);
   if (g.ntaps == 1 && g.dh[0] == 0 && g.dw[0] == 0 &&
       conv_p1_eligible(M, Kp, Np, g.ntaps, g.stride, g.parity, mode, out_nchw)) {
     // large-map pointwise convolution: persistent kernel with the weights resident in shared memory

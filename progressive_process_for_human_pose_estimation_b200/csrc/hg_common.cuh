@@ -61,7 +61,61 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
                 const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */,
                 const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swz);
 
+
+// Epilogue / prologue fusion modes of the tensor-core convolution kernels (conv_tc.cu, conv_p1.cu, conv_p3.cu).
+//   kPlain : y = conv(x) [+bias][+residual][+stats]                                   (fprop, dgrad)
+//   kFold  : the A operand is a RAW tensor x that a BatchNorm(+ReLU) normalises: every A tile is rewritten in
+//            shared memory as a = [relu](scale_c * x + shift_c) before the tensor core reads it, so the normalised
+//            activation never exists in HBM (fprop of BN -> ReLU -> conv, reference try_with_torch.py:196-205)
+//   kMask  : dgrad whose result is the gradient of a BatchNorm(+ReLU) output: the epilogue applies the ReLU mask
+//            g = da * [bn(x) > 0], stores g and accumulates the two BatchNorm-backward sums (sum g, sum g*xhat)
+//   kPlainBnOut : kPlain whose epilogue also applies an inference-mode BatchNorm(+ReLU) to the OUTPUT channels,
+//            y = [relu](scale_c * (conv + bias_c) + shift_c) with running statistics (no residual, no statistics)
+enum { kPlain = 0, kFold = 1, kMask = 2, kPlainBnOut = 3 };
+
+// BatchNorm folded into a convolution (device view of HgBnFold)
+struct BnFoldDev {
+  const float* stats;   // shifted sums {S1, S2, pivot}[3*Cp] of the raw tensor (training mode, bn.cu)
+  const float* gamma;
+  const float* beta;
+  const float* rmean;
+  const float* rvar;
+  float count;
+  float eps;
+  int relu;
+  int use_running;
+  int C, Cp;
+};
+
 #ifdef __CUDACC__
+__device__ __forceinline__ void bn_fold_coeffs(const BnFoldDev& f, int c, float& mean, float& invstd, float& scale,
+                                               float& shift) {
+  if (c < f.C) {
+    float mu, var;
+    if (f.use_running) {
+      mu = f.rmean[c];
+      var = f.rvar[c];
+    } else {
+      const float m1 = f.stats[c] / f.count;     // shifted sums: {S1, S2, pivot} (bn.cu)
+      mu = f.stats[2 * f.Cp + c] + m1;
+      var = fmaxf(f.stats[f.Cp + c] / f.count - m1 * m1, 0.f);
+    }
+    invstd = rsqrtf(var + f.eps);
+    mean = mu;
+    scale = f.gamma[c] * invstd;
+    shift = f.beta[c] - mu * scale;
+  } else {
+    mean = invstd = scale = shift = 0.f;
+  }
+}
+
+__device__ __forceinline__ void load_coef8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -196,6 +250,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Column sums of a 32 x 32 register tile (lane = row, v[i] = column i): afterwards lane l holds the sum of column l.
+// Each step sends one half of the remaining columns to the partner lane and keeps the other: 31 shuffles in all
+// (a butterfly per column would be 160).  v[] is destroyed.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int off = 16 >> step;          // partner distance == number of columns kept
+    const bool up = (lane & off) != 0;   // lanes with this bit set keep the upper half of the columns
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1051,10 +1051,14 @@ class Plan:
 
     def _run_calls_lanes(self, calls, bwd=False):
         if os.environ.get("HG_DEBUG_SKIP"):   # timing experiments only: drop some entry points (results are wrong)
-            skip = os.environ["HG_DEBUG_SKIP"].split(",")
-            calls = [c for c in calls if c.name not in skip]
+            # entries: `entry_point` or `entry_point:tag substring` (e.g. hg_conv_wgrad:@4x4)
+            skip = [tuple(e.split(":", 1)) for e in os.environ["HG_DEBUG_SKIP"].split(",")]
+
+            def dropped(c):
+                return any(c.name == e[0] and (len(e) == 1 or e[1] in (c.tag or "")) for e in skip)
+            calls = [c for c in calls if not dropped(c)]
             for c in calls:
-                c.deps = tuple(d for d in c.deps if d.name not in skip)
+                c.deps = tuple(d for d in c.deps if not dropped(d))
         """Issue the calls on their stream lanes; cross-lane dependencies become event waits (graph edges when
         captured).  Every lane is joined back into the main stream at the end."""
         main = torch.cuda.current_stream()

@@ -148,6 +148,114 @@ def test_persistent_pointwise_kernel(case):
         L.call("hg_set_option", b"persist_1x1", 0)
 
 
+P3_CASES = [
+    (2, 64, 64, 128, 128, 3, 1, False, False),    # 64 units on 32 CTAs
+    (19, 64, 64, 128, 128, 3, 1, False, False),   # 608 units on 148 CTAs: ranges of 4 / 5 units (odd: 128-pixel tiles)
+    (5, 32, 32, 128, 128, 3, 1, True, False),     # + residual
+    (40, 32, 32, 128, 128, 3, 1, False, False),   # 320 units: ranges of 2 / 3 units, an image is 8 units
+    (3, 128, 128, 64, 64, 3, 1, False, False),    # one 64-channel slice, 64-channel N tile, 2-row tiles
+    (9, 16, 16, 128, 64, 3, 1, False, False),     # a tile is a whole 16x16 image
+    (3, 32, 32, 256, 128, 3, 1, False, False),    # four 64-channel slices
+]
+
+
+@pytest.mark.parametrize("case", P3_CASES)
+def test_persistent_3x3_kernel(case):
+    """conv3x3_persist_kernel (256-pixel tiles, one activation box per three taps, two TMEM accumulator sets, one CTA
+    per SM over a contiguous unit range) forced for every size: same checks as the tile-per-CTA kernel -- fprop (+bias,
+    +residual, statistics), dgrad (+addend, in place) against PyTorch fp32 on bf16-rounded operands."""
+    L.call("hg_set_option", b"persist_3x3", 1)
+    L.call("hg_set_option", b"persist3_min_units", 1)
+    try:
+        n0 = L.load().hg_launch_count()
+        test_conv_fprop_dgrad_wgrad(case, torch.bfloat16)
+        assert L.load().hg_launch_count() > n0
+    finally:
+        L.call("hg_set_option", b"persist3_min_units", 256)
+
+
+def test_persistent_3x3_kernel_matches_tile_kernel():
+    """Same convolution through the persistent kernel and through conv_gemm_kernel (persist_3x3 = 0): the outputs differ
+    only by the fp32 accumulation order of the 18 K blocks (a bf16 rounding step at most), the statistics by 1e-4."""
+    torch.manual_seed(11)
+    dev, dtype = "cuda", torch.bfloat16
+    N, H, W, Cc = 32, 32, 32, 128
+    d = L.HgConvDesc(N, H, W, Cc, Cc, 3, 3, 1, 1, 1, L.HG_BF16)
+    x = torch.randn(N, H, W, Cc, device=dev).to(dtype)
+    w = torch.randn(Cc, Cc, 3, 3, device=dev) / (Cc * 9) ** 0.5
+    wf = torch.empty(9, Cc, Cc, device=dev, dtype=dtype)
+    wd = torch.empty(9, Cc, Cc, device=dev, dtype=dtype)
+    bias = torch.randn(Cc, device=dev)
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
+    outs = []
+    for on in (1, 0):
+        L.call("hg_set_option", b"persist_3x3", on)
+        try:
+            y = torch.empty(N, H, W, Cc, device=dev, dtype=dtype)
+            stats = torch.zeros(3 * Cc, device=dev)
+            L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(x), L.ptr(wf), L.ptr(bias), None, L.ptr(y), L.ptr(stats), None, st)
+            outs.append((y.float(), stats.clone()))
+        finally:
+            L.call("hg_set_option", b"persist_3x3", 1)
+    (y1, s1), (y0, s0) = outs
+    assert (y1 - y0).abs().max().item() <= 2 ** -7 * y0.abs().max().item()
+    assert (y1 != y0).float().mean().item() < 0.02
+    close(s1[:2 * Cc], s0[:2 * Cc], 1e-4, "statistics")
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 128, 128, 3, 1, False, True, False), (19, 64, 64, 128, 128, 3, 1, False, True, False),
+                                  (40, 32, 32, 128, 128, 3, 1, False, True, False), (2, 32, 32, 64, 64, 3, 1, False, False, False),
+                                  (5, 16, 16, 128, 128, 3, 1, False, True, True)])
+def test_persistent_3x3_kernel_masked_dgrad(case):
+    """The ReLU-mask / BatchNorm-backward-sums epilogue (hg_conv_dgrad_bn) of the persistent 3x3 kernel: bit-identical
+    masked gradient, same sums as hg_bn_bwd_reduce."""
+    N, H, W, Cin, Cout, k, dil, res, relu, eval_mode = case
+    torch.manual_seed(4)
+    dev, dtype = "cuda", torch.bfloat16
+    M = N * H * W
+    xq = nhwc(torch.randn(N, Cin, H, W, device=dev) * 1.7 + 0.3, dtype)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+    gamma = torch.rand(Cin, device=dev) + 0.5
+    beta = torch.randn(Cin, device=dev) * 0.3
+    rmean = torch.randn(Cin, device=dev) * 0.2 + 0.3
+    rvar = torch.rand(Cin, device=dev) * 2 + 1.5
+    d = L.HgConvDesc(N, H, W, Cin, Cout, k, k, 1, 1, 1, L.HG_BF16)
+    Cin_p, Cout_p = L.pad64(Cin), L.pad64(Cout)
+    wf = torch.empty(k * k, Cout_p, Cin_p, device=dev, dtype=dtype)
+    wd = torch.empty(k * k, Cin_p, Cout_p, device=dev, dtype=dtype)
+    st = L.stream_ptr()
+    L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
+    bnd = L.HgBnDesc(M, Cin, L.HG_BF16, 1e-5, 1 if relu else 0, 1 if eval_mode else 0)
+    xstats = torch.zeros(3 * Cin_p, device=dev)
+    L.call("hg_bn_stats", C.byref(bnd), L.ptr(xq), L.ptr(xstats), st)
+    fold = L.HgBnFold(xstats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr(), 1e-5,
+                      1 if relu else 0, 1 if eval_mode else 0, 0)
+    a = torch.empty_like(xq)
+    L.call("hg_bn_apply", C.byref(bnd), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta), L.ptr(rmean),
+           L.ptr(rvar), L.ptr(a), st)
+    dyq = nhwc(torch.randn(N, Cout, H, W, device=dev), dtype)
+    L.call("hg_set_option", b"persist3_min_units", 1)
+    try:
+        da = torch.empty(N, H, W, Cin_p, device=dev, dtype=dtype)
+        L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), None, L.ptr(da), st)
+        g1 = torch.full((N, H, W, Cin_p), float("nan"), device=dev, dtype=dtype)
+        red1 = torch.zeros(2 * Cin_p, device=dev)
+        L.call("hg_conv_dgrad_bn", C.byref(d), C.byref(fold), L.ptr(dyq), L.ptr(wd), L.ptr(xq), L.ptr(g1), L.ptr(red1), st)
+    finally:
+        L.call("hg_set_option", b"persist3_min_units", 256)
+    ref_da = torch.nn.grad.conv2d_input((N, Cin, H, W), w.to(dtype).float(), nchw(dyq, Cout), 1, 1, 1)
+    close(nchw(da, Cin), ref_da, 2e-2, "dgrad vs torch")
+    red0 = torch.zeros(2 * Cin_p, device=dev)
+    L.call("hg_bn_bwd_reduce", C.byref(bnd), L.ptr(da), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta),
+           L.ptr(rmean), L.ptr(rvar), L.ptr(red0), st)
+    mask = (a.float() > 0) if relu else torch.ones_like(a, dtype=torch.bool)
+    g0 = torch.where(mask, da.float(), torch.zeros((), device=dev))
+    assert torch.equal(g1.float(), g0), f"masked dgrad differs: {(g1.float() - g0).abs().max()}"
+    scale = red0.abs().max().item()
+    assert (red1 - red0).abs().max().item() <= 2e-3 * scale, ((red1 - red0).abs().max().item(), scale)
+
+
 def test_batchnorm_shifted_statistics_survive_large_means():
     """Statistics slots hold sums of (x - pivot) (include/hg_sm100a.h): with the pivot near the channel mean -- the plan
     uses the consuming BatchNorm's running mean -- the variance of a channel whose mean is 1000x its spread is exact to

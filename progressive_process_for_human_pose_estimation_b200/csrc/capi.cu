@@ -11,8 +11,8 @@ unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 static int g_allow_ref_conv = 0;
 int g_use_pdl = 1;
-extern int g_persist_3x3, g_persist3_min_units, g_p3_dbg;
-extern int g_wgrad_fused_bias, g_persist_1x1, g_persist_min_tiles, g_mid_n_tiles, g_wgrad_kpx;
+extern int g_persist_3x3, g_persist_1x1, g_persist_min_units, g_ps_dbg;
+extern int g_wgrad_fused_bias, g_mid_n_tiles, g_wgrad_kpx;
 extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta, g_short_1stage;
 extern int g_bn_blocks_per_sm, g_bn_bwd_blocks_per_sm, g_bn_apply_u4;
 extern long long* g_dbg_ts;
@@ -174,7 +174,7 @@ int hg_set_option(const char* name, int value) {
       fprintf(stderr, "\n  MMA warp saw tile k at:");
       for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[24 + i] - h[0]);
       fprintf(stderr, "\n");
-    } else if (value == 3 && g_dbg_ts) {   // conv3x3_persist_kernel (DBG build): per-role wait / phase cycles of CTA 0
+    } else if (value == 3 && g_dbg_ts) {   // conv_persist_kernel (DBG build): per-role wait / phase cycles of CTA 0
       long long h[32];
       cudaDeviceSynchronize();
       cudaMemcpy(h, g_dbg_ts, sizeof(h), cudaMemcpyDeviceToHost);
@@ -199,24 +199,20 @@ int hg_set_option(const char* name, int value) {
     g_bn_bwd_blocks_per_sm = value;
     return HG_OK;
   }
-  if (strcmp(name, "persist_1x1") == 0) {
+  if (strcmp(name, "persist_1x1") == 0) {   // large-map 1x1 convolutions through conv_persist_kernel (default 1)
     g_persist_1x1 = value;
     return HG_OK;
   }
-  if (strcmp(name, "p3_dbg") == 0) {
-    g_p3_dbg = value;
-    return HG_OK;
-  }
-  if (strcmp(name, "persist_3x3") == 0) {
+  if (strcmp(name, "persist_3x3") == 0) {   // large-map 3x3 convolutions through conv_persist_kernel (default 0)
     g_persist_3x3 = value;
     return HG_OK;
   }
-  if (strcmp(name, "persist3_min_units") == 0 && value > 0) {
-    g_persist3_min_units = value;
+  if (strcmp(name, "persist_min_units") == 0 && value > 0) {   // smallest launch (in 128-pixel units) it is used for
+    g_persist_min_units = value;
     return HG_OK;
   }
-  if (strcmp(name, "persist_min_tiles") == 0 && value > 0) {
-    g_persist_min_tiles = value;
+  if (strcmp(name, "ps_dbg") == 0) {
+    g_ps_dbg = value;
     return HG_OK;
   }
   if (strcmp(name, "wgrad_fused_bias") == 0) {

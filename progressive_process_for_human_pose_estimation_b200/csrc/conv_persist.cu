@@ -1,0 +1,706 @@
+// Persistent convolution kernel for the large maps (64x64 / 32x32 levels at batch 32): 1x1 and 3x3 (stride 1,
+// dilation 1), fprop and dgrad, y[m, co] = sum_{dh, dw, ci} a[m + (dh, dw), ci] * w[tap(dh, dw)][co][ci].
+// (conv1 / conv2 / conv3 of every ResidualBlock, lin, conv3 / conv4 of creatModel: reference try_with_torch.py:186-193,
+// 199-207,248,272-273, and their data gradients.)
+//
+// Why: the tile-per-CTA kernel of conv_tc.cu pays barrier / TMEM / descriptor set-up, a cold two-stage pipeline and a
+// serial epilogue for every 128 pixels.  Measured on B200 (tools/gpu_l2_probe.py): its 1x1 256->128 launch at 64x64
+// takes 29.5 us with every operand L2-resident and 30.5 us streaming from HBM -- the kernel is bound by the life of
+// its CTAs, not by memory (the HBM time of its 100 MB is 15 us).  Here ONE CTA per SM stays resident and walks a
+// contiguous range of 128-pixel units:
+//   * warp 0 streams activation boxes (and weight tiles) through TMA rings, running ahead across tiles;
+//   * warp 1 issues tcgen05.mma into one of TWO accumulator sets in TMEM (2 x 256 columns);
+//   * warps 2..17 drain the other set meanwhile: TMEM -> registers -> (+bias, +residual | ReLU mask) -> bf16 -> swizzled
+//     staging -> TMA store, and keep the per-channel sums (BatchNorm statistics of the output / the two
+//     BatchNorm-backward sums) in REGISTERS across all tiles of the CTA: one shared-memory reduction and one vector
+//     atomic per 4 channels per CTA at the end of the kernel.
+// An accumulator set holds two 128 x 128 parts: two 128-pixel sub-tiles of a 256-pixel tile (Np <= 128: both share
+// every weight tile), or the two 128-column halves of a 128-pixel tile (Np = 256: one MMA with N = 256).
+// 1x1: the whole weight matrix stays resident in shared memory when it fits next to the rings.
+// 3x3: ONE activation box of R+2 image rows (the tile plus a halo row above and below), shifted by dw, serves the three
+// taps dh = -1, 0, +1 -- the A operand of tap dh is the same shared-memory image read (dh+1)*W pixel rows further
+// down (whole image rows: every start stays 1024-byte aligned for the 128-byte swizzle).  That halves the operand bytes
+// per FLOP twice over (96 KB per 12.6 MFLOP at 64x64 instead of 32 KB per 2.1 MFLOP); measured, the 3x3 kernel is then
+// bound by shared-memory bandwidth (an M=128, N=128 tcgen05.mma reads 8 KB of operands per 64 cycles = the whole 128 B/clk
+// of the SM, next to the TMA writes) and by the chip-wide L2 -> SM rate (340 MB per launch at ~12.3 TB/s = 27.6 us with
+// the MMAs switched off), so it only draws level with the tile kernel: persist_3x3 is off by default.
+#include "hg_common.cuh"
+
+// -DHG_DBG_TS=1 (make DBG=1): CTA 0 accumulates the cycles each role spends waiting on each barrier / in each epilogue
+// phase into the dbg_ts buffer (hg_set_option("dbg_ts", 1), printed by ("dbg_ts", 3)); ps_dbg 1 = no epilogue work,
+// 2 = no MMAs issued, 3 = both (what the TMA stream alone takes)
+#ifndef HG_DBG_TS
+#define HG_DBG_TS 0
+#endif
+#if HG_DBG_TS
+#define PS_TIC long long _t0 = clock64()
+#define PS_TOC(var) var += clock64() - _t0
+#else
+#define PS_TIC
+#define PS_TOC(var)
+#endif
+
+namespace hg {
+
+extern long long* g_dbg_ts;
+int g_ps_dbg = 0;
+int g_persist_1x1 = 1;
+int g_persist_3x3 = 0;
+int g_persist_min_units = 512;    // at least this many 128-pixel units: two 256-pixel tiles per SM and more (64x64 at
+                                  // batch 32; at 32x32 every CTA has ONE tile, nothing to pipeline: step 883 vs 894 images/s)
+
+struct PsParams {
+  int M_total;        // N*H*W (a multiple of 128)
+  int H, W;
+  int units;          // M_total / 128
+  int upi;            // 128-pixel units per image (3x3: a tile never crosses an image; 1x1: = units)
+  int tile_units;     // 2 (Np <= 128) or 1 (Np = 256)
+  int kchunks;        // Kp / 64
+  int tw, th;         // tap columns / tap rows: 1 x 1 or 3 x 3
+  int nA, nB;         // ring depths
+  int nY;             // residual / raw-input buffers (2: the next part's tile is requested one part ahead)
+  int a_bytes;        // one activation box
+  int b_resident;     // 1: every weight tile has its own slot and is loaded once
+  int has_res;        // kPlain: residual added;  kMask: tmR is the raw BatchNorm input (always)
+  const float* bias;  // [Np] or null
+  float* stats;       // kPlain: {S1, S2, pivot}[3*Np] or null;  kMask: {sum g, sum g*xhat}[2*Np]
+  BnFoldDev fold;     // kMask: BatchNorm of the OUTPUT channels
+  signed char wt[3][3];   // weight matrix of the tap whose A offset is (dh, dw) = (i - th/2, j - tw/2)
+  long long* ts;      // debug counters or null
+  int dbg;
+  int offB, offC, offY, offBar;
+};
+
+constexpr int kPsThreads = 576;   // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
+constexpr int kPsEpi = 512;       // four epilogue warps per SM sub-partition: the row / column passes are chains of
+                                  // dependent shared-memory round trips, two warps per scheduler left them latency-bound
+constexpr int kPsMisc = 8192;     // barriers (512 B) + bias [256] + coefficients [4][256] + column sums [2][256]
+
+// 128-pixel units [u, u1) of this CTA, cut into tiles of `tile_units` units (one where the range or the image ends)
+struct PsTiles {
+  int u, u1, upi, tu;
+  __device__ __forceinline__ PsTiles(const PsParams& p) {
+    const int base = p.units / (int)gridDim.x, rem = p.units % (int)gridDim.x;
+    const int b = (int)blockIdx.x;
+    u = b * base + (b < rem ? b : rem);
+    u1 = u + base + (b < rem ? 1 : 0);
+    upi = p.upi;
+    tu = p.tile_units;
+  }
+  __device__ __forceinline__ bool next(int& m0, int& mt) {
+    if (u >= u1) return false;
+    mt = (tu == 2 && u1 - u >= 2 && (u % upi) != upi - 1) ? 2 : 1;
+    m0 = u * 128;
+    u += mt;
+    return true;
+  }
+};
+
+template <int MODE, int NP>
+__global__ void __launch_bounds__(kPsThreads, 1)
+conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                    const PsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kBBytes = NP * 128;                  // one weight tile: NP out-channels x 64 in-channels
+  constexpr int kPartCols = NP > 128 ? 128 : NP;     // columns of one accumulator part
+  constexpr int kPanels = kPartCols / 64;
+  constexpr int kCBytes = kPanels * 16384;           // one part of the output: 128 pixels x kPartCols channels
+  constexpr uint32_t kTmemCols = 4 * kPartCols;      // two accumulator sets x two parts
+  uint8_t* sA = smem;                          // [nA][a_bytes]
+  uint8_t* sB = smem + p.offB;                 // [nB][NP rows x 128 B]
+  uint8_t* sC = smem + p.offC;                 // [kPanels][128 rows x 128 B]: output staging (TMA store source)
+  uint8_t* sY = smem + p.offY;                 // [nY] residual (kPlain) / raw BatchNorm input (kMask) of a part
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.offBar);
+  uint64_t* a_full = bars;                     // [8]
+  uint64_t* a_empty = bars + 8;                // [8]
+  uint64_t* b_full = bars + 16;                // [8]
+  uint64_t* b_empty = bars + 24;               // [8]
+  uint64_t* tmem_full = bars + 32;             // [2]
+  uint64_t* tmem_empty = bars + 34;            // [2]
+  uint64_t* y_full = bars + 36;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+  float* bias_s = reinterpret_cast<float*>(bars + 64);   // [256]
+  float* coef_s = bias_s + 256;                            // kMask: scale / shift / A / B [4][256];  kPlain: pivots
+  float* acc_s = coef_s + 1024;                            // [2][256] per-CTA column sums
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+    prefetch_tmap(&tmR);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 1);
+    }
+    mbar_init(&y_full[0], 1);
+    mbar_init(&y_full[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int hw = p.H * p.W;
+      PsTiles tiles(p);
+      int m0, mt;
+      int ia = 0, ib = 0;
+      bool first_tile = true;
+      long long w_ae = 0, w_be = 0;
+      const long long tstart = clock64();
+      while (tiles.next(m0, mt)) {
+        const int n = m0 / hw;
+        const int h0 = (m0 - n * hw) / p.W;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int j = 0; j < p.tw; ++j) {
+            const int sa = ia % p.nA;
+            {
+              PS_TIC;
+              mbar_wait(&a_empty[sa], ((ia / p.nA) & 1) ^ 1);
+              PS_TOC(w_ae);
+            }
+            mbar_expect_tx(&a_full[sa], (uint32_t)p.a_bytes);
+            if (p.th == 1) tma_load_2d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, m0);
+            else tma_load_4d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, j - 1, h0 - 1, n);
+            ++ia;
+            for (int i = 0; i < p.th; ++i) {
+              if (p.b_resident) {
+                if (first_tile) {
+                  const int sb = (kc * p.tw + j) * p.th + i;
+                  mbar_expect_tx(&b_full[sb], kBBytes);
+                  tma_load_3d(sB + sb * kBBytes, &tmB, &b_full[sb], kc * 64, 0, p.wt[i][j]);
+                }
+              } else {
+                const int sb = ib % p.nB;
+                {
+                  PS_TIC;
+                  mbar_wait(&b_empty[sb], ((ib / p.nB) & 1) ^ 1);
+                  PS_TOC(w_be);
+                }
+                mbar_expect_tx(&b_full[sb], kBBytes);
+                tma_load_3d(sB + sb * kBBytes, &tmB, &b_full[sb], kc * 64, 0, p.wt[i][j]);
+                ++ib;
+              }
+            }
+          }
+        }
+        first_tile = false;
+      }
+      if (HG_DBG_TS && p.ts && blockIdx.x == 0) {
+        p.ts[0] = clock64() - tstart;
+        p.ts[1] = w_ae;
+        p.ts[2] = w_be;
+      }
+    }
+    __syncwarp();
+    pdl_trigger();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, NP, 0, 0);
+    PsTiles tiles(p);
+    int m0, mt;
+    int ia = 0, ib = 0;
+    long long w_te = 0, w_af = 0, w_bf = 0;
+    const long long tstart = clock64();
+    for (int it = 0; tiles.next(m0, mt); ++it) {
+      const int acc = it & 1;
+      {
+        PS_TIC;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        PS_TOC(w_te);
+      }
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * 2 * kPartCols;
+      uint32_t accum = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int j = 0; j < p.tw; ++j) {
+          const int sa = ia % p.nA;
+          {
+            PS_TIC;
+            mbar_wait(&a_full[sa], (ia / p.nA) & 1);
+            PS_TOC(w_af);
+          }
+          ++ia;
+          const uint32_t a_addr = smem_u32(sA + sa * p.a_bytes);
+          for (int i = 0; i < p.th; ++i) {
+            int sb;
+            uint32_t bph;
+            if (p.b_resident) {
+              sb = (kc * p.tw + j) * p.th + i;
+              bph = 0;      // completed once (first tile); the parity-0 wait stays satisfied afterwards
+            } else {
+              sb = ib % p.nB;
+              bph = (ib / p.nB) & 1;
+              ++ib;
+            }
+            {
+              PS_TIC;
+              mbar_wait(&b_full[sb], bph);
+              PS_TOC(w_bf);
+            }
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t bdesc = make_smem_desc(smem_u32(sB + sb * kBBytes), 16, 1024);
+              for (int t = 0; t < ((HG_DBG_TS && (p.dbg & 2)) ? 0 : mt); ++t) {
+                // tap row i: the same box, (i * W) pixel rows further down; sub-tile t: 128 pixel rows further
+                const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(i * p.W + t * 128) * 128u, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tacc + t * kPartCols, adesc + 2 * k, bdesc + 2 * k, idesc, (accum | (uint32_t)k) ? 1u : 0u);
+              }
+              if (!p.b_resident) umma_commit(&b_empty[sb]);
+              if (i == p.th - 1) umma_commit(&a_empty[sa]);
+            }
+            accum = 1;
+            __syncwarp();
+          }
+        }
+      }
+      if (lane == 0) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+    }
+    if (HG_DBG_TS && p.ts && blockIdx.x == 0 && lane == 0) {
+      p.ts[4] = clock64() - tstart;
+      p.ts[5] = w_te;
+      p.ts[6] = w_af;
+      p.ts[7] = w_bf;
+    }
+    pdl_trigger();
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int et = threadIdx.x - 64;            // 0..255
+    const int sub = warp & 3;                   // TMEM lane quarter of this warp
+    const int colq = (warp - 2) >> 2;           // which 32-column chunk of the part this warp stages
+    const int row = sub * 32 + lane;
+    const bool row_warp = colq * 32 < kPartCols;   // 64-column parts: half of the warps only take part in the column pass
+    const bool need_y = MODE == kMask || p.has_res;
+    for (int c = et; c < NP; c += kPsEpi) bias_s[c] = p.bias ? p.bias[c] : 0.f;
+    for (int c = et; c < 2 * 256; c += kPsEpi) acc_s[c] = 0.f;
+    if constexpr (MODE == kMask) {
+      for (int c = et; c < NP; c += kPsEpi) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
+        coef_s[c] = sc;                 // ReLU mask: scale * y + shift > 0 (the forward's own expression)
+        coef_s[256 + c] = sh;
+        coef_s[512 + c] = is;           // xhat = y * A + B  ->  sum g*xhat = A * sum(g*y) + B * sum(g)
+        coef_s[768 + c] = -mu * is;
+      }
+    } else {
+      // statistics are sums of (y - pivot) (bn.cu): the pivots of the output channels
+      if (p.stats != nullptr)
+        for (int c = et; c < NP; c += kPsEpi) coef_s[c] = p.stats[2 * NP + c];
+    }
+    const bool relu = p.fold.relu != 0;
+    // column pass: thread = 4 adjacent channels (quad) x a slice of the rows (rg); its sums stay in registers over
+    // every tile of the CTA.  Np = 256: the two parts of a tile are different channels -> two register sets.
+    constexpr int kQuads = kPartCols / 4;          // 16 or 32 column quads
+    constexpr int kGroups = kPsEpi / kQuads;       // 16 or 8 row slices
+    constexpr int kRows = 128 / kGroups;           // 8 or 16 rows each
+    constexpr int kSets = NP > 128 ? 2 : 1;
+    const int quad = et % kQuads, rg = et / kQuads;
+    float cs[kSets][4], cq[kSets][4];
+#pragma unroll
+    for (int s = 0; s < kSets; ++s)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cs[s][e] = cq[s][e] = 0.f;
+
+    auto load_y = [&](int buf, int m, int ccol) {
+      mbar_expect_tx(&y_full[buf], kCBytes);
+      for (int pnl = 0; pnl < kPanels; ++pnl)
+        tma_load_2d(sY + buf * kCBytes + pnl * 16384, &tmR, &y_full[buf], ccol + pnl * 64, m);
+    };
+    PsTiles tiles(p);
+    int m0, mt;
+    bool have = tiles.next(m0, mt);
+    if (need_y && have && et == 0) load_y(0, m0, 0);
+    named_bar_sync(1, kPsEpi);
+    int g = 0;                                  // parts drained so far
+    long long w_tf = 0, w_y = 0, t_row = 0, t_col = 0, t_sw = 0;
+    const long long tstart = clock64();
+    for (int it = 0; have; ++it) {
+      const int acc = it & 1;
+      int m0n = 0, mtn = 0;
+      const bool have_next = tiles.next(m0n, mtn);
+      {
+        PS_TIC;
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+        PS_TOC(w_tf);
+      }
+      tc_fence_after();
+      if (HG_DBG_TS && (p.dbg & 1)) {
+        tc_fence_before();
+        named_bar_sync(1, kPsEpi);
+        if (et == 0) mbar_arrive(&tmem_empty[acc]);
+        have = have_next;
+        m0 = m0n;
+        mt = mtn;
+        continue;
+      }
+      const int nparts = NP > 128 ? 2 : mt;
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        if (pp >= nparts) break;
+        const int ybuf = p.nY == 2 ? (g & 1) : 0;
+        const int mp = NP > 128 ? m0 : m0 + pp * 128;      // first pixel of the part
+        const int ccol = NP > 128 ? pp * 128 : 0;          // first output channel of the part
+        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * 2 * kPartCols + pp * kPartCols + colq * 32;
+        float v[32];
+        if (row_warp) tmem_ld32(taddr, v);
+        {
+          PS_TIC;
+          if (need_y) mbar_wait(&y_full[ybuf], (g / p.nY) & 1);
+          if (row_warp) tmem_ld_wait();
+          PS_TOC(w_y);
+        }
+        const uint8_t* sYp = sY + ybuf * kCBytes;
+        if (need_y && p.nY == 2 && et == 0) {
+          // the other buffer is free (its part was finished before this one started): request the next part now
+          if (pp + 1 < nparts) load_y(ybuf ^ 1, NP > 128 ? m0 : m0 + (pp + 1) * 128, NP > 128 ? (pp + 1) * 128 : 0);
+          else if (have_next) load_y(ybuf ^ 1, m0n, 0);
+        }
+#if HG_DBG_TS
+        const long long _tr = clock64();
+#endif
+        // ---- row pass: registers -> (+bias, +residual | mask) -> bf16 -> swizzled staging ----
+        if (row_warp) {
+          const int col0 = colq * 32;                           // first column of the chunk inside the part
+          const int pnl = col0 / 64;
+          const int chunk0 = (col0 % 64) / 8;
+          const int rowoff = pnl * 16384 + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int swz = ((chunk0 + q) ^ (row & 7)) << 4;
+            const int ch = ccol + col0 + q * 8;                 // output channel of o[0]
+            float o[8];
+            if constexpr (MODE == kMask) {
+              const uint4 u = *reinterpret_cast<const uint4*>(sYp + rowoff + swz);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              float cS[8], cT[8];
+              load_coef8(coef_s + ch, cS);
+              load_coef8(coef_s + 256 + ch, cT);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                const bool k0 = !relu || fmaf(f.x, cS[2 * e], cT[2 * e]) > 0.f;
+                const bool k1 = !relu || fmaf(f.y, cS[2 * e + 1], cT[2 * e + 1]) > 0.f;
+                o[2 * e] = k0 ? v[q * 8 + 2 * e] : 0.f;
+                o[2 * e + 1] = k1 ? v[q * 8 + 2 * e + 1] : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[ch + e];
+              if (p.has_res) {
+                const uint4 u = *reinterpret_cast<const uint4*>(sYp + rowoff + swz);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  o[2 * e] += f.x;
+                  o[2 * e + 1] += f.y;
+                }
+              }
+            }
+            uint4 w;
+            __nv_bfloat162* hw2 = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hw2[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+            *reinterpret_cast<uint4*>(sC + rowoff + swz) = w;
+          }
+        }
+        // every TMEM read of this accumulator set is done after its last part: hand it back to the MMA warp
+        if (pp == nparts - 1) tc_fence_before();
+        fence_proxy_async_smem();
+        named_bar_sync(1, kPsEpi);
+#if HG_DBG_TS
+        const long long _tc = clock64();
+        t_row += _tc - _tr;
+#endif
+        if (et == 0) {
+          if (pp == nparts - 1) mbar_arrive(&tmem_empty[acc]);
+          for (int pnl = 0; pnl < kPanels; ++pnl) tma_store_2d(&tmC, sC + pnl * 16384, ccol + pnl * 64, mp);
+          tma_store_commit();
+        }
+        // ---- column pass: per-channel sums of what was just staged (bf16, exactly what the consumers read) ----
+        if (p.stats != nullptr) {
+          constexpr int kS = NP > 128 ? 1 : 0;
+          const int si = kS * pp;                        // register set (compile-time: pp is unrolled)
+          const int c = quad * 4;
+          const int coff = (c >> 6) * 16384 + (c & 7) * 2;
+          const int chunk = (c & 63) >> 3;
+          const uint8_t* vcol = sC + coff;
+          const uint8_t* ycol = (MODE == kMask ? sYp : sC) + coff;
+          float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);   // statistics are sums of (y - pivot)
+          if constexpr (MODE != kMask) pv = *reinterpret_cast<const float4*>(coef_s + ccol + c);
+#pragma unroll 8
+          for (int k = 0; k < kRows; ++k) {
+            const int r = rg * kRows + k;
+            const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+            const uint2 u = *reinterpret_cast<const uint2*>(vcol + off);
+            float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            if constexpr (MODE != kMask) {
+              f0.x -= pv.x; f0.y -= pv.y; f1.x -= pv.z; f1.y -= pv.w;
+            }
+            float2 y0 = f0, y1 = f1;
+            if constexpr (MODE == kMask) {
+              const uint2 uy = *reinterpret_cast<const uint2*>(ycol + off);
+              y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.x));
+              y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.y));
+            }
+            cs[si][0] += f0.x; cs[si][1] += f0.y; cs[si][2] += f1.x; cs[si][3] += f1.y;
+            cq[si][0] = fmaf(f0.x, y0.x, cq[si][0]); cq[si][1] = fmaf(f0.y, y0.y, cq[si][1]);
+            cq[si][2] = fmaf(f1.x, y1.x, cq[si][2]); cq[si][3] = fmaf(f1.y, y1.y, cq[si][3]);
+          }
+        }
+#if HG_DBG_TS
+        const long long _ts = clock64();
+        t_col += _ts - _tc;
+#endif
+        // the TMA store must have read the staging tile before the next row pass rewrites it
+        if (et == 0) tma_store_wait_read();
+        named_bar_sync(1, kPsEpi);
+#if HG_DBG_TS
+        t_sw += clock64() - _ts;
+#endif
+        if (need_y && p.nY == 1 && et == 0) {
+          if (pp + 1 < nparts) load_y(0, NP > 128 ? m0 : m0 + (pp + 1) * 128, NP > 128 ? (pp + 1) * 128 : 0);
+          else if (have_next) load_y(0, m0n, 0);
+        }
+        ++g;
+      }
+      have = have_next;
+      m0 = m0n;
+      mt = mtn;
+    }
+    if (p.stats != nullptr) {
+      // the row slices add up in shared memory (once per kernel), then one vector atomic per 4 channels per CTA
+#pragma unroll
+      for (int s = 0; s < kSets; ++s)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          atomicAdd(acc_s + s * 128 + quad * 4 + e, cs[s][e]);
+          atomicAdd(acc_s + 256 + s * 128 + quad * 4 + e, cq[s][e]);
+        }
+      named_bar_sync(1, kPsEpi);
+      for (int q = et; q < 2 * (NP / 4); q += kPsEpi) {
+        const int which = q / (NP / 4), qd = q % (NP / 4);
+        float4 v4 = *reinterpret_cast<const float4*>(acc_s + which * 256 + qd * 4);
+        if (MODE == kMask && which == 1) {
+          const float4 sg = *reinterpret_cast<const float4*>(acc_s + qd * 4);
+          const float4 cA = *reinterpret_cast<const float4*>(coef_s + 512 + qd * 4);
+          const float4 cB = *reinterpret_cast<const float4*>(coef_s + 768 + qd * 4);
+          v4 = make_float4(fmaf(cA.x, v4.x, cB.x * sg.x), fmaf(cA.y, v4.y, cB.y * sg.y),
+                           fmaf(cA.z, v4.z, cB.z * sg.z), fmaf(cA.w, v4.w, cB.w * sg.w));
+        }
+        float* dst = p.stats + which * NP + qd * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v4.x), "f"(v4.y), "f"(v4.z),
+                     "f"(v4.w)
+                     : "memory");
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+    if (HG_DBG_TS && p.ts && blockIdx.x == 0 && et == 0) {
+      p.ts[8] = clock64() - tstart;
+      p.ts[9] = w_tf;
+      p.ts[10] = w_y;
+      p.ts[11] = t_row;
+      p.ts[12] = t_col;
+      p.ts[13] = t_sw;
+    }
+    pdl_trigger();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// Shared-memory plan; returns the dynamic shared-memory size or 0 when the shape does not fit.
+static int ps_plan(int W, int Kp, int Np, int taps, bool need_y, PsParams& p) {
+  const int tile_units = Np > 128 ? 1 : 2;
+  const int tile_px = tile_units * 128;
+  const int th = taps == 9 ? 3 : 1;
+  const int part_cols = Np > 128 ? 128 : Np;
+  const int budget = 227 * 1024 - 1024 /*alignment slack*/ - kPsMisc;
+  p.tile_units = tile_units;
+  p.tw = p.th = th;
+  p.kchunks = Kp / 64;
+  p.a_bytes = th == 3 ? (tile_px / W + 2) * W * 128 : tile_px * 128;
+  const int bbytes = Np * 128;
+  const int cbytes = (part_cols / 64) * 16384;
+  const int btot = taps * p.kchunks * bbytes;
+  int nA = 0, nB = 0, nY = 0;
+  // preference: two residual / raw-input buffers (the next part's tile is in flight while this one is consumed) as long
+  // as the rings keep their depth; resident weights next to >= 2 activation boxes; else rings for both operands (two
+  // activation boxes are the minimum; a third one only when a box's worth of weight tiles still fits next to it)
+  for (int ny = need_y ? 2 : 0; ny >= (need_y ? 1 : 0) && nA == 0; --ny) {
+    const int ring = budget - cbytes - ny * cbytes;
+    if (taps * p.kchunks <= 8 && ring - btot >= (ny == 2 ? 3 : 2) * p.a_bytes) {
+      p.b_resident = 1;
+      nB = taps * p.kchunks;
+      nA = (ring - btot) / p.a_bytes;
+      nY = ny;
+    } else if (ny <= 1 || ring - 3 * p.a_bytes >= 3 * bbytes) {
+      p.b_resident = 0;
+      nA = 3;
+      if (ring - 3 * p.a_bytes < 3 * bbytes) nA = 2;
+      nB = (ring - nA * p.a_bytes) / bbytes;
+      nY = ny;
+      if (nB < (th == 3 ? 3 : 2)) return 0;
+    }
+  }
+  const int ybytes = nY * cbytes;
+  if (nA > 6) nA = 6;
+  if (nB > 8) nB = 8;
+  if (nA < 2) return 0;
+  p.nA = nA;
+  p.nB = nB;
+  p.nY = nY;
+  p.offB = nA * p.a_bytes;
+  p.offC = p.offB + nB * bbytes;
+  p.offY = p.offC + cbytes;
+  p.offBar = p.offY + ybytes;
+  return p.offBar + kPsMisc + 1024;
+}
+
+// taps of the launch as (dh, dw): eligible = one tap (0, 0), or the nine offsets {-1,0,1}^2, each once
+bool conv_persist_eligible(int N, int H, int W, int Kp, int Np, int ntaps, const signed char* dh, const signed char* dw,
+                           int stride, int parity, int mode, const float* out_nchw, bool has_res) {
+  if (stride != 1 || parity || out_nchw != nullptr) return false;
+  if (mode != kPlain && mode != kMask) return false;
+  if (!(Np == 64 || Np == 128 || Np == 256) || Kp % 64 || Kp > 256) return false;
+  const long long M = (long long)N * H * W;
+  if (M % 128 != 0 || M / 128 < g_persist_min_units || M > 0x7fffffffLL) return false;
+  if (ntaps == 1) {
+    if (!g_persist_1x1 || dh[0] != 0 || dw[0] != 0) return false;
+  } else if (ntaps == 9) {
+    if (!g_persist_3x3) return false;
+    const int tile_px = Np > 128 ? 128 : 256;
+    if (!is_pow2(W) || !is_pow2(H) || W > 128 || W < 16 || tile_px / W > H || tile_px % W || (H * W) % tile_px) return false;
+    unsigned seen = 0;
+    for (int t = 0; t < 9; ++t) {
+      if (dh[t] < -1 || dh[t] > 1 || dw[t] < -1 || dw[t] > 1) return false;
+      seen |= 1u << ((dh[t] + 1) * 3 + dw[t] + 1);
+    }
+    if (seen != 0x1FFu) return false;
+  } else {
+    return false;
+  }
+  PsParams p;
+  return ps_plan(W, Kp, Np, ntaps, mode == kMask || has_res, p) > 0;
+}
+
+template <int MODE, int NP>
+static int ps_launch(int grid, int smem, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                     const CUtensorMap& tmR, const PsParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_persist_kernel<MODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  launch_k(conv_persist_kernel<MODE, NP>, dim3(grid), dim3(kPsThreads), (size_t)smem, st, tmA, tmB, tmC, tmR, p);
+  HG_LAUNCH_OK("conv_persist_kernel");
+  count_launch();
+  return HG_OK;
+}
+
+int conv_persist_launch(int N, int H, int W, int Kp, int Np, int mode, int ntaps, const signed char* dh,
+                        const signed char* dw, const signed char* wt, const void* act, const void* wpk, int wtaps,
+                        const float* bias, const void* res, void* out, float* stats, const BnFoldDev* fold,
+                        cudaStream_t st) {
+  PsParams p;
+  memset(&p, 0, sizeof(p));
+  const bool need_y = mode == kMask || res != nullptr;
+  const int smem = ps_plan(W, Kp, Np, ntaps, need_y, p);
+  if (smem <= 0) {
+    set_error("conv_persist_launch: %d -> %d (%d taps) @%dx%d does not fit the persistent kernel", Kp, Np, ntaps, H, W);
+    return HG_ERR_UNSUPPORTED;
+  }
+  if (mode == kMask && (!res || !stats)) {
+    set_error("conv_persist_launch: mask mode needs the raw BatchNorm input and the reduction buffer");
+    return HG_ERR_BAD_ARG;
+  }
+  const long long M = (long long)N * H * W;
+  const int tile_px = p.tile_units * 128;
+  CUtensorMap tmA, tmB, tmC, tmR;
+  if (ntaps == 9) {
+    uint64_t dims[4] = {(uint64_t)Kp, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Kp * 2, (uint64_t)W * Kp * 2, (uint64_t)H * W * Kp * 2};
+    uint32_t box[4] = {64, (uint32_t)W, (uint32_t)(tile_px / W + 2), 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, act, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
+    uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)Kp * 2};
+    uint32_t box[2] = {64, (uint32_t)tile_px};
+    uint32_t es[2] = {1, 1};
+    int rc = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, act, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)Np, (uint64_t)wtaps};
+    uint64_t str[2] = {(uint64_t)Kp * 2, (uint64_t)Np * Kp * 2};
+    uint32_t box[3] = {64, (uint32_t)Np, 1};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wpk, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Np, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)Np * 2};
+    uint32_t box[2] = {64, 128};
+    uint32_t es[2] = {1, 1};
+    int rc = encode_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tmap(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, res ? res : out, dims, str, box, es,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  p.M_total = (int)M;
+  p.H = H;
+  p.W = W;
+  p.units = (int)(M / 128);
+  p.upi = ntaps == 9 ? H * W / 128 : p.units;
+  p.has_res = res != nullptr ? 1 : 0;
+  p.bias = bias;
+  p.stats = stats;
+  if (fold) p.fold = *fold;
+  p.ts = g_dbg_ts;
+  p.dbg = g_ps_dbg;
+  if (ntaps == 9) {
+    for (int t = 0; t < 9; ++t) p.wt[dh[t] + 1][dw[t] + 1] = wt[t];
+  } else {
+    p.wt[0][0] = wt[0];
+  }
+  // one CTA per SM; every CTA gets at least one full tile
+  int grid = (p.units + p.tile_units - 1) / p.tile_units;
+  if (grid > kNumSMs) grid = kNumSMs;
+  if (Np == 256)
+    return mode == kMask ? ps_launch<kMask, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st)
+                         : ps_launch<kPlain, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st);
+  if (Np == 128)
+    return mode == kMask ? ps_launch<kMask, 128>(grid, smem, tmA, tmB, tmC, tmR, p, st)
+                         : ps_launch<kPlain, 128>(grid, smem, tmA, tmB, tmC, tmR, p, st);
+  return mode == kMask ? ps_launch<kMask, 64>(grid, smem, tmA, tmB, tmC, tmR, p, st)
+                       : ps_launch<kPlain, 64>(grid, smem, tmA, tmB, tmC, tmR, p, st);
+}
+
+}  // namespace hg

@@ -606,18 +606,13 @@ static int dispatch_conv_gemm(bool long_k, bool has_res, const CUtensorMap& tmA,
   }
 }
 
-// persistent pointwise kernel (conv_p1.cu)
-bool conv_p1_eligible(long long M, int Kp, int Np, int ntaps, int stride, int parity, int mode, const float* out_nchw);
-int conv_p1_launch(long long M, int Kp, int Np, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                   const CUtensorMap& tmC, const CUtensorMap& tmR, const float* bias, float* stats, const void* res,
-                   const BnFoldDev* fold, cudaStream_t st);
-
-// persistent 3x3 kernel (conv_p3.cu)
-bool conv_p3_eligible(int N, int H, int W, int Kp, int Np, int ntaps, const signed char* dh, const signed char* dw,
-                      int stride, int parity, int mode, const float* out_nchw, bool has_res);
-int conv_p3_launch(int N, int H, int W, int Kp, int Np, int mode, const signed char* dh, const signed char* dw,
-                   const signed char* wt, const void* act, const void* wpk, int wtaps, const float* bias,
-                   const void* res, void* out, float* stats, const BnFoldDev* fold, cudaStream_t st);
+// persistent large-map kernel (conv_persist.cu)
+bool conv_persist_eligible(int N, int H, int W, int Kp, int Np, int ntaps, const signed char* dh, const signed char* dw,
+                           int stride, int parity, int mode, const float* out_nchw, bool has_res);
+int conv_persist_launch(int N, int H, int W, int Kp, int Np, int mode, int ntaps, const signed char* dh,
+                        const signed char* dw, const signed char* wt, const void* act, const void* wpk, int wtaps,
+                        const float* bias, const void* res, void* out, float* stats, const BnFoldDev* fold,
+                        cudaStream_t st);
 
 // Geometry of one GEMM launch: the output grid [N,H,W] (128-pixel tiles), the A-operand tensor it gathers from and
 // the list of filter taps (A offset + weight index) it walks.
@@ -652,46 +647,10 @@ static int conv_gemm_bf16(const GemmGeom& g, int Kp, int Np, const void* act, co
   const int bn = 128 / (bw * bh);
   const long long M = (long long)N * H * W;
   if (g.Ha == H && g.Wa == W &&
-      conv_p3_eligible(N, H, W, Kp, Np, g.ntaps, g.dh, g.dw, g.stride, g.parity, mode, out_nchw, res != nullptr))
-    // large-map 3x3 convolution: persistent kernel, 256-pixel tiles, one activation box per three taps
-    return conv_p3_launch(N, H, W, Kp, Np, mode, g.dh, g.dw, g.wt, act, wpk, g.wtaps, bias, res, out, stats, fold, st);
-  if (g.ntaps == 1 && g.dh[0] == 0 && g.dw[0] == 0 &&
-      conv_p1_eligible(M, Kp, Np, g.ntaps, g.stride, g.parity, mode, out_nchw)) {
-    // large-map pointwise convolution: persistent kernel with the weights resident in shared memory
-    if (mode == kMask && (!res || !stats)) {
-      set_error("conv_gemm_bf16: mask mode needs the raw BatchNorm input and the reduction buffer");
-      return HG_ERR_BAD_ARG;
-    }
-    CUtensorMap tA, tB, tC, tR;
-    {
-      uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)M};
-      uint64_t str[1] = {(uint64_t)Kp * 2};
-      uint32_t box[2] = {64, 128};
-      uint32_t es[2] = {1, 1};
-      int rc = encode_tmap(&tA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, act, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc) return rc;
-    }
-    {
-      uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)Np, (uint64_t)g.wtaps};
-      uint64_t str[2] = {(uint64_t)Kp * 2, (uint64_t)Np * Kp * 2};
-      uint32_t box[3] = {64, (uint32_t)Np, 1};
-      uint32_t es[3] = {1, 1, 1};
-      int rc = encode_tmap(&tB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wpk, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc) return rc;
-    }
-    {
-      uint64_t dims[2] = {(uint64_t)Np, (uint64_t)M};
-      uint64_t str[1] = {(uint64_t)Np * 2};
-      uint32_t box[2] = {64, 128};
-      uint32_t es[2] = {1, 1};
-      int rc = encode_tmap(&tC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc) return rc;
-      rc = encode_tmap(&tR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, res ? res : out, dims, str, box, es,
-                       CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc) return rc;
-    }
-    return conv_p1_launch(M, Kp, Np, mode, tA, tB, tC, tR, bias, stats, res, fold, st);
-  }
+      conv_persist_eligible(N, H, W, Kp, Np, g.ntaps, g.dh, g.dw, g.stride, g.parity, mode, out_nchw, res != nullptr))
+    // large-map 1x1 / 3x3 convolution: one resident CTA per SM (conv_persist.cu)
+    return conv_persist_launch(N, H, W, Kp, Np, mode, g.ntaps, g.dh, g.dw, g.wt, act, wpk, g.wtaps, bias, res, out, stats,
+                               fold, st);
   // N tile of at most 128 channels: short-K (1x1) kernels then fit two CTAs per SM (one CTA's epilogue overlaps
   // the other's TMA/MMA phase); 256 output channels = two N tiles that share the activation tile through L2.
   // One-wave grids (4x4 .. 16x16 levels) are pure latency: 64-channel N tiles double the CTA count, which halves

@@ -125,27 +125,34 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     close(dbias, 2 * dyr.sum((0, 2, 3)), 1e-3, "dbias")
 
 
-P1_CASES = [c for c in CONV_CASES if c[5] == 1 and not c[8]] + [
-    (12, 64, 64, 256, 128, 1, 1, False, False),   # 384 tiles: the size class the dispatcher picks by itself
-    (10, 64, 64, 128, 256, 1, 1, True, False),
-    (3, 32, 32, 256, 256, 1, 1, True, False),     # 24 tiles < 148 CTAs
-    (1, 8, 8, 64, 64, 1, 1, False, False),        # half a tile
-    (5, 16, 16, 128, 64, 1, 1, True, False),      # 10 tiles, Np = 64 (one 64-column panel)
+P1_CASES = [c for c in CONV_CASES if c[5] == 1 and not c[8] and (c[0] * c[1] * c[2]) % 128 == 0] + [
+    (12, 64, 64, 256, 128, 1, 1, False, False),   # 384 units: the size class the dispatcher picks by itself
+    (10, 64, 64, 128, 256, 1, 1, True, False),    # Np = 256: two 128-column parts per 128-pixel tile, weights resident
+    (3, 32, 32, 256, 256, 1, 1, True, False),     # 24 units < 148 CTAs
+    (19, 32, 32, 256, 128, 1, 1, False, False),   # 152 units on 76 CTAs ... 148: ranges of 1 / 2 units
+    (5, 16, 16, 128, 64, 1, 1, True, False),      # 10 units, Np = 64 (one 64-column panel)
+    (37, 16, 16, 64, 256, 1, 1, False, False),    # one 64-channel slice, 74 units
 ]
+
+
+def _persist(min_units=512, p1=1, p3=0):
+    L.call("hg_set_option", b"persist_1x1", p1)
+    L.call("hg_set_option", b"persist_3x3", p3)
+    L.call("hg_set_option", b"persist_min_units", min_units)
 
 
 @pytest.mark.parametrize("case", P1_CASES)
 def test_persistent_pointwise_kernel(case):
-    """conv1x1_persist_kernel (weights resident in shared memory, two TMEM accumulators, 148 resident CTAs) forced for
-    every size (persist_min_tiles = 1): same checks as the tile-per-CTA kernel -- fprop (+bias, +residual, statistics),
-    dgrad (+addend, in place), against PyTorch fp32 on bf16-rounded operands."""
-    L.call("hg_set_option", b"persist_1x1", 1)
-    L.call("hg_set_option", b"persist_min_tiles", 1)
+    """conv_persist_kernel on 1x1 convolutions (one resident CTA per SM, weights resident in shared memory, two TMEM
+    accumulator sets) forced for every size (persist_min_units = 1): same checks as the tile-per-CTA kernel -- fprop
+    (+bias, +residual, statistics), dgrad (+addend, in place), against PyTorch fp32 on bf16-rounded operands."""
+    _persist(1)
     try:
+        n0 = L.load().hg_launch_count()
         test_conv_fprop_dgrad_wgrad(case, torch.bfloat16)
+        assert L.load().hg_launch_count() > n0
     finally:
-        L.call("hg_set_option", b"persist_min_tiles", 296)
-        L.call("hg_set_option", b"persist_1x1", 0)
+        _persist(512)
 
 
 P3_CASES = [
@@ -164,19 +171,18 @@ def test_persistent_3x3_kernel(case):
     """conv3x3_persist_kernel (256-pixel tiles, one activation box per three taps, two TMEM accumulator sets, one CTA
     per SM over a contiguous unit range) forced for every size: same checks as the tile-per-CTA kernel -- fprop (+bias,
     +residual, statistics), dgrad (+addend, in place) against PyTorch fp32 on bf16-rounded operands."""
-    L.call("hg_set_option", b"persist_3x3", 1)
-    L.call("hg_set_option", b"persist3_min_units", 1)
+    _persist(1, p3=1)
     try:
         n0 = L.load().hg_launch_count()
         test_conv_fprop_dgrad_wgrad(case, torch.bfloat16)
         assert L.load().hg_launch_count() > n0
     finally:
-        L.call("hg_set_option", b"persist3_min_units", 256)
+        _persist(512)
 
 
 def test_persistent_3x3_kernel_matches_tile_kernel():
-    """Same convolution through the persistent kernel and through conv_gemm_kernel (persist_3x3 = 0): the outputs differ
-    only by the fp32 accumulation order of the 18 K blocks (a bf16 rounding step at most), the statistics by 1e-4."""
+    """Same 3x3 convolution through the persistent kernel and through conv_gemm_kernel (persist_3x3 = 0): the outputs
+    differ only by the fp32 accumulation order of the 18 K blocks (a bf16 rounding step at most), the statistics by 1e-4."""
     torch.manual_seed(11)
     dev, dtype = "cuda", torch.bfloat16
     N, H, W, Cc = 32, 32, 32, 128
@@ -197,7 +203,7 @@ def test_persistent_3x3_kernel_matches_tile_kernel():
             L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(x), L.ptr(wf), L.ptr(bias), None, L.ptr(y), L.ptr(stats), None, st)
             outs.append((y.float(), stats.clone()))
         finally:
-            L.call("hg_set_option", b"persist_3x3", 1)
+            L.call("hg_set_option", b"persist_3x3", 0)
     (y1, s1), (y0, s0) = outs
     assert (y1 - y0).abs().max().item() <= 2 ** -7 * y0.abs().max().item()
     assert (y1 != y0).float().mean().item() < 0.02
@@ -235,7 +241,7 @@ def test_persistent_3x3_kernel_masked_dgrad(case):
     L.call("hg_bn_apply", C.byref(bnd), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta), L.ptr(rmean),
            L.ptr(rvar), L.ptr(a), st)
     dyq = nhwc(torch.randn(N, Cout, H, W, device=dev), dtype)
-    L.call("hg_set_option", b"persist3_min_units", 1)
+    _persist(1, p3=1)
     try:
         da = torch.empty(N, H, W, Cin_p, device=dev, dtype=dtype)
         L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), None, L.ptr(da), st)
@@ -243,7 +249,7 @@ def test_persistent_3x3_kernel_masked_dgrad(case):
         red1 = torch.zeros(2 * Cin_p, device=dev)
         L.call("hg_conv_dgrad_bn", C.byref(d), C.byref(fold), L.ptr(dyq), L.ptr(wd), L.ptr(xq), L.ptr(g1), L.ptr(red1), st)
     finally:
-        L.call("hg_set_option", b"persist3_min_units", 256)
+        _persist(512)
     ref_da = torch.nn.grad.conv2d_input((N, Cin, H, W), w.to(dtype).float(), nchw(dyq, Cout), 1, 1, 1)
     close(nchw(da, Cin), ref_da, 2e-2, "dgrad vs torch")
     red0 = torch.zeros(2 * Cin_p, device=dev)
@@ -504,18 +510,17 @@ def test_conv_with_folded_batchnorm(case):
     close(dx1.float(), dx0.float(), 1e-2, "bn backward from the fused sums")
 
 
-@pytest.mark.parametrize("case", [c for c in FOLD_CASES if c[5] == 1] + [(10, 64, 64, 256, 128, 1, 1, False, True, False),
-                                                                       (10, 64, 64, 128, 256, 1, 1, False, True, False)])
+@pytest.mark.parametrize("case", [c for c in FOLD_CASES if c[5] == 1 and (c[0] * c[1] * c[2]) % 128 == 0] +
+                         [(10, 64, 64, 256, 128, 1, 1, False, True, False), (10, 64, 64, 128, 256, 1, 1, False, True, False),
+                          (19, 32, 32, 256, 256, 1, 1, False, True, False)])
 def test_persistent_pointwise_kernel_masked_dgrad(case):
-    """The ReLU-mask / BatchNorm-backward-sums epilogue (hg_conv_dgrad_bn) of the persistent pointwise kernel, forced
-    for every size: bit-identical masked gradient, same sums as hg_bn_bwd_reduce."""
-    L.call("hg_set_option", b"persist_1x1", 1)
-    L.call("hg_set_option", b"persist_min_tiles", 1)
+    """The ReLU-mask / BatchNorm-backward-sums epilogue (hg_conv_dgrad_bn) of the persistent kernel on 1x1 convolutions,
+    forced for every size: bit-identical masked gradient, same sums as hg_bn_bwd_reduce."""
+    _persist(1)
     try:
         test_conv_with_folded_batchnorm(case)
     finally:
-        L.call("hg_set_option", b"persist_min_tiles", 296)
-        L.call("hg_set_option", b"persist_1x1", 0)
+        _persist(512)
 
 
 def test_folded_entry_points_reject_unsupported_geometry():

@@ -111,7 +111,7 @@ struct ConvGemmSmem {
   static constexpr int kBarBytes = 256;          // mbarriers + TMEM slot
   static constexpr int kBiasBytes = BN * 4;
   static constexpr int kCoefBytes = 2048;        // kFold: scale/shift[256];  kMask: scale/shift/A/B[BN]
-  static constexpr int kAccBytes = 2 * BN * 4;   // per-channel column sums of the epilogue
+  // + per-channel column sums of the epilogue: one {sum, sum of squares}[2*BN] slice per row group (kAccBytes below)
   static constexpr int kTotal = kMainBytes + kBarBytes + kBiasBytes + kCoefBytes + 1024 /*align slack*/;
 };
 
@@ -123,6 +123,7 @@ template <int MINB, int BN>
 struct ConvThreads {
   static constexpr int kEpi = MINB == 1 ? (BN >= 128 ? HG_EPI_ONEWAVE : 256) : 128;
   static constexpr int kAll = 64 + kEpi;
+  static constexpr int kAccBytes = (kEpi / (BN / 4)) * 2 * BN * 4;   // column-sum slices of the epilogue's row groups
 };
 
 template <int BN, int STAGES, int MINB, int MODE, bool ALIAS>
@@ -148,7 +149,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);  // [BN]
   float* coef_s = bias_s + BN;                                                                // 512 floats
-  float* acc_s = coef_s + 512;                                                                // [2 * BN]
+  float* acc_s = coef_s + 512;                                       // [row groups][2 * BN] (ConvThreads::kAccBytes)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -446,16 +447,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // Per-channel column sums of the values just staged (bf16, exactly what the consumers will read):
       //   kPlain / kFold: sum y, sum y^2 (statistics for the BatchNorm that consumes this tensor)
       //   kMask         : sum g, sum g*xhat (BatchNorm backward)
-      // thread = 4 adjacent channels x a slice of the rows; the slices are combined with shared-memory atomics and
+      // thread = 4 adjacent channels x a slice of the rows; every slice leaves its partial sums in shared memory, 2*BN/4
+      // threads add the slices up in a fixed order (shared-memory float atomics are compare-and-swap loops: with 8 - 16
+      // slices per address they were ~0.5 us of every launch) and
       // ONE vector reduction per 4 channels leaves the CTA (every CTA of the grid adds into the same 2*Cout floats:
       // the L2 serialises per cache line, so the number of global atomics is what this costs).
       int valid = p.M_total - m0;
       valid = valid > 128 ? 128 : valid;
       constexpr int kQuads = BN / 4;            // 32 or 16
-      constexpr int kGroups = kEpiThreads / kQuads;   // row slices: 8 or 16
-      constexpr int kRows = 128 / kGroups;            // 16 or 8
-      for (int i = et; i < 2 * BN; i += kEpiThreads) acc_s[i] = 0.f;
-      named_bar_sync(1, kEpiThreads);
+      constexpr int kGroups = kEpiThreads / kQuads;   // row slices: 4 .. 32
+      constexpr int kRows = 128 / kGroups;            // 32 .. 4
       {
         const int quad = et % kQuads, grp = et / kQuads;
         const int c = quad * 4;
@@ -489,19 +490,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             q4[2] = fmaf(f1.x, y1.x, q4[2]); q4[3] = fmaf(f1.y, y1.y, q4[3]);
           }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          atomicAdd(acc_s + c + e, s4[e]);
-          atomicAdd(acc_s + BN + c + e, q4[e]);
-        }
+        *reinterpret_cast<float4*>(acc_s + grp * 2 * BN + c) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+        *reinterpret_cast<float4*>(acc_s + grp * 2 * BN + BN + c) = make_float4(q4[0], q4[1], q4[2], q4[3]);
       }
       named_bar_sync(1, kEpiThreads);
       if (et < 2 * kQuads) {
         const int which = et / kQuads, quad = et % kQuads;
-        float4 v4 = *reinterpret_cast<const float4*>(acc_s + which * BN + quad * 4);
+        auto slices = [&](int w) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int g = 0; g < kGroups; ++g) {
+            const float4 a = *reinterpret_cast<const float4*>(acc_s + g * 2 * BN + w * BN + quad * 4);
+            t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+          }
+          return t;
+        };
+        float4 v4 = slices(which);
         if (MODE == kMask && which == 1) {
           // sum g*xhat = A * sum(g*y) + B * sum(g)
-          const float4 sg = *reinterpret_cast<const float4*>(acc_s + quad * 4);
+          const float4 sg = slices(0);
           const float4 cA = *reinterpret_cast<const float4*>(coef_s + 2 * BN + quad * 4);
           const float4 cB = *reinterpret_cast<const float4*>(coef_s + 3 * BN + quad * 4);
           v4 = make_float4(fmaf(cA.x, v4.x, cB.x * sg.x), fmaf(cA.y, v4.y, cB.y * sg.y),
@@ -553,11 +560,12 @@ static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   static bool attr_set = false;
   if (!attr_set) {
     HG_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal + ConvThreads<MINB, BN>::kAccBytes));
     attr_set = true;
   }
   dim3 grid(ceil_div(p.M_total, 128) * p.n_tiles);
-  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB, BN>::kAll), L::kTotal, st, tmA,
+  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB, BN>::kAll),
+           L::kTotal + ConvThreads<MINB, BN>::kAccBytes, st, tmA,
            tmB, tmC, tmR, p);
   HG_LAUNCH_OK("conv_gemm_kernel");
   count_launch();

@@ -42,6 +42,11 @@ _BWD_PRIO = [int(v) for v in os.environ.get("HG_BWD_PRIORITY", "-3,0,0").split("
 _UNPACK_BARRIER = os.environ.get("HG_UNPACK_BARRIER", "0") == "1"
 # 1: the per-step weight repacking runs on a side lane under the stem convolution (which needs no packed weight)
 _PACK_SIDE_LANE = os.environ.get("HG_PACK_SIDE_LANE", "1") == "1"
+# 1: max-pool backward lowered after the other gradient contributions of its input (it adds into their sum: the 32
+# hg_add launches of a step disappear, 134 MB less traffic each at 64x64).  Measured: backward phase 23.3 -> 22.8 ms but
+# the steady-state step 35.25 -> 35.5 ms (the pool backward then sits at the END of the level's gradient chain instead
+# of running early next to it), so it stays off.
+_DEFER_POOL_BWD = os.environ.get("HG_DEFER_POOL_BWD", "0") == "1"
 
 
 class Val:
@@ -781,7 +786,24 @@ class Plan:
     def _lower_backward(self, convs):
         g, st = self.bwd_calls, self.stream
         self._last_writer = {}
+        done = set()      # ids of the ops whose backward has been lowered
+        deferred = []     # max-pool backwards waiting for the other gradient contributions of their input
+
+        def emit_pool_bwd(op):
+            x, G = op.ins[0], op.out.grad
+            self._cur_lane = op.lane
+            addend, dst = self._grad_target(x)
+            self._emit(g, "hg_maxpool2_bwd", self.hdt, L.ptr(x.buf), L.ptr(G), L.ptr(addend), x.N, x.H, x.W,
+                       x.C, L.ptr(dst), st)
+
         for op in reversed(self.b.ops):
+            # a deferred max-pool backward goes out as soon as every other consumer of its input has contributed
+            # (before the producer of that input is lowered: producers precede all consumers in forward order)
+            for dop in list(deferred):
+                if all(id(c) in done for c in dop.ins[0].consumers if c is not dop):
+                    deferred.remove(dop)
+                    emit_pool_bwd(dop)
+            done.add(id(op))
             k = op.kind
             self._cur_lane = op.lane
             if k == "export":
@@ -883,9 +905,14 @@ class Plan:
             elif k == "pool":
                 x = op.ins[0]
                 if x.requires_grad:
-                    addend, dst = self._grad_target(x)
-                    self._emit(g, "hg_maxpool2_bwd", self.hdt, L.ptr(x.buf), L.ptr(G), L.ptr(addend), x.N, x.H, x.W,
-                               x.C, L.ptr(dst), st)
+                    # The hourglass input feeds the skip branch (a residual block: its gradient arrives as an identity
+                    # pass-through plus a BatchNorm backward) and this pool.  Lowered in reverse op order the pool would
+                    # come first and the pass-through would then cost a separate hg_add (201 MB at 64x64, 32 per step):
+                    # the max-pool backward has an addend input, so it goes LAST instead and adds into the sum.
+                    if _DEFER_POOL_BWD and any(id(c) not in done for c in x.consumers):
+                        deferred.append(op)
+                    else:
+                        emit_pool_bwd(op)
             elif k == "up":
                 low, skip = op.ins[0], op.ins[1]
                 if skip is not None:
@@ -922,6 +949,8 @@ class Plan:
                 self._emit(g, "hg_stem_bwd", self.hdt, L.ptr(x.buf), L.ptr(out.buf), L.ptr(G), x.N, x.H, x.W,
                            1 if op.attrs["relu"] else 0, L.ptr(self._gslot(cv.weight)),
                            L.ptr(self._gslot(cv.bias)) if cv.bias is not None else None, st)
+        for dop in deferred:   # (inputs without a producer op)
+            emit_pool_bwd(dop)
         self._cur_lane = 0
         # graph inputs that want a gradient (sub-module use): NHWC -> NCHW fp32
         self.gin_static = None

@@ -1,5 +1,5 @@
 # step-level A/B runs: tools/ablation.sh name ENV=... [name ENV=...]...   (one bench.py training run per pair)
-B="python bench.py --no-cpu-baseline --no-inference --no-extras --steps 10 --warmup 3"
+B="python bench.py --no-cpu-baseline --no-inference --no-extras --steps ${STEPS:-10} --warmup 3"
 while [ $# -ge 2 ]; do
   name=$1; envs=$2; shift 2
   env $envs $B > gpurun_out/abl_$name.json 2> gpurun_out/abl_$name.err

@@ -703,22 +703,36 @@ def test_maxpool_fwd_bwd_first_max_tiebreak(dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("hw", [4, 8, 32])
-def test_upsample_add_fwd_bwd(dtype, mode, hw):
+@pytest.mark.parametrize("hw,Cc", [(4, 64), (8, 64), (32, 64), (32, 256), (16, 128), (5, 96)])
+@pytest.mark.parametrize("sep", [1, 0])
+def test_upsample_add_fwd_bwd(dtype, mode, hw, Cc, sep):
+    """x2 up-sampling (+ skip add, + statistics) and its adjoint (+ addend) against F.interpolate / autograd, through the
+    separable shared-memory kernels (sep = 1, the default) and the gather kernels (sep = 0)."""
     torch.manual_seed(0)
     dev = "cuda"
-    N, Cc = 2, 64
+    N = 2
+    Cp = L.pad64(Cc)
     low = torch.randn(N, Cc, hw, hw, device=dev)
     skip = torch.randn(N, Cc, 2 * hw, 2 * hw, device=dev)
     lq, sq = nhwc(low, dtype), nhwc(skip, dtype)
     out = torch.empty_like(sq)
     st = L.stream_ptr()
-    ustats = torch.zeros(3 * 64, device=dev)
-    L.call("hg_upsample2x_add_fwd", L.hg_dtype(dtype), mode, L.ptr(lq), L.ptr(sq), N, hw, hw, Cc, L.ptr(out),
-           L.ptr(ustats), st)
+    ustats = torch.zeros(3 * Cp, device=dev)
+    L.call("hg_set_option", b"upsample_sep", sep)
+    try:
+        L.call("hg_upsample2x_add_fwd", L.hg_dtype(dtype), mode, L.ptr(lq), L.ptr(sq), N, hw, hw, Cc, L.ptr(out),
+               L.ptr(ustats), st)
+        dout = nhwc(torch.randn(N, Cc, 2 * hw, 2 * hw, device=dev), dtype)
+        dlow = torch.empty_like(lq)
+        L.call("hg_upsample2x_bwd", L.hg_dtype(dtype), mode, L.ptr(dout), None, N, hw, hw, Cc, L.ptr(dlow), st)
+        addq = nhwc(torch.randn(N, Cc, hw, hw, device=dev), dtype)
+        dlow2 = torch.empty_like(lq)
+        L.call("hg_upsample2x_bwd", L.hg_dtype(dtype), mode, L.ptr(dout), L.ptr(addq), N, hw, hw, Cc, L.ptr(dlow2), st)
+    finally:
+        L.call("hg_set_option", b"upsample_sep", 1)
     ov = nchw(out, Cc)
     close(ustats[:Cc], ov.sum((0, 2, 3)), 1e-4, "upsample stats sum (of the stored values)")
-    close(ustats[64:64 + Cc], (ov * ov).sum((0, 2, 3)), 1e-4, "upsample stats sumsq")
+    close(ustats[Cp:Cp + Cc], (ov * ov).sum((0, 2, 3)), 1e-4, "upsample stats sumsq")
     lr = nchw(lq, Cc).requires_grad_(True)
     if mode == 0:
         up = F.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=True)
@@ -726,11 +740,9 @@ def test_upsample_add_fwd_bwd(dtype, mode, hw):
         up = F.interpolate(lr, scale_factor=2, mode="nearest")
     ref = up + nchw(sq, Cc)
     close(nchw(out, Cc), ref.detach(), tol(dtype), "upsample+add fwd")
-    dout = nhwc(torch.randn(N, Cc, 2 * hw, 2 * hw, device=dev), dtype)
     up.backward(nchw(dout, Cc))
-    dlow = torch.empty_like(lq)
-    L.call("hg_upsample2x_bwd", L.hg_dtype(dtype), mode, L.ptr(dout), None, N, hw, hw, Cc, L.ptr(dlow), st)
     close(nchw(dlow, Cc), lr.grad, tol(dtype) if dtype == torch.bfloat16 else 1e-5, "upsample bwd")
+    close(nchw(dlow2, Cc), lr.grad + nchw(addq, Cc), tol(dtype) if dtype == torch.bfloat16 else 1e-5, "upsample bwd + addend")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -46,6 +46,10 @@ long long* g_dbg_ts = nullptr;  // debug: per-phase clock64 stamps of CTA 0 (hg_
 int g_single_wave_deep = 1;   // 1: one-wave grids use the deep (6/4-stage, ~190 KB) pipelines
 int g_wgrad_smem_kb = 196;    // shared-memory budget of the wgrad pipeline
 int g_wgrad_kpx = 128;        // pixels per K block on the large maps (64 or 128; 128: 3x3 @32x32 29.1 -> 20.7 us, @64x64 71 -> 60 us)
+int g_wgrad_halo = 1;          // 1: 3x3 weight gradients on the large maps take one filter column per CTA (one x box + halo rows)
+int g_wgrad_halo_min_kb = 512; // ... from this many 128-pixel K blocks on (64x64 at batch 32: 57.2 -> 52.8 us; at 32x32 three
+                               // accumulators per CTA and 43 instead of 16 K splits triple the atomics: 18.9 -> 24.1 us)
+int g_onewave_cluster = 0;    // experiment: cluster size for one-wave grids of <= 32 CTAs (0 = plain launch)
 int g_wgrad_fused_bias = 1;   // 1: the bias gradient is an extra all-ones N slab of the wgrad GEMM (no column-sum kernel)
 
 // a = [relu](scale * x + shift) on 8 consecutive channels held in one 16-byte register quad
@@ -564,9 +568,24 @@ static int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     attr_set = true;
   }
   dim3 grid(ceil_div(p.M_total, 128) * p.n_tiles);
-  launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB, BN>::kAll),
-           L::kTotal + ConvThreads<MINB, BN>::kAccBytes, st, tmA,
-           tmB, tmC, tmR, p);
+  int cl = 0;   // experiment (hg_set_option "onewave_cluster"): launch the small one-wave grids as thread-block clusters
+  if (MINB == 1 && g_onewave_cluster > 1 && (int)grid.x <= 32) {
+    cl = g_onewave_cluster;
+    while (cl > 1 && grid.x % cl) cl >>= 1;
+  }
+  if (cl > 1) {
+    static bool np_set = false;
+    if (!np_set) {
+      HG_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>,
+                                      cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      np_set = true;
+    }
+    launch_k_cluster(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB, BN>::kAll),
+                     L::kTotal + ConvThreads<MINB, BN>::kAccBytes, st, cl, tmA, tmB, tmC, tmR, p);
+  } else {
+    launch_k(conv_gemm_kernel<BN, STAGES, MINB, MODE, ALIAS>, dim3(grid), dim3(ConvThreads<MINB, BN>::kAll),
+             L::kTotal + ConvThreads<MINB, BN>::kAccBytes, st, tmA, tmB, tmC, tmR, p);
+  }
   HG_LAUNCH_OK("conv_gemm_kernel");
   count_launch();
   return HG_OK;
@@ -905,6 +924,9 @@ struct WgradParams {
   int dbg;
   int bulk_reduce;   // epilogue: partial tile -> shared memory -> cp.reduce.async.bulk (else per-thread red.v4)
   int stage_bytes;
+  int halo;          // 1: the T = 3 taps of a CTA are ONE filter column (dh = -1, 0, +1): one x box with a halo row above
+                     //    and below serves all three (the B operand of tap dh starts dh * W pixel rows further down)
+  int xp_bytes;      // bytes of one 64-channel x panel of a stage (halo: (rows + 2) * W * 128)
   float* dw;         // [taps][Cout_p][Cin_p] fp32, accumulated
   float* dbias;      // optional [Cout]: += sum over pixels of dy (bias gradient), from an extra all-ones N slab
   int Cout;          // real output channels (rows of dbias)
@@ -935,7 +957,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int N = p.n_panels * 64;
   const int T = p.tap_rows;
-  const int tap0 = (blockIdx.y / p.n_groups) * T;
+  const int tap0 = p.halo ? (int)(blockIdx.y / p.n_groups) : (int)(blockIdx.y / p.n_groups) * T;   // halo: filter column
+  const int tap_step = p.halo ? p.taps_s : 1;                                                    // tap of accumulator t = tap0 + t * tap_step
   const int pn0 = (blockIdx.y % p.n_groups) * p.n_panels;   // first input-channel panel of this CTA
   const int co_off = blockIdx.z * 128;
   const int kb_beg = blockIdx.x * p.kb_per_cta;
@@ -989,13 +1012,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           mbar_expect_tx(&full_bar[st], p.stage_bytes);
           tma_load_2d(sA, &tmDy, &full_bar[st], co_off, m0);
           tma_load_2d(sA + pb, &tmDy, &full_bar[st], co_off + 64, m0);
-          for (int t = 0; t < T; ++t) {
-            const int tap = tap0 + t;
-            const int r = tap / p.taps_s, s = tap - r * p.taps_s;
-            const int dh = r * p.dil - p.pad, dw = s * p.dil - p.pad;
+          if (p.halo) {
+            // one box of (rows + 2) image rows per input-channel panel: column tap0, rows h0 - 1 .. h0 + rows
             for (int pn = 0; pn < p.n_panels; ++pn)
-              tma_load_4d(sB + (t * p.n_panels + pn) * pb, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 * p.stride + dw,
-                          h0 * p.stride + dh, n0);
+              tma_load_4d(sB + pn * p.xp_bytes, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 + tap0 - p.pad, h0 - p.pad, n0);
+          } else {
+            for (int t = 0; t < T; ++t) {
+              const int tap = tap0 + t;
+              const int r = tap / p.taps_s, s = tap - r * p.taps_s;
+              const int dh = r * p.dil - p.pad, dw = s * p.dil - p.pad;
+              for (int pn = 0; pn < p.n_panels; ++pn)
+                tma_load_4d(sB + (t * p.n_panels + pn) * pb, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 * p.stride + dw,
+                            h0 * p.stride + dh, n0);
+            }
           }
         }
       }
@@ -1016,7 +1045,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 #pragma unroll 4
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t adesc = make_smem_desc(sA + k * 2048, pb, 1024);
-              const uint64_t bdesc = make_smem_desc(sB + t * p.n_panels * pb + k * 2048, pb, 1024);
+              const uint64_t bdesc = p.halo ? make_smem_desc(sB + t * p.W * 128 + k * 2048, p.xp_bytes, 1024)
+                                            : make_smem_desc(sB + t * p.n_panels * pb + k * 2048, pb, 1024);
               umma_bf16(tmem_base + t * N, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
             }
           }
@@ -1139,7 +1169,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           int rows = p.Cout_p - co_off;
           if (rows > 128) rows = 128;
           for (int t = 0; t < T; ++t)
-            bulk_reduce_add_f32(p.dw + ((size_t)(tap0 + t) * p.Cout_p + co_off) * p.Cin_p, stage + (size_t)t * 128 * N,
+            bulk_reduce_add_f32(p.dw + ((size_t)(tap0 + t * tap_step) * p.Cout_p + co_off) * p.Cin_p, stage + (size_t)t * 128 * N,
                                 (uint32_t)rows * N * 4);
           tma_store_commit();
           tma_store_wait_read();
@@ -1150,7 +1180,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         const int nchunk = N / 32;
         for (int tt = 0; tt < ((HG_DBG_TS && p.dbg == 2) ? 0 : T); ++tt) {
           const int t = (tt + blockIdx.x) % T;
-          float* dst = p.dw + ((size_t)(tap0 + t) * p.Cout_p + co) * p.Cin_p + pn0 * 64;
+          float* dst = p.dw + ((size_t)(tap0 + t * tap_step) * p.Cout_p + co) * p.Cin_p + pn0 * 64;
           for (int jj = 0; jj < nchunk; ++jj) {
             const int j = (jj + blockIdx.x) % nchunk;
             float v[32];
@@ -1215,6 +1245,18 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     int bh = kpx / bw;
     if (bh > H) bh = H;
     const int bn = kpx / (bw * bh);
+    // 3x3 on the large maps: a CTA takes one filter COLUMN (three taps dh = -1, 0, +1) and loads ONE x box with a halo
+    // row above and below per K block instead of three shifted boxes: 96 KB instead of 192 KB of operands per 128
+    // pixels and three taps at 64x64 (the kernel runs at the per-SM operand rate, ~50 B/clk)
+    bool halo = false;
+    if (g_wgrad_halo && taps == 9 && d->R == 3 && d->S == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && !fold &&
+        kpx == 128 && bn == 1 && bh * bw == kpx && H % bh == 0 && Cin_p <= 128 && M / kpx >= g_wgrad_halo_min_kb) {
+      const int sbh = 2 * 16384 + (Cin_p / 64) * (bh + 2) * bw * 128;
+      if (2 * sbh <= g_wgrad_smem_kb * 1024) {
+        halo = true;
+        T = 3;
+      }
+    }
     CUtensorMap tmDy, tmX;
     {
       uint64_t dims[2] = {(uint64_t)Cout_p, (uint64_t)M};
@@ -1228,7 +1270,7 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     {
       uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
       uint64_t str[3] = {(uint64_t)Cin_p * 2, (uint64_t)d->W * Cin_p * 2, (uint64_t)d->H * d->W * Cin_p * 2};
-      uint32_t box[4] = {64, (uint32_t)(bw * d->stride), (uint32_t)(bh * d->stride), (uint32_t)bn};
+      uint32_t box[4] = {64, (uint32_t)(bw * d->stride), (uint32_t)((halo ? bh + 2 : bh) * d->stride), (uint32_t)bn};
       uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
       int rc = encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, str, box, es,
                            CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1263,7 +1305,9 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     p.Cin_p = Cin_p;
     p.Cout_p = Cout_p;
     p.total_kb = (int)((M + kpx - 1) / kpx);
-    p.stage_bytes = (2 + T * p.n_panels) * kpx * 128;
+    p.halo = halo ? 1 : 0;
+    p.xp_bytes = halo ? (bh + 2) * bw * 128 : kpx * 128;
+    p.stage_bytes = halo ? 2 * kpx * 128 + p.n_panels * p.xp_bytes : (2 + T * p.n_panels) * kpx * 128;
     p.stages = (g_wgrad_smem_kb * 1024) / p.stage_bytes;
     if (p.stages < 2) p.stages = 2;
     if (p.stages > 6) p.stages = 6;

@@ -139,11 +139,32 @@ def kernel_roofline(name, tag, n, t_ms, B, peaks, src, total_ms, traffic_db):
     if name.startswith("hg_conv_") and mconv and name in _KERNEL_NAMES:
         ci, co, k, h, w = (int(v) for v in mconv.groups())
         flops = 2.0 * B * h * w * ci * co * k * k
-        ach = flops / avg_s / 1e12
-        peak = float(peaks["bf16_tflops"])
-        row = {"kernel": f"{_KERNEL_NAMES[name]} {tag} (tcgen05 + TMA)", "bound": "tensor", "achieved": round(ach, 2),
-               "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "algorithmic_flops_per_launch": flops,
-               "peak_source": f"{src} bf16_tflops (burst: per-launch timing)"}
+        kname = _KERNEL_NAMES[name]
+        # large-map 1x1 fprop / dgrad launches run the persistent kernel (csrc/conv_persist.cu: >= 512 units of 128 pixels)
+        if k == 1 and B * h * w >= 512 * 128 and name in ("hg_conv_fprop_ex", "hg_conv_dgrad", "hg_conv_dgrad_bn"):
+            kname = kname.replace("conv_gemm_kernel", "conv_persist_kernel")
+        if k == 1:
+            # 1x1 convolutions are HBM-bound (8.6 GFLOP over >= 100 MB at 64x64): bf16 tensors read + written per launch
+            cip, cop = (ci + 63) // 64 * 64, (co + 63) // 64 * 64
+            if name == "hg_conv_wgrad":
+                chans = cip + cop                                  # x, dy
+            elif name.startswith("hg_conv_dgrad"):
+                chans = cop + cip + (cip if name == "hg_conv_dgrad_bn" or "+add" in tag else 0)   # dy, dx (+ raw BN input)
+            else:
+                chans = cip + cop + (cop if "+res" in tag else 0)  # x, y (+ residual)
+            nbytes = B * h * w * chans * 2
+            gbs = nbytes / avg_s / 1e9
+            peak = float(peaks["hbm_gbs"])
+            row = {"kernel": f"{kname} {tag} (tcgen05 + TMA)", "bound": "hbm", "achieved": round(gbs, 1), "peak": peak,
+                   "unit": "GB/s", "frac": round(gbs / peak, 4), "algorithmic_bytes_per_launch": nbytes,
+                   "algorithmic_flops_per_launch": flops, "tflops": round(flops / avg_s / 1e12, 1),
+                   "peak_source": f"{src} hbm_gbs"}
+        else:
+            ach = flops / avg_s / 1e12
+            peak = float(peaks["bf16_tflops"])
+            row = {"kernel": f"{kname} {tag} (tcgen05 + TMA)", "bound": "tensor", "achieved": round(ach, 2),
+                   "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "algorithmic_flops_per_launch": flops,
+                   "peak_source": f"{src} bf16_tflops (burst: per-launch timing)"}
     mbn = re.match(r"C(\d+) M(\d+)( \+addend)?", tag or "")
     if name in ("hg_bn_apply", "hg_bn_bwd_apply") and mbn:
         c, m = int(mbn.group(1)), int(mbn.group(2))
@@ -491,7 +512,7 @@ def run_ours(args):
         table = sorted(((k[0], k[1], v[0], v[1]) for k, v in agg.items()), key=lambda r: -r[3])
         peaks, src = measured_peaks()
         traffic_db = {}
-        for tp in ("r02_roofline_traffic.json", "r01_roofline_traffic.json"):
+        for tp in ("r02f_roofline_traffic.json", "r02_roofline_traffic.json", "r01_roofline_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", tp)
             if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, B=32)
                 traffic_db = json.load(open(tpath))

@@ -691,7 +691,7 @@ class Plan:
                     self._emit(f, "hg_conv_fprop_ex", C.byref(d), L.ptr(x.buf), L.ptr(info["wf"]), bias,
                                L.ptr(res.buf) if res else None,
                                L.ptr(out.buf), L.ptr(out.stats) if out.needs_stats else None, L.ptr(nchw),
-                               st).tag = self._conv_tag(cv, x)
+                               st).tag = self._conv_tag(cv, x) + (" +res" if res else "")
             elif k == "bn":
                 bn, x, out = op.attrs["bn"], op.ins[0], op.out
                 d = self._bn_desc(bn, x, op.attrs["relu"])

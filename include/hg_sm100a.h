@@ -164,7 +164,10 @@ HG_API int hg_mix_rows_rect(const float* T, const float* in, float* out, int row
 
 /* Switches: "allow_ref_conv" = 1 lets bf16 convolutions outside the tensor-core geometry run on the CUDA-core kernels
  * (default 0: they fail with HG_ERR_UNSUPPORTED -- no silent slow path); "force_ref_conv" = 1 routes EVERY bf16
- * convolution there (validation). */
+ * convolution there (validation).  Kernel selection (defaults = measured best): "persist_1x1" (1) /
+ * "persist_3x3" (0): large-map stride-1 convolutions through the persistent kernel, from "persist_min_units" (512)
+ * 128-pixel units on; "wgrad_halo" (1): 3x3 weight gradients of the 64x64 maps with one x box per filter column;
+ * "upsample_sep" (1): separable up-sampling kernels; "pdl" (1): programmatic dependent launch. */
 HG_API int hg_set_option(const char* name, int value);
 
 /* ---- BatchNorm2d + ReLU (try_with_torch.py:184-192,196-204,249-250,254-255) ------------------------- */

@@ -11,7 +11,7 @@ unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 static int g_allow_ref_conv = 0;
 int g_use_pdl = 1;
-extern int g_persist_3x3, g_persist_1x1, g_persist_min_units, g_ps_dbg, g_upsample_sep, g_upsample_fwd_cap, g_onewave_cluster, g_wgrad_halo;
+extern int g_persist_transposed, g_persist_3x3, g_persist_1x1, g_persist_min_units, g_ps_dbg, g_upsample_sep, g_upsample_fwd_cap, g_onewave_cluster, g_wgrad_halo;
 extern int g_wgrad_fused_bias, g_mid_n_tiles, g_wgrad_kpx;
 extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta, g_short_1stage;
 extern int g_bn_blocks_per_sm, g_bn_bwd_blocks_per_sm, g_bn_apply_u4;
@@ -179,7 +179,8 @@ int hg_set_option(const char* name, int value) {
       cudaDeviceSynchronize();
       cudaMemcpy(h, g_dbg_ts, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "  producer: total %lld, a_empty %lld, b_empty %lld\n", h[0], h[1], h[2]);
-      fprintf(stderr, "  mma     : total %lld, tmem_empty %lld, a_full %lld, b_full %lld\n", h[4], h[5], h[6], h[7]);
+      fprintf(stderr, "  mma     : total %lld, tmem_empty %lld, a_full %lld, b_full %lld, mma issue %lld, commits %lld, fence %lld, syncwarp %lld\n", h[4], h[5],
+              h[6], h[7], h[14], h[15], h[16], h[17]);
       fprintf(stderr, "  epilogue: total %lld, tmem_full %lld, y+ld %lld, row %lld, col %lld, store wait %lld\n", h[8], h[9],
               h[10], h[11], h[12], h[13]);
     } else if (value == 0) {
@@ -205,6 +206,10 @@ int hg_set_option(const char* name, int value) {
   }
   if (strcmp(name, "persist_3x3") == 0) {   // large-map 3x3 convolutions through conv_persist_kernel (default 0)
     g_persist_3x3 = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "persist_transposed") == 0) {   // persistent 3x3 kernel, 128 output channels: [channel][pixel] accumulators
+    g_persist_transposed = value;
     return HG_OK;
   }
   if (strcmp(name, "persist_min_units") == 0 && value > 0) {   // smallest launch (in 128-pixel units) it is used for

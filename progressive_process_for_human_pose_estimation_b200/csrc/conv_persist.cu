@@ -46,6 +46,8 @@ extern long long* g_dbg_ts;
 int g_ps_dbg = 0;
 int g_persist_1x1 = 1;
 int g_persist_3x3 = 0;
+int g_persist_transposed = 1;     // 3x3 with 128 output channels: accumulators as [channel][pixel] (one N = 256 MMA per
+                                  // 256-pixel tile and K step instead of two N = 128 ones; no column pass in the epilogue)
 int g_persist_min_units = 512;    // at least this many 128-pixel units: two 256-pixel tiles per SM and more (64x64 at
                                   // batch 32; at 32x32 every CTA has ONE tile, nothing to pipeline: step 883 vs 894 images/s)
 
@@ -96,13 +98,14 @@ struct PsTiles {
   }
 };
 
-template <int MODE, int NP>
+template <int MODE, int NP, bool TR>
 __global__ void __launch_bounds__(kPsThreads, 1)
 conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const PsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  static_assert(!TR || NP == 128, "transposed accumulators: the weight tile is the M = 128 operand");
   constexpr int kBBytes = NP * 128;                  // one weight tile: NP out-channels x 64 in-channels
   constexpr int kPartCols = NP > 128 ? 128 : NP;     // columns of one accumulator part
   constexpr int kPanels = kPartCols / 64;
@@ -160,42 +163,52 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int hw = p.H * p.W;
       PsTiles tiles(p);
       int m0, mt;
-      int ia = 0, ib = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 1, phb = 1;          // empty-barrier parities (a fresh barrier passes a parity-1 wait)
       bool first_tile = true;
       long long w_ae = 0, w_be = 0;
       const long long tstart = clock64();
+      const int nA = p.nA, nB = p.nB, th = p.th, tw = p.tw;
+      const bool nodata = HG_DBG_TS && (p.dbg & 4);   // debug: no data movement at all (what the MMA stream alone takes)
       while (tiles.next(m0, mt)) {
         const int n = m0 / hw;
         const int h0 = (m0 - n * hw) / p.W;
+        int sbr = 0;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int j = 0; j < p.tw; ++j) {
-            const int sa = ia % p.nA;
+          for (int j = 0; j < tw; ++j) {
             {
               PS_TIC;
-              mbar_wait(&a_empty[sa], ((ia / p.nA) & 1) ^ 1);
+              mbar_wait(&a_empty[sa], pha);
               PS_TOC(w_ae);
             }
-            mbar_expect_tx(&a_full[sa], (uint32_t)p.a_bytes);
-            if (p.th == 1) tma_load_2d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, m0);
-            else tma_load_4d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, j - 1, h0 - 1, n);
-            ++ia;
-            for (int i = 0; i < p.th; ++i) {
+            if (nodata) {
+              mbar_arrive(&a_full[sa]);
+            } else {
+              mbar_expect_tx(&a_full[sa], (uint32_t)p.a_bytes);
+              if (th == 1) tma_load_2d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, m0);
+              else tma_load_4d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, j - 1, h0 - 1, n);
+            }
+            if (++sa == nA) { sa = 0; pha ^= 1; }
+            for (int i = 0; i < th; ++i) {
               if (p.b_resident) {
                 if (first_tile) {
-                  const int sb = (kc * p.tw + j) * p.th + i;
+                  mbar_expect_tx(&b_full[sbr], kBBytes);
+                  tma_load_3d(sB + sbr * kBBytes, &tmB, &b_full[sbr], kc * 64, 0, p.wt[i][j]);
+                }
+                ++sbr;
+              } else {
+                {
+                  PS_TIC;
+                  mbar_wait(&b_empty[sb], phb);
+                  PS_TOC(w_be);
+                }
+                if (nodata) {
+                  mbar_arrive(&b_full[sb]);
+                } else {
                   mbar_expect_tx(&b_full[sb], kBBytes);
                   tma_load_3d(sB + sb * kBBytes, &tmB, &b_full[sb], kc * 64, 0, p.wt[i][j]);
                 }
-              } else {
-                const int sb = ib % p.nB;
-                {
-                  PS_TIC;
-                  mbar_wait(&b_empty[sb], ((ib / p.nB) & 1) ^ 1);
-                  PS_TOC(w_be);
-                }
-                mbar_expect_tx(&b_full[sb], kBBytes);
-                tma_load_3d(sB + sb * kBBytes, &tmB, &b_full[sb], kc * 64, 0, p.wt[i][j]);
-                ++ib;
+                if (++sb == nB) { sb = 0; phb ^= 1; }
               }
             }
           }
@@ -212,75 +225,92 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     pdl_trigger();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(128, NP, 0, 0);
-    PsTiles tiles(p);
-    int m0, mt;
-    int ia = 0, ib = 0;
-    long long w_te = 0, w_af = 0, w_bf = 0;
-    const long long tstart = clock64();
-    for (int it = 0; tiles.next(m0, mt); ++it) {
-      const int acc = it & 1;
-      {
-        PS_TIC;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-        PS_TOC(w_te);
-      }
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + acc * 2 * kPartCols;
-      uint32_t accum = 0;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        for (int j = 0; j < p.tw; ++j) {
-          const int sa = ia % p.nA;
+    // ONE thread runs the whole loop.  It is a chain of dependent scalar instructions, and what it costs per weight tile is
+    // what the tensor core idles: with ring slots found by integer division, descriptors rebuilt per tile and the warp
+    // re-converged around every instruction group it took ~1000 cycles per weight tile (four N = 256 MMAs need 512) --
+    // measured with every data movement switched off (ps_dbg 5).  Slots and phases are counters, descriptors are adds.
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NP, 0, 0);
+      PsTiles tiles(p);
+      int m0, mt;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      long long w_te = 0, w_af = 0, w_bf = 0;
+      const long long tstart = clock64();
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024);
+      const uint32_t a_step = (uint32_t)p.a_bytes >> 4;       // descriptor address field counts 16-byte units
+      const uint32_t row_step = (uint32_t)p.W * 128u >> 4;    // one image row of pixels (tap row i)
+      const int nA = p.nA, nB = p.nB, th = p.th, per_kc = p.tw;
+      const bool resident = p.b_resident != 0;
+      const bool no_mma = HG_DBG_TS && (p.dbg & 2);
+      for (int it = 0; tiles.next(m0, mt); ++it) {
+        const int acc = it & 1;
+        {
+          PS_TIC;
+          mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+          PS_TOC(w_te);
+        }
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * 2 * kPartCols;
+        const uint32_t idt = TR ? (mt == 2 ? make_idesc_bf16(128, 256, 0, 0) : make_idesc_bf16(128, 128, 0, 0)) : idesc;
+        uint32_t accum = 0;
+        int sbr = 0;                       // resident weights: slot = running tile index
+        for (int kj = p.kchunks * per_kc; kj > 0; --kj) {
           {
             PS_TIC;
-            mbar_wait(&a_full[sa], (ia / p.nA) & 1);
+            mbar_wait(&a_full[sa], pha);
             PS_TOC(w_af);
           }
-          ++ia;
-          const uint32_t a_addr = smem_u32(sA + sa * p.a_bytes);
-          for (int i = 0; i < p.th; ++i) {
-            int sb;
-            uint32_t bph;
-            if (p.b_resident) {
-              sb = (kc * p.tw + j) * p.th + i;
-              bph = 0;      // completed once (first tile); the parity-0 wait stays satisfied afterwards
-            } else {
-              sb = ib % p.nB;
-              bph = (ib / p.nB) & 1;
-              ++ib;
-            }
+          const uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)sa * a_step);
+          for (int i = 0; i < th; ++i) {
+            const int slot = resident ? sbr : sb;
             {
               PS_TIC;
-              mbar_wait(&b_full[sb], bph);
+              mbar_wait(&b_full[slot], resident ? 0u : phb);   // resident: completed once, parity 0 stays satisfied
               PS_TOC(w_bf);
             }
             tc_fence_after();
-            if (lane == 0) {
-              const uint64_t bdesc = make_smem_desc(smem_u32(sB + sb * kBBytes), 16, 1024);
-              for (int t = 0; t < ((HG_DBG_TS && (p.dbg & 2)) ? 0 : mt); ++t) {
-                // tap row i: the same box, (i * W) pixel rows further down; sub-tile t: 128 pixel rows further
-                const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(i * p.W + t * 128) * 128u, 16, 1024);
+            const uint64_t bdesc = b_desc0 + (uint64_t)((uint32_t)slot * (uint32_t)(kBBytes >> 4));
+            const uint64_t xdesc = a_desc + (uint64_t)((uint32_t)i * row_step);
+            if (!no_mma) {
+              if constexpr (TR) {
+                // transposed: D[channel][pixel] -- the weight tile is the M = 128 operand, the mt * 128 pixel rows of the
+                // box (tap row i: i image rows further down) are ONE N = 128 / 256 operand
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(tacc + t * kPartCols, adesc + 2 * k, bdesc + 2 * k, idesc, (accum | (uint32_t)k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) umma_bf16(tacc, bdesc + 2 * k, xdesc + 2 * k, idt, (accum | (uint32_t)k) ? 1u : 0u);
+              } else {
+                // sub-tile t: 128 pixel rows (16 KB) further down
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tacc, xdesc + 2 * k, bdesc + 2 * k, idt, (accum | (uint32_t)k) ? 1u : 0u);
+                if (mt == 2) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(tacc + kPartCols, xdesc + 1024 + 2 * k, bdesc + 2 * k, idt, (accum | (uint32_t)k) ? 1u : 0u);
+                }
               }
-              if (!p.b_resident) umma_commit(&b_empty[sb]);
-              if (i == p.th - 1) umma_commit(&a_empty[sa]);
             }
             accum = 1;
-            __syncwarp();
+            if (resident) {
+              ++sbr;
+            } else {
+              umma_commit(&b_empty[sb]);
+              if (++sb == nB) { sb = 0; phb ^= 1; }
+            }
           }
+          umma_commit(&a_empty[sa]);
+          if (++sa == nA) { sa = 0; pha ^= 1; }
         }
+        umma_commit(&tmem_full[acc]);
       }
-      if (lane == 0) umma_commit(&tmem_full[acc]);
-      __syncwarp();
+      if (HG_DBG_TS && p.ts && blockIdx.x == 0) {
+        p.ts[4] = clock64() - tstart;
+        p.ts[5] = w_te;
+        p.ts[6] = w_af;
+        p.ts[7] = w_bf;
+      }
     }
-    if (HG_DBG_TS && p.ts && blockIdx.x == 0 && lane == 0) {
-      p.ts[4] = clock64() - tstart;
-      p.ts[5] = w_te;
-      p.ts[6] = w_af;
-      p.ts[7] = w_bf;
-    }
+    __syncwarp();
     pdl_trigger();
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -378,7 +408,47 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long long _tr = clock64();
 #endif
         // ---- row pass: registers -> (+bias, +residual | mask) -> bf16 -> swizzled staging ----
-        if (row_warp) {
+        if constexpr (TR) {
+          // transposed accumulator: this thread owns ONE channel (TMEM lane) and 32 pixels (columns) of the part.  Bias,
+          // mask coefficients and pivot are per-thread constants, the per-channel sums are plain register adds (no
+          // column pass); the staging tile is written (and the residual / raw-input tile read) 2 bytes at a time --
+          // the 32 lanes of a warp cover 64 contiguous bytes of one pixel row, so neither access conflicts.
+          const int ch = row;                                   // output channel (NP == 128: one part = all channels)
+          const int boff = (ch >> 6) * 16384 + (ch & 7) * 2;
+          const int chunk = (ch & 63) >> 3;
+          const int r0 = colq * 32;                             // first pixel row of this warp inside the part
+          if constexpr (MODE == kMask) {
+            const float cS = coef_s[ch], cT = coef_s[256 + ch];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int r = r0 + i;
+              const int off = boff + r * 128 + ((chunk ^ (r & 7)) << 4);
+              const __nv_bfloat16 yb = *reinterpret_cast<const __nv_bfloat16*>(sYp + off);
+              const float y = __bfloat162float(yb);
+              const bool keep = !relu || fmaf(y, cS, cT) > 0.f;
+              const __nv_bfloat16 gb = __float2bfloat16_rn(keep ? v[i] : 0.f);
+              *reinterpret_cast<__nv_bfloat16*>(sC + off) = gb;
+              const float gq = __bfloat162float(gb);
+              cs[0][0] += gq;
+              cq[0][0] = fmaf(gq, y, cq[0][0]);
+            }
+          } else {
+            const float bch = bias_s[ch];
+            const float pv = p.stats != nullptr ? coef_s[ch] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int r = r0 + i;
+              const int off = boff + r * 128 + ((chunk ^ (r & 7)) << 4);
+              float o = v[i] + bch;
+              if (p.has_res) o += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sYp + off));
+              const __nv_bfloat16 ob = __float2bfloat16_rn(o);
+              *reinterpret_cast<__nv_bfloat16*>(sC + off) = ob;
+              const float f = __bfloat162float(ob) - pv;
+              cs[0][0] += f;
+              cq[0][0] = fmaf(f, f, cq[0][0]);
+            }
+          }
+        } else if (row_warp) {
           const int col0 = colq * 32;                           // first column of the chunk inside the part
           const int pnl = col0 / 64;
           const int chunk0 = (col0 % 64) / 8;
@@ -437,7 +507,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_store_commit();
         }
         // ---- column pass: per-channel sums of what was just staged (bf16, exactly what the consumers read) ----
-        if (p.stats != nullptr) {
+        if (!TR && p.stats != nullptr) {
           constexpr int kS = NP > 128 ? 1 : 0;
           const int si = kS * pp;                        // register set (compile-time: pp is unrolled)
           const int c = quad * 4;
@@ -490,6 +560,11 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (p.stats != nullptr) {
       // the row slices add up in shared memory (once per kernel), then one vector atomic per 4 channels per CTA
+      if constexpr (TR) {
+        // four warps (pixel-column groups) per channel
+        atomicAdd(acc_s + row, cs[0][0]);
+        atomicAdd(acc_s + 256 + row, cq[0][0]);
+      } else {
 #pragma unroll
       for (int s = 0; s < kSets; ++s)
 #pragma unroll
@@ -497,6 +572,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           atomicAdd(acc_s + s * 128 + quad * 4 + e, cs[s][e]);
           atomicAdd(acc_s + 256 + s * 128 + quad * 4 + e, cq[s][e]);
         }
+      }
       named_bar_sync(1, kPsEpi);
       for (int q = et; q < 2 * (NP / 4); q += kPsEpi) {
         const int which = q / (NP / 4), qd = q % (NP / 4);
@@ -607,15 +683,15 @@ bool conv_persist_eligible(int N, int H, int W, int Kp, int Np, int ntaps, const
   return ps_plan(W, Kp, Np, ntaps, mode == kMask || has_res, p) > 0;
 }
 
-template <int MODE, int NP>
+template <int MODE, int NP, bool TR = false>
 static int ps_launch(int grid, int smem, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                      const CUtensorMap& tmR, const PsParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    HG_CUDA_OK(cudaFuncSetAttribute(conv_persist_kernel<MODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_persist_kernel<MODE, NP, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  launch_k(conv_persist_kernel<MODE, NP>, dim3(grid), dim3(kPsThreads), (size_t)smem, st, tmA, tmB, tmC, tmR, p);
+  launch_k(conv_persist_kernel<MODE, NP, TR>, dim3(grid), dim3(kPsThreads), (size_t)smem, st, tmA, tmB, tmC, tmR, p);
   HG_LAUNCH_OK("conv_persist_kernel");
   count_launch();
   return HG_OK;
@@ -696,6 +772,9 @@ int conv_persist_launch(int N, int H, int W, int Kp, int Np, int mode, int ntaps
   if (Np == 256)
     return mode == kMask ? ps_launch<kMask, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st)
                          : ps_launch<kPlain, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st);
+  if (Np == 128 && ntaps == 9 && g_persist_transposed)
+    return mode == kMask ? ps_launch<kMask, 128, true>(grid, smem, tmA, tmB, tmC, tmR, p, st)
+                         : ps_launch<kPlain, 128, true>(grid, smem, tmA, tmB, tmC, tmR, p, st);
   if (Np == 128)
     return mode == kMask ? ps_launch<kMask, 128>(grid, smem, tmA, tmB, tmC, tmR, p, st)
                          : ps_launch<kPlain, 128>(grid, smem, tmA, tmB, tmC, tmR, p, st);

@@ -229,28 +229,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     pdl_trigger();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int st = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      if constexpr (MODE == kFold) mbar_wait(&ready_bar[st], ph);
-      else mbar_wait(&full_bar[st], ph);
-      tc_fence_after();
-      if (HG_TS && blockIdx.x == 0 && lane == 0 && kb == 0) p.ts[4] = clock64();
-      if (HG_TS && blockIdx.x == 0 && lane == 0 && kb < 8) p.ts[24 + kb] = clock64();
-      if (lane == 0) {
-        const uint64_t adesc = make_smem_desc(smem_u32(sA + st * L::kABytes), 16, 1024);
-        const uint64_t bdesc = make_smem_desc(smem_u32(sB + st * L::kBBytes), 16, 1024);
+    // ONE thread runs the loop: it is a chain of dependent scalar instructions whose length per K block is what the
+    // tensor core idles between K blocks (four N = 128 MMAs need 256 cycles): slot / phase are counters, the
+    // descriptors of a slot are one add away from those of slot 0.
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 1024);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if constexpr (MODE == kFold) mbar_wait(&ready_bar[st], ph);
+        else mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        if (HG_TS && blockIdx.x == 0 && kb == 0) p.ts[4] = clock64();
+        if (HG_TS && blockIdx.x == 0 && kb < 8) p.ts[24 + kb] = clock64();
+        const uint64_t adesc = adesc0 + (uint64_t)(uint32_t)(st * (L::kABytes >> 4));
+        const uint64_t bdesc = bdesc0 + (uint64_t)(uint32_t)(st * (L::kBBytes >> 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // advance 16 K-elements = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[st]);  // frees the smem slot once these MMAs have read it
-        if (kb == num_kb - 1) umma_commit(tmem_full);
+        if (++st == STAGES) { st = 0; ph ^= 1; }
       }
-      __syncwarp();
+      umma_commit(tmem_full);
     }
+    __syncwarp();
     if (HG_TS && blockIdx.x == 0 && lane == 0) p.ts[5] = clock64();
     pdl_trigger();
   } else {
@@ -1031,39 +1037,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       __syncwarp();
       pdl_trigger();
     } else if (warp == 1) {
-      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
-      for (int i = 0; i < nkb; ++i) {
-        const int st = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
-        if constexpr (FOLD) mbar_wait(&ready_bar[st], ph);
-        else mbar_wait(&full_bar[st], ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sA = smem_u32(smem + st * p.stage_bytes);
-          const uint32_t sB = sA + a_bytes;
-          for (int t = 0; t < T; ++t) {
+      // one thread, counters instead of divisions, descriptors by addition (see conv_gemm_kernel)
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+        const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
+        const uint32_t s0 = smem_u32(smem);
+        const uint64_t adesc0 = make_smem_desc(s0, pb, 1024);
+        const uint64_t bdesc0 = make_smem_desc(s0 + a_bytes, p.halo ? p.xp_bytes : pb, 1024);
+        const uint64_t odesc0 = make_smem_desc(smem_u32(ones_s), pb, 1024);
+        const uint32_t st_step = (uint32_t)p.stage_bytes >> 4;
+        const uint32_t t_step = (uint32_t)(p.halo ? p.W * 128 : p.n_panels * pb) >> 4;   // B operand of the next tap
+        const int nst = p.stages;
+        int st = 0;
+        uint32_t ph = 0;
+        uint32_t accum = 0;
+        for (int i = 0; i < nkb; ++i) {
+          if constexpr (FOLD) mbar_wait(&ready_bar[st], ph);
+          else mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)st * st_step);
+          uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)st * st_step);
+          for (int t = 0; t < T; ++t, bdesc += t_step) {
 #pragma unroll 4
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = make_smem_desc(sA + k * 2048, pb, 1024);
-              const uint64_t bdesc = p.halo ? make_smem_desc(sB + t * p.W * 128 + k * 2048, p.xp_bytes, 1024)
-                                            : make_smem_desc(sB + t * p.n_panels * pb + k * 2048, pb, 1024);
-              umma_bf16(tmem_base + t * N, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < ksteps; ++k)   // 16 pixels further = 2048 B in both MN-major operands
+              umma_bf16(tmem_base + t * N, adesc + 128 * k, bdesc + 128 * k, idesc, (accum | (uint32_t)k) ? 1u : 0u);
           }
           if (with_bias) {
-            const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
 #pragma unroll 4
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = make_smem_desc(sA + k * 2048, pb, 1024);
-              const uint64_t bdesc = make_smem_desc(smem_u32(ones_s) + k * 2048, pb, 1024);
-              umma_bf16(tmem_base + T * N, adesc, bdesc, idesc1, (i > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(tmem_base + T * N, adesc + 128 * k, odesc0 + 128 * k, idesc1, (accum | (uint32_t)k) ? 1u : 0u);
           }
+          accum = 1;
           umma_commit(&empty_bar[st]);
-          if (i == nkb - 1) umma_commit(tmem_full);
+          if (++st == nst) { st = 0; ph ^= 1; }
         }
-        __syncwarp();
+        umma_commit(tmem_full);
       }
+      __syncwarp();
       pdl_trigger();
     } else {
       const int sub = warp & 3;

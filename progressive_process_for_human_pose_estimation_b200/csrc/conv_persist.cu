@@ -45,7 +45,7 @@ namespace hg {
 extern long long* g_dbg_ts;
 int g_ps_dbg = 0;
 int g_persist_1x1 = 1;
-int g_persist_3x3 = 0;
+int g_persist_3x3 = 1;               // 128-channel 3x3 convolutions at >= persist_min_units: transposed persistent kernel (43 vs 51 us @64x64)
 int g_persist_transposed = 1;     // 3x3 with 128 output channels: accumulators as [channel][pixel] (one N = 256 MMA per
                                   // 256-pixel tile and K step instead of two N = 128 ones; no column pass in the epilogue)
 int g_persist_min_units = 512;    // at least this many 128-pixel units: two 256-pixel tiles per SM and more (64x64 at
@@ -229,7 +229,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // what the tensor core idles: with ring slots found by integer division, descriptors rebuilt per tile and the warp
     // re-converged around every instruction group it took ~1000 cycles per weight tile (four N = 256 MMAs need 512) --
     // measured with every data movement switched off (ps_dbg 5).  Slots and phases are counters, descriptors are adds.
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, NP, 0, 0);
       PsTiles tiles(p);
       int m0, mt;
@@ -273,7 +273,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             const uint64_t bdesc = b_desc0 + (uint64_t)((uint32_t)slot * (uint32_t)(kBBytes >> 4));
             const uint64_t xdesc = a_desc + (uint64_t)((uint32_t)i * row_step);
-            if (!no_mma) {
+            const bool leader = elect_one();
+            if (leader && !no_mma) {
               if constexpr (TR) {
                 // transposed: D[channel][pixel] -- the weight tile is the M = 128 operand, the mt * 128 pixel rows of the
                 // box (tap row i: i image rows further down) are ONE N = 128 / 256 operand
@@ -294,16 +295,19 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (resident) {
               ++sbr;
             } else {
-              umma_commit(&b_empty[sb]);
+              if (leader) umma_commit(&b_empty[sb]);
               if (++sb == nB) { sb = 0; phb ^= 1; }
             }
+            __syncwarp();
           }
-          umma_commit(&a_empty[sa]);
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
           if (++sa == nA) { sa = 0; pha ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
       }
-      if (HG_DBG_TS && p.ts && blockIdx.x == 0) {
+      if (HG_DBG_TS && p.ts && blockIdx.x == 0 && lane == 0) {
         p.ts[4] = clock64() - tstart;
         p.ts[5] = w_te;
         p.ts[6] = w_af;
@@ -668,6 +672,9 @@ bool conv_persist_eligible(int N, int H, int W, int Kp, int Np, int ntaps, const
     if (!g_persist_1x1 || dh[0] != 0 || dw[0] != 0) return false;
   } else if (ntaps == 9) {
     if (!g_persist_3x3) return false;
+    // 1 (default): only the shape with transposed accumulators (128 output channels), which beats the tile kernel;
+    // 2: every 3x3 shape the kernel supports (tests / probes)
+    if (g_persist_3x3 == 1 && !(Np == 128 && g_persist_transposed)) return false;
     const int tile_px = Np > 128 ? 128 : 256;
     if (!is_pow2(W) || !is_pow2(H) || W > 128 || W < 16 || tile_px / W > H || tile_px % W || (H * W) % tile_px) return false;
     unsigned seen = 0;

@@ -232,7 +232,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ONE thread runs the loop: it is a chain of dependent scalar instructions whose length per K block is what the
     // tensor core idles between K blocks (four N = 128 MMAs need 256 cycles): slot / phase are counters, the
     // descriptors of a slot are one add away from those of slot 0.
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       const uint64_t adesc0 = make_smem_desc(smem_u32(sA), 16, 1024);
       const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, 1024);
@@ -242,21 +242,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (MODE == kFold) mbar_wait(&ready_bar[st], ph);
         else mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        if (HG_TS && blockIdx.x == 0 && kb == 0) p.ts[4] = clock64();
-        if (HG_TS && blockIdx.x == 0 && kb < 8) p.ts[24 + kb] = clock64();
+        if (HG_TS && blockIdx.x == 0 && lane == 0 && kb == 0) p.ts[4] = clock64();
+        if (HG_TS && blockIdx.x == 0 && lane == 0 && kb < 8) p.ts[24 + kb] = clock64();
         const uint64_t adesc = adesc0 + (uint64_t)(uint32_t)(st * (L::kABytes >> 4));
         const uint64_t bdesc = bdesc0 + (uint64_t)(uint32_t)(st * (L::kBBytes >> 4));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // advance 16 K-elements = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 K-elements = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[st]);  // frees the smem slot once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(tmem_full);
         }
-        umma_commit(&empty_bar[st]);  // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
-      umma_commit(tmem_full);
     }
-    __syncwarp();
     if (HG_TS && blockIdx.x == 0 && lane == 0) p.ts[5] = clock64();
     pdl_trigger();
   } else {
@@ -1038,7 +1040,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       pdl_trigger();
     } else if (warp == 1) {
       // one thread, counters instead of divisions, descriptors by addition (see conv_gemm_kernel)
-      if (lane == 0) {
+      {
         const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
         const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
         const uint32_t s0 = smem_u32(smem);
@@ -1057,23 +1059,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           tc_fence_after();
           const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)st * st_step);
           uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)st * st_step);
-          for (int t = 0; t < T; ++t, bdesc += t_step) {
+          if (elect_one()) {
+            for (int t = 0; t < T; ++t, bdesc += t_step) {
 #pragma unroll 4
-            for (int k = 0; k < ksteps; ++k)   // 16 pixels further = 2048 B in both MN-major operands
-              umma_bf16(tmem_base + t * N, adesc + 128 * k, bdesc + 128 * k, idesc, (accum | (uint32_t)k) ? 1u : 0u);
-          }
-          if (with_bias) {
+              for (int k = 0; k < ksteps; ++k)   // 16 pixels further = 2048 B in both MN-major operands
+                umma_bf16(tmem_base + t * N, adesc + 128 * k, bdesc + 128 * k, idesc, (accum | (uint32_t)k) ? 1u : 0u);
+            }
+            if (with_bias) {
 #pragma unroll 4
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16(tmem_base + T * N, adesc + 128 * k, odesc0 + 128 * k, idesc1, (accum | (uint32_t)k) ? 1u : 0u);
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(tmem_base + T * N, adesc + 128 * k, odesc0 + 128 * k, idesc1, (accum | (uint32_t)k) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[st]);
+            if (i == nkb - 1) umma_commit(tmem_full);
           }
+          __syncwarp();
           accum = 1;
-          umma_commit(&empty_bar[st]);
           if (++st == nst) { st = 0; ph ^= 1; }
         }
-        umma_commit(tmem_full);
       }
-      __syncwarp();
       pdl_trigger();
     } else {
       const int sub = warp & 3;

@@ -135,7 +135,7 @@ P1_CASES = [c for c in CONV_CASES if c[5] == 1 and not c[8] and (c[0] * c[1] * c
 ]
 
 
-def _persist(min_units=512, p1=1, p3=0):
+def _persist(min_units=512, p1=1, p3=1):
     L.call("hg_set_option", b"persist_1x1", p1)
     L.call("hg_set_option", b"persist_3x3", p3)
     L.call("hg_set_option", b"persist_min_units", min_units)
@@ -171,7 +171,7 @@ def test_persistent_3x3_kernel(case):
     """conv3x3_persist_kernel (256-pixel tiles, one activation box per three taps, two TMEM accumulator sets, one CTA
     per SM over a contiguous unit range) forced for every size: same checks as the tile-per-CTA kernel -- fprop (+bias,
     +residual, statistics), dgrad (+addend, in place) against PyTorch fp32 on bf16-rounded operands."""
-    _persist(1, p3=1)
+    _persist(1, p3=2)
     try:
         n0 = L.load().hg_launch_count()
         test_conv_fprop_dgrad_wgrad(case, torch.bfloat16)
@@ -196,14 +196,15 @@ def test_persistent_3x3_kernel_matches_tile_kernel():
     L.call("hg_pack_conv_weight", C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), st)
     outs = []
     for on in (1, 0):
-        L.call("hg_set_option", b"persist_3x3", on)
+        _persist(1, p3=on)
         try:
+            n0 = L.load().hg_launch_count()
             y = torch.empty(N, H, W, Cc, device=dev, dtype=dtype)
             stats = torch.zeros(3 * Cc, device=dev)
             L.call("hg_conv_fprop_ex", C.byref(d), L.ptr(x), L.ptr(wf), L.ptr(bias), None, L.ptr(y), L.ptr(stats), None, st)
             outs.append((y.float(), stats.clone()))
         finally:
-            L.call("hg_set_option", b"persist_3x3", 0)
+            _persist(512)
     (y1, s1), (y0, s0) = outs
     assert (y1 - y0).abs().max().item() <= 2 ** -7 * y0.abs().max().item()
     assert (y1 != y0).float().mean().item() < 0.02
@@ -241,7 +242,7 @@ def test_persistent_3x3_kernel_masked_dgrad(case):
     L.call("hg_bn_apply", C.byref(bnd), L.ptr(xq), L.ptr(xstats), L.ptr(gamma), L.ptr(beta), L.ptr(rmean),
            L.ptr(rvar), L.ptr(a), st)
     dyq = nhwc(torch.randn(N, Cout, H, W, device=dev), dtype)
-    _persist(1, p3=1)
+    _persist(1, p3=2)
     try:
         da = torch.empty(N, H, W, Cin_p, device=dev, dtype=dtype)
         L.call("hg_conv_dgrad", C.byref(d), L.ptr(dyq), L.ptr(wd), None, L.ptr(da), st)

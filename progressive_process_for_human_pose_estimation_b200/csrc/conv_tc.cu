@@ -183,6 +183,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (HG_TS && blockIdx.x == 0 && threadIdx.x == 0) p.ts[1] = clock64();
+  // tile origin (n0, h0, w0): three integer divisions that must not sit between the dependency wait and the first load
+  const int hw_t = p.H * p.W;
+  const int n0_t = m0 / hw_t;
+  const int rem_t = m0 - n0_t * hw_t;
+  const int h0_t = rem_t / p.W;
+  const int w0_t = rem_t - h0_t * p.W;
   // PDL: everything above overlapped the previous kernel's tail; global memory is ours from here.  The producer warp
   // starts its TMA loads at once; the per-channel coefficients are fetched by the epilogue warps meanwhile.
   pdl_wait();
@@ -190,12 +196,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      const int hw = p.H * p.W;
-      const int n0 = m0 / hw;
-      const int rem = m0 - n0 * hw;
-      const int h0 = rem / p.W;
-      const int w0 = rem - h0 * p.W;
+    // warp-uniform loop, one elected lane issues (tensor-map and barrier operands stay in uniform registers)
+    {
+      const int n0 = n0_t, h0 = h0_t, w0 = w0_t;
       auto load_res = [&]() {
         mbar_expect_tx(res_full, L::kCBytes);
         for (int pnl = 0; pnl < L::kCPanels; ++pnl) {
@@ -203,26 +206,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else tma_load_2d(sC + pnl * 16384, &tmR, res_full, n_off + pnl * 64, m0);
         }
       };
-      if (!ALIAS && p.has_res) load_res();
-      if (HG_TS && blockIdx.x == 0) p.ts[15] = clock64();
-      int kb = 0;
+      if (!ALIAS && p.has_res && elect_one()) load_res();
+      __syncwarp();
+      if (HG_TS && blockIdx.x == 0 && lane == 0) p.ts[15] = clock64();
+      const int ws = w0 * p.stride, hs = h0 * p.stride;
+      int kb = 0, st = 0;
+      uint32_t ph = 1;                      // empty-barrier parity: a fresh barrier passes a parity-1 wait
       for (int t = 0; t < p.ntaps; ++t) {
         const int dh = p.tap_dh[t], dw = p.tap_dw[t], wt = p.tap_w[t];
         for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
-          const int st = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          mbar_expect_tx(&full_bar[st], L::kABytes + L::kBBytes);
-          tma_load_4d(sA + st * L::kABytes, &tmA, &full_bar[st], kc * 64, w0 * p.stride + dw, h0 * p.stride + dh, n0);
-          tma_load_3d(sB + st * L::kBBytes, &tmB, &full_bar[st], kc * 64, n_off, wt);
-          if (HG_TS && blockIdx.x == 0 && kb == 0) p.ts[3] = clock64();
-          if (HG_TS && blockIdx.x == 0 && kb < 8) p.ts[16 + kb] = clock64();
+          mbar_wait(&empty_bar[st], ph);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[st], L::kABytes + L::kBBytes);
+            tma_load_4d(sA + st * L::kABytes, &tmA, &full_bar[st], kc * 64, ws + dw, hs + dh, n0);
+            tma_load_3d(sB + st * L::kBBytes, &tmB, &full_bar[st], kc * 64, n_off, wt);
+            if (HG_TS && blockIdx.x == 0 && kb == 0) p.ts[3] = clock64();
+            if (HG_TS && blockIdx.x == 0 && kb < 8) p.ts[16 + kb] = clock64();
+          }
+          __syncwarp();
+          if (++st == STAGES) { st = 0; ph ^= 1; }
         }
       }
       if (ALIAS && p.has_res) {
         // C aliases the pipeline stages: the residual / raw BatchNorm input may only land once every MMA has read them
         mbar_wait(tmem_full, 0);
-        load_res();
+        if (elect_one()) load_res();
       }
     }
     __syncwarp();
@@ -270,6 +278,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       const int et = threadIdx.x - 64;
     for (int c = et; c < BN; c += kEpiThreads) bias_s[c] = p.bias ? p.bias[n_off + c] : 0.f;
+    if constexpr (MODE == kPlain) {
+      // pivots of the output statistics (sums of y - pivot): fetched now, under the main loop -- a global load in the
+      // middle of the epilogue is a whole L2 round trip on the critical path of every one-wave kernel
+      if (p.stats != nullptr)
+        for (int c = et; c < BN; c += kEpiThreads) coef_s[c] = p.stats[2 * p.n_total + n_off + c];
+    }
     if constexpr (MODE == kPlainBnOut) {   // y = scale * acc + (scale * bias + shift)
       for (int c = et; c < BN; c += kEpiThreads) {
         float mu, is, sc, sh;
@@ -479,7 +493,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
         // BatchNorm statistics are sums of (y - pivot): the pivot of these four channels (0 for the backward sums)
         float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (MODE != kMask) pv = *reinterpret_cast<const float4*>(p.stats + 2 * p.n_total + n_off + c);
+        if constexpr (MODE == kPlain) pv = *reinterpret_cast<const float4*>(coef_s + c);
+        else if constexpr (MODE != kMask) pv = *reinterpret_cast<const float4*>(p.stats + 2 * p.n_total + n_off + c);
 #pragma unroll 8
         for (int i = 0; i < kRows; ++i) {
           const int r = grp * kRows + i;
@@ -1004,36 +1019,42 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        const int hw = p.H * p.W;
+      // warp-uniform loop, one elected lane issues; H and W are powers of two (tc_eligible): shifts, no divisions
+      {
+        const int lw = 31 - __clz(p.W), lhw = 31 - __clz(p.H * p.W);
+        const int nst = p.stages;
+        int st = 0;
+        uint32_t ph = 1;                    // empty-barrier parity: a fresh barrier passes a parity-1 wait
         for (int i = 0; i < nkb; ++i) {
-          const int st = i % p.stages;
-          const uint32_t ph = (i / p.stages) & 1;
           uint8_t* sA = smem + st * p.stage_bytes;
           uint8_t* sB = sA + a_bytes;
           const int m0 = (kb_beg + i) * p.kpx;
-          const int n0 = m0 / hw;
-          const int rem = m0 - n0 * hw;
-          const int h0 = rem / p.W;
-          const int w0 = rem - h0 * p.W;
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          mbar_expect_tx(&full_bar[st], p.stage_bytes);
-          tma_load_2d(sA, &tmDy, &full_bar[st], co_off, m0);
-          tma_load_2d(sA + pb, &tmDy, &full_bar[st], co_off + 64, m0);
-          if (p.halo) {
-            // one box of (rows + 2) image rows per input-channel panel: column tap0, rows h0 - 1 .. h0 + rows
-            for (int pn = 0; pn < p.n_panels; ++pn)
-              tma_load_4d(sB + pn * p.xp_bytes, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 + tap0 - p.pad, h0 - p.pad, n0);
-          } else {
-            for (int t = 0; t < T; ++t) {
-              const int tap = tap0 + t;
-              const int r = tap / p.taps_s, s = tap - r * p.taps_s;
-              const int dh = r * p.dil - p.pad, dw = s * p.dil - p.pad;
+          const int n0 = m0 >> lhw;
+          const int rem = m0 & ((1 << lhw) - 1);
+          const int h0 = rem >> lw;
+          const int w0 = rem & (p.W - 1);
+          mbar_wait(&empty_bar[st], ph);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[st], p.stage_bytes);
+            tma_load_2d(sA, &tmDy, &full_bar[st], co_off, m0);
+            tma_load_2d(sA + pb, &tmDy, &full_bar[st], co_off + 64, m0);
+            if (p.halo) {
+              // one box of (rows + 2) image rows per input-channel panel: column tap0, rows h0 - 1 .. h0 + rows
               for (int pn = 0; pn < p.n_panels; ++pn)
-                tma_load_4d(sB + (t * p.n_panels + pn) * pb, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 * p.stride + dw,
-                            h0 * p.stride + dh, n0);
+                tma_load_4d(sB + pn * p.xp_bytes, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 + tap0 - p.pad, h0 - p.pad, n0);
+            } else {
+              int r = tap0 / p.taps_s, sx = tap0 - r * p.taps_s;
+              for (int t = 0; t < T; ++t) {
+                const int dh = r * p.dil - p.pad, dw = sx * p.dil - p.pad;
+                for (int pn = 0; pn < p.n_panels; ++pn)
+                  tma_load_4d(sB + (t * p.n_panels + pn) * pb, &tmX, &full_bar[st], (pn0 + pn) * 64, w0 * p.stride + dw,
+                              h0 * p.stride + dh, n0);
+                if (++sx == p.taps_s) { sx = 0; ++r; }
+              }
             }
           }
+          __syncwarp();
+          if (++st == nst) { st = 0; ph ^= 1; }
         }
       }
       __syncwarp();

@@ -159,7 +159,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // warp-uniform loop; one elected lane issues (see the MMA issuer)
+    {
       const int hw = p.H * p.W;
       PsTiles tiles(p);
       int m0, mt;
@@ -181,20 +182,24 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               mbar_wait(&a_empty[sa], pha);
               PS_TOC(w_ae);
             }
-            if (nodata) {
-              mbar_arrive(&a_full[sa]);
-            } else {
-              mbar_expect_tx(&a_full[sa], (uint32_t)p.a_bytes);
-              if (th == 1) tma_load_2d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, m0);
-              else tma_load_4d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, j - 1, h0 - 1, n);
+            if (elect_one()) {
+              if (nodata) {
+                mbar_arrive(&a_full[sa]);
+              } else {
+                mbar_expect_tx(&a_full[sa], (uint32_t)p.a_bytes);
+                if (th == 1) tma_load_2d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, m0);
+                else tma_load_4d(sA + sa * p.a_bytes, &tmA, &a_full[sa], kc * 64, j - 1, h0 - 1, n);
+              }
             }
+            __syncwarp();
             if (++sa == nA) { sa = 0; pha ^= 1; }
             for (int i = 0; i < th; ++i) {
               if (p.b_resident) {
-                if (first_tile) {
+                if (first_tile && elect_one()) {
                   mbar_expect_tx(&b_full[sbr], kBBytes);
                   tma_load_3d(sB + sbr * kBBytes, &tmB, &b_full[sbr], kc * 64, 0, p.wt[i][j]);
                 }
+                __syncwarp();
                 ++sbr;
               } else {
                 {
@@ -202,12 +207,15 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   mbar_wait(&b_empty[sb], phb);
                   PS_TOC(w_be);
                 }
-                if (nodata) {
-                  mbar_arrive(&b_full[sb]);
-                } else {
-                  mbar_expect_tx(&b_full[sb], kBBytes);
-                  tma_load_3d(sB + sb * kBBytes, &tmB, &b_full[sb], kc * 64, 0, p.wt[i][j]);
+                if (elect_one()) {
+                  if (nodata) {
+                    mbar_arrive(&b_full[sb]);
+                  } else {
+                    mbar_expect_tx(&b_full[sb], kBBytes);
+                    tma_load_3d(sB + sb * kBBytes, &tmB, &b_full[sb], kc * 64, 0, p.wt[i][j]);
+                  }
                 }
+                __syncwarp();
                 if (++sb == nB) { sb = 0; phb ^= 1; }
               }
             }
@@ -215,7 +223,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         first_tile = false;
       }
-      if (HG_DBG_TS && p.ts && blockIdx.x == 0) {
+      if (HG_DBG_TS && p.ts && blockIdx.x == 0 && lane == 0) {
         p.ts[0] = clock64() - tstart;
         p.ts[1] = w_ae;
         p.ts[2] = w_be;

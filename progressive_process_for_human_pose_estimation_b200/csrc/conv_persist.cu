@@ -478,25 +478,29 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               load_coef8(coef_s + 256 + ch, cT);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
-                const bool k0 = !relu || fmaf(f.x, cS[2 * e], cT[2 * e]) > 0.f;
-                const bool k1 = !relu || fmaf(f.y, cS[2 * e + 1], cT[2 * e + 1]) > 0.f;
+                const float2 t = f2fma(__bfloat1622float2(h[e]), make_float2(cS[2 * e], cS[2 * e + 1]),
+                                       make_float2(cT[2 * e], cT[2 * e + 1]));
+                const bool k0 = !relu || t.x > 0.f;
+                const bool k1 = !relu || t.y > 0.f;
                 o[2 * e] = k0 ? v[q * 8 + 2 * e] : 0.f;
                 o[2 * e + 1] = k1 ? v[q * 8 + 2 * e + 1] : 0.f;
               }
             } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[ch + e];
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch), b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
+              float2 o2[4];
+              o2[0] = f2add(make_float2(v[q * 8 + 0], v[q * 8 + 1]), make_float2(b0.x, b0.y));
+              o2[1] = f2add(make_float2(v[q * 8 + 2], v[q * 8 + 3]), make_float2(b0.z, b0.w));
+              o2[2] = f2add(make_float2(v[q * 8 + 4], v[q * 8 + 5]), make_float2(b1.x, b1.y));
+              o2[3] = f2add(make_float2(v[q * 8 + 6], v[q * 8 + 7]), make_float2(b1.z, b1.w));
               if (p.has_res) {
                 const uint4 u = *reinterpret_cast<const uint4*>(sYp + rowoff + swz);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(h[e]);
-                  o[2 * e] += f.x;
-                  o[2 * e + 1] += f.y;
-                }
+                o2[0] = f2add(o2[0], bf2_to_f2(u.x));
+                o2[1] = f2add(o2[1], bf2_to_f2(u.y));
+                o2[2] = f2add(o2[2], bf2_to_f2(u.z));
+                o2[3] = f2add(o2[3], bf2_to_f2(u.w));
               }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { o[2 * e] = o2[e].x; o[2 * e + 1] = o2[e].y; }
             }
             uint4 w;
             __nv_bfloat162* hw2 = reinterpret_cast<__nv_bfloat162*>(&w);
@@ -529,26 +533,32 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint8_t* ycol = (MODE == kMask ? sYp : sC) + coff;
           float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);   // statistics are sums of (y - pivot)
           if constexpr (MODE != kMask) pv = *reinterpret_cast<const float4*>(coef_s + ccol + c);
+          const float2 npv0 = make_float2(-pv.x, -pv.y), npv1 = make_float2(-pv.z, -pv.w);
+          float2 s01 = make_float2(cs[si][0], cs[si][1]), s23 = make_float2(cs[si][2], cs[si][3]);
+          float2 q01 = make_float2(cq[si][0], cq[si][1]), q23 = make_float2(cq[si][2], cq[si][3]);
 #pragma unroll 8
           for (int k = 0; k < kRows; ++k) {
             const int r = rg * kRows + k;
             const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
             const uint2 u = *reinterpret_cast<const uint2*>(vcol + off);
-            float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-            float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            float2 f0 = bf2_to_f2(u.x), f1 = bf2_to_f2(u.y);
             if constexpr (MODE != kMask) {
-              f0.x -= pv.x; f0.y -= pv.y; f1.x -= pv.z; f1.y -= pv.w;
+              f0 = f2add(f0, npv0);      // x + (-p) == x - p
+              f1 = f2add(f1, npv1);
             }
             float2 y0 = f0, y1 = f1;
             if constexpr (MODE == kMask) {
               const uint2 uy = *reinterpret_cast<const uint2*>(ycol + off);
-              y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.x));
-              y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.y));
+              y0 = bf2_to_f2(uy.x);
+              y1 = bf2_to_f2(uy.y);
             }
-            cs[si][0] += f0.x; cs[si][1] += f0.y; cs[si][2] += f1.x; cs[si][3] += f1.y;
-            cq[si][0] = fmaf(f0.x, y0.x, cq[si][0]); cq[si][1] = fmaf(f0.y, y0.y, cq[si][1]);
-            cq[si][2] = fmaf(f1.x, y1.x, cq[si][2]); cq[si][3] = fmaf(f1.y, y1.y, cq[si][3]);
+            s01 = f2add(s01, f0);
+            s23 = f2add(s23, f1);
+            q01 = f2fma(f0, y0, q01);
+            q23 = f2fma(f1, y1, q23);
           }
+          cs[si][0] = s01.x; cs[si][1] = s01.y; cs[si][2] = s23.x; cs[si][3] = s23.y;
+          cq[si][0] = q01.x; cq[si][1] = q01.y; cq[si][2] = q23.x; cq[si][3] = q23.y;
         }
 #if HG_DBG_TS
         const long long _ts = clock64();

@@ -406,9 +406,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool relu = p.fold.relu != 0;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(h[e]);
-            const bool k0 = !relu || fmaf(f.x, cS[2 * e], cT[2 * e]) > 0.f;
-            const bool k1 = !relu || fmaf(f.y, cS[2 * e + 1], cT[2 * e + 1]) > 0.f;
+            const float2 t = f2fma(__bfloat1622float2(h[e]), make_float2(cS[2 * e], cS[2 * e + 1]),
+                                   make_float2(cT[2 * e], cT[2 * e + 1]));
+            const bool k0 = !relu || t.x > 0.f;
+            const bool k1 = !relu || t.y > 0.f;
             o[2 * e] = k0 ? v[q * 8 + 2 * e] : 0.f;
             o[2 * e + 1] = k1 ? v[q * 8 + 2 * e + 1] : 0.f;
           }
@@ -422,18 +423,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o[e] = relu ? fmaxf(t, 0.f) : t;
             }
           } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bias_s[j * 32 + q * 8 + e];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + j * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + j * 32 + q * 8 + 4);
+            const float2 o0 = f2add(make_float2(v[q * 8 + 0], v[q * 8 + 1]), make_float2(b0.x, b0.y));
+            const float2 o1 = f2add(make_float2(v[q * 8 + 2], v[q * 8 + 3]), make_float2(b0.z, b0.w));
+            const float2 o2 = f2add(make_float2(v[q * 8 + 4], v[q * 8 + 5]), make_float2(b1.x, b1.y));
+            const float2 o3 = f2add(make_float2(v[q * 8 + 6], v[q * 8 + 7]), make_float2(b1.z, b1.w));
+            o[0] = o0.x; o[1] = o0.y; o[2] = o1.x; o[3] = o1.y; o[4] = o2.x; o[5] = o2.y; o[6] = o3.x; o[7] = o3.y;
           }
           if (p.has_res) {
-            uint4 u = *cp;
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __bfloat1622float2(h[e]);
-              o[2 * e] += f.x;
-              o[2 * e + 1] += f.y;
-            }
+            const uint4 u = *cp;
+            const float2 r0 = f2add(make_float2(o[0], o[1]), bf2_to_f2(u.x));
+            const float2 r1 = f2add(make_float2(o[2], o[3]), bf2_to_f2(u.y));
+            const float2 r2 = f2add(make_float2(o[4], o[5]), bf2_to_f2(u.z));
+            const float2 r3 = f2add(make_float2(o[6], o[7]), bf2_to_f2(u.w));
+            o[0] = r0.x; o[1] = r0.y; o[2] = r1.x; o[3] = r1.y; o[4] = r2.x; o[5] = r2.y; o[6] = r3.x; o[7] = r3.y;
           }
           if (nchw_row != nullptr) {
 #pragma unroll
@@ -490,35 +494,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int chunk = (c & 63) >> 3;
         const uint8_t* vcol = (MODE == kMask ? sQ : sC) + coff;   // the values whose sum is taken
         const uint8_t* ycol = sC + coff;                          // kMask: raw BatchNorm input
-        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 s01 = make_float2(0.f, 0.f), s23 = s01, q01 = s01, q23 = s01;
         // BatchNorm statistics are sums of (y - pivot): the pivot of these four channels (0 for the backward sums)
         float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (MODE == kPlain) pv = *reinterpret_cast<const float4*>(coef_s + c);
         else if constexpr (MODE != kMask) pv = *reinterpret_cast<const float4*>(p.stats + 2 * p.n_total + n_off + c);
+        const float2 npv0 = make_float2(-pv.x, -pv.y), npv1 = make_float2(-pv.z, -pv.w);
 #pragma unroll 8
         for (int i = 0; i < kRows; ++i) {
           const int r = grp * kRows + i;
           const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
           const uint2 u = *reinterpret_cast<const uint2*>(vcol + off);
-          float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-          float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+          float2 f0 = bf2_to_f2(u.x), f1 = bf2_to_f2(u.y);
           if constexpr (MODE != kMask) {
-            f0.x -= pv.x; f0.y -= pv.y; f1.x -= pv.z; f1.y -= pv.w;
+            f0 = f2add(f0, npv0);      // x + (-p) == x - p
+            f1 = f2add(f1, npv1);
           }
           float2 y0 = f0, y1 = f1;
           if constexpr (MODE == kMask) {
             const uint2 uy = *reinterpret_cast<const uint2*>(ycol + off);
-            y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.x));
-            y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uy.y));
+            y0 = bf2_to_f2(uy.x);
+            y1 = bf2_to_f2(uy.y);
           }
           if (r < valid) {
-            s4[0] += f0.x; s4[1] += f0.y; s4[2] += f1.x; s4[3] += f1.y;
-            q4[0] = fmaf(f0.x, y0.x, q4[0]); q4[1] = fmaf(f0.y, y0.y, q4[1]);
-            q4[2] = fmaf(f1.x, y1.x, q4[2]); q4[3] = fmaf(f1.y, y1.y, q4[3]);
+            s01 = f2add(s01, f0);
+            s23 = f2add(s23, f1);
+            q01 = f2fma(f0, y0, q01);
+            q23 = f2fma(f1, y1, q23);
           }
         }
-        *reinterpret_cast<float4*>(acc_s + grp * 2 * BN + c) = make_float4(s4[0], s4[1], s4[2], s4[3]);
-        *reinterpret_cast<float4*>(acc_s + grp * 2 * BN + BN + c) = make_float4(q4[0], q4[1], q4[2], q4[3]);
+        *reinterpret_cast<float4*>(acc_s + grp * 2 * BN + c) = make_float4(s01.x, s01.y, s23.x, s23.y);
+        *reinterpret_cast<float4*>(acc_s + grp * 2 * BN + BN + c) = make_float4(q01.x, q01.y, q23.x, q23.y);
       }
       named_bar_sync(1, kEpiThreads);
       if (et < 2 * kQuads) {

@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
 //   i.e. the bias gradient of the convolution that produced x.
 // ------------------------------------------------------------------------------------------------------
 template <typename T, bool ADD, bool CS>
-__global__ void __launch_bounds__(256, HG_BN_BWD_MINB) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ x,
+__global__ void __launch_bounds__(256, ADD ? 1 : HG_BN_BWD_MINB) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ x,
                                                            const T* __restrict__ addend, T* __restrict__ dx,
                                                            long long M, BnArgs a, const float* __restrict__ redin,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -363,7 +363,11 @@ __global__ void __launch_bounds__(256, HG_BN_BWD_MINB) bn_bwd_apply_kernel(const
   const int vc = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
   const int rlanes = 256 / vecs;
-  constexpr int U = sizeof(T) == 2 ? 4 : 2;  // rows in flight per thread (three tensors each, kept unconverted)
+  // rows in flight per thread (three / four tensors each, kept unconverted).  With the addend (four streams) ONE block
+  // per SM with eight rows in flight per thread (196 registers) runs at 0.84 of the copy bandwidth where two blocks with
+  // four rows each reach 0.67 (C256 @64x64, batch 32: 60.0 -> 49.2 us); the three-stream kernel is the other way round
+  // (18.4 vs 20.6 us at C128).
+  constexpr int U = sizeof(T) == 2 ? (ADD ? 8 : 4) : 2;
   const long long m0 = (long long)blockIdx.x * rows_per_block;
   long long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
@@ -607,7 +611,8 @@ int hg_bn_bwd_apply(const HgBnDesc* d, const void* da, const void* x, const floa
   HG_REQUIRE(d->use_running ? (running_mean && running_var) : (stats && red),
              "hg_bn_bwd_apply: statistics missing for the selected mode");
   BnArgs a = make_args(d, stats, gamma, beta, running_mean, running_var);
-  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3), atomic_grid_per_sm(d->M));
+  const bool wide = addend != nullptr && d->dtype == HG_BF16;   // U = 8, one block per SM (see the kernel)
+  const int rpb = rows_per_block_for(d->M, 256 / (a.Cp >> 3), wide && g_bn_bwd_blocks_per_sm <= 0 ? 1 : atomic_grid_per_sm(d->M));
   const int blocks = ceil_div(d->M, rpb);
   cudaStream_t st = (cudaStream_t)stream;
 #define HG_BWD_APPLY(T, ADD, CS)                                                                                 \

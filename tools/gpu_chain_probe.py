@@ -249,6 +249,15 @@ if __name__ == "__main__":
             L.call("hg_set_option", b"dbg_ts", 2)
         L.call("hg_set_option", b"dbg_ts", 0)
         sys.exit(0)
+    for opt in os.environ.get("HG_OPTIONS", "").split(","):
+        if "=" in opt:
+            k_, v_ = opt.split("=")
+            L.call("hg_set_option", k_.encode(), int(v_))
+    if os.environ.get("BN_ONLY"):
+        for hw in (16, 32, 64):
+            print(f"B=32 @{hw}x{hw}: bn_bwd_apply C256+add {bn_bwd_chain(32, hw, 256, with_addend=True):7.2f} us | "
+                  f"bn_bwd_apply C128 {bn_bwd_chain(32, hw, 128):7.2f} us | bn_apply C256 {bn_chain(32, hw, 256):7.2f} us", flush=True)
+        sys.exit(0)
     print(f"trivial kernel chain (hg_add 64 elems): {empty_chain():.2f} us/call")
     for hw in (4, 8, 16, 32, 64):
         print(f"B=32 @{hw}x{hw}: conv3x3 128->128 {conv_chain(32, hw, 128, 128, 3):7.2f} us | "

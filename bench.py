@@ -140,9 +140,14 @@ def kernel_roofline(name, tag, n, t_ms, B, peaks, src, total_ms, traffic_db):
         ci, co, k, h, w = (int(v) for v in mconv.groups())
         flops = 2.0 * B * h * w * ci * co * k * k
         kname = _KERNEL_NAMES[name]
-        # large-map 1x1 fprop / dgrad launches run the persistent kernel (csrc/conv_persist.cu: >= 512 units of 128 pixels)
-        if k == 1 and B * h * w >= 512 * 128 and name in ("hg_conv_fprop_ex", "hg_conv_dgrad", "hg_conv_dgrad_bn"):
-            kname = kname.replace("conv_gemm_kernel", "conv_persist_kernel")
+        # large-map 1x1 fprop / dgrad launches run the persistent kernel (csrc/conv_persist.cu: >= 512 units of 128 pixels),
+        # and so do the 3x3 convolutions with 128 output channels (its transposed-accumulator variant)
+        if B * h * w >= 512 * 128 and name in ("hg_conv_fprop_ex", "hg_conv_dgrad", "hg_conv_dgrad_bn"):
+            gemm_n = (co if name == "hg_conv_fprop_ex" else ci)
+            if k == 1:
+                kname = kname.replace("conv_gemm_kernel", "conv_persist_kernel")
+            elif k == 3 and (gemm_n + 63) // 64 * 64 == 128:
+                kname = kname.replace("conv_gemm_kernel", "conv_persist_kernel<TR>")
         if k == 1:
             # 1x1 convolutions are HBM-bound (8.6 GFLOP over >= 100 MB at 64x64): bf16 tensors read + written per launch
             cip, cop = (ci + 63) // 64 * 64, (co + 63) // 64 * 64

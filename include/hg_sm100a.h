@@ -279,6 +279,13 @@ typedef struct HgMseDesc {
 HG_API int hg_mse_multi(const HgMseDesc* d, const float* const* preds_host, const float* target,
                         float* const* dpreds_host, float* loss, void* stream);
 
+/* In place t_s[i] *= scales[s] for s < num_tensors (<= HG_MSE_MAX_STACKS) fp32 tensors of `numel` elements (16-byte
+ * aligned; tensors_host is a HOST array of DEVICE pointers, NULL entries are skipped; scales is a DEVICE array): the
+ * upstream gradient of `losses[s]` applied to the per-stack gradients hg_mse_multi already produced -- one launch where
+ * autograd's `g * gloss[s]` is one elementwise kernel per stack (try_with_torch.py:341 `loss.backward()`). */
+HG_API int hg_scale_multi(int64_t numel, int32_t num_tensors, float* const* tensors_host, const float* scales,
+                          void* stream);
+
 /* ---- per-pixel class cross-entropy heads --------------------------------------------------------- */
 /* nn.CrossEntropyLoss (mean over labels != ignore_index) on fp32 NCHW logits with int64 [B,H,W] labels
  * (only_one_hourgless.py:348,370; try_different_stack.py:360-361,388-389; the [:, :18] / [:, 18:] slices of every

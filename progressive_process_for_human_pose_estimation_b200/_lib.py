@@ -137,6 +137,7 @@ SIGNATURES = {
     "hg_mix_rows_rect": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "hg_gather_annotations": [C.POINTER(HgAnnotDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
+    "hg_scale_multi": [_LL, _I, _P, _P, _P],
     "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
     "hg_image_u8_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "hg_resize_bicubic_u8": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -269,7 +269,47 @@ __global__ void __launch_bounds__(256) mse_weighted_kernel(const float* __restri
 
 using namespace hg;
 
+struct ScaleArgs {
+  float* t[HG_MSE_MAX_STACKS];
+  const float* scales;
+  long long n4;
+};
+
+__global__ void __launch_bounds__(256) scale_multi_kernel(const ScaleArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  float* t = a.t[blockIdx.y];
+  if (t == nullptr) return;
+  const float sc = a.scales[blockIdx.y];
+  float4* p = reinterpret_cast<float4*>(t);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = p[i];
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    p[i] = v;
+  }
+}
+
 extern "C" {
+
+int hg_scale_multi(int64_t numel, int32_t num_tensors, float* const* tensors_host, const float* scales, void* stream) {
+  HG_REQUIRE(tensors_host && scales, "hg_scale_multi: NULL pointer");
+  HG_REQUIRE(num_tensors > 0 && num_tensors <= HG_MSE_MAX_STACKS, "hg_scale_multi: 1..%d tensors supported", HG_MSE_MAX_STACKS);
+  HG_REQUIRE(numel > 0 && numel % 4 == 0, "hg_scale_multi: numel must be a positive multiple of 4");
+  ScaleArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int s = 0; s < num_tensors; ++s) {
+    HG_REQUIRE((reinterpret_cast<uintptr_t>(tensors_host[s]) & 15) == 0, "hg_scale_multi: tensors must be 16-byte aligned");
+    a.t[s] = tensors_host[s];
+  }
+  a.scales = scales;
+  a.n4 = numel / 4;
+  long long blocks = (a.n4 + 255) / 256;
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  launch_k(scale_multi_kernel, dim3((unsigned)blocks, (unsigned)num_tensors), dim3(256), 0, (cudaStream_t)stream, a);
+  HG_LAUNCH_OK("scale_multi_kernel");
+  count_launch();
+  return HG_OK;
+}
 
 int hg_mse_multi(const HgMseDesc* d, const float* const* preds_host, const float* target, float* const* dpreds_host,
                  float* loss, void* stream) {

@@ -37,11 +37,20 @@ class _MseMulti(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss):
-        out = [None]
-        for s, g in enumerate(ctx.grads):
-            out.append(None if g is None else g * gloss[s])
+        grads = ctx.grads
         ctx.grads = None
-        return tuple(out)
+        live = [g for g in grads if g is not None]
+        if live:
+            # d(losses[s]) scales the gradient hg_mse_multi already wrote for stack s: one launch, in place
+            numel = live[0].numel()
+            if numel % 4 == 0 and gloss.is_cuda:
+                gl = gloss.detach().to(torch.float32).contiguous()
+                arr = (C.c_void_p * len(grads))(*[g.data_ptr() if g is not None else None for g in grads])
+                with torch.cuda.device(gl.device):
+                    L.call("hg_scale_multi", numel, len(grads), arr, L.ptr(gl), L.stream_ptr())
+            else:
+                grads = [None if g is None else g * gloss[s] for s, g in enumerate(grads)]
+        return (None, *grads)
 
 
 def mse_losses(result, target):

@@ -517,7 +517,7 @@ def run_ours(args):
         table = sorted(((k[0], k[1], v[0], v[1]) for k, v in agg.items()), key=lambda r: -r[3])
         peaks, src = measured_peaks()
         traffic_db = {}
-        for tp in ("r02f_roofline_traffic.json", "r02_roofline_traffic.json", "r01_roofline_traffic.json"):
+        for tp in ("r02g_roofline_traffic.json", "r02f_roofline_traffic.json", "r02_roofline_traffic.json", "r01_roofline_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", tp)
             if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, B=32)
                 traffic_db = json.load(open(tpath))

@@ -48,6 +48,10 @@ int g_persist_1x1 = 1;
 int g_persist_3x3 = 1;               // 128-channel 3x3 convolutions at >= persist_min_units: transposed persistent kernel (43 vs 51 us @64x64)
 int g_persist_transposed = 1;     // 3x3 with 128 output channels: accumulators as [channel][pixel] (one N = 256 MMA per
                                   // 256-pixel tile and K step instead of two N = 128 ones; no column pass in the epilogue)
+int g_persist_dynamic = 0;        // 1: tiles handed out by a grid-wide atomic counter (see PsQueue); measured: isolated launches 2 - 8 % slower, step 970 -> 961 images/s
+static int* g_ps_ctr_pool = nullptr;      // kPsCtrSlots x {next tile, CTAs done}; every launch (graph node) takes the next slot
+static int g_ps_ctr_next = 0;
+constexpr int kPsCtrSlots = 8192;
 int g_persist_min_units = 512;    // at least this many 128-pixel units: two 256-pixel tiles per SM and more (64x64 at
                                   // batch 32; at 32x32 every CTA has ONE tile, nothing to pipeline: step 883 vs 894 images/s)
 
@@ -67,6 +71,8 @@ struct PsParams {
   const float* bias;  // [Np] or null
   float* stats;       // kPlain: {S1, S2, pivot}[3*Np] or null;  kMask: {sum g, sum g*xhat}[2*Np]
   BnFoldDev fold;     // kMask: BatchNorm of the OUTPUT channels
+  int* ctr;           // dynamic tile scheduling: {next tile, CTAs done} (self-resetting) or null = static unit ranges
+  int num_tiles;      // dynamic: tiles of tile_units units
   signed char wt[3][3];   // weight matrix of the tap whose A offset is (dh, dw) = (i - th/2, j - tw/2)
   long long* ts;      // debug counters or null
   int dbg;
@@ -98,6 +104,29 @@ struct PsTiles {
   }
 };
 
+// Tile queue: the producer warp decides which tile comes next -- its static unit range, or (p.ctr != null) the next
+// tile of a grid-wide atomic counter -- and publishes {first unit, units} through a small shared-memory ring; the MMA
+// issuer and the epilogue warps read the same sequence.  Dynamic order matters in the training step: the persistent
+// kernels share the GPU with the one-wave kernels of the low-resolution hourglass levels (other stream lanes, higher
+// priority), so some CTAs start several microseconds late; with static ranges the launch lasts until the LAST CTA has
+// worked through its whole range, with the counter a late CTA simply finds less left to do.
+constexpr int kPsQ = 8;
+struct PsQueue {
+  int* tq;
+  uint64_t* full;
+  uint64_t* empty;
+  __device__ __forceinline__ bool get(int idx, int& m0, int& mt) const {
+    const int q = idx & (kPsQ - 1);
+    mbar_wait(&full[q], (uint32_t)(idx / kPsQ) & 1u);
+    const int v = *reinterpret_cast<volatile int*>(tq + q);
+    if (v < 0) return false;
+    m0 = (v >> 2) * 128;
+    mt = v & 3;
+    return true;
+  }
+  __device__ __forceinline__ void release(int idx) const { mbar_arrive(&empty[idx & (kPsQ - 1)]); }
+};
+
 template <int MODE, int NP, bool TR>
 __global__ void __launch_bounds__(kPsThreads, 1)
 conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -124,6 +153,10 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_empty = bars + 34;            // [2]
   uint64_t* y_full = bars + 36;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+  PsQueue tqu;
+  tqu.full = bars + 40;                        // [kPsQ]
+  tqu.empty = bars + 48;                       // [kPsQ]
+  tqu.tq = reinterpret_cast<int*>(bars + 56);  // [kPsQ]
   float* bias_s = reinterpret_cast<float*>(bars + 64);   // [256]
   float* coef_s = bias_s + 256;                            // kMask: scale / shift / A / B [4][256];  kPlain: pivots
   float* acc_s = coef_s + 1024;                            // [2][256] per-CTA column sums
@@ -148,6 +181,10 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_init(&y_full[0], 1);
     mbar_init(&y_full[1], 1);
+    for (int s = 0; s < kPsQ; ++s) {
+      mbar_init(&tqu.full[s], 1);
+      mbar_init(&tqu.empty[s], 2);             // MMA issuer + epilogue
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -171,7 +208,44 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long tstart = clock64();
       const int nA = p.nA, nB = p.nB, th = p.th, tw = p.tw;
       const bool nodata = HG_DBG_TS && (p.dbg & 4);   // debug: no data movement at all (what the MMA stream alone takes)
-      while (tiles.next(m0, mt)) {
+      // tile sequence: static range, or first tile = blockIdx.x and then whatever the grid-wide counter hands out
+      const bool dyn = p.ctr != nullptr;
+      int qi = 0;
+      auto publish = [&](int v) {
+        const int q = qi & (kPsQ - 1);
+        mbar_wait(&tqu.empty[q], ((uint32_t)(qi / kPsQ) & 1u) ^ 1u);
+        if (elect_one()) {
+          tqu.tq[q] = v;
+          mbar_arrive(&tqu.full[q]);
+        }
+        __syncwarp();
+        ++qi;
+      };
+      auto dyn_tile = [&](int t) {              // tile index -> {first unit * 4 + units} or -1
+        if (t >= p.num_tiles) return -1;
+        const int u0 = t * p.tile_units;
+        const int n = p.units - u0 < p.tile_units ? p.units - u0 : p.tile_units;
+        return u0 * 4 + n;
+      };
+      int cur;
+      if (dyn) cur = dyn_tile((int)blockIdx.x);
+      else cur = tiles.next(m0, mt) ? (m0 / 128) * 4 + mt : -1;
+      publish(cur);
+      while (cur >= 0) {
+        m0 = (cur >> 2) * 128;
+        mt = cur & 3;
+        // the next tile is decided (and published) before this one's loads are issued: the consumers can look ahead
+        int nxt;
+        if (dyn) {
+          int t = 0;
+          if (lane == 0) t = atomicAdd(p.ctr, 1) + (int)gridDim.x;
+          t = __shfl_sync(0xffffffffu, t, 0);
+          nxt = dyn_tile(t);
+        } else {
+          int m0n, mtn;
+          nxt = tiles.next(m0n, mtn) ? (m0n / 128) * 4 + mtn : -1;
+        }
+        publish(nxt);
         const int n = m0 / hw;
         const int h0 = (m0 - n * hw) / p.W;
         int sbr = 0;
@@ -222,6 +296,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         first_tile = false;
+        cur = nxt;
       }
       if (HG_DBG_TS && p.ts && blockIdx.x == 0 && lane == 0) {
         p.ts[0] = clock64() - tstart;
@@ -239,7 +314,6 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // measured with every data movement switched off (ps_dbg 5).  Slots and phases are counters, descriptors are adds.
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, NP, 0, 0);
-      PsTiles tiles(p);
       int m0, mt;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
@@ -252,8 +326,10 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int nA = p.nA, nB = p.nB, th = p.th, per_kc = p.tw;
       const bool resident = p.b_resident != 0;
       const bool no_mma = HG_DBG_TS && (p.dbg & 2);
-      for (int it = 0; tiles.next(m0, mt); ++it) {
+      for (int it = 0; tqu.get(it, m0, mt); ++it) {
         const int acc = it & 1;
+        __syncwarp();                                  // every lane has read the queue slot
+        if (elect_one()) tqu.release(it);
         {
           PS_TIC;
           mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
@@ -367,9 +443,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int pnl = 0; pnl < kPanels; ++pnl)
         tma_load_2d(sY + buf * kCBytes + pnl * 16384, &tmR, &y_full[buf], ccol + pnl * 64, m);
     };
-    PsTiles tiles(p);
     int m0, mt;
-    bool have = tiles.next(m0, mt);
+    bool have = tqu.get(0, m0, mt);
     if (need_y && have && et == 0) load_y(0, m0, 0);
     named_bar_sync(1, kPsEpi);
     int g = 0;                                  // parts drained so far
@@ -378,7 +453,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int it = 0; have; ++it) {
       const int acc = it & 1;
       int m0n = 0, mtn = 0;
-      const bool have_next = tiles.next(m0n, mtn);
+      const bool have_next = tqu.get(it + 1, m0n, mtn);
       {
         PS_TIC;
         mbar_wait(&tmem_full[acc], (it >> 1) & 1);
@@ -389,6 +464,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         named_bar_sync(1, kPsEpi);
         if (et == 0) mbar_arrive(&tmem_empty[acc]);
+        if (et == 0) tqu.release(it);
         have = have_next;
         m0 = m0n;
         mt = mtn;
@@ -576,6 +652,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ++g;
       }
+      // every epilogue thread read this tile's queue slot before the barriers above
+      if (et == 0) tqu.release(it);
       have = have_next;
       m0 = m0n;
       mt = mtn;
@@ -627,6 +705,15 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+  if (p.ctr != nullptr && threadIdx.x == 0) {
+    // the last CTA to get here (every CTA has made its final fetch) re-arms the counter for the next launch of this node
+    __threadfence();
+    if (atomicAdd(p.ctr + 1, 1) == (int)gridDim.x - 1) {
+      p.ctr[0] = 0;
+      p.ctr[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -793,7 +880,23 @@ int conv_persist_launch(int N, int H, int W, int Kp, int Np, int mode, int ntaps
   }
   // one CTA per SM; every CTA gets at least one full tile
   int grid = (p.units + p.tile_units - 1) / p.tile_units;
+  p.num_tiles = grid;
   if (grid > kNumSMs) grid = kNumSMs;
+  // dynamic order needs whole tiles that never straddle an image (3x3): units per image a multiple of the tile
+  if (g_persist_dynamic && p.num_tiles > grid && (ntaps == 1 || p.upi % p.tile_units == 0)) {
+    if (!g_ps_ctr_pool) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      if (cs == cudaStreamCaptureStatusNone) {
+        HG_CUDA_OK(cudaMalloc(&g_ps_ctr_pool, kPsCtrSlots * 2 * sizeof(int)));
+        HG_CUDA_OK(cudaMemset(g_ps_ctr_pool, 0, kPsCtrSlots * 2 * sizeof(int)));
+      }
+    }
+    if (g_ps_ctr_pool) {
+      p.ctr = g_ps_ctr_pool + 2 * g_ps_ctr_next;
+      g_ps_ctr_next = (g_ps_ctr_next + 1) % kPsCtrSlots;
+    }
+  }
   if (Np == 256)
     return mode == kMask ? ps_launch<kMask, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st)
                          : ps_launch<kPlain, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st);

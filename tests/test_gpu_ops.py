@@ -180,6 +180,21 @@ def test_persistent_3x3_kernel(case):
         _persist(512)
 
 
+@pytest.mark.parametrize("case", [(19, 64, 64, 128, 128, 3, 1, False, False), (12, 64, 64, 256, 128, 1, 1, False, False),
+                                  (10, 64, 64, 128, 256, 1, 1, True, False), (40, 32, 32, 128, 128, 3, 1, False, False)])
+def test_persistent_kernel_dynamic_tile_order(case):
+    """persist_dynamic = 1: tiles handed out by a grid-wide atomic counter through the shared-memory tile queue (off by
+    default: measured slower) -- same checks as the static unit ranges, twice (the counter re-arms itself)."""
+    _persist(1, p3=2)
+    L.call("hg_set_option", b"persist_dynamic", 1)
+    try:
+        for _ in range(2):
+            test_conv_fprop_dgrad_wgrad(case, torch.bfloat16)
+    finally:
+        L.call("hg_set_option", b"persist_dynamic", 0)
+        _persist(512)
+
+
 def test_persistent_3x3_kernel_matches_tile_kernel():
     """Same 3x3 convolution through the persistent kernel and through conv_gemm_kernel (persist_3x3 = 0): the outputs
     differ only by the fp32 accumulation order of the 18 K blocks (a bf16 rounding step at most), the statistics by 1e-4."""

@@ -279,6 +279,10 @@ typedef struct HgMseDesc {
 HG_API int hg_mse_multi(const HgMseDesc* d, const float* const* preds_host, const float* target,
                         float* const* dpreds_host, float* loss, void* stream);
 
+/* cudaMemsetAsync(p, 0, bytes) on `stream` (a memset node when captured into a CUDA graph): the gradient / reduction
+ * arenas of a step are cleared without an elementwise fill kernel. */
+HG_API int hg_zero_async(void* p, int64_t bytes, void* stream);
+
 /* In place t_s[i] *= scales[s] for s < num_tensors (<= HG_MSE_MAX_STACKS) fp32 tensors of `numel` elements (16-byte
  * aligned; tensors_host is a HOST array of DEVICE pointers, NULL entries are skipped; scales is a DEVICE array): the
  * upstream gradient of `losses[s]` applied to the per-stack gradients hg_mse_multi already produced -- one launch where

@@ -138,6 +138,7 @@ SIGNATURES = {
     "hg_gather_annotations": [C.POINTER(HgAnnotDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "hg_mse_multi": [C.POINTER(HgMseDesc), _P, _P, _P, _P, _P],
     "hg_scale_multi": [_LL, _I, _P, _P, _P],
+    "hg_zero_async": [_P, _LL, _P],
     "hg_ce_multi": [C.POINTER(HgCeDesc), _P, _P, _P, _P, _P],
     "hg_image_u8_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "hg_resize_bicubic_u8": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -205,6 +206,12 @@ def check(rc, what=""):
 
 def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def zero_(t):
+    """Clear a contiguous CUDA tensor with cudaMemsetAsync on the current stream (no fill kernel)."""
+    call("hg_zero_async", ptr(t), t.numel() * t.element_size(), stream_ptr())
+    return t
 
 
 def ptr(t):

@@ -291,6 +291,12 @@ __global__ void __launch_bounds__(256) scale_multi_kernel(const ScaleArgs a) {
 
 extern "C" {
 
+int hg_zero_async(void* p, int64_t bytes, void* stream) {
+  HG_REQUIRE(p != nullptr && bytes >= 0, "hg_zero_async: bad arguments");
+  if (bytes > 0) HG_CUDA_OK(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
+  return HG_OK;
+}
+
 int hg_scale_multi(int64_t numel, int32_t num_tensors, float* const* tensors_host, const float* scales, void* stream) {
   HG_REQUIRE(tensors_host && scales, "hg_scale_multi: NULL pointer");
   HG_REQUIRE(num_tensors > 0 && num_tensors <= HG_MSE_MAX_STACKS, "hg_scale_multi: 1..%d tensors supported", HG_MSE_MAX_STACKS);

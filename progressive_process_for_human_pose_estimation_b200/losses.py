@@ -26,11 +26,12 @@ class _MseMulti(torch.autograd.Function):
         target = target.contiguous().to(torch.float32)
         need = [ctx.needs_input_grad[i + 1] for i in range(S)]
         grads = [torch.empty_like(p) if n else None for p, n in zip(preds, need)]
-        loss = torch.zeros(S, device=target.device, dtype=torch.float32)
+        loss = torch.empty(S, device=target.device, dtype=torch.float32)
         d = L.HgMseDesc(target.numel(), S, 1.0)
         parr = (C.c_void_p * S)(*[p.data_ptr() for p in preds])
         garr = (C.c_void_p * S)(*[g.data_ptr() if g is not None else None for g in grads])
         with torch.cuda.device(target.device):
+            L.zero_(loss)
             L.call("hg_mse_multi", C.byref(d), parr, L.ptr(target), garr, L.ptr(loss), L.stream_ptr())
         ctx.grads = grads
         return loss

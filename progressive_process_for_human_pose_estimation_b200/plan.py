@@ -1157,9 +1157,9 @@ class Plan:
 
     def _bwd_body(self, a=0, b=None):
         if a == 0:
-            self.grad_arena.zero_()
-            self.packed_arena.zero_()
-            self.red_arena.zero_()
+            L.zero_(self.grad_arena)      # memset nodes, no fill kernels
+            L.zero_(self.packed_arena)
+            L.zero_(self.red_arena)
         self._run_calls(self.bwd_calls[a:b], bwd=True)
 
     def prepare(self):
@@ -1179,17 +1179,21 @@ class Plan:
         else:
             self._fwd_body()
         self.n_fwd_runs += 1
-        # the caller owns what it gets (a stock module returns new tensors every call): one multi-tensor copy
-        outs = [torch.empty_like(t) for t in self.out_static]
-        torch._foreach_copy_(outs, self.out_static)
-        return outs
+        # the caller owns what it gets (a stock module returns new tensors every call): ONE device-to-device copy of the
+        # output arena (a memcpy, no kernel); the returned tensors are views of the copy
+        flat = self.out_arena.clone()
+        return [flat[o:o + shp[0] * shp[1] * shp[2] * shp[3]].view(shp) for o, shp in self._out_slices]
 
     def run_backward(self, gouts):
         present = [(gbuf, gouts[i]) for i, gbuf in enumerate(self.gout_static) if i < len(gouts) and gouts[i] is not None]
         if len(present) < len(self.gout_static):
-            self.gout_arena.zero_()
-        if present:   # one multi-tensor copy for the incoming heatmap gradients
-            torch._foreach_copy_([p[0] for p in present], [p[1].to(torch.float32) for p in present])
+            L.zero_(self.gout_arena)
+        if present:   # incoming heatmap gradients: device-to-device memcpys when they are plain fp32 tensors
+            if all(g.dtype == torch.float32 and g.is_contiguous() and g.is_cuda for _, g in present):
+                for dst, g in present:
+                    dst.copy_(g, non_blocking=True)
+            else:
+                torch._foreach_copy_([p[0] for p in present], [p[1].to(torch.float32) for p in present])
         segments = self.bwd_segments if (self.reducer is not None and self.bwd_segments) else [(0, None, None)]
         for a, b, ranges in segments:
             if _USE_GRAPHS and self.n_fwd_runs >= 2 and self.profile_records is None:

@@ -419,6 +419,14 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         coef_s[512 + c] = is;           // xhat = y * A + B  ->  sum g*xhat = A * sum(g*y) + B * sum(g)
         coef_s[768 + c] = -mu * is;
       }
+    } else if constexpr (MODE == kPlainBnOut) {
+      // inference: y = [relu](scale * (acc + bias) + shift) with the running statistics of the OUTPUT channels
+      for (int c = et; c < NP; c += kPsEpi) {
+        float mu, is, sc, sh;
+        bn_fold_coeffs(p.fold, c, mu, is, sc, sh);
+        coef_s[c] = sc;
+        bias_s[c] = fmaf(p.bias ? p.bias[c] : 0.f, sc, sh);
+      }
     } else {
       // statistics are sums of (y - pivot) (bn.cu): the pivots of the output channels
       if (p.stats != nullptr)
@@ -520,6 +528,15 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               cs[0][0] += gq;
               cq[0][0] = fmaf(gq, y, cq[0][0]);
             }
+          } else if constexpr (MODE == kPlainBnOut) {
+            const float sc = coef_s[ch], bi = bias_s[ch];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int r = r0 + i;
+              const int off = boff + r * 128 + ((chunk ^ (r & 7)) << 4);
+              const float t = fmaf(v[i], sc, bi);
+              *reinterpret_cast<__nv_bfloat16*>(sC + off) = __float2bfloat16_rn(relu ? fmaxf(t, 0.f) : t);
+            }
           } else {
             const float bch = bias_s[ch];
             const float pv = p.stats != nullptr ? coef_s[ch] : 0.f;
@@ -560,6 +577,12 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const bool k1 = !relu || t.y > 0.f;
                 o[2 * e] = k0 ? v[q * 8 + 2 * e] : 0.f;
                 o[2 * e + 1] = k1 ? v[q * 8 + 2 * e + 1] : 0.f;
+              }
+            } else if constexpr (MODE == kPlainBnOut) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float t = fmaf(v[q * 8 + e], coef_s[ch + e], bias_s[ch + e]);
+                o[e] = relu ? fmaxf(t, 0.f) : t;
               }
             } else {
               const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch), b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
@@ -769,7 +792,7 @@ static int ps_plan(int W, int Kp, int Np, int taps, bool need_y, PsParams& p) {
 bool conv_persist_eligible(int N, int H, int W, int Kp, int Np, int ntaps, const signed char* dh, const signed char* dw,
                            int stride, int parity, int mode, const float* out_nchw, bool has_res) {
   if (stride != 1 || parity || out_nchw != nullptr) return false;
-  if (mode != kPlain && mode != kMask) return false;
+  if (mode != kPlain && mode != kMask && mode != kPlainBnOut) return false;
   if (!(Np == 64 || Np == 128 || Np == 256) || Kp % 64 || Kp > 256) return false;
   const long long M = (long long)N * H * W;
   if (M % 128 != 0 || M / 128 < g_persist_min_units || M > 0x7fffffffLL) return false;
@@ -823,6 +846,10 @@ int conv_persist_launch(int N, int H, int W, int Kp, int Np, int mode, int ntaps
   }
   if (mode == kMask && (!res || !stats)) {
     set_error("conv_persist_launch: mask mode needs the raw BatchNorm input and the reduction buffer");
+    return HG_ERR_BAD_ARG;
+  }
+  if (mode == kPlainBnOut && (!fold || !fold->use_running || res || stats)) {
+    set_error("conv_persist_launch: output BatchNorm needs running statistics and takes no residual / statistics");
     return HG_ERR_BAD_ARG;
   }
   const long long M = (long long)N * H * W;
@@ -896,6 +923,12 @@ int conv_persist_launch(int N, int H, int W, int Kp, int Np, int mode, int ntaps
       p.ctr = g_ps_ctr_pool + 2 * g_ps_ctr_next;
       g_ps_ctr_next = (g_ps_ctr_next + 1) % kPsCtrSlots;
     }
+  }
+  if (mode == kPlainBnOut) {
+    if (Np == 128 && ntaps == 9 && g_persist_transposed) return ps_launch<kPlainBnOut, 128, true>(grid, smem, tmA, tmB, tmC, tmR, p, st);
+    if (Np == 256) return ps_launch<kPlainBnOut, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st);
+    if (Np == 128) return ps_launch<kPlainBnOut, 128>(grid, smem, tmA, tmB, tmC, tmR, p, st);
+    return ps_launch<kPlainBnOut, 64>(grid, smem, tmA, tmB, tmC, tmR, p, st);
   }
   if (Np == 256)
     return mode == kMask ? ps_launch<kMask, 256>(grid, smem, tmA, tmB, tmC, tmR, p, st)

@@ -802,6 +802,20 @@ def test_layout_roundtrip_and_add():
         assert torch.equal(s.float(), (q.float() * 2).to(dtype).float())
 
 
+def test_conv_with_output_batchnorm_eval_persistent_kernel():
+    """The same inference epilogue through conv_persist_kernel (forced for every size): pixel-major (1x1, Np = 64 / 128 /
+    256) and transposed (3x3, 128 output channels)."""
+    _persist(1, p3=1)
+    try:
+        n0 = L.load().hg_launch_count()
+        for c in [(2, 32, 32, 128, 128, 3, True), (2, 32, 32, 256, 128, 1, True), (3, 16, 16, 128, 256, 1, False),
+                  (4, 16, 16, 64, 64, 1, True), (19, 64, 64, 128, 128, 3, True)]:
+            test_conv_with_output_batchnorm_eval(c)
+        assert L.load().hg_launch_count() > n0
+    finally:
+        _persist(512)
+
+
 @pytest.mark.parametrize("case", [
     # N, H, W, Cin, Cout, k, relu
     (4, 64, 64, 256, 128, 1, True), (4, 32, 32, 128, 128, 3, True), (32, 4, 4, 128, 256, 1, False),

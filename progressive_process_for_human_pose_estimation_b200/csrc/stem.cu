@@ -37,21 +37,30 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
   float* ws = sm;               // [147][64]
   float* patch = sm + 147 * 64; // [3][21][38]
   const int Ho = H / 2, Wo = W / 2;
-  const int n = blockIdx.z, oy0 = blockIdx.y * kTileH, ox0 = blockIdx.x * kTileW;
+  // The weights are transposed into shared memory ONCE per block (coalesced global reads: consecutive threads read
+  // consecutive k of one output channel); the block then walks tiles (a block per tile re-read the 37 KB with a
+  // 147-float stride between neighbouring threads for every 128 output pixels).
   for (int i = threadIdx.x; i < 147 * 64; i += 128) {
-    const int co = i & 63, k = i >> 6;  // w is OIHW: [co][ci][r][s] -> k = ci*49 + r*7 + s
-    ws[i] = w[co * 147 + k];
+    const int co = i / 147, k = i - co * 147;  // w is OIHW: [co][ci][r][s] -> k = ci*49 + r*7 + s
+    ws[k * 64 + co] = w[i];
   }
-  load_patch(patch, x, n, H, W, oy0, ox0, threadIdx.x, 128);
-  __syncthreads();
+  const int tiles_x = Wo / kTileW, tiles_y = Ho / kTileH;
+  const int ntiles = N * tiles_x * tiles_y;
   const int cg = threadIdx.x >> 5;       // 16-channel group (warp-uniform -> weight reads broadcast)
   const int q = threadIdx.x & 31;
   const int prow = q >> 2, pcol = (q & 3) * 4;
-  float acc[4][16];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+  const int oy0 = ty * kTileH, ox0 = tx * kTileW;
+  __syncthreads();                        // the previous tile's patch has been consumed
+  load_patch(patch, x, n, H, W, oy0, ox0, threadIdx.x, 128);
+  __syncthreads();
+  // accumulators as packed fp32 pairs (FFMA2: two channels per issue slot; same IEEE results as scalar FFMA)
+  float2 acc2[4][8];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[j][c] = 0.f;
+    for (int c = 0; c < 8; ++c) acc2[j][c] = make_float2(0.f, 0.f);
   for (int ci = 0; ci < 3; ++ci) {
     for (int r = 0; r < 7; ++r) {
       const float* prow_p = patch + (ci * kPatchH + 2 * prow + r) * kPatchWS + 2 * pcol;
@@ -61,19 +70,30 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
 #pragma unroll
       for (int s = 0; s < 7; ++s) {
         const float4* wp = reinterpret_cast<const float4*>(ws + (ci * 49 + r * 7 + s) * 64 + cg * 16);
-        float wv[16];
+        float2 wv2[8];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const float4 f = wp[v];
-          wv[4 * v] = f.x; wv[4 * v + 1] = f.y; wv[4 * v + 2] = f.z; wv[4 * v + 3] = f.w;
+          wv2[2 * v] = make_float2(f.x, f.y);
+          wv2[2 * v + 1] = make_float2(f.z, f.w);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j) {
+          const float2 iv = make_float2(in[2 * j + s], in[2 * j + s]);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) acc[j][c] = fmaf(in[2 * j + s], wv[c], acc[j][c]);
+          for (int c = 0; c < 8; ++c) acc2[j][c] = f2fma(iv, wv2[c], acc2[j][c]);
+        }
       }
     }
   }
+  float acc[4][16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[j][2 * c] = acc2[j][c].x;
+      acc[j][2 * c + 1] = acc2[j][c].y;
+    }
   const int oy = oy0 + prow;
   if (oy < Ho) {
 #pragma unroll
@@ -92,6 +112,7 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
         store8(dst + h * 8, o);
       }
     }
+  }
   }
 }
 
@@ -124,11 +145,11 @@ __global__ void __launch_bounds__(160) stem_bwd_kernel(const float* __restrict__
       kmul[j] = 0;
     }
   }
-  float acc[4][16];
+  float2 acc2[4][8];   // packed fp32 pairs (FFMA2): two channels per issue slot
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[j][c] = 0.f;
+    for (int c = 0; c < 8; ++c) acc2[j][c] = make_float2(0.f, 0.f);
   if (t == 0) patch[kPatch] = 1.f;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tx = (int)(tile % tiles_x);
@@ -152,22 +173,32 @@ __global__ void __launch_bounds__(160) stem_bwd_kernel(const float* __restrict__
       for (int p = 0; p < 128; ++p) {
         const int poff = (2 * (p >> 4)) * kPatchWS + 2 * (p & 15);
         const float4* gp = reinterpret_cast<const float4*>(gs + p * 64 + cg * 16);
-        float g[16];
+        float2 g2[8];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const float4 f = gp[v];
-          g[4 * v] = f.x; g[4 * v + 1] = f.y; g[4 * v + 2] = f.z; g[4 * v + 3] = f.w;
+          g2[2 * v] = make_float2(f.x, f.y);
+          g2[2 * v + 1] = make_float2(f.z, f.w);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float xv = patch[koff[j] + kmul[j] * poff];
+          const float2 xv2 = make_float2(xv, xv);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) acc[j][c] = fmaf(xv, g[c], acc[j][c]);
+          for (int c = 0; c < 8; ++c) acc2[j][c] = f2fma(xv2, g2[c], acc2[j][c]);
         }
       }
     }
   }
   if (worker) {
+    float acc[4][16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        acc[j][2 * c] = acc2[j][c].x;
+        acc[j][2 * c + 1] = acc2[j][c].y;
+      }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = kq * 4 + j;
@@ -200,7 +231,8 @@ int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float
     return HG_ERR_UNSUPPORTED;
   }
   const int smem = (147 * 64 + kPatch) * sizeof(float);
-  dim3 grid(W / 2 / kTileW, H / 2 / kTileH, N);
+  long long ntiles = (long long)(W / 2 / kTileW) * (H / 2 / kTileH) * N;
+  dim3 grid((unsigned)(ntiles < 4 * kNumSMs ? ntiles : 4 * kNumSMs));   // four resident blocks per SM walk the tiles
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == HG_BF16) {
     static bool set = false;

@@ -7,6 +7,7 @@
 
 namespace hg {
 
+int g_stem_bwd_blocks_per_sm = 2;                  // persistent blocks of the stem weight gradient (hg_set_option)
 constexpr int kTileH = 8, kTileW = 16;             // output pixels per block
 constexpr int kPatchH = 2 * kTileH + 5;            // 21
 constexpr int kPatchW = 2 * kTileW + 5;            // 37
@@ -264,7 +265,7 @@ int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, i
   }
   const int smem = (kPatchPad + 128 * 64) * sizeof(float);
   const long long ntiles = (long long)N * (W / 2 / kTileW) * (H / 2 / kTileH);
-  int blocks = 2 * kNumSMs;
+  int blocks = g_stem_bwd_blocks_per_sm * kNumSMs;
   if (blocks > ntiles) blocks = (int)ntiles;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == HG_BF16) {

@@ -11,7 +11,7 @@ unsigned long long g_launches = 0;
 static int g_force_ref_conv = 0;
 static int g_allow_ref_conv = 0;
 int g_use_pdl = 1;
-extern int g_stem_bwd_blocks_per_sm, g_persist_dynamic, g_persist_transposed, g_persist_3x3, g_persist_1x1, g_persist_min_units, g_ps_dbg, g_upsample_sep, g_upsample_fwd_cap, g_onewave_cluster, g_wgrad_halo;
+extern int g_stem_tc, g_stem_bwd_blocks_per_sm, g_persist_dynamic, g_persist_transposed, g_persist_3x3, g_persist_1x1, g_persist_min_units, g_ps_dbg, g_upsample_sep, g_upsample_fwd_cap, g_onewave_cluster, g_wgrad_halo;
 extern int g_wgrad_fused_bias, g_mid_n_tiles, g_wgrad_kpx;
 extern int g_single_wave_deep, g_wgrad_smem_kb, g_small_n_tiles, g_wgrad_dbg, g_wgrad_bulk_reduce, g_wgrad_t1_max_kb, g_wgrad_small_n_panels, g_wgrad_big_n_panels, g_short_alias, g_long_k_3cta, g_short_1stage;
 extern int g_bn_blocks_per_sm, g_bn_bwd_blocks_per_sm, g_bn_apply_u4;
@@ -206,6 +206,10 @@ int hg_set_option(const char* name, int value) {
   }
   if (strcmp(name, "persist_3x3") == 0) {   // large-map 3x3 convolutions through conv_persist_kernel (default 0)
     g_persist_3x3 = value;
+    return HG_OK;
+  }
+  if (strcmp(name, "stem_tc") == 0) {   // bf16 stem on the tensor cores (default 1); 0: the CUDA-core kernels
+    g_stem_tc = value;
     return HG_OK;
   }
   if (strcmp(name, "stem_bwd_blocks_per_sm") == 0 && value > 0) {

@@ -218,6 +218,14 @@ __global__ void __launch_bounds__(160) stem_bwd_kernel(const float* __restrict__
 
 }  // namespace hg
 
+namespace hg {
+extern int g_stem_tc;
+int stem_tc_fwd_launch(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int relu,
+                       cudaStream_t st);
+int stem_tc_bwd_launch(const float* x, const void* y, const void* dy, float* dw, float* db, int N, int H, int W, int relu,
+                       cudaStream_t st);
+}  // namespace hg
+
 using namespace hg;
 
 extern "C" {
@@ -231,6 +239,8 @@ int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float
     set_error("hg_stem_fwd: image size %dx%d must be a multiple of 16x32", H, W);
     return HG_ERR_UNSUPPORTED;
   }
+  if (dtype == HG_BF16 && g_stem_tc)   // bf16 path: im2col tile built in shared memory, tcgen05 GEMM (stem_tc.cu)
+    return stem_tc_fwd_launch(x_nchw, w_oihw, bias, y, N, H, W, relu, (cudaStream_t)stream);
   const int smem = (147 * 64 + kPatch) * sizeof(float);
   long long ntiles = (long long)(W / 2 / kTileW) * (H / 2 / kTileH) * N;
   dim3 grid((unsigned)(ntiles < 4 * kNumSMs ? ntiles : 4 * kNumSMs));   // four resident blocks per SM walk the tiles
@@ -263,6 +273,8 @@ int hg_stem_bwd(int dtype, const float* x_nchw, const void* y, const void* dy, i
     set_error("hg_stem_bwd: image size %dx%d must be a multiple of 16x32", H, W);
     return HG_ERR_UNSUPPORTED;
   }
+  if (dtype == HG_BF16 && g_stem_tc)
+    return stem_tc_bwd_launch(x_nchw, y, dy, dw_oihw, dbias, N, H, W, relu, (cudaStream_t)stream);
   const int smem = (kPatchPad + 128 * 64) * sizeof(float);
   const long long ntiles = (long long)N * (W / 2 / kTileW) * (H / 2 / kTileH);
   int blocks = g_stem_bwd_blocks_per_sm * kNumSMs;

@@ -771,18 +771,35 @@ def test_stem_fwd_bwd(dtype):
     y = torch.empty(N, H // 2, W // 2, 64, device=dev, dtype=dtype)
     st = L.stream_ptr()
     L.call("hg_stem_fwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(conv.weight), L.ptr(conv.bias), N, H, W, 1, L.ptr(y), st)
-    ref = F.relu(conv(x))
+    # bf16 path: the tensor-core stem reads the image and the weights as bf16 (what autocast does to this convolution):
+    # the reference is taken on bf16-representable operands, as for every other convolution
+    xr = x.to(dtype).float()
+    ref = F.relu(F.conv2d(xr, conv.weight.to(dtype).float(), conv.bias, 2, 3))
     close(nchw(y, 64), ref.detach(), 1e-2 if dtype == torch.bfloat16 else 1e-5, "stem fwd")
+    if dtype == torch.bfloat16:
+        close(nchw(y, 64), F.relu(conv(x)).detach(), 2e-2, "stem fwd vs fp32 operands")
     dy = nhwc(torch.randn(N, 64, H // 2, W // 2, device=dev), dtype)
     # reference backward with the kernel's own stored activation as ReLU mask
     mask = (nchw(y, 64) > 0).float()
     g = nchw(dy, 64) * mask
-    ref_dw = torch.nn.grad.conv2d_weight(x, conv.weight.shape, g, 2, 3)
+    ref_dw = torch.nn.grad.conv2d_weight(xr, conv.weight.shape, g, 2, 3)
     dw = torch.zeros_like(conv.weight)
     db = torch.zeros(64, device=dev)
     L.call("hg_stem_bwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(y), L.ptr(dy), N, H, W, 1, L.ptr(dw), L.ptr(db), st)
     close(dw, ref_dw, 1e-4, "stem dw")
     close(db, g.sum((0, 2, 3)), 1e-4, "stem db")
+    if dtype == torch.bfloat16:
+        # the CUDA-core kernels (fp32 image and weights) stay selectable
+        L.call("hg_set_option", b"stem_tc", 0)
+        try:
+            y0 = torch.empty_like(y)
+            L.call("hg_stem_fwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(conv.weight), L.ptr(conv.bias), N, H, W, 1, L.ptr(y0), st)
+            close(nchw(y0, 64), F.relu(conv(x)).detach(), 1e-2, "stem fwd (CUDA cores)")
+            dw0, db0 = torch.zeros_like(conv.weight), torch.zeros(64, device=dev)
+            L.call("hg_stem_bwd", L.hg_dtype(dtype), L.ptr(x), L.ptr(y), L.ptr(dy), N, H, W, 1, L.ptr(dw0), L.ptr(db0), st)
+            close(dw0, torch.nn.grad.conv2d_weight(x, conv.weight.shape, g, 2, 3), 1e-4, "stem dw (CUDA cores)")
+        finally:
+            L.call("hg_set_option", b"stem_tc", 1)
 
 
 def test_layout_roundtrip_and_add():

@@ -488,14 +488,28 @@ __global__ void bn_running_kernel(const BnRunningModule* __restrict__ mods, cons
   const BnRunningModule md = mods[blockIdx.x];
   for (int c = threadIdx.x; c < md.C; c += blockDim.x) {
     float rm = md.rmean[c], rv = md.rvar[c];
-    for (int i = 0; i < md.num_sites; ++i) {
-      const BnRunningSite s = sites[md.first_site + i];
-      const float m1 = s.stats[c] / s.count;
-      const float mu = s.stats[2 * md.Cp + c] + m1;
-      const float var = fmaxf(s.stats[md.Cp + c] / s.count - m1 * m1, 0.f);
-      const float unb = s.count > 1.f ? var * s.count / (s.count - 1.f) : var;
-      rm = (1.f - md.momentum) * rm + md.momentum * mu;
-      rv = (1.f - md.momentum) * rv + md.momentum * unb;
+    // The EMA is a sequential recurrence over the call sites, but its inputs are not: the statistics of eight sites are
+    // requested together (a site at a time was two dependent L2 round trips per site: 80 us for the 64 calls of a shared
+    // module at the end of every forward; 54 us now).
+    for (int i0 = 0; i0 < md.num_sites; i0 += 8) {
+      float mu[8], unb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j < md.num_sites ? i0 + j : md.num_sites - 1;
+        const BnRunningSite s = sites[md.first_site + i];
+        const float s1 = s.stats[c], s2 = s.stats[md.Cp + c], pv = s.stats[2 * md.Cp + c];
+        const float m1 = s1 / s.count;
+        mu[j] = pv + m1;
+        const float var = fmaxf(s2 / s.count - m1 * m1, 0.f);
+        unb[j] = s.count > 1.f ? var * s.count / (s.count - 1.f) : var;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (i0 + j < md.num_sites) {
+          rm = (1.f - md.momentum) * rm + md.momentum * mu[j];
+          rv = (1.f - md.momentum) * rv + md.momentum * unb[j];
+        }
+      }
     }
     md.rmean[c] = rm;
     md.rvar[c] = rv;

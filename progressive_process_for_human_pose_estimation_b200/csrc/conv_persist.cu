@@ -20,10 +20,13 @@
 // 3x3: ONE activation box of R+2 image rows (the tile plus a halo row above and below), shifted by dw, serves the three
 // taps dh = -1, 0, +1 -- the A operand of tap dh is the same shared-memory image read (dh+1)*W pixel rows further
 // down (whole image rows: every start stays 1024-byte aligned for the 128-byte swizzle).  That halves the operand bytes
-// per FLOP twice over (96 KB per 12.6 MFLOP at 64x64 instead of 32 KB per 2.1 MFLOP); measured, the 3x3 kernel is then
-// bound by shared-memory bandwidth (an M=128, N=128 tcgen05.mma reads 8 KB of operands per 64 cycles = the whole 128 B/clk
-// of the SM, next to the TMA writes) and by the chip-wide L2 -> SM rate (340 MB per launch at ~12.3 TB/s = 27.6 us with
-// the MMAs switched off), so it only draws level with the tile kernel: persist_3x3 is off by default.
+// per FLOP twice over (96 KB per 12.6 MFLOP at 64x64 instead of 32 KB per 2.1 MFLOP).  What paces it (measured,
+// profiles/r02g_mma_issue_probe.txt): an SS-mode tcgen05.mma reads its shared-memory operands at ~64 B/clk -- M=128, N=128,
+// K=16 is 8 KB = 125 cycles (64 if MAC-bound) -- and the chip-wide L2 -> SM rate (340 MB per launch = 28.7 us with the
+// MMAs switched off).  With 128 output channels (TR) the accumulators are therefore TRANSPOSED: the weight tile is the
+// M = 128 operand, the 256 pixel rows of the box ONE N = 256 operand (12 KB per 2 x 128x128x16 MACs instead of 16 KB),
+// D[channel][pixel] in TMEM, per-channel sums in registers: 42.9 us at 64x64 vs 51.0 us on the tile kernel; on by default
+// at >= persist_min_units (persist_3x3 = 1; 2 = also the pixel-major 3x3 shapes, which only draw level).
 #include "hg_common.cuh"
 
 // -DHG_DBG_TS=1 (make DBG=1): CTA 0 accumulates the cycles each role spends waiting on each barrier / in each epilogue

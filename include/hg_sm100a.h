@@ -256,7 +256,10 @@ HG_API int hg_nchw_f32_to_nhwc(int dtype, const float* src_nchw, const void* add
                         void* stream);
 HG_API int hg_nhwc_to_nchw_f32(int dtype, const void* src, int N, int C, int H, int W, float* dst_nchw, void* stream);
 
-/* ---- stem: Conv2d(3,64,7,2,3) + ReLU on the fp32 NCHW image batch (try_with_torch.py:262,276-277) ---- */
+/* ---- stem: Conv2d(3,64,7,2,3) + ReLU on the fp32 NCHW image batch (try_with_torch.py:262,276-277) ----
+ * dtype HG_BF16: tcgen05 GEMMs on an im2col tile built in shared memory (image as a hi + lo bf16 pair in the forward, as
+ * bf16 in the weight gradient; weights as bf16); dtype HG_F32, or hg_set_option("stem_tc", 0): CUDA-core kernels on the
+ * fp32 operands. */
 /* relu = 1: ReLU fused (try_with_torch.py:276-277); relu = 0: raw output for the BatchNorm that follows in
  * hourglass_compare.py:549-552.  bias may be NULL. */
 HG_API int hg_stem_fwd(int dtype, const float* x_nchw, const float* w_oihw, const float* bias, int N, int H, int W,

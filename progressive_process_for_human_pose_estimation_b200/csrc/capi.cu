@@ -179,8 +179,7 @@ int hg_set_option(const char* name, int value) {
       cudaDeviceSynchronize();
       cudaMemcpy(h, g_dbg_ts, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "  producer: total %lld, a_empty %lld, b_empty %lld\n", h[0], h[1], h[2]);
-      fprintf(stderr, "  mma     : total %lld, tmem_empty %lld, a_full %lld, b_full %lld, mma issue %lld, commits %lld, fence %lld, syncwarp %lld\n", h[4], h[5],
-              h[6], h[7], h[14], h[15], h[16], h[17]);
+      fprintf(stderr, "  mma     : total %lld, tmem_empty %lld, a_full %lld, b_full %lld\n", h[4], h[5], h[6], h[7]);
       fprintf(stderr, "  epilogue: total %lld, tmem_full %lld, y+ld %lld, row %lld, col %lld, store wait %lld\n", h[8], h[9],
               h[10], h[11], h[12], h[13]);
     } else if (value == 0) {

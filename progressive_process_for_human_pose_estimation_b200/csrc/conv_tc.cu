@@ -36,7 +36,8 @@ int g_short_alias = 1;         // 1: multi-wave 1x1 kernels with a residual / ra
                                // into the aliased staging tile: 64 KB per CTA, 3 CTAs/SM instead of 2
 int g_small_n_tiles = 0;       // 1: one-wave grids use 64-channel N tiles
 int g_mid_n_tiles = 0;         // 1: grids of 1..2 waves of 128-wide tiles use 64-channel N tiles
-int g_wgrad_big_n_panels = 0;   // larger maps: input-channel panels per CTA (0 = all): fewer K splits, fewer atomics
+int g_wgrad_big_n_panels = -1;  // larger maps: input-channel panels per CTA (< 0 = all (default), 0 = policy: 1x1 -> one panel,
+                                // 3x3 -> all: isolated 1x1 launches -5 .. -30 %, step unchanged, 978 vs 980 images/s; > 0 = fixed)
 int g_wgrad_small_n_panels = 0; // small maps (see g_wgrad_t1_max_kb): input-channel panels (of 64) per CTA; 0 = policy
                                 // (1x1 or <= 32 K blocks: 1 panel, else 2), -1 = never split the input channels
 int g_wgrad_t1_max_kb = 128;    // "small map": at most this many 64-pixel K blocks (16x16 at batch 32); 3x3: one tap per CTA     // 3x3 wgrad: one tap per CTA when the map has at most this many 64-pixel K blocks
@@ -1334,9 +1335,15 @@ int conv_wgrad_bf16(const HgConvDesc* d, const void* x, const void* dy, float* d
     // pushes through its SM's L2 port are what a small wgrad launch costs)
     // (B200, batch 32, us per launch: 3x3 128->128 @4x4 11.5 -> 4.5, 1x1 256->128 8.1 -> 4.5, 3x3 @16x16 15.8 -> 10.7)
     p.n_groups = 1;
-    if ((M + 63) / 64 > g_wgrad_t1_max_kb && g_wgrad_big_n_panels > 0 && Cin_p / 64 > g_wgrad_big_n_panels &&
-        (Cin_p / 64) % g_wgrad_big_n_panels == 0)
-      p.n_groups = Cin_p / 64 / g_wgrad_big_n_panels;
+    // larger maps, 1x1: ONE 64-channel input panel per CTA as well (two for 256 -> 256 at 64x64).  The CTAs then split K
+    // less finely (148 / n_groups slices) and each adds a quarter of the columns: a quarter of the fp32 atomics, which
+    // outweighs the N = 64 MMAs and the dy tile re-read through L2 (B200, batch 32, us per launch: 256->128 @64x64
+    // 29.8 -> 21.2, @32x32 14.2 -> 10.1; 256->256 @32x32 17.4 -> 12.3; 128->256 @32x32 12.6 -> 10.2; 256->16 @64x64
+    // 23.7 -> 17.6).  3x3: slower (42.7 -> 49.3 at 64x64), stays whole.
+    int big_panels = g_wgrad_big_n_panels;   // 0 = this policy, > 0 = fixed, < 0 = never
+    if (big_panels == 0) big_panels = taps == 1 ? ((Cin_p == 256 && Cout_p == 256 && M >= 131072) ? 2 : 1) : -1;
+    if ((M + 63) / 64 > g_wgrad_t1_max_kb && big_panels > 0 && Cin_p / 64 > big_panels && (Cin_p / 64) % big_panels == 0)
+      p.n_groups = Cin_p / 64 / big_panels;
     if ((M + 63) / 64 <= g_wgrad_t1_max_kb && g_wgrad_small_n_panels >= 0) {
       int per_cta = g_wgrad_small_n_panels;
       if (per_cta == 0) per_cta = (taps == 1 || (M + 63) / 64 <= 32) ? 1 : 2;
